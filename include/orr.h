@@ -1,0 +1,212 @@
+/*
+ * orr.h — C ABI of liborr.so, the B200-native hybrid recall scorer.
+ *
+ * The reference (fchchen/omni-recall-rag, .NET 10) has NO native/FFI boundary for
+ * this path: its seams are two DI-registered C# interfaces,
+ *   IRecallSearchService.SearchAsync      src/OmniRecall.Api/Services/RecallSearchService.cs:6-9
+ *   IIngestionStore (8 async methods)     src/OmniRecall.Api/Services/IIngestionStore.cs:5-17
+ * A drop-in therefore adds two C# classes (GpuIngestionStore, GpuRecallSearchService,
+ * see INTEGRATION.md and dotnet/) that P/Invoke the functions below.  Each entry point
+ * cites the reference code whose work it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every buffer is caller-owned; inputs are borrowed for the
+ *     duration of the call; outputs are written into caller-allocated arrays;
+ *   - return 0 (ORR_OK) or a negative ORR_E_* code, never an exception/abort;
+ *     orr_last_error() returns a thread-local message for the last failing call;
+ *   - one orr_store per GPU shard; orr_search* may be called concurrently from any
+ *     number of host threads; mutators are serialised internally (RW lock) and are
+ *     safe against in-flight searches;
+ *   - there is NO CPU fallback: without a usable CUDA device orr_store_create fails
+ *     with ORR_E_CUDA.
+ *   - "ticks" are .NET DateTime ticks (100 ns since 0001-01-01), the unit
+ *     RecencyScore subtracts (RecallSearchService.cs:115-119).
+ */
+#ifndef ORR_H_
+#define ORR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORR_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------ */
+#define ORR_OK              0
+#define ORR_E_INVALID      -1   /* bad argument (NULL, negative size, dim mismatch of a buffer) */
+#define ORR_E_CUDA         -2   /* CUDA runtime/driver failure, no device, kernel fault         */
+#define ORR_E_OOM          -3   /* HBM or pinned-host allocation failed / capacity exhausted    */
+#define ORR_E_UNSUPPORTED  -4   /* shape outside what the kernels implement (see limits below)  */
+#define ORR_E_INTERNAL     -5   /* invariant violated (bug)                                     */
+
+/* ---- limits ------------------------------------------------------------------------ */
+#define ORR_MAX_QUERY_TERMS   64    /* distinct query terms after A-2 filtering           */
+#define ORR_MAX_QUERY_PROBES  128   /* (hash,term) probe pairs per query                  */
+#define ORR_TICKS_PER_DAY     864000000000LL
+
+typedef struct orr_store orr_store;    /* opaque: one GPU shard */
+
+/* Scorer constants are hard-coded in the reference (RecallSearchService.cs:66,118);
+ * they are carried here so the defaults are explicit.  orr_config_default() fills
+ * 0.7 / 0.2 / 0.1 / 30.0. */
+typedef struct orr_config {
+    int32_t  abi_version;        /* ORR_ABI_VERSION                                           */
+    int32_t  device;             /* CUDA ordinal of the GPU that owns this shard              */
+    int32_t  dim;                /* embedding width D (fp32 per row); multiple of 4, <= 8192  */
+    int32_t  term_slots;         /* hashed-term slots per chunk: 32, 64 or 128                */
+    int64_t  capacity_rows;      /* rows of HBM reserved up front (row-major fp32[cap][D])    */
+    uint64_t row_base;           /* global row id of local row 0 (row-sharded corpora)        */
+    double   w_cos, w_kw, w_rec; /* RecallSearchService.cs:66                                 */
+    double   recency_days;       /* RecallSearchService.cs:118                                */
+} orr_config;
+
+/* One citation, in final reference order (score desc, ticks desc, row asc):
+ * what RecallSearchService.cs:34-37 leaves in `scored`.  `row` is the global row id
+ * (row_base + local row) the C# shim maps back to its CosmosChunkRecord. */
+typedef struct orr_hit {
+    uint64_t row;
+    double   score;
+    int64_t  created_ticks;
+} orr_hit;
+
+/* Device/host timing of the last orr_search* call made on the calling thread. */
+typedef struct orr_timing {
+    float   scan_ms;        /* K1 fused scan kernel(s), CUDA events                       */
+    float   finalize_ms;    /* K2 merge + exact fp64 re-score + order                     */
+    float   total_device_ms;/* first launch to last kernel end                            */
+    float   wall_ms;        /* host wall clock around the whole C-ABI call                */
+    int32_t path;           /* ORR_PATH_*                                                 */
+    int32_t n_survivors;    /* rows re-scored exactly                                     */
+    int64_t rows_scanned;
+} orr_timing;
+
+#define ORR_PATH_FUSED      1   /* K1 fused fp32 scan + register top-k, K2 exact re-score     */
+#define ORR_PATH_EXACT      2   /* full fp64 scan (no-embedding mode, large k, or escalation) */
+#define ORR_PATH_SUBSET     3   /* candidate_cap > 0: exact scoring of the capped subset      */
+#define ORR_PATH_BATCH      4   /* tcgen05 batched contraction + re-rank                      */
+#define ORR_PATH_ESCALATED  0x100 /* OR-ed in when the fused path's bound check failed        */
+
+void orr_config_default(orr_config* cfg);
+
+/* ---- store: replaces InMemoryIngestionStore's chunk side ----------------------------
+ * (src/OmniRecall.Api/Services/InMemoryIngestionStore.cs:8-9 dictionaries). */
+int  orr_store_create(const orr_config* cfg, orr_store** out);
+void orr_store_destroy(orr_store* s);
+
+/* Replace-by-document, the semantics of UpsertChunksAsync
+ * (InMemoryIngestionStore.cs:17-25): the document's previous rows are tombstoned and
+ * the n chunks are appended in the order given (caller passes them in ChunkIndex order,
+ * :23).  emb is n x dim row-major fp32 (may be NULL = no chunk has an embedding);
+ * has_emb[i]==0 marks a chunk whose Embedding is null/empty/of another length
+ * (RecallSearchService.cs:71-72 -> cosine 0).  term_hashes/term_offsets is a CSR of the
+ * DISTINCT orr_hash_term() values of each chunk's lower-cased whitespace tokens
+ * (use orr_tokenize_content); at most cfg.term_slots per chunk.  out_rows (may be
+ * NULL) receives the n global row ids. */
+int  orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n,
+        const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
+        const uint64_t* term_hashes, const uint32_t* term_offsets, uint64_t* out_rows);
+
+/* DeleteDocumentAsync (InMemoryIngestionStore.cs:50-55): tombstones the rows. */
+int  orr_store_delete_document(orr_store* s, uint64_t doc_key);
+
+/* Live (non-tombstoned) rows, and rows physically occupied. */
+int64_t orr_store_count(const orr_store* s);
+int64_t orr_store_rows_used(const orr_store* s);
+
+/* ---- text -> terms: the single definition of tokenising and hashing -----------------
+ * orr_tokenize_query restates KeywordScore's query side (RecallSearchService.cs:95-108):
+ * split on Unicode white space, lower-case, ordinal-distinct (first occurrence kept),
+ * drop the 28 stop words (:13-18) unless that empties the list.  Returns the number of
+ * terms in *n (0 => keyword score 0 for every chunk).
+ * orr_tokenize_content produces the distinct token hashes of one chunk's Content. */
+uint64_t orr_hash_term(const char* utf8_lower, int32_t len);
+int  orr_tokenize_query(const char* utf8, int32_t len, uint64_t* out_hashes, int32_t cap, int32_t* n);
+int  orr_tokenize_content(const char* utf8, int32_t len, uint64_t* out_hashes, int32_t cap, int32_t* n);
+
+/* ---- search: replaces the scoring loop + ordering of SearchAsync ----------------------
+ * (RecallSearchService.cs:28-37 with ScoreChunk :59-67, CosineSimilarity :69-88,
+ * KeywordScore :90-113, RecencyScore :115-119).
+ *   q/q_dim      query embedding in HOST memory; q_dim==0 => no embedding (cosine 0, :71)
+ *   n_terms      |terms| (the denominator of :112); 0 => keyword 0
+ *   probe_hash   n_probes term hashes; probe_term[i] in [0,n_terms) says which query term
+ *                hash i satisfies (NULL => identity, n_probes==n_terms).  More than one
+ *                probe per term lets the host express substring expansion (:111).
+ *   now_ticks    the clock RecencyScore reads (:117), injected once per query
+ *   top_k        clamped to max(1, top_k) (:36)
+ *   candidate_cap 0 = score every live row (north-star behaviour); 300 = the
+ *                reference's GetRecentChunksAsync(maxCount: 300) pre-selection (:26)
+ *   out/n_out    caller array of >= max(1,top_k) hits; *n_out = hits written (0 if empty)
+ */
+int  orr_search(orr_store* s, const float* q, int32_t q_dim,
+        int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+        int64_t now_ticks, int32_t top_k, int32_t candidate_cap,
+        orr_hit* out, int32_t* n_out);
+
+/* Same work with every buffer already resident in HBM on cfg.device and no host
+ * synchronisation: q_dev fp32[q_dim], probes copied at enqueue time (host arrays),
+ * out_dev orr_hit[max(1,top_k)], status_dev int32[2] = {n_out, flags}; flags bit0 set
+ * means the fp32 selection bound check failed and the caller must re-run through
+ * orr_search (which escalates to the exact path).  Enqueued on `cuda_stream`
+ * (a cudaStream_t passed as void*). */
+int  orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim,
+        int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+        int64_t now_ticks, int32_t top_k,
+        orr_hit* out_dev, int32_t* status_dev, void* cuda_stream);
+
+/* Batched queries (tcgen05 contraction + exact re-rank).  q is batch x q_dim row-major
+ * in HOST memory; terms are a CSR over queries: query b owns probes
+ * [probe_offsets[b], probe_offsets[b+1]) and n_terms[b] terms.  out is
+ * batch x max(1,top_k); n_out[b] hits are valid in row b. */
+int  orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
+        const int32_t* n_terms, const uint64_t* probe_hash, const int32_t* probe_term,
+        const uint32_t* probe_offsets,
+        int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
+
+/* Merge per-shard hit lists (each already in reference order) into the global top-k
+ * with the same tie chain; used after the NCCL all-gather of per-GPU candidates. */
+int  orr_merge_hits(const orr_hit* lists, const int32_t* list_len, int32_t n_lists,
+        int32_t list_stride, int32_t top_k, orr_hit* out, int32_t* n_out);
+
+/* Device-side form of the same merge, for the multi-GPU path: lists_dev is the
+ * all-gathered [n_lists][list_stride] hit array, status_dev the all-gathered
+ * [n_lists][2] {n_out, flags}; out_status_dev = {n_out, OR of flags}.  Enqueued on
+ * `cuda_stream` of `device`, no host synchronisation. */
+int  orr_merge_hits_device(int32_t device, const orr_hit* lists_dev, const int32_t* status_dev,
+        int32_t n_lists, int32_t list_stride, int32_t top_k,
+        orr_hit* out_dev, int32_t* out_status_dev, void* cuda_stream);
+
+const char* orr_last_error(void);
+int  orr_last_timing(orr_timing* out);
+
+/* ---- synthetic corpora (bench/test utility) ---------------------
+ * Counter-based generator: every value is a pure function of (seed,row,col), computed
+ * with integer arithmetic and correctly-rounded IEEE operations only, so the device
+ * fill and the host generator are bit-identical.  orr_synth_rows_host produces the
+ * rows on the host (oracle input); orr_store_fill_synthetic appends n rows generated
+ * on the device straight into HBM. */
+typedef struct orr_synth_spec {
+    uint64_t seed;
+    int32_t  dim;            /* stored width; rows are the first `dim` components ...     */
+    int32_t  gen_dim;        /* ... of a unit vector of this width (dim==gen_dim: unit)   */
+    int32_t  terms_per_chunk;/* distinct vocabulary tokens per chunk (<= term_slots)       */
+    int32_t  vocab;          /* vocabulary size V, tokens "t%07d"                          */
+    int64_t  now_ticks;      /* timestamps are now_ticks - U[0, 365 d)                     */
+    int32_t  zero_row_ppm;   /* rows whose embedding is all-zero, parts per million        */
+    int32_t  dup_row_ppm;    /* rows that duplicate an earlier row (tie stress)            */
+} orr_synth_spec;
+
+void orr_synth_spec_default(orr_synth_spec* spec, int32_t dim);
+int  orr_synth_rows_host(const orr_synth_spec* spec, uint64_t first_row, int64_t n,
+        float* emb, int64_t* ticks, uint32_t* term_ids /* n x terms_per_chunk */,
+        uint64_t* doc_first_row /* n */);
+int  orr_synth_query_host(const orr_synth_spec* spec, uint64_t query_index, uint64_t corpus_rows,
+        int32_t n_terms, int32_t frequent_terms, float* q /* dim */, uint32_t* term_ids /* n_terms */);
+int  orr_synth_term_text(uint32_t term_id, char* out9 /* 8 chars + NUL */);
+int  orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t first_row, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORR_H_ */

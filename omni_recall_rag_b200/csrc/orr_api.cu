@@ -1,0 +1,573 @@
+// orr_api.cu — the C ABI (include/orr.h): HBM-resident store + search orchestration.
+//
+// Store = the chunk side of InMemoryIngestionStore
+// (src/OmniRecall.Api/Services/InMemoryIngestionStore.cs:8-9,17-25,50-55) laid out for the
+// scan: row-major fp32 embeddings, an int64 CreatedAtUtc column (INT64_MIN = tombstone) and
+// two fixed-width hashed term tables (32-bit for the scan, 64-bit for the exact re-score).
+// Rows are append-only; replace-by-document tombstones the old rows and appends.
+//
+// Search = RecallSearchService.SearchAsync's scoring loop and ordering (:26-37):
+//   fused   K1 scan (fp32 select, orr_scan.cu) -> K3 exact re-score/order/bound check
+//   exact   full fp64 pass + stable two-key radix sort (no-embedding mode, large k, or when
+//           K3's bound check could not prove the fp32 selection safe)
+//   subset  candidate_cap > 0: the reference's "300 most recent chunks" pre-selection
+//           (:26, InMemoryIngestionStore.cs:57-65) on the host tick mirror, exact scoring of
+//           just those rows.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "orr_internal.h"
+
+namespace {
+
+struct SearchCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    OrrScratch sc{};
+    float* h_q = nullptr;          // pinned
+    orr_hit* h_hits = nullptr;     // pinned
+    int32_t* h_status = nullptr;   // pinned [2]
+    uint32_t* h_rows = nullptr;    // pinned [ORR_SORT_MAX]
+    int32_t hits_cap = 0;
+    int64_t exact_rows_cap = 0;
+};
+
+thread_local orr_timing g_timing{};
+
+}  // namespace
+
+struct orr_store {
+    orr_config cfg{};
+    int sms = 148;
+    float* d_emb = nullptr;
+    int64_t* d_ticks = nullptr;
+    uint32_t* d_terms32 = nullptr;
+    uint64_t* d_terms64 = nullptr;
+    int64_t rows_used = 0;
+    int64_t live_rows = 0;
+    uint64_t version = 0;
+    std::unordered_map<uint64_t, std::vector<std::pair<int64_t, int64_t>>> docs;   // doc -> [first,count) runs
+    std::vector<int64_t> h_ticks;                                                   // host mirror (lazy)
+    std::shared_mutex mu;                                                           // searches shared, mutators exclusive
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<SearchCtx>> pool;
+    std::mutex dev_mu;
+    std::unique_ptr<SearchCtx> dev_ctx;                                             // orr_search_device scratch
+    std::mutex cap_mu;
+    uint64_t cap_version = ~0ull;
+    int32_t cap_value = -1;
+    std::vector<uint32_t> cap_rows;
+    cudaStream_t mut_stream = nullptr;
+};
+
+namespace {
+
+OrrShard shard_view(const orr_store* s) {
+    OrrShard v;
+    v.emb = s->d_emb; v.ticks = s->d_ticks; v.terms32 = s->d_terms32; v.terms64 = s->d_terms64;
+    v.rows = s->rows_used; v.dim = s->cfg.dim; v.slots = s->cfg.term_slots; v.row_base = s->cfg.row_base;
+    return v;
+}
+OrrWeights weights_of(const orr_store* s) {
+    return OrrWeights{s->cfg.w_cos, s->cfg.w_kw, s->cfg.w_rec, s->cfg.recency_days};
+}
+
+void free_ctx(SearchCtx* c) {
+    if (!c) return;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->sc.q); cudaFree(c->sc.cta_cands); cudaFree(c->sc.cta_floor); cudaFree(c->sc.surv_rows);
+    cudaFree(c->sc.exact); cudaFree(c->sc.sel); cudaFree(c->sc.hits); cudaFree(c->sc.status);
+    cudaFree(c->sc.scores64); cudaFree(c->sc.cub_tmp);
+    cudaFree(c->sc.sort_keys[0]); cudaFree(c->sc.sort_keys[1]);
+    cudaFree(c->sc.sort_vals[0]); cudaFree(c->sc.sort_vals[1]);
+    cudaFreeHost(c->h_q); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_status); cudaFreeHost(c->h_rows);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+int ensure_hits(SearchCtx* c, int k) {
+    if (k <= c->hits_cap) return ORR_OK;
+    int cap = std::max(k, 256);
+    cudaFree(c->sc.hits); c->sc.hits = nullptr;
+    cudaFreeHost(c->h_hits); c->h_hits = nullptr;
+    c->hits_cap = 0;
+    ORR_CUDA_OK(cudaMalloc(&c->sc.hits, sizeof(orr_hit) * (size_t)cap));
+    ORR_CUDA_OK(cudaMallocHost(&c->h_hits, sizeof(orr_hit) * (size_t)cap));
+    c->hits_cap = cap;
+    return ORR_OK;
+}
+
+int make_ctx(orr_store* s, std::unique_ptr<SearchCtx>& out, bool own_stream) {
+    std::unique_ptr<SearchCtx> c(new SearchCtx());
+    const int dim = s->cfg.dim;
+    int rc = [&]() -> int {
+        if (own_stream) {
+            ORR_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            for (auto& e : c->ev) ORR_CUDA_OK(cudaEventCreate(&e));
+        }
+        ORR_CUDA_OK(cudaMalloc(&c->sc.q, sizeof(float) * (size_t)dim));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.cta_cands, sizeof(uint2) * (size_t)s->sms * ORR_MAX_SURVIVORS));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.cta_floor, sizeof(float) * (size_t)s->sms));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.surv_rows, sizeof(uint32_t) * ORR_SORT_MAX));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.exact, sizeof(OrrExact) * ORR_SORT_MAX));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.sel, sizeof(int32_t) * 8));
+        ORR_CUDA_OK(cudaMemset(c->sc.sel, 0, sizeof(int32_t) * 8));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.status, sizeof(int32_t) * 2));
+        ORR_CUDA_OK(cudaMallocHost(&c->h_q, sizeof(float) * (size_t)dim));
+        ORR_CUDA_OK(cudaMallocHost(&c->h_status, sizeof(int32_t) * 2));
+        ORR_CUDA_OK(cudaMallocHost(&c->h_rows, sizeof(uint32_t) * ORR_SORT_MAX));
+        return ensure_hits(c.get(), 256);
+    }();
+    if (rc != ORR_OK) { free_ctx(c.get()); return rc; }
+    out = std::move(c);
+    return ORR_OK;
+}
+
+int ensure_exact_buffers(orr_store* s, SearchCtx* c) {
+    const int64_t need = s->cfg.capacity_rows;
+    if (c->exact_rows_cap >= need) return ORR_OK;
+    ORR_CUDA_OK(cudaMalloc(&c->sc.scores64, sizeof(double) * (size_t)need));
+    for (int i = 0; i < 2; ++i) {
+        ORR_CUDA_OK(cudaMalloc(&c->sc.sort_keys[i], sizeof(uint64_t) * (size_t)need));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.sort_vals[i], sizeof(uint32_t) * (size_t)need));
+    }
+    c->exact_rows_cap = need;
+    return ORR_OK;
+}
+
+struct CtxLease {
+    orr_store* s;
+    std::unique_ptr<SearchCtx> c;
+    CtxLease(orr_store* st) : s(st) {}
+    int acquire() {
+        {
+            std::lock_guard<std::mutex> g(s->pool_mu);
+            if (!s->pool.empty()) { c = std::move(s->pool.back()); s->pool.pop_back(); return ORR_OK; }
+        }
+        return make_ctx(s, c, true);
+    }
+    ~CtxLease() {
+        if (c) { std::lock_guard<std::mutex> g(s->pool_mu); s->pool.push_back(std::move(c)); }
+    }
+};
+
+int build_probes(int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+                 OrrProbes* out) {
+    memset(out, 0, sizeof *out);
+    if (n_terms < 0 || n_probes < 0 || (n_probes > 0 && !probe_hash)) {
+        orr_set_error("search: bad term arguments");
+        return ORR_E_INVALID;
+    }
+    if (n_terms == 0) return ORR_OK;                                   // keyword 0 (:100-101)
+    if (n_terms > ORR_MAX_QUERY_TERMS || n_probes > ORR_MAX_QUERY_PROBES) {
+        orr_set_error("search: %d terms / %d probes exceed the limits (%d / %d)", n_terms, n_probes,
+                      ORR_MAX_QUERY_TERMS, ORR_MAX_QUERY_PROBES);
+        return ORR_E_UNSUPPORTED;
+    }
+    if (!probe_term && n_probes != n_terms) {
+        orr_set_error("search: probe_term is NULL but n_probes != n_terms");
+        return ORR_E_INVALID;
+    }
+    out->n_terms = n_terms;
+    out->n_probes = n_probes;
+    for (int i = 0; i < n_probes; ++i) {
+        const int32_t t = probe_term ? probe_term[i] : i;
+        if (t < 0 || t >= n_terms) { orr_set_error("search: probe_term[%d]=%d out of range", i, t); return ORR_E_INVALID; }
+        const uint64_t h = probe_hash[i] ? probe_hash[i] : 1ULL;
+        out->h64[i] = h;
+        out->h32[i] = orr_hash_low(h);
+        out->term[i] = (uint8_t)t;
+    }
+    return ORR_OK;
+}
+
+int survivors_for(int k) { return k <= 32 ? 64 : (k <= 96 ? 128 : 256); }
+
+// the reference's candidate pre-selection: newest `cap` live rows, (ticks desc, row asc)
+int capped_rows(orr_store* s, int32_t cap, std::vector<uint32_t>* out) {
+    std::lock_guard<std::mutex> g(s->cap_mu);
+    if (s->cap_version == s->version && s->cap_value == cap) { *out = s->cap_rows; return ORR_OK; }
+    if ((int64_t)s->h_ticks.size() < s->rows_used) {                   // refresh the host mirror
+        const size_t have = s->h_ticks.size();
+        s->h_ticks.resize((size_t)s->rows_used);
+        ORR_CUDA_OK(cudaMemcpy(s->h_ticks.data() + have, s->d_ticks + have,
+                               sizeof(int64_t) * (s->h_ticks.size() - have), cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint32_t> rows;
+    rows.reserve((size_t)s->live_rows);
+    for (int64_t i = 0; i < s->rows_used; ++i)
+        if (s->h_ticks[(size_t)i] != ORR_DEAD_TICKS) rows.push_back((uint32_t)i);
+    const auto& tk = s->h_ticks;
+    auto newer = [&](uint32_t a, uint32_t b) { return tk[a] != tk[b] ? tk[a] > tk[b] : a < b; };
+    const size_t keep = std::min<size_t>(rows.size(), (size_t)std::max(1, cap));
+    std::partial_sort(rows.begin(), rows.begin() + (ptrdiff_t)keep, rows.end(), newer);
+    rows.resize(keep);
+    s->cap_rows = rows; s->cap_version = s->version; s->cap_value = cap;
+    *out = std::move(rows);
+    return ORR_OK;
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" {
+
+void orr_config_default(orr_config* cfg) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->abi_version = ORR_ABI_VERSION;
+    cfg->device = 0;
+    cfg->dim = 3072;
+    cfg->term_slots = 64;
+    cfg->capacity_rows = 1 << 20;
+    cfg->row_base = 0;
+    cfg->w_cos = 0.7; cfg->w_kw = 0.2; cfg->w_rec = 0.1;   // RecallSearchService.cs:66
+    cfg->recency_days = 30.0;                              // :118
+}
+
+int orr_store_create(const orr_config* cfg, orr_store** out) {
+    if (!cfg || !out) { orr_set_error("orr_store_create: NULL argument"); return ORR_E_INVALID; }
+    *out = nullptr;
+    if (cfg->abi_version != ORR_ABI_VERSION) { orr_set_error("ABI version %d != %d", cfg->abi_version, ORR_ABI_VERSION); return ORR_E_INVALID; }
+    if (cfg->dim < 4 || cfg->dim > 8192 || (cfg->dim & 3)) { orr_set_error("dim %d must be a multiple of 4 in [4, 8192]", cfg->dim); return ORR_E_UNSUPPORTED; }
+    if (cfg->term_slots != 32 && cfg->term_slots != 64 && cfg->term_slots != 128) { orr_set_error("term_slots must be 32, 64 or 128"); return ORR_E_UNSUPPORTED; }
+    if (cfg->capacity_rows < 1 || cfg->capacity_rows > 0xfffffff0LL) { orr_set_error("capacity_rows out of range"); return ORR_E_INVALID; }
+    if (!(cfg->recency_days > 0.0)) { orr_set_error("recency_days must be positive"); return ORR_E_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device || cfg->device < 0) {
+        orr_set_error("no usable CUDA device %d (found %d); liborr has no CPU fallback", cfg->device, ndev);
+        cudaGetLastError();
+        return ORR_E_CUDA;
+    }
+    ORR_CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop{};
+    ORR_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        orr_set_error("device %d is sm_%d%d; liborr is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        return ORR_E_CUDA;
+    }
+    std::unique_ptr<orr_store> s(new orr_store());
+    s->cfg = *cfg;
+    s->sms = prop.multiProcessorCount;
+    const size_t cap = (size_t)cfg->capacity_rows;
+    int rc = [&]() -> int {
+        ORR_CUDA_OK(cudaMalloc(&s->d_emb, cap * (size_t)cfg->dim * sizeof(float)));
+        ORR_CUDA_OK(cudaMalloc(&s->d_ticks, cap * sizeof(int64_t)));
+        ORR_CUDA_OK(cudaMalloc(&s->d_terms32, cap * (size_t)cfg->term_slots * sizeof(uint32_t)));
+        ORR_CUDA_OK(cudaMalloc(&s->d_terms64, cap * (size_t)cfg->term_slots * sizeof(uint64_t)));
+        ORR_CUDA_OK(cudaStreamCreateWithFlags(&s->mut_stream, cudaStreamNonBlocking));
+        return ORR_OK;
+    }();
+    if (rc != ORR_OK) { orr_store_destroy(s.release()); return rc; }
+    *out = s.release();
+    return ORR_OK;
+}
+
+void orr_store_destroy(orr_store* s) {
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    for (auto& c : s->pool) free_ctx(c.get());
+    if (s->dev_ctx) free_ctx(s->dev_ctx.get());
+    if (s->mut_stream) cudaStreamDestroy(s->mut_stream);
+    cudaFree(s->d_emb); cudaFree(s->d_ticks); cudaFree(s->d_terms32); cudaFree(s->d_terms64);
+    delete s;
+}
+
+int64_t orr_store_count(const orr_store* s) { return s ? s->live_rows : 0; }
+int64_t orr_store_rows_used(const orr_store* s) { return s ? s->rows_used : 0; }
+
+static int tombstone_locked(orr_store* s, uint64_t doc_key) {
+    auto it = s->docs.find(doc_key);
+    if (it == s->docs.end()) return ORR_OK;
+    for (auto& run : it->second) {
+        std::vector<int64_t> dead((size_t)run.second, ORR_DEAD_TICKS);
+        ORR_CUDA_OK(cudaMemcpy(s->d_ticks + run.first, dead.data(), sizeof(int64_t) * dead.size(), cudaMemcpyHostToDevice));
+        for (int64_t r = run.first; r < run.first + run.second && r < (int64_t)s->h_ticks.size(); ++r)
+            s->h_ticks[(size_t)r] = ORR_DEAD_TICKS;
+        s->live_rows -= run.second;
+    }
+    s->docs.erase(it);
+    s->version++;
+    return ORR_OK;
+}
+
+int orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n, const float* emb,
+                                     const uint8_t* has_emb, const int64_t* created_ticks,
+                                     const uint64_t* term_hashes, const uint32_t* term_offsets,
+                                     uint64_t* out_rows) {
+    if (!s || n < 0 || (n > 0 && !created_ticks)) { orr_set_error("upsert: bad argument"); return ORR_E_INVALID; }
+    if (n == 0) return ORR_OK;                         // UpsertChunksAsync ignores empty batches (:19-20)
+    const int dim = s->cfg.dim, slots = s->cfg.term_slots;
+    for (int32_t i = 0; i < n; ++i) {
+        if (created_ticks[i] == ORR_DEAD_TICKS) { orr_set_error("upsert: ticks value reserved"); return ORR_E_INVALID; }
+        if (term_offsets) {
+            if (term_offsets[i + 1] < term_offsets[i] || (int64_t)(term_offsets[i + 1] - term_offsets[i]) > slots) {
+                orr_set_error("upsert: chunk %d has %u distinct terms, store has %d slots", i,
+                              term_offsets[i + 1] - term_offsets[i], slots);
+                return ORR_E_UNSUPPORTED;
+            }
+        }
+    }
+    std::unique_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (s->rows_used + n > s->cfg.capacity_rows) {
+        orr_set_error("upsert: store full (%lld + %d > %lld rows)", (long long)s->rows_used, n, (long long)s->cfg.capacity_rows);
+        return ORR_E_OOM;
+    }
+    int rc = tombstone_locked(s, doc_key);
+    if (rc != ORR_OK) return rc;
+    const int64_t first = s->rows_used;
+    if (emb) {
+        ORR_CUDA_OK(cudaMemcpy(s->d_emb + first * (int64_t)dim, emb, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice));
+        if (has_emb)
+            for (int32_t i = 0; i < n; ++i)
+                if (!has_emb[i]) ORR_CUDA_OK(cudaMemset(s->d_emb + (first + i) * (int64_t)dim, 0, sizeof(float) * (size_t)dim));
+    } else {
+        ORR_CUDA_OK(cudaMemset(s->d_emb + first * (int64_t)dim, 0, sizeof(float) * (size_t)n * dim));
+    }
+    std::vector<uint32_t> t32((size_t)n * slots, 0u);
+    std::vector<uint64_t> t64((size_t)n * slots, 0ull);
+    if (term_hashes && term_offsets) {
+        for (int32_t i = 0; i < n; ++i) {
+            int w = 0;
+            for (uint32_t j = term_offsets[i]; j < term_offsets[i + 1]; ++j, ++w) {
+                const uint64_t h = term_hashes[j] ? term_hashes[j] : 1ULL;
+                t64[(size_t)i * slots + w] = h;
+                t32[(size_t)i * slots + w] = orr_hash_low(h);
+            }
+        }
+    }
+    ORR_CUDA_OK(cudaMemcpy(s->d_terms32 + first * (int64_t)slots, t32.data(), sizeof(uint32_t) * t32.size(), cudaMemcpyHostToDevice));
+    ORR_CUDA_OK(cudaMemcpy(s->d_terms64 + first * (int64_t)slots, t64.data(), sizeof(uint64_t) * t64.size(), cudaMemcpyHostToDevice));
+    ORR_CUDA_OK(cudaMemcpy(s->d_ticks + first, created_ticks, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice));
+    if ((int64_t)s->h_ticks.size() == first) s->h_ticks.insert(s->h_ticks.end(), created_ticks, created_ticks + n);
+    s->docs[doc_key].push_back({first, (int64_t)n});
+    s->rows_used += n;
+    s->live_rows += n;
+    s->version++;
+    if (out_rows) for (int32_t i = 0; i < n; ++i) out_rows[i] = s->cfg.row_base + (uint64_t)(first + i);
+    return ORR_OK;
+}
+
+int orr_store_delete_document(orr_store* s, uint64_t doc_key) {
+    if (!s) { orr_set_error("delete: NULL store"); return ORR_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    return tombstone_locked(s, doc_key);
+}
+
+int orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t first_row, int64_t n) {
+    if (!s || !spec || n < 0) { orr_set_error("fill_synthetic: bad argument"); return ORR_E_INVALID; }
+    if (spec->dim != s->cfg.dim || spec->terms_per_chunk > s->cfg.term_slots || spec->gen_dim < spec->dim ||
+        spec->terms_per_chunk < 0 || spec->vocab != (1 << 20)) {
+        orr_set_error("fill_synthetic: spec does not match the store");
+        return ORR_E_INVALID;
+    }
+    std::unique_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (s->rows_used + n > s->cfg.capacity_rows) { orr_set_error("fill_synthetic: store full"); return ORR_E_OOM; }
+    int rc = orr_launch_synth_fill(s->d_emb, s->d_ticks, s->d_terms32, s->d_terms64, s->cfg.dim, s->cfg.term_slots,
+                                   *spec, first_row, s->rows_used, n, s->mut_stream);
+    if (rc != ORR_OK) return rc;
+    ORR_CUDA_OK(cudaStreamSynchronize(s->mut_stream));
+    s->rows_used += n;
+    s->live_rows += n;
+    s->version++;
+    return ORR_OK;
+}
+
+// ---- search --------------------------------------------------------------------------------
+static int run_exact(orr_store* s, SearchCtx* c, const OrrShard& sh, const OrrProbes& pr, int64_t now_ticks,
+                     int q_dim, int top_k) {
+    int rc = ensure_exact_buffers(s, c);
+    if (rc != ORR_OK) return rc;
+    rc = orr_launch_exact_scores(sh, c->sc, pr, weights_of(s), now_ticks, q_dim, c->stream);
+    if (rc != ORR_OK) return rc;
+    return orr_exact_select(sh, c->sc, top_k, c->stream);
+}
+
+int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
+               const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, int32_t top_k,
+               int32_t candidate_cap, orr_hit* out, int32_t* n_out) {
+    const double t0 = now_ms();
+    if (!s || !out || !n_out || q_dim < 0 || (q_dim > 0 && !q) || candidate_cap < 0) {
+        orr_set_error("orr_search: bad argument");
+        return ORR_E_INVALID;
+    }
+    *n_out = 0;
+    OrrProbes pr;
+    int rc = build_probes(n_terms, probe_hash, probe_term, n_probes, &pr);
+    if (rc != ORR_OK) return rc;
+    const int k = std::max(1, top_k);                                   // Math.Max(1, topK) :36
+    std::shared_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    memset(&g_timing, 0, sizeof g_timing);
+    if (s->live_rows == 0) { g_timing.wall_ms = (float)(now_ms() - t0); return ORR_OK; }   // empty store: no citations
+    CtxLease lease(s);
+    rc = lease.acquire();
+    if (rc != ORR_OK) return rc;
+    SearchCtx* c = lease.c.get();
+    const OrrShard sh = shard_view(s);
+    // :71-72 — a query whose length differs from the stored width scores cosine 0 everywhere
+    const int eff_q_dim = (q_dim == s->cfg.dim) ? q_dim : 0;
+    const int64_t kk = std::min<int64_t>(k, s->rows_used);
+    rc = ensure_hits(c, (int)kk);
+    if (rc != ORR_OK) return rc;
+    if (eff_q_dim > 0) {
+        memcpy(c->h_q, q, sizeof(float) * (size_t)q_dim);
+        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.q, c->h_q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream));
+    }
+    int path = 0;
+    ORR_CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+    if (candidate_cap > 0) {
+        path = ORR_PATH_SUBSET;
+        if (candidate_cap > ORR_SORT_MAX) { orr_set_error("candidate_cap %d > %d", candidate_cap, ORR_SORT_MAX); return ORR_E_UNSUPPORTED; }
+        std::vector<uint32_t> rows;
+        rc = capped_rows(s, candidate_cap, &rows);
+        if (rc != ORR_OK) return rc;
+        const int32_t nl = (int32_t)rows.size();
+        memcpy(c->h_rows, rows.data(), sizeof(uint32_t) * rows.size());
+        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.surv_rows, c->h_rows, sizeof(uint32_t) * rows.size(), cudaMemcpyHostToDevice, c->stream));
+        c->h_status[0] = nl;
+        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.sel, c->h_status, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+        rc = orr_launch_rescore(sh, c->sc, pr, weights_of(s), now_ticks, eff_q_dim, (int)kk, nl, false, c->stream);
+        if (rc != ORR_OK) return rc;
+        g_timing.n_survivors = nl;
+    } else if (eff_q_dim == 0 || k > ORR_FUSED_MAX_K) {
+        path = ORR_PATH_EXACT;
+        ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+        rc = run_exact(s, c, sh, pr, now_ticks, eff_q_dim, (int)kk);
+        if (rc != ORR_OK) return rc;
+    } else {
+        path = ORR_PATH_FUSED;
+        const int M = survivors_for(k);
+        rc = orr_launch_scan(sh, c->sc, pr, weights_of(s), now_ticks, M, s->sms, c->stream);
+        if (rc != ORR_OK) return rc;
+        ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+        rc = orr_launch_rescore(sh, c->sc, pr, weights_of(s), now_ticks, eff_q_dim, k, M, true, c->stream);
+        if (rc != ORR_OK) return rc;
+        g_timing.n_survivors = M;
+    }
+    ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+    ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+    ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+    ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
+    float scan_ms = 0.f, fin_ms = 0.f;
+    cudaEventElapsedTime(&scan_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&fin_ms, c->ev[1], c->ev[2]);
+    if (path == ORR_PATH_FUSED && (c->h_status[1] & 1)) {
+        // K3 could not prove the fp32 selection safe (ties / near-ties at the survivor
+        // boundary): re-run on the exact path.
+        path = ORR_PATH_EXACT | ORR_PATH_ESCALATED;
+        ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+        rc = run_exact(s, c, sh, pr, now_ticks, eff_q_dim, (int)kk);
+        if (rc != ORR_OK) return rc;
+        ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+        ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
+        float extra = 0.f;
+        cudaEventElapsedTime(&extra, c->ev[1], c->ev[2]);
+        fin_ms += extra;
+    }
+    const int got = std::min<int>(c->h_status[0], (int)kk);
+    memcpy(out, c->h_hits, sizeof(orr_hit) * (size_t)got);
+    *n_out = got;
+    g_timing.scan_ms = scan_ms;
+    g_timing.finalize_ms = fin_ms;
+    g_timing.total_device_ms = scan_ms + fin_ms;
+    g_timing.path = path;
+    g_timing.rows_scanned = (candidate_cap > 0) ? g_timing.n_survivors : s->rows_used;
+    g_timing.wall_ms = (float)(now_ms() - t0);
+    return ORR_OK;
+}
+
+int orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim, int32_t n_terms,
+                      const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+                      int64_t now_ticks, int32_t top_k, orr_hit* out_dev, int32_t* status_dev,
+                      void* cuda_stream) {
+    if (!s || !q_dev || !out_dev || !status_dev) { orr_set_error("orr_search_device: NULL argument"); return ORR_E_INVALID; }
+    if (q_dim != s->cfg.dim) { orr_set_error("orr_search_device: q_dim %d != store dim %d", q_dim, s->cfg.dim); return ORR_E_INVALID; }
+    const int k = std::max(1, top_k);
+    if (k > ORR_FUSED_MAX_K) { orr_set_error("orr_search_device: top_k %d > %d", k, ORR_FUSED_MAX_K); return ORR_E_UNSUPPORTED; }
+    OrrProbes pr;
+    int rc = build_probes(n_terms, probe_hash, probe_term, n_probes, &pr);
+    if (rc != ORR_OK) return rc;
+    std::shared_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (s->live_rows == 0) { ORR_CUDA_OK(cudaMemsetAsync(status_dev, 0, 2 * sizeof(int32_t), st)); return ORR_OK; }
+    std::lock_guard<std::mutex> g(s->dev_mu);
+    if (!s->dev_ctx) { rc = make_ctx(s, s->dev_ctx, false); if (rc != ORR_OK) return rc; }
+    OrrScratch sc = s->dev_ctx->sc;
+    sc.q = const_cast<float*>(q_dev);
+    sc.hits = out_dev;
+    sc.status = status_dev;
+    const OrrShard sh = shard_view(s);
+    const int M = survivors_for(k);
+    rc = orr_launch_scan(sh, sc, pr, weights_of(s), now_ticks, M, s->sms, st);
+    if (rc != ORR_OK) return rc;
+    return orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, q_dim, k, M, true, st);
+}
+
+int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim, const int32_t* n_terms,
+                     const uint64_t* probe_hash, const int32_t* probe_term, const uint32_t* probe_offsets,
+                     int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
+    // Round-1 batch path: the queries run back to back through the single-query path
+    // (the tcgen05 contraction replaces this loop).
+    if (!s || batch < 0 || !out || !n_out) { orr_set_error("orr_search_batch: bad argument"); return ORR_E_INVALID; }
+    const int k = std::max(1, top_k);
+    for (int32_t b = 0; b < batch; ++b) {
+        const uint32_t p0 = probe_offsets ? probe_offsets[b] : 0, p1 = probe_offsets ? probe_offsets[b + 1] : 0;
+        int rc = orr_search(s, q ? q + (int64_t)b * q_dim : nullptr, q_dim, n_terms ? n_terms[b] : 0,
+                            probe_hash ? probe_hash + p0 : nullptr, probe_term ? probe_term + p0 : nullptr,
+                            (int32_t)(p1 - p0), now_ticks, top_k, 0, out + (int64_t)b * k, n_out + b);
+        if (rc != ORR_OK) return rc;
+    }
+    return ORR_OK;
+}
+
+// host merge of per-shard lists with the reference tie chain (score desc / NaN last,
+// ticks desc, row asc); lists are independent so a k-way pick is enough
+int orr_merge_hits(const orr_hit* lists, const int32_t* list_len, int32_t n_lists, int32_t list_stride,
+                   int32_t top_k, orr_hit* out, int32_t* n_out) {
+    if (!lists || !list_len || !out || !n_out || n_lists < 0 || list_stride < 0) { orr_set_error("orr_merge_hits: bad argument"); return ORR_E_INVALID; }
+    const int k = std::max(1, top_k);
+    std::vector<orr_hit> all;
+    for (int32_t l = 0; l < n_lists; ++l)
+        for (int32_t i = 0; i < list_len[l] && i < list_stride; ++i) all.push_back(lists[(int64_t)l * list_stride + i]);
+    auto before = [](const orr_hit& x, const orr_hit& y) {
+        const bool xn = std::isnan(x.score), yn = std::isnan(y.score);
+        if (xn != yn) return yn;
+        if (!xn && x.score != y.score) return x.score > y.score;
+        if (x.created_ticks != y.created_ticks) return x.created_ticks > y.created_ticks;
+        return x.row < y.row;
+    };
+    std::sort(all.begin(), all.end(), before);
+    const int got = std::min<int>(k, (int)all.size());
+    for (int i = 0; i < got; ++i) out[i] = all[(size_t)i];
+    *n_out = got;
+    return ORR_OK;
+}
+
+int orr_merge_hits_device(int32_t device, const orr_hit* lists_dev, const int32_t* status_dev, int32_t n_lists,
+                          int32_t list_stride, int32_t top_k, orr_hit* out_dev, int32_t* out_status_dev,
+                          void* cuda_stream) {
+    if (!lists_dev || !status_dev || !out_dev || !out_status_dev) { orr_set_error("orr_merge_hits_device: NULL argument"); return ORR_E_INVALID; }
+    ORR_CUDA_OK(cudaSetDevice(device));
+    return orr_launch_merge(lists_dev, status_dev, n_lists, list_stride, top_k, out_dev, out_status_dev,
+                            (cudaStream_t)cuda_stream);
+}
+
+int orr_last_timing(orr_timing* out) {
+    if (!out) return ORR_E_INVALID;
+    *out = g_timing;
+    return ORR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// orr_internal.h — shared declarations of liborr.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/orr.h"
+
+// ---- error plumbing -----------------------------------------------------------------------
+void orr_set_error(const char* fmt, ...);
+#define ORR_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            orr_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                          __LINE__);                                                        \
+            return _e == cudaErrorMemoryAllocation ? ORR_E_OOM : ORR_E_CUDA;                \
+        }                                                                                   \
+    } while (0)
+
+// ---- constants ----------------------------------------------------------------------------
+constexpr int64_t ORR_DEAD_TICKS = INT64_MIN;   // tombstone marker in the ticks column
+constexpr int ORR_SCAN_WARPS = 8;               // consumer warps per scan CTA
+constexpr int ORR_SCAN_STAGES = 2;              // TMA stages per warp
+constexpr int ORR_WARP_LIST = 32;               // per-warp register top list (one entry per lane)
+constexpr int ORR_MAX_SURVIVORS = 256;          // rows re-scored exactly on the fused path
+constexpr int ORR_FUSED_MAX_K = 224;            // largest top_k the fused path serves
+constexpr int ORR_SORT_MAX = 4096;              // entries the single-CTA exact sorter handles
+constexpr float ORR_SELECT_EPS = 2.0e-5f;       // bound on |fp32 scan score - exact score| (unit weights)
+
+// A query's keyword side as the kernels see it (passed by value in kernel params).
+struct OrrProbes {
+    int32_t  n_terms;                            // denominator of KeywordScore (:112)
+    int32_t  n_probes;
+    uint32_t h32[ORR_MAX_QUERY_PROBES];          // low word of the 64-bit hash (scan)
+    uint64_t h64[ORR_MAX_QUERY_PROBES];          // full hash (exact re-score)
+    uint8_t  term[ORR_MAX_QUERY_PROBES];         // query term index each probe satisfies
+};
+
+struct OrrWeights {
+    double w_cos, w_kw, w_rec, recency_days;
+};
+
+// exact per-row record produced by the re-score kernels and ordered by the sorter
+struct OrrExact {
+    double   score;
+    int64_t  ticks;
+    uint64_t row;      // LOCAL row index
+};
+
+// per-search device scratch (one per concurrent search; see SearchCtx in orr_api.cu)
+struct OrrScratch {
+    float*    q;              // [dim] query embedding on device
+    uint2*    cta_cands;      // [grid][ORR_MAX_SURVIVORS] (ordered-key, row) per CTA
+    float*    cta_floor;      // [grid] best score a CTA discarded (-inf if none)
+    uint32_t* surv_rows;      // [ORR_SORT_MAX] rows to re-score exactly
+    OrrExact* exact;          // [ORR_SORT_MAX] exact records
+    int32_t*  sel;            // [8]: {n_surv, tau_bits, ticket_scan, ticket_rescore, ...}
+    orr_hit*  hits;           // [max k] results
+    int32_t*  status;         // [2] {n_out, flags}
+    double*   scores64;       // [capacity] exact path: every row's score (lazily allocated)
+    void*     cub_tmp;        // exact path: cub temp storage (lazily allocated)
+    size_t    cub_tmp_bytes;
+    uint64_t* sort_keys[2];   // exact path: key double buffer
+    uint32_t* sort_vals[2];   // exact path: value double buffer
+};
+
+struct OrrShard {              // device view of one shard
+    const float*    emb;       // [rows][dim]
+    const int64_t*  ticks;     // [rows]  ORR_DEAD_TICKS = tombstone
+    const uint32_t* terms32;   // [rows][slots] low words, 0 = empty slot
+    const uint64_t* terms64;   // [rows][slots] full hashes, 0 = empty slot
+    int64_t rows;              // rows in use (live + dead)
+    int32_t dim;
+    int32_t slots;
+    uint64_t row_base;
+};
+
+// ---- launchers (each returns ORR_OK or sets the error) -----------------------------------
+int orr_scan_smem_bytes(int dim, int* warps_out, int* tile_rows_out);
+
+// K1: fused fp32 scan + per-warp register top list + per-CTA merge; the last CTA to finish
+// selects the global survivors.
+int orr_launch_scan(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
+                    const OrrWeights& w, int64_t now_ticks, int n_survivors, int grid,
+                    cudaStream_t st);
+
+// K3: exact fp64 re-score of the listed rows (warp per row); the last CTA orders them by the
+// reference tie chain, runs the selection bound check and emits the top-k hits.
+int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
+                       const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
+                       int n_listed_max, bool check_bound, cudaStream_t st);
+
+// exact path: every row's fp64 score, then a stable two-key radix sort.
+int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
+                            const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st);
+int orr_exact_select(const OrrShard& sh, OrrScratch& sc, int top_k, cudaStream_t st);
+
+int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_lists, int stride, int top_k,
+                     orr_hit* out_dev, int32_t* out_status_dev, cudaStream_t st);
+
+int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_t* terms64,
+                          int dim, int slots, const orr_synth_spec& spec, uint64_t first_row,
+                          int64_t local_first, int64_t n, cudaStream_t st);
+
+// text
+uint64_t orr_hash_bytes(const char* s, int64_t n);
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline uint32_t orr_hash_low(uint64_t h) {
+    uint32_t l = (uint32_t)h;
+    return l ? l : 0x9E3779B9u;
+}

@@ -1,0 +1,416 @@
+// orr_rescore.cu — K3 and the exact path: the reference's fp64 arithmetic on the device.
+//
+// exact_row() is the one definition of a chunk's score on the GPU.  It restates
+//   CosineSimilarity  RecallSearchService.cs:69-88  (fp32 products widened to fp64, fp64 sums,
+//                                                    sqrt(nA)*sqrt(nB), one divide)
+//   KeywordScore      :110-112  (matches / |terms| over the chunk's 64-bit term hashes)
+//   RecencyScore      :115-119  (ticks -> days -> exp(-age/30))
+//   ScoreChunk        :66       ((cos*0.7 + kw*0.2) + rec*0.1, no FMA contraction)
+// with every fp64 operation spelled as a round-to-nearest intrinsic so nvcc cannot fuse
+// multiply-adds.  The only departure from the reference's instruction stream is the ORDER of
+// the fp64 additions inside the dot products (lane-strided partial sums + a fixed shuffle
+// butterfly instead of one sequential chain), a difference of a few 1e-16 relative, and the
+// CUDA libm exp (<= 1 ulp) instead of the host's: scores agree with the CPU oracle to ~1e-15
+// relative, five orders of magnitude inside the 1e-5 contract.
+//
+// K3 (orr_rescore_kernel): warp per listed row; the last CTA to finish orders the records by
+// the reference tie chain (score desc with NaN last, CreatedAtUtc desc, row asc — :34-35 plus
+// the stable-sort fallback), runs the selection bound check and emits hits.
+#include <cfloat>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "orr_internal.h"
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+struct ExactArgs {
+    OrrShard  sh;
+    const float* q;
+    int32_t   q_dim;             // 0 => no query embedding (cosine 0, :71)
+    OrrProbes pr;
+    OrrWeights w;
+    int64_t   now_ticks;
+};
+
+// fp64 ||q||^2 in the lane-strided order; all lanes return the same value
+__device__ __forceinline__ double exact_qnorm(const ExactArgs& a, int lane) {
+    double nA = 0.0;
+    const int nv4 = a.sh.dim >> 2;
+    const float4* q4 = reinterpret_cast<const float4*>(a.q);
+    for (int i = lane; i < nv4; i += 32) {
+        const float4 v = __ldg(q4 + i);
+        nA = __dadd_rn(nA, (double)__fmul_rn(v.x, v.x));
+        nA = __dadd_rn(nA, (double)__fmul_rn(v.y, v.y));
+        nA = __dadd_rn(nA, (double)__fmul_rn(v.z, v.z));
+        nA = __dadd_rn(nA, (double)__fmul_rn(v.w, v.w));
+    }
+    return warp_sum_f64(nA);
+}
+
+// exact fused score of one row, computed by a full warp; all lanes return the same value
+__device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int lane, double nA,
+                                            int64_t* ticks_out) {
+    const int64_t ticks = a.sh.ticks[row];
+    *ticks_out = ticks;
+    double cosv = 0.0;
+    if (a.q_dim == a.sh.dim && a.q_dim > 0) {                       // :71-72 length check
+        const int nv4 = a.sh.dim >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(a.sh.emb + row * (int64_t)a.sh.dim);
+        const float4* q4 = reinterpret_cast<const float4*>(a.q);
+        double dot = 0.0, nB = 0.0;
+        for (int i = lane; i < nv4; i += 32) {
+            const float4 x = __ldg(x4 + i);
+            const float4 v = __ldg(q4 + i);
+            dot = __dadd_rn(dot, (double)__fmul_rn(v.x, x.x)); nB = __dadd_rn(nB, (double)__fmul_rn(x.x, x.x));
+            dot = __dadd_rn(dot, (double)__fmul_rn(v.y, x.y)); nB = __dadd_rn(nB, (double)__fmul_rn(x.y, x.y));
+            dot = __dadd_rn(dot, (double)__fmul_rn(v.z, x.z)); nB = __dadd_rn(nB, (double)__fmul_rn(x.z, x.z));
+            dot = __dadd_rn(dot, (double)__fmul_rn(v.w, x.w)); nB = __dadd_rn(nB, (double)__fmul_rn(x.w, x.w));
+        }
+        dot = warp_sum_f64(dot);
+        nB = warp_sum_f64(nB);
+        if (!(nA <= 0.0) && !(nB <= 0.0))                             // :84-85 (NaN falls through)
+            cosv = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(nA), __dsqrt_rn(nB)));   // :87
+    }
+    double kw = 0.0;
+    if (a.pr.n_probes > 0) {                                          // :110-112
+        const int spl = a.sh.slots >> 5;
+        const uint64_t* t64 = a.sh.terms64 + row * (int64_t)a.sh.slots;
+        uint64_t th[4] = {0, 0, 0, 0};
+        for (int w = 0; w < spl; ++w) th[w] = __ldg(t64 + w * 32 + lane);
+        uint32_t m0 = 0, m1 = 0;
+        for (int p = 0; p < a.pr.n_probes; ++p) {
+            const uint64_t h = a.pr.h64[p];
+            const bool hit = (th[0] == h) | (th[1] == h) | (th[2] == h) | (th[3] == h);
+            if (hit) {
+                const uint32_t t = a.pr.term[p];
+                if (t < 32) m0 |= 1u << t; else m1 |= 1u << (t - 32);
+            }
+        }
+        m0 = __reduce_or_sync(FULL, m0);
+        m1 = __reduce_or_sync(FULL, m1);
+        kw = __ddiv_rn((double)(__popc(m0) + __popc(m1)), (double)a.pr.n_terms);
+    }
+    // RecencyScore: TimeSpan.TotalDays = ticks / 864e9; Math.Max(0, .); exp(-age/30)
+    double age = __ddiv_rn((double)(a.now_ticks - ticks), 864000000000.0);
+    if (!(age > 0.0)) age = 0.0;
+    const double rec = exp(__ddiv_rn(-age, a.w.recency_days));
+    // ScoreChunk :66
+    return __dadd_rn(__dadd_rn(__dmul_rn(cosv, a.w.w_cos), __dmul_rn(kw, a.w.w_kw)),
+                     __dmul_rn(rec, a.w.w_rec));
+}
+
+// reference ordering: true if x ranks strictly before y
+__device__ __forceinline__ bool ranks_before(const OrrExact& x, const OrrExact& y) {
+    const bool xn = (x.score != x.score), yn = (y.score != y.score);
+    if (xn != yn) return yn;                                          // NaN last (:34)
+    if (!xn && x.score != y.score) return x.score > y.score;
+    if (x.ticks != y.ticks) return x.ticks > y.ticks;                 // :35
+    return x.row < y.row;                                             // stable fallback (A-6)
+}
+
+struct RescoreArgs {
+    ExactArgs ex;
+    const uint32_t* rows;        // listed local rows
+    const int32_t*  n_listed;    // device count (sel[0])
+    const int32_t*  tau_bits;    // device float bits (sel[1])
+    int32_t   n_listed_max;
+    int32_t   top_k;
+    int32_t   check_bound;
+    double    eps;
+    OrrExact* exact;
+    int32_t*  ticket;            // sel[3]
+    orr_hit*  hits;
+    int32_t*  status;
+};
+
+__global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = min(*a.n_listed, a.n_listed_max);
+    const int idx = blockIdx.x * 4 + warp;
+    if (idx < n) {
+        const double nA = (a.ex.q_dim == a.ex.sh.dim && a.ex.q_dim > 0) ? exact_qnorm(a.ex, lane) : 0.0;
+        const int64_t row = a.rows[idx];
+        int64_t ticks;
+        const double s = exact_row(a.ex, row, lane, nA, &ticks);
+        if (lane == 0) { a.exact[idx].score = s; a.exact[idx].ticks = ticks; a.exact[idx].row = (uint64_t)row; }
+    }
+    // ---- the last CTA orders the records and emits the hits ----
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+
+    OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const volatile OrrExact* src = a.exact;
+    for (int i = tid; i < np2; i += blockDim.x) {
+        OrrExact v;
+        if (i < n) { v.score = src[i].score; v.ticks = src[i].ticks; v.row = src[i].row; }
+        else { v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull; }  // pads rank last
+        e[i] = v;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const OrrExact x = e[i], y = e[p];
+                    const bool up = ((i & k2) == 0);                  // ascending rank in this run
+                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int k = max(1, a.top_k);                                    // Math.Max(1, topK) :36
+    const int n_out = min(k, n);
+    for (int i = tid; i < n_out; i += blockDim.x) {
+        orr_hit h;
+        h.row = a.ex.sh.row_base + e[i].row;
+        h.score = e[i].score;
+        h.created_ticks = e[i].ticks;
+        a.hits[i] = h;
+    }
+    if (tid == 0) {
+        int flags = 0;
+        if (a.check_bound) {
+            // every row outside the list has fp32 score <= tau and |fp32 - exact| <= eps:
+            // safe iff the k-th exact score clears tau by more than eps.
+            const float tau = __int_as_float(*a.tau_bits);
+            if (tau != -INFINITY) {
+                const double sk = (n >= k) ? e[k - 1].score : __longlong_as_double(0x7ff8000000000000LL);
+                if (!(sk - a.eps > (double)tau)) flags |= 1;
+            }
+        }
+        a.status[0] = n_out;
+        a.status[1] = flags;
+        *a.ticket = 0;                                                // re-arm
+        __threadfence();
+    }
+}
+
+// ---- exact path: every row's score -------------------------------------------------------
+// key for a descending radix sort: larger = ranks earlier; dead rows 0, NaN 1
+__device__ __forceinline__ uint64_t score_key(double s, bool dead) {
+    if (dead) return 0ull;
+    if (s != s) return 1ull;
+    const uint64_t b = (uint64_t)__double_as_longlong(s);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256) orr_exact_scores_kernel(const ExactArgs a, double* scores,
+                                                               uint64_t* tick_keys, uint32_t* vals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool has_q = (a.q_dim == a.sh.dim && a.q_dim > 0);
+    const double nA = has_q ? exact_qnorm(a, lane) : 0.0;
+    for (int64_t row = gw; row < a.sh.rows; row += W) {
+        int64_t ticks;
+        const double s = exact_row(a, row, lane, nA, &ticks);
+        if (lane == 0) {
+            scores[row] = s;
+            // first sort key: CreatedAtUtc, descending (flip the sign bit for unsigned order)
+            tick_keys[row] = (uint64_t)ticks ^ 0x8000000000000000ull;
+            vals[row] = (uint32_t)row;
+        }
+    }
+}
+
+__global__ void orr_gather_score_keys(const double* scores, const int64_t* ticks, const uint32_t* vals,
+                                      uint64_t* keys, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t r = vals[i];
+        keys[i] = score_key(scores[r], ticks[r] == ORR_DEAD_TICKS);
+    }
+}
+
+__global__ void orr_emit_sorted(const uint64_t* keys, const uint32_t* vals, const double* scores,
+                                const int64_t* ticks, uint64_t row_base, int64_t n, int top_k,
+                                orr_hit* hits, int32_t* status) {
+    const int k = max(1, top_k);
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < k && i < n; i += blockDim.x) {
+        if (keys[i] != 0ull) {                                        // dead rows sort to the end
+            const uint32_t r = vals[i];
+            orr_hit h; h.row = row_base + r; h.score = scores[r]; h.created_ticks = ticks[r];
+            hits[i] = h;
+            atomicAdd(&s_n, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { status[0] = s_n; status[1] = 0; }
+}
+
+// ---- merge of all-gathered per-GPU hit lists (multi-GPU) -----------------------------------
+// lists[G][stride] hits + status[G][2] ({n, flags}); one CTA orders the union by the reference
+// tie chain and writes the global top-k.  flags are OR-ed so a failed bound check on any
+// shard is visible to the caller.
+__global__ void __launch_bounds__(256) orr_merge_kernel(const orr_hit* lists, const int32_t* status, int n_lists,
+                                                        int stride, int top_k, orr_hit* out, int32_t* out_status) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int total = n_lists * stride;
+    int np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    __shared__ int s_n, s_flags;
+    if (tid == 0) { s_n = 0; s_flags = 0; }
+    __syncthreads();
+    for (int i = tid; i < np2; i += blockDim.x) {
+        OrrExact v; v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull;
+        if (i < total) {
+            const int l = i / stride, j = i - l * stride;
+            if (j < status[2 * l]) {
+                const orr_hit h = lists[i];
+                v.score = h.score; v.ticks = h.created_ticks; v.row = h.row;
+                atomicAdd(&s_n, 1);
+            }
+        }
+        e[i] = v;
+    }
+    if (tid < n_lists) atomicOr(&s_flags, status[2 * tid + 1]);
+    __syncthreads();
+    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const OrrExact x = e[i], y = e[p];
+                    const bool up = ((i & k2) == 0);
+                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int n_out = min(max(1, top_k), s_n);
+    for (int i = tid; i < n_out; i += blockDim.x) {
+        orr_hit h; h.row = e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
+        out[i] = h;
+    }
+    if (tid == 0) { out_status[0] = n_out; out_status[1] = s_flags; }
+}
+
+}  // namespace
+
+static void fill_exact_args(ExactArgs& e, const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
+                            const OrrWeights& w, int64_t now_ticks, int q_dim) {
+    e.sh = sh; e.q = sc.q; e.q_dim = q_dim; e.pr = pr; e.w = w; e.now_ticks = now_ticks;
+}
+
+int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
+                       const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
+                       int n_listed_max, bool check_bound, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ORR_SORT_MAX * (int)sizeof(OrrExact)));
+        configured = true;
+    }
+    if (n_listed_max < 1) n_listed_max = 1;
+    if (n_listed_max > ORR_SORT_MAX) { orr_set_error("rescore: %d rows exceed the sorter", n_listed_max); return ORR_E_INTERNAL; }
+    RescoreArgs a;
+    fill_exact_args(a.ex, sh, sc, pr, w, now_ticks, q_dim);
+    a.rows = sc.surv_rows;
+    a.n_listed = sc.sel + 0;
+    a.tau_bits = sc.sel + 1;
+    a.n_listed_max = n_listed_max;
+    a.top_k = top_k;
+    a.check_bound = check_bound ? 1 : 0;
+    a.eps = (double)ORR_SELECT_EPS * (fabs(w.w_cos) + fabs(w.w_kw) + fabs(w.w_rec));
+    a.exact = sc.exact;
+    a.ticket = sc.sel + 3;
+    a.hits = sc.hits;
+    a.status = sc.status;
+    int np2 = 1;
+    while (np2 < n_listed_max) np2 <<= 1;
+    const int grid = (n_listed_max + 3) / 4;
+    orr_rescore_kernel<<<grid, 128, np2 * sizeof(OrrExact), st>>>(a);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
+                            const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st) {
+    if (sh.rows == 0) return ORR_OK;
+    ExactArgs e;
+    fill_exact_args(e, sh, sc, pr, w, now_ticks, q_dim);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    orr_exact_scores_kernel<<<sms * 8, 256, 0, st>>>(e, sc.scores64, sc.sort_keys[0], sc.sort_vals[0]);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+// two stable LSD passes: by CreatedAtUtc desc (initial order = row asc), then by score desc
+int orr_exact_select(const OrrShard& sh, OrrScratch& sc, int top_k, cudaStream_t st) {
+    const int64_t n = sh.rows;
+    if (n == 0) {
+        ORR_CUDA_OK(cudaMemsetAsync(sc.status, 0, 2 * sizeof(int32_t), st));
+        return ORR_OK;
+    }
+    if (n > 0x7fffffff) { orr_set_error("exact path: shard too large"); return ORR_E_UNSUPPORTED; }
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, need, sc.sort_keys[0], sc.sort_keys[1],
+                                              sc.sort_vals[0], sc.sort_vals[1], (int)n, 0, 64, st);
+    if (need > sc.cub_tmp_bytes) {
+        if (sc.cub_tmp) cudaFree(sc.cub_tmp);
+        sc.cub_tmp = nullptr; sc.cub_tmp_bytes = 0;
+        ORR_CUDA_OK(cudaMalloc(&sc.cub_tmp, need));
+        sc.cub_tmp_bytes = need;
+    }
+    size_t bytes = sc.cub_tmp_bytes;
+    ORR_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(sc.cub_tmp, bytes, sc.sort_keys[0], sc.sort_keys[1],
+                                                          sc.sort_vals[0], sc.sort_vals[1], (int)n, 0, 64, st));
+    const int threads = 256;
+    orr_gather_score_keys<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
+        sc.scores64, sh.ticks, sc.sort_vals[1], sc.sort_keys[0], n);
+    ORR_CUDA_OK(cudaGetLastError());
+    bytes = sc.cub_tmp_bytes;
+    ORR_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(sc.cub_tmp, bytes, sc.sort_keys[0], sc.sort_keys[1],
+                                                          sc.sort_vals[1], sc.sort_vals[0], (int)n, 0, 64, st));
+    orr_emit_sorted<<<1, 256, 0, st>>>(sc.sort_keys[1], sc.sort_vals[0], sc.scores64, sh.ticks, sh.row_base, n,
+                                       top_k, sc.hits, sc.status);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_lists, int stride, int top_k,
+                     orr_hit* out_dev, int32_t* out_status_dev, cudaStream_t st) {
+    const int total = n_lists * stride;
+    if (n_lists < 1 || n_lists > 256 || stride < 1 || total > ORR_SORT_MAX) {
+        orr_set_error("merge: %d lists x %d exceed the sorter", n_lists, stride);
+        return ORR_E_UNSUPPORTED;
+    }
+    static bool configured = false;
+    if (!configured) {
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ORR_SORT_MAX * (int)sizeof(OrrExact)));
+        configured = true;
+    }
+    int np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    orr_merge_kernel<<<1, 256, np2 * sizeof(OrrExact), st>>>(lists_dev, status_dev, n_lists, stride, top_k, out_dev,
+                                                            out_status_dev);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}

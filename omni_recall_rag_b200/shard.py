@@ -1,0 +1,194 @@
+"""RecallShard — one GPU's slice of the chunk store, a thin typed wrapper over the C ABI.
+
+Everything here goes through liborr.so (include/orr.h); there is no Python-side scoring.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+
+@dataclass
+class Hits:
+    rows: np.ndarray      # uint64 global row ids, reference order
+    scores: np.ndarray    # float64
+    ticks: np.ndarray     # int64 CreatedAtUtc ticks
+
+    def __len__(self) -> int:
+        return int(self.rows.shape[0])
+
+
+@dataclass
+class QueryTerms:
+    """A query's keyword side: |terms| and the (hash, term) probes that satisfy them."""
+    n_terms: int
+    probe_hash: np.ndarray            # uint64[n_probes]
+    probe_term: Optional[np.ndarray]  # int32[n_probes] or None (identity)
+
+    @staticmethod
+    def none() -> "QueryTerms":
+        return QueryTerms(0, np.zeros(0, dtype=np.uint64), None)
+
+
+def hash_term(term_lower: str) -> int:
+    b = term_lower.encode("utf-8")
+    return int(N.lib().orr_hash_term(b, len(b)))
+
+
+def tokenize_query(query: str) -> np.ndarray:
+    """KeywordScore's query side (RecallSearchService.cs:95-108) -> uint64 term hashes."""
+    b = query.encode("utf-8")
+    cap = max(16, len(b))
+    out = np.zeros(cap, dtype=np.uint64)
+    n = C.c_int32(0)
+    N.check(N.lib().orr_tokenize_query(b, len(b), out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+    return out[: n.value].copy()
+
+
+def tokenize_content(content: str) -> np.ndarray:
+    """Distinct lower-cased white-space tokens of a chunk's Content -> uint64 hashes."""
+    b = content.encode("utf-8")
+    cap = max(16, len(b))
+    out = np.zeros(cap, dtype=np.uint64)
+    n = C.c_int32(0)
+    N.check(N.lib().orr_tokenize_content(b, len(b), out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+    return out[: n.value].copy()
+
+
+def merge_hits(lists: Sequence[Hits], top_k: int) -> Hits:
+    """Global top-k of per-shard hit lists with the reference tie chain (orr_merge_hits)."""
+    stride = max([len(h) for h in lists] + [1])
+    buf = (N.OrrHit * (stride * len(lists)))()
+    lens = np.zeros(len(lists), dtype=np.int32)
+    for l, h in enumerate(lists):
+        lens[l] = len(h)
+        for i in range(len(h)):
+            e = buf[l * stride + i]
+            e.row, e.score, e.created_ticks = int(h.rows[i]), float(h.scores[i]), int(h.ticks[i])
+    k = max(1, int(top_k))
+    out = (N.OrrHit * k)()
+    n = C.c_int32(0)
+    N.check(N.lib().orr_merge_hits(C.cast(buf, C.c_void_p), lens.ctypes.data_as(C.c_void_p), len(lists), stride,
+                                   top_k, C.cast(out, C.c_void_p), C.byref(n)))
+    return _hits_from(out, n.value)
+
+
+def _hits_from(arr, n: int) -> Hits:
+    a = np.frombuffer(arr, dtype=np.dtype([("row", "<u8"), ("score", "<f8"), ("ticks", "<i8")]), count=n)
+    return Hits(a["row"].copy(), a["score"].copy(), a["ticks"].copy())
+
+
+class RecallShard:
+    """Owns one orr_store (one GPU).  Thread-safe for concurrent search()."""
+
+    def __init__(self, dim: int, capacity_rows: int, *, device: int = 0, term_slots: int = 64,
+                 row_base: int = 0, w_cos: float = 0.7, w_kw: float = 0.2, w_rec: float = 0.1,
+                 recency_days: float = 30.0):
+        L = N.lib()
+        cfg = N.OrrConfig()
+        L.orr_config_default(C.byref(cfg))
+        cfg.device, cfg.dim, cfg.term_slots = device, dim, term_slots
+        cfg.capacity_rows, cfg.row_base = capacity_rows, row_base
+        cfg.w_cos, cfg.w_kw, cfg.w_rec, cfg.recency_days = w_cos, w_kw, w_rec, recency_days
+        self.cfg = cfg
+        self.dim, self.term_slots, self.row_base, self.device = dim, term_slots, row_base, device
+        self._h = C.c_void_p()
+        N.check(L.orr_store_create(C.byref(cfg), C.byref(self._h)))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().orr_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- mutation ---------------------------------------------------------------------------
+    def upsert_document_chunks(self, doc_key: int, emb: Optional[np.ndarray], ticks: np.ndarray,
+                               term_hashes: Optional[Sequence[np.ndarray]] = None,
+                               has_emb: Optional[np.ndarray] = None) -> np.ndarray:
+        ticks = np.ascontiguousarray(ticks, dtype=np.int64)
+        n = int(ticks.shape[0])
+        if emb is not None:
+            emb = np.ascontiguousarray(emb, dtype=np.float32)
+            if emb.shape != (n, self.dim):
+                raise ValueError(f"emb must be ({n}, {self.dim}), got {emb.shape}")
+        if has_emb is not None:
+            has_emb = np.ascontiguousarray(has_emb, dtype=np.uint8)
+        flat = off = None
+        if term_hashes is not None:
+            off = np.zeros(n + 1, dtype=np.uint32)
+            off[1:] = np.cumsum([len(t) for t in term_hashes])
+            flat = (np.concatenate([np.asarray(t, dtype=np.uint64) for t in term_hashes])
+                    if n and off[-1] else np.zeros(1, dtype=np.uint64))
+            flat = np.ascontiguousarray(flat, dtype=np.uint64)
+        out_rows = np.zeros(max(n, 1), dtype=np.uint64)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        N.check(N.lib().orr_store_upsert_document_chunks(self._h, doc_key, n, p(emb), p(has_emb), p(ticks),
+                                                         p(flat), p(off), p(out_rows)))
+        return out_rows[:n]
+
+    def delete_document(self, doc_key: int) -> None:
+        N.check(N.lib().orr_store_delete_document(self._h, doc_key))
+
+    def fill_synthetic(self, spec: "N.OrrSynthSpec", first_row: int, n: int) -> None:
+        N.check(N.lib().orr_store_fill_synthetic(self._h, C.byref(spec), first_row, n))
+
+    @property
+    def count(self) -> int:
+        return int(N.lib().orr_store_count(self._h))
+
+    @property
+    def rows_used(self) -> int:
+        return int(N.lib().orr_store_rows_used(self._h))
+
+    # -- search -----------------------------------------------------------------------------
+    def search(self, q: Optional[np.ndarray], terms: QueryTerms, now_ticks: int, top_k: int,
+               candidate_cap: int = 0) -> Hits:
+        """orr_search: host buffers in, hits out (H2D/D2H inside the call)."""
+        if q is None:
+            q = np.zeros(0, dtype=np.float32)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        k = max(1, int(top_k))
+        out = (N.OrrHit * k)()
+        n = C.c_int32(0)
+        ph = np.ascontiguousarray(terms.probe_hash, dtype=np.uint64)
+        pt = None if terms.probe_term is None else np.ascontiguousarray(terms.probe_term, dtype=np.int32)
+        N.check(N.lib().orr_search(
+            self._h, q.ctypes.data_as(C.c_void_p) if q.size else None, int(q.size), int(terms.n_terms),
+            ph.ctypes.data_as(C.c_void_p) if ph.size else None,
+            None if pt is None else pt.ctypes.data_as(C.c_void_p), int(ph.size),
+            int(now_ticks), int(top_k), int(candidate_cap), C.cast(out, C.c_void_p), C.byref(n)))
+        return _hits_from(out, n.value)
+
+    def search_device(self, q_dev_ptr: int, terms: QueryTerms, now_ticks: int, top_k: int,
+                      out_dev_ptr: int, status_dev_ptr: int, stream_ptr: int) -> None:
+        """orr_search_device: every buffer already in HBM, enqueued on `stream_ptr`, no sync."""
+        ph = np.ascontiguousarray(terms.probe_hash, dtype=np.uint64)
+        pt = None if terms.probe_term is None else np.ascontiguousarray(terms.probe_term, dtype=np.int32)
+        N.check(N.lib().orr_search_device(
+            self._h, C.c_void_p(q_dev_ptr), self.dim, int(terms.n_terms),
+            ph.ctypes.data_as(C.c_void_p) if ph.size else None,
+            None if pt is None else pt.ctypes.data_as(C.c_void_p), int(ph.size),
+            int(now_ticks), int(top_k), C.c_void_p(out_dev_ptr), C.c_void_p(status_dev_ptr),
+            C.c_void_p(stream_ptr)))
+
+    def last_timing(self) -> dict:
+        t = N.OrrTiming()
+        N.lib().orr_last_timing(C.byref(t))
+        return {f: getattr(t, f) for f, _ in N.OrrTiming._fields_}

@@ -1,0 +1,132 @@
+"""Row-sharded recall across the GPUs of one box: one process per GPU (torch.distributed),
+each rank owns rows [row_base, row_base + n_local) of the corpus, computes its exact local
+top-k, and the small candidate lists are all-gathered (NCCL over NVLink on GPUs, gloo in
+the CPU tests) and merged with the reference tie chain.
+
+Correctness: every chunk's score depends only on (query, row, now) and the exact score of a
+row is computed by the same deterministic function on every rank, so
+global top-k  ⊆  ∪ local top-k   and the merge (score desc, ticks desc, global row asc) gives
+exactly what the single-shard scorer would return.
+
+The only collective on the data path is the all-gather of k·24 B per rank.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .shard import Hits, QueryTerms, RecallShard, merge_hits
+
+HIT_BYTES = 24  # sizeof(orr_hit)
+
+
+def shard_rows(total_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row block of `rank`: (row_base, n_local).  Blocks differ by at most 1 row."""
+    base, rem = divmod(total_rows, world_size)
+    n_local = base + (1 if rank < rem else 0)
+    row_base = rank * base + min(rank, rem)
+    return row_base, n_local
+
+
+def _pack(h: Hits, k: int) -> np.ndarray:
+    """Hits -> int64[k, 3] (row bits, score bits, ticks) + valid count in the last slot."""
+    buf = np.zeros((k + 1, 3), dtype=np.int64)
+    n = len(h)
+    buf[:n, 0] = h.rows.view(np.int64)
+    buf[:n, 1] = h.scores.view(np.int64)
+    buf[:n, 2] = h.ticks
+    buf[k, 0] = n
+    return buf
+
+
+def _unpack(buf: np.ndarray, k: int) -> Hits:
+    n = int(buf[k, 0])
+    return Hits(buf[:n, 0].copy().view(np.uint64), buf[:n, 1].copy().view(np.float64), buf[:n, 2].copy())
+
+
+class ShardedRecall:
+    """Search over a row-sharded corpus.  `local_search(q, terms, now_ticks, top_k) -> Hits`
+    defaults to this rank's RecallShard; tests inject a CPU scorer to exercise the
+    gather/merge logic under gloo."""
+
+    def __init__(self, shard: Optional[RecallShard] = None, *, group=None,
+                 local_search: Optional[Callable[..., Hits]] = None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.shard = shard
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if local_search is None:
+            if shard is None:
+                raise ValueError("ShardedRecall needs a RecallShard or a local_search callable")
+            local_search = lambda q, terms, now, k: shard.search(q, terms, now, k)  # noqa: E731
+        self.local_search = local_search
+        self._dev_bufs = {}
+
+    # -- host-buffer path (end-to-end: query in host memory, hits back in host memory) --------
+    def search(self, q: Optional[np.ndarray], terms: QueryTerms, now_ticks: int, top_k: int) -> Hits:
+        import torch
+
+        k = max(1, int(top_k))
+        local = self.local_search(q, terms, now_ticks, top_k)
+        if self.world == 1:
+            return local
+        mine = torch.from_numpy(_pack(local, k))
+        backend = self.dist.get_backend(self.group)
+        if backend == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            mine = mine.to(dev)
+            gathered = torch.empty((self.world, k + 1, 3), dtype=torch.int64, device=dev)
+            self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            gathered = gathered.cpu().numpy()
+        else:
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(parts, mine, group=self.group)
+            gathered = np.stack([p.numpy() for p in parts])
+        return merge_hits([_unpack(gathered[r], k) for r in range(self.world)], top_k)
+
+    # -- device-resident path (query and hits stay in HBM; nothing synchronises the host) -----
+    def search_device(self, q_dev, terms: QueryTerms, now_ticks: int, top_k: int):
+        """q_dev: torch float32 CUDA tensor [dim].  Returns (hits_dev uint8[k*24], status_dev
+        int32[2] = {n_out, flags}) on the current stream: local fused scan + exact re-score
+        (orr_search_device), all_gather_into_tensor of the k·24 B candidate lists over NCCL,
+        one-CTA merge (orr_merge_hits_device)."""
+        import torch
+
+        k = max(1, int(top_k))
+        key = (k, q_dev.device.index)
+        if key not in self._dev_bufs:
+            dev = q_dev.device
+            self._dev_bufs[key] = dict(
+                hits=torch.zeros(k * HIT_BYTES, dtype=torch.uint8, device=dev),
+                status=torch.zeros(2, dtype=torch.int32, device=dev),
+                all_hits=torch.zeros(self.world * k * HIT_BYTES, dtype=torch.uint8, device=dev),
+                all_status=torch.zeros(self.world * 2, dtype=torch.int32, device=dev),
+                out_hits=torch.zeros(k * HIT_BYTES, dtype=torch.uint8, device=dev),
+                out_status=torch.zeros(2, dtype=torch.int32, device=dev))
+        b = self._dev_bufs[key]
+        stream = torch.cuda.current_stream(q_dev.device).cuda_stream
+        self.shard.search_device(q_dev.data_ptr(), terms, now_ticks, top_k, b["hits"].data_ptr(),
+                                 b["status"].data_ptr(), stream)
+        if self.world == 1:
+            return b["hits"], b["status"]
+        self.dist.all_gather_into_tensor(b["all_hits"], b["hits"], group=self.group)
+        self.dist.all_gather_into_tensor(b["all_status"], b["status"], group=self.group)
+        stream = torch.cuda.current_stream(q_dev.device).cuda_stream
+        N.check(N.lib().orr_merge_hits_device(
+            q_dev.device.index, b["all_hits"].data_ptr(), b["all_status"].data_ptr(), self.world, k, top_k,
+            b["out_hits"].data_ptr(), b["out_status"].data_ptr(), stream))
+        return b["out_hits"], b["out_status"]
+
+
+def hits_from_device(hits_dev, status_dev) -> Tuple[Hits, int]:
+    """D2H of a device hit list -> (Hits, flags)."""
+    st = status_dev.cpu().numpy()
+    raw = hits_dev.cpu().numpy()
+    a = np.frombuffer(raw.tobytes(), dtype=np.dtype([("row", "<u8"), ("score", "<f8"), ("ticks", "<i8")]))
+    n = int(st[0])
+    return Hits(a["row"][:n].copy(), a["score"][:n].copy(), a["ticks"][:n].copy()), int(st[1])

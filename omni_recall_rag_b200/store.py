@@ -1,0 +1,197 @@
+"""GpuIngestionStore — host-side mirror of the reference's IIngestionStore
+(src/OmniRecall.Api/Services/IIngestionStore.cs:5-17) whose chunk rows live in HBM.
+
+Python stands in for the C# host here (no .NET toolchain in this image); the C# class of
+the same name in dotnet/GpuIngestionStore.cs makes the same calls through P/Invoke.  Method
+names are the reference's, snake-cased; behaviour follows InMemoryIngestionStore.cs line by
+line, including its quirks (whole batch filed under chunks[0].DocumentId, :22-23).
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .shard import RecallShard, hash_term, tokenize_content
+
+
+@dataclass(frozen=True)
+class CosmosDocumentRecord:  # Data/Models/CosmosIngestionRecords.cs:5-17
+    id: str = ""
+    file_name: str = ""
+    source_type: str = "file"
+    blob_path: str = ""
+    content_hash: str = ""
+    chunk_count: int = 0
+    created_at_utc: int = 0  # .NET ticks
+
+
+@dataclass(frozen=True)
+class CosmosChunkRecord:  # Data/Models/CosmosIngestionRecords.cs:19-30
+    id: str = ""
+    document_id: str = ""
+    chunk_index: int = 0
+    content: str = ""
+    embedding: Optional[Sequence[float]] = None
+    created_at_utc: int = 0  # .NET ticks
+
+
+class GpuIngestionStore:
+    """IIngestionStore over one RecallShard.  Document records, chunk text and ids stay on
+    the host (they are only needed for the <= top_k citations); embeddings, timestamps and
+    hashed term sets are mirrored into HBM on every upsert."""
+
+    def __init__(self, dim: int, capacity_rows: int = 1 << 16, *, device: int = 0, term_slots: int = 128):
+        self.shard = RecallShard(dim, capacity_rows, device=device, term_slots=term_slots)
+        self.dim = dim
+        self._lock = threading.RLock()
+        self._documents: Dict[str, CosmosDocumentRecord] = {}
+        self._chunks_by_document: Dict[str, List[CosmosChunkRecord]] = {}
+        self._rows_by_document: Dict[str, np.ndarray] = {}
+        self._chunk_by_row: Dict[int, CosmosChunkRecord] = {}
+        self._vocab: Dict[str, int] = {}          # lower-cased token -> live chunks containing it
+
+    def close(self) -> None:
+        self.shard.close()
+
+    # -- IIngestionStore --------------------------------------------------------------------
+    def upsert_document(self, document: CosmosDocumentRecord) -> CosmosDocumentRecord:  # :11-15
+        with self._lock:
+            self._documents[document.id] = document
+        return document
+
+    def upsert_chunks(self, chunks: Sequence[CosmosChunkRecord]) -> None:  # :17-25
+        if len(chunks) == 0:
+            return
+        document_id = chunks[0].document_id
+        ordered = sorted(chunks, key=lambda c: c.chunk_index)  # OrderBy is stable (:23)
+        n = len(ordered)
+        emb = np.zeros((n, self.dim), dtype=np.float32)
+        has = np.zeros(n, dtype=np.uint8)
+        ticks = np.zeros(n, dtype=np.int64)
+        hashes = []
+        tokens_per_chunk = []
+        for i, c in enumerate(ordered):
+            e = c.embedding
+            # an Embedding that is null/empty/of another width scores cosine 0 against any
+            # query of the store's width (RecallSearchService.cs:71-72)
+            if e is not None and len(e) == self.dim:
+                emb[i] = np.asarray(e, dtype=np.float32)
+                has[i] = 1
+            ticks[i] = c.created_at_utc
+            toks = _distinct_lower_tokens(c.content)
+            if len(toks) > self.shard.term_slots:
+                raise ValueError(f"chunk {c.id!r} has {len(toks)} distinct tokens; the store was created "
+                                 f"with term_slots={self.shard.term_slots}")
+            tokens_per_chunk.append(toks)
+            hashes.append(np.array([hash_term(t) for t in toks], dtype=np.uint64))
+        with self._lock:
+            self._forget_rows(document_id)
+            rows = self.shard.upsert_document_chunks(_doc_key(document_id), emb, ticks, hashes, has)
+            self._chunks_by_document[document_id] = ordered
+            self._rows_by_document[document_id] = rows
+            for r, c, toks in zip(rows, ordered, tokens_per_chunk):
+                self._chunk_by_row[int(r)] = c
+                for t in toks:
+                    self._vocab[t] = self._vocab.get(t, 0) + 1
+
+    def get_document(self, document_id: str) -> Optional[CosmosDocumentRecord]:  # :27-31
+        return self._documents.get(document_id)
+
+    def list_documents(self, max_count: int) -> List[CosmosDocumentRecord]:  # :33-40
+        with self._lock:
+            docs = sorted(self._documents.values(), key=lambda d: -d.created_at_utc)
+        return docs[: max(1, max_count)]
+
+    def get_chunks_by_document_id(self, document_id: str) -> List[CosmosChunkRecord]:  # :42-48
+        return list(self._chunks_by_document.get(document_id, []))
+
+    def delete_document(self, document_id: str) -> None:  # :50-55
+        with self._lock:
+            self._documents.pop(document_id, None)
+            if document_id in self._chunks_by_document:
+                self._forget_rows(document_id)
+                self.shard.delete_document(_doc_key(document_id))
+                del self._chunks_by_document[document_id]
+
+    def get_recent_chunks(self, max_count: int) -> List[CosmosChunkRecord]:  # :57-65
+        with self._lock:
+            flat = [c for chunks in self._chunks_by_document.values() for c in chunks]
+        flat.sort(key=lambda c: -c.created_at_utc)
+        return flat[: max(1, max_count)]
+
+    def get_documents_by_ids(self, document_ids: Sequence[str]) -> Dict[str, CosmosDocumentRecord]:  # :67-76
+        wanted = set(document_ids)
+        with self._lock:
+            return {k: v for k, v in self._documents.items() if k in wanted}
+
+    # -- used by GpuRecallSearchService -------------------------------------------------------
+    def chunk_of_row(self, row: int) -> CosmosChunkRecord:
+        return self._chunk_by_row[int(row)]
+
+    def vocabulary_words_containing(self, term: str) -> List[str]:
+        """Words of the live corpus that contain `term` as an ordinal substring — the host
+        half of `contentLower.Contains(term)` (RecallSearchService.cs:111)."""
+        with self._lock:
+            return [w for w in self._vocab if term in w]
+
+    def _forget_rows(self, document_id: str) -> None:
+        rows = self._rows_by_document.pop(document_id, None)
+        if rows is None:
+            return
+        for r in rows:
+            c = self._chunk_by_row.pop(int(r), None)
+            if c is not None:
+                for t in _distinct_lower_tokens(c.content):
+                    left = self._vocab.get(t, 0) - 1
+                    if left <= 0:
+                        self._vocab.pop(t, None)
+                    else:
+                        self._vocab[t] = left
+
+
+def _doc_key(document_id: str) -> int:
+    return hash_term("doc:" + document_id)
+
+
+_WS = {0x20, 0x85, 0xA0, 0x1680, 0x2028, 0x2029, 0x202F, 0x205F, 0x3000, *range(0x09, 0x0E), *range(0x2000, 0x200B)}
+
+
+def _lower_invariant(s: str) -> str:
+    out = []
+    for ch in s:
+        c = ord(ch)
+        if c < 0x80:
+            out.append(ch.lower())
+        elif c == 0x130:
+            out.append("i")
+        elif (0xC0 <= c <= 0xDE and c != 0xD7) or 0x100 <= c <= 0x17E or 0x391 <= c <= 0x3A9 or 0x400 <= c <= 0x42F:
+            lo = ch.lower()
+            out.append(lo if len(lo) == 1 else ch)
+        else:
+            out.append(ch)
+    return "".join(out)
+
+
+def _distinct_lower_tokens(content: str) -> List[str]:
+    """Host copy of orr_tokenize_content's token list (needed as strings for the vocabulary)."""
+    toks: List[str] = []
+    seen = set()
+    cur: List[str] = []
+    for ch in content or "":
+        if ord(ch) in _WS:
+            if cur:
+                t = _lower_invariant("".join(cur))
+                if t not in seen:
+                    seen.add(t)
+                    toks.append(t)
+                cur = []
+        else:
+            cur.append(ch)
+    if cur:
+        t = _lower_invariant("".join(cur))
+        if t not in seen:
+            toks.append(t)
+    return toks
