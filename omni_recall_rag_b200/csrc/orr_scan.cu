@@ -450,11 +450,11 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
 
 template <int NV, int TR>
 int launch_t(const ScanArgs& args, int grid, int smem, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static int configured = 0;                 // largest dynamic smem opted into so far
+    if (smem > configured) {
         ORR_CUDA_OK(cudaFuncSetAttribute(orr_scan_kernel<NV, TR>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
     }
     orr_scan_kernel<NV, TR><<<grid, args.warps * 32, smem, st>>>(args);
     ORR_CUDA_OK(cudaGetLastError());

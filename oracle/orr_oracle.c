@@ -78,6 +78,8 @@ static uint32_t lower_cp(uint32_t c) {
 static int64_t lower_utf8(const char* s, int64_t n, char* out) {
     int64_t i = 0, o = 0;
     while (i < n) {
+        const unsigned char b = (unsigned char)s[i];
+        if (b < 0x80) { out[o++] = (char)((b >= 'A' && b <= 'Z') ? b + 32 : b); i += 1; continue; }  /* ASCII fast path */
         uint32_t cp; int k = utf8_decode((const unsigned char*)s + i, n - i, &cp);
         if (k == 1 && ((unsigned char)s[i]) >= 0x80) { out[o++] = s[i]; i += 1; continue; }
         o += utf8_encode(lower_cp(cp), (unsigned char*)out + o);
