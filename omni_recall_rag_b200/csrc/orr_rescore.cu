@@ -40,17 +40,32 @@ struct ExactArgs {
     int64_t   now_ticks;
 };
 
+// Loads are issued in batches of EX_CHUNK float4 per lane BEFORE the dependent fp64 chains
+// so a row costs ~2 memory round trips instead of one per 128 columns; the ORDER of the fp64
+// additions (lane-strided, increasing column, then the shuffle butterfly) is unchanged.
+constexpr int EX_CHUNK = 12;
+
 // fp64 ||q||^2 in the lane-strided order; all lanes return the same value
 __device__ __forceinline__ double exact_qnorm(const ExactArgs& a, int lane) {
     double nA = 0.0;
     const int nv4 = a.sh.dim >> 2;
     const float4* q4 = reinterpret_cast<const float4*>(a.q);
-    for (int i = lane; i < nv4; i += 32) {
-        const float4 v = __ldg(q4 + i);
-        nA = __dadd_rn(nA, (double)__fmul_rn(v.x, v.x));
-        nA = __dadd_rn(nA, (double)__fmul_rn(v.y, v.y));
-        nA = __dadd_rn(nA, (double)__fmul_rn(v.z, v.z));
-        nA = __dadd_rn(nA, (double)__fmul_rn(v.w, v.w));
+    for (int base = 0; base < nv4; base += 32 * EX_CHUNK) {
+        float4 v[EX_CHUNK];
+#pragma unroll
+        for (int j = 0; j < EX_CHUNK; ++j) {
+            const int i = base + j * 32 + lane;
+            v[j] = (i < nv4) ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < EX_CHUNK; ++j) {
+            if (base + j * 32 + lane < nv4) {
+                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].x, v[j].x));
+                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].y, v[j].y));
+                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].z, v[j].z));
+                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].w, v[j].w));
+            }
+        }
     }
     return warp_sum_f64(nA);
 }
@@ -60,19 +75,38 @@ __device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int
                                             int64_t* ticks_out) {
     const int64_t ticks = a.sh.ticks[row];
     *ticks_out = ticks;
+    // term hashes are fetched up front so their latency overlaps the embedding loads
+    uint64_t th[4] = {0, 0, 0, 0};
+    if (a.pr.n_probes > 0) {
+        const int spl = a.sh.slots >> 5;
+        const uint64_t* t64 = a.sh.terms64 + row * (int64_t)a.sh.slots;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) if (w < spl) th[w] = __ldg(t64 + w * 32 + lane);
+    }
     double cosv = 0.0;
     if (a.q_dim == a.sh.dim && a.q_dim > 0) {                       // :71-72 length check
         const int nv4 = a.sh.dim >> 2;
         const float4* x4 = reinterpret_cast<const float4*>(a.sh.emb + row * (int64_t)a.sh.dim);
         const float4* q4 = reinterpret_cast<const float4*>(a.q);
         double dot = 0.0, nB = 0.0;
-        for (int i = lane; i < nv4; i += 32) {
-            const float4 x = __ldg(x4 + i);
-            const float4 v = __ldg(q4 + i);
-            dot = __dadd_rn(dot, (double)__fmul_rn(v.x, x.x)); nB = __dadd_rn(nB, (double)__fmul_rn(x.x, x.x));
-            dot = __dadd_rn(dot, (double)__fmul_rn(v.y, x.y)); nB = __dadd_rn(nB, (double)__fmul_rn(x.y, x.y));
-            dot = __dadd_rn(dot, (double)__fmul_rn(v.z, x.z)); nB = __dadd_rn(nB, (double)__fmul_rn(x.z, x.z));
-            dot = __dadd_rn(dot, (double)__fmul_rn(v.w, x.w)); nB = __dadd_rn(nB, (double)__fmul_rn(x.w, x.w));
+        for (int base = 0; base < nv4; base += 32 * EX_CHUNK) {
+            float4 x[EX_CHUNK], v[EX_CHUNK];
+#pragma unroll
+            for (int j = 0; j < EX_CHUNK; ++j) {
+                const int i = base + j * 32 + lane;
+                const bool in = i < nv4;
+                x[j] = in ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[j] = in ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < EX_CHUNK; ++j) {
+                if (base + j * 32 + lane < nv4) {
+                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
+                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
+                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
+                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
+                }
+            }
         }
         dot = warp_sum_f64(dot);
         nB = warp_sum_f64(nB);
@@ -81,10 +115,6 @@ __device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int
     }
     double kw = 0.0;
     if (a.pr.n_probes > 0) {                                          // :110-112
-        const int spl = a.sh.slots >> 5;
-        const uint64_t* t64 = a.sh.terms64 + row * (int64_t)a.sh.slots;
-        uint64_t th[4] = {0, 0, 0, 0};
-        for (int w = 0; w < spl; ++w) th[w] = __ldg(t64 + w * 32 + lane);
         uint32_t m0 = 0, m1 = 0;
         for (int p = 0; p < a.pr.n_probes; ++p) {
             const uint64_t h = a.pr.h64[p];

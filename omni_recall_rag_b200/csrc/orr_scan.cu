@@ -22,8 +22,14 @@
 //   - tail: per-CTA bitonic merge of the warp lists, then the LAST CTA to finish (ticket)
 //     radix-selects the global survivors and the discard bound tau for K3's check.
 #include <cfloat>
+#include <cstdlib>
 
 #include "orr_internal.h"
+
+static int env_int(const char* name, int dflt) {      // tuning knobs for experiments
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 namespace {
 
@@ -64,6 +70,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_nohint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -96,6 +108,20 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
     uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
     return __uint_as_float(b);
 }
+// Returns 0 after a warp vote over a predicate computed from `dep`: the result is only
+// available once every lane has produced its `dep`, i.e. once all the loads feeding it
+// have returned.  Opaque to the compiler on purpose.
+__device__ __forceinline__ uint32_t all_lanes_done(uint32_t dep) {
+    uint32_t z;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+        "vote.sync.all.pred q, p, 0xffffffff;\n\t"
+        "selp.u32 %0, 0, 0, q;\n\t}"
+        : "=r"(z)
+        : "r"(dep));
+    return z;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -107,9 +133,12 @@ struct ScanArgs {
     const float* q;          // device fp32[dim]
     OrrProbes pr;
     float     w_cos, w_kw, w_rec;
-    double    inv_decay_ticks;   // 1 / (ticks per day * recency_days)
+    float     decay_per_2p20;    // 2^20 / (ticks per day * recency_days)
+    float     inv_nterms;        // 1 / |terms|
     int64_t   now_ticks;
     int32_t   warps;             // consumer warps per CTA
+    int32_t   stages;            // TMA stages per warp
+    int32_t   l2_hint;           // 1: evict_first on the row stream
     int32_t   stage_bytes;       // bytes of one smem stage (tile_rows * dim * 4)
     int32_t   n_surv;            // survivors to hand to K3 (64, 128 or 256)
     uint2*    cta_cands;         // [grid][n_surv]
@@ -148,12 +177,13 @@ __device__ __forceinline__ float fuse_row(const ScanArgs& a, float dot, float nb
         }
         m0 = __reduce_or_sync(FULL, m0);
         if (a.pr.n_terms > 32) m1 = __reduce_or_sync(FULL, m1);
-        kw = (float)(__popc(m0) + __popc(m1)) / (float)a.pr.n_terms;
+        kw = (float)(__popc(m0) + __popc(m1)) * a.inv_nterms;
     }
-    // recency (:115-119)
-    float x = (float)((double)(a.now_ticks - ticks) * a.inv_decay_ticks);
-    x = fmaxf(x, 0.f);
-    float rec = expf(-x);
+    // recency (:115-119): age in units of 2^20 ticks (0.1 s) fits int32 for ~7 years, beyond
+    // which exp(-age/30d) < 1e-37; selection-grade only, K3 recomputes it in fp64
+    int64_t age20 = (a.now_ticks - ticks) >> 20;
+    age20 = age20 < 0 ? 0 : (age20 > 0x7fffffffLL ? 0x7fffffffLL : age20);
+    const float rec = __expf(-(float)(int32_t)age20 * a.decay_per_2p20);
     float s = a.w_cos * cosv + a.w_kw * kw + a.w_rec * rec;
     if (force) s = FLT_MAX;
     if (s != s) s = -FLT_MAX;                                      // NaN ranks last (:34)
@@ -162,7 +192,7 @@ __device__ __forceinline__ float fuse_row(const ScanArgs& a, float dot, float nb
 
 // NV = float4 per lane per row (dim/128) with the query in registers; NV == 0: generic dim,
 // query read from smem.  TR = rows per tile.
-template <int NV, int TR>
+template <int NV, int TR, bool PIPE>
 __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -172,13 +202,13 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
     const uint32_t q_bytes = (uint32_t)((dim * 4 + 127) & ~127);
     float* sq = reinterpret_cast<float*>(smem);
     uint8_t* stage_base = smem + q_bytes;
-    const uint32_t ring_bytes = (uint32_t)a.warps * ORR_SCAN_STAGES * (uint32_t)a.stage_bytes;
+    const uint32_t ring_bytes = (uint32_t)a.warps * (uint32_t)a.stages * (uint32_t)a.stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + ring_bytes);
 
     // ---- prologue: query -> smem (+registers), barriers ----
     for (int i = tid; i < nv4; i += nthreads)
         reinterpret_cast<float4*>(sq)[i] = __ldg(reinterpret_cast<const float4*>(a.q) + i);
-    if (tid < a.warps * ORR_SCAN_STAGES) mbar_init(smem_u32(&bars[tid]), 1);
+    if (tid < a.warps * a.stages) mbar_init(smem_u32(&bars[tid]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -204,27 +234,30 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
     const int64_t n_tiles = (rows + TR - 1) / TR;
     const int64_t gw = (int64_t)blockIdx.x * a.warps + warp;
     const int64_t W = (int64_t)gridDim.x * a.warps;
-    const uint32_t my_stage0 = smem_u32(stage_base) + (uint32_t)warp * ORR_SCAN_STAGES * (uint32_t)a.stage_bytes;
-    const uint32_t my_bar0 = smem_u32(&bars[warp * ORR_SCAN_STAGES]);
+    const uint32_t my_stage0 = smem_u32(stage_base) + (uint32_t)warp * (uint32_t)a.stages * (uint32_t)a.stage_bytes;
+    const uint32_t my_bar0 = smem_u32(&bars[warp * a.stages]);
     const uint32_t row_bytes = (uint32_t)dim * 4u;
     const uint64_t policy = policy_evict_first();
     const int spl = a.sh.slots >> 5;                              // term words per lane per row
 
-    auto issue = [&](int64_t tile, int stage) {
+    auto issue = [&](int64_t tile, int stage, uint32_t zero) {
         const int64_t r0 = tile * TR;
         const int64_t nr = (rows - r0 < TR) ? (rows - r0) : TR;
-        const uint32_t bytes = (uint32_t)nr * row_bytes;
+        const uint32_t bytes = (uint32_t)nr * row_bytes + zero;
         const uint32_t bar = my_bar0 + (uint32_t)stage * 8u;
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(my_stage0 + (uint32_t)stage * (uint32_t)a.stage_bytes,
-                 a.sh.emb + r0 * (int64_t)dim, bytes, bar, policy);
+        if (a.l2_hint)
+            bulk_g2s(my_stage0 + (uint32_t)stage * (uint32_t)a.stage_bytes,
+                     a.sh.emb + r0 * (int64_t)dim, bytes, bar, policy);
+        else
+            bulk_g2s_nohint(my_stage0 + (uint32_t)stage * (uint32_t)a.stage_bytes,
+                            a.sh.emb + r0 * (int64_t)dim, bytes, bar);
     };
 
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < ORR_SCAN_STAGES; ++s) {
+        for (int s = 0; s < a.stages; ++s) {
             const int64_t t = gw + (int64_t)s * W;
-            if (t < n_tiles) issue(t, s);
+            if (t < n_tiles) issue(t, s, 0u);
         }
     }
 
@@ -234,14 +267,43 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
     float wmin = -INFINITY;
     int wmin_lane = 0;
 
-    int it = 0;
-    for (int64_t tile = gw; tile < n_tiles; tile += W, ++it) {
-        const int stage = it % ORR_SCAN_STAGES;
-        const uint32_t parity = (uint32_t)(it / ORR_SCAN_STAGES) & 1u;
+    // Software pipeline.  A tile's scalar epilogue (shuffle butterflies, keyword probe,
+    // recency, fuse, list insert) is a long dependent chain; it is issued one iteration late,
+    // after the NEXT tile's LDS/FMA phase, so the two chains overlap inside one warp and the
+    // per-row ticks/term loads have a whole iteration to land.
+    float pd[TR], pn[TR];                      // pending tile: per-lane partial sums
+    uint32_t pth[TR][4];                       // pending tile: this lane's term words
+    int64_t ptk = 0, pr0 = 0;
+    int pnr = 0;
+#pragma unroll
+    for (int r = 0; r < TR; ++r) { pd[r] = pn[r] = 0.f; pth[r][0] = pth[r][1] = pth[r][2] = pth[r][3] = 0u; }
+
+    auto finish_pending = [&]() {
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+            if (r < pnr) {                                               // warp-uniform
+                const float dot = warp_sum(pd[r]);
+                const float nb = warp_sum(pn[r]);
+                const int64_t ticks = __shfl_sync(FULL, ptk, r);
+                const float s = fuse_row(a, dot, nb, inv_qn, ticks, pth[r], spl);
+                if (s > wmin) {                                          // warp-uniform
+                    if (lane == wmin_lane) { es = s; er = (uint32_t)(pr0 + r); }
+                    const uint32_t k = order_key(es);
+                    const uint32_t mk = __reduce_min_sync(FULL, k);
+                    wmin_lane = __ffs(__ballot_sync(FULL, k == mk)) - 1;
+                    wmin = key_to_float(mk);
+                }
+            }
+        }
+    };
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t tile = gw; tile < n_tiles; tile += W) {
         const int64_t r0 = tile * TR;
         const int nr = (int)((rows - r0 < TR) ? (rows - r0) : TR);
 
-        // per-row scalars straight from global, issued before the wait so they overlap it
+        // this tile's per-row scalars straight from global; consumed one iteration later
         int64_t tk = 0;
         if (lane < nr) tk = ldg_nc_s64(a.sh.ticks + r0 + lane);
         uint32_t th[TR][4];
@@ -259,18 +321,19 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
         }
 
         mbar_wait(my_bar0 + (uint32_t)stage * 8u, parity);
-        const uint32_t sbase = my_stage0 + (uint32_t)stage * (uint32_t)a.stage_bytes;
+        const uint8_t* sptr = stage_base + ((size_t)warp * a.stages + stage) * (size_t)a.stage_bytes;
 
-        float dots[TR], nbs[TR];
+        float cd[TR], cn[TR];
+        uint32_t dep = 0;
 #pragma unroll
         for (int r = 0; r < TR; ++r) {
             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
             if (r < nr) {
-                const uint32_t rbase = sbase + (uint32_t)r * row_bytes + (uint32_t)lane * 16u;
+                const float4* xrow = reinterpret_cast<const float4*>(sptr + (size_t)r * row_bytes);
                 if (NV > 0) {
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        const float4 x = lds128(rbase + (uint32_t)j * 512u);
+                        const float4 x = xrow[j * 32 + lane];
                         d0 = fmaf(qr[j].x, x.x, d0); d1 = fmaf(qr[j].y, x.y, d1);
                         d2 = fmaf(qr[j].z, x.z, d2); d3 = fmaf(qr[j].w, x.w, d3);
                         n0 = fmaf(x.x, x.x, n0); n1 = fmaf(x.y, x.y, n1);
@@ -278,7 +341,7 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
                     }
                 } else {
                     for (int i = lane; i < nv4; i += 32) {
-                        const float4 x = lds128(sbase + (uint32_t)r * row_bytes + (uint32_t)i * 16u);
+                        const float4 x = xrow[i];
                         const float4 qq = reinterpret_cast<const float4*>(sq)[i];
                         d0 = fmaf(qq.x, x.x, d0); d1 = fmaf(qq.y, x.y, d1);
                         d2 = fmaf(qq.z, x.z, d2); d3 = fmaf(qq.w, x.w, d3);
@@ -287,33 +350,30 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
                     }
                 }
             }
-            dots[r] = (d0 + d1) + (d2 + d3);
-            nbs[r] = (n0 + n1) + (n2 + n3);
+            cd[r] = (d0 + d1) + (d2 + d3);
+            cn[r] = (n0 + n1) + (n2 + n3);
+            dep |= __float_as_uint(cd[r]) | __float_as_uint(cn[r]);
         }
-#pragma unroll
-        for (int r = 0; r < TR; ++r) { dots[r] = warp_sum(dots[r]); nbs[r] = warp_sum(nbs[r]); }
 
-        // every lane's smem reads have been consumed by the reductions above: refill the stage
+        // Refill this stage.  The vote consumes a value derived from every lane's loads, so the
+        // bulk copy cannot be issued before all of this tile's smem reads have returned.
         {
-            const int64_t nt = tile + (int64_t)ORR_SCAN_STAGES * W;
-            if (lane == 0 && nt < n_tiles) issue(nt, stage);
+            const uint32_t z = all_lanes_done(dep);                      // always 0
+            const int64_t nt = tile + (int64_t)a.stages * W;
+            if (lane == 0 && nt < n_tiles) issue(nt, stage, z);
         }
 
+        if (PIPE) finish_pending();                                      // previous tile
 #pragma unroll
         for (int r = 0; r < TR; ++r) {
-            if (r < nr) {
-                const int64_t ticks = __shfl_sync(FULL, tk, r);
-                const float s = fuse_row(a, dots[r], nbs[r], inv_qn, ticks, th[r], spl);
-                if (s > wmin) {                                      // warp-uniform
-                    if (lane == wmin_lane) { es = s; er = (uint32_t)(r0 + r); }
-                    const uint32_t k = order_key(es);
-                    const uint32_t mk = __reduce_min_sync(FULL, k);
-                    wmin_lane = __ffs(__ballot_sync(FULL, k == mk)) - 1;
-                    wmin = key_to_float(mk);
-                }
-            }
+            pd[r] = cd[r]; pn[r] = cn[r];
+            pth[r][0] = th[r][0]; pth[r][1] = th[r][1]; pth[r][2] = th[r][2]; pth[r][3] = th[r][3];
         }
+        ptk = tk; pr0 = r0; pnr = nr;
+        if (!PIPE) { finish_pending(); pnr = 0; }                        // this tile, immediately
+        if (++stage == a.stages) { stage = 0; parity ^= 1u; }
     }
+    finish_pending();                                                    // last tile
 
     // ---- tail 1: per-CTA merge of the warp lists -> best n_surv of this CTA ----
     __syncthreads();                                                 // all stages idle
@@ -385,7 +445,7 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
         // MSB-first radix select of the M-th largest key
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 24 - 8 * pass;
-            if (tid < 256) hist[tid] = 0;
+            for (int i = tid; i < 256; i += nthreads) hist[i] = 0;
             __syncthreads();
             const uint32_t prefix = s_prefix;
             const uint32_t pmask = pass ? (0xffffffffu << (shift + 8)) : 0u;
@@ -448,17 +508,25 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
     }
 }
 
-template <int NV, int TR>
-int launch_t(const ScanArgs& args, int grid, int smem, cudaStream_t st) {
+template <int NV, int TR, bool PIPE>
+int launch_p(const ScanArgs& args, int grid, int smem, cudaStream_t st) {
     static int configured = 0;                 // largest dynamic smem opted into so far
     if (smem > configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_scan_kernel<NV, TR>,
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_scan_kernel<NV, TR, PIPE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    orr_scan_kernel<NV, TR><<<grid, args.warps * 32, smem, st>>>(args);
+    orr_scan_kernel<NV, TR, PIPE><<<grid, args.warps * 32, smem, st>>>(args);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
+}
+template <int NV, int TR>
+int launch_t(const ScanArgs& args, int grid, int smem, cudaStream_t st) {
+    // measured on B200 (profiles/r01_scan_variants.md): with 8 warps the row stream is the
+    // bottleneck and the immediate epilogue (PIPE=0) is 5% faster; deferral only wins when
+    // fewer warps fit (wide rows).
+    static const int pipe = env_int("ORR_SCAN_PIPE", 0);
+    return pipe ? launch_p<NV, TR, true>(args, grid, smem, st) : launch_p<NV, TR, false>(args, grid, smem, st);
 }
 
 }  // namespace
@@ -466,23 +534,28 @@ int launch_t(const ScanArgs& args, int grid, int smem, cudaStream_t st) {
 // smem layout: [query, 128-B padded][warps x stages x stage_bytes ring][mbarriers]; the ring
 // is reused by the tail as merge scratch (256 x 8 B + per-warp floors), so it is never
 // smaller than that.
-static void scan_layout(int dim, int* warps, int* tile_rows, int* stage_bytes, int* total) {
+static void scan_layout(int dim, int* warps, int* stages, int* tile_rows, int* stage_bytes, int* total) {
     int tr = 1;
     if (dim == 1536) tr = 2;
     if (dim == 768) tr = 4;
     int stage = (tr * dim * 4 + 127) & ~127;
     if (stage < 256) stage = 256;
     const int q_bytes = (dim * 4 + 127) & ~127;
-    int w = ORR_SCAN_WARPS;
+    int w = env_int("ORR_SCAN_WARPS", ORR_SCAN_WARPS);
+    int st = env_int("ORR_SCAN_STAGES", ORR_SCAN_STAGES);
+    if (w < 1) w = 1;
+    if (w > ORR_SCAN_WARPS) w = ORR_SCAN_WARPS;
+    if (st < 2) st = 2;
+    if (st > 8) st = 8;
     const int budget = 227 * 1024 - 2048;                          // minus the tail's static smem
-    while (w > 1 && q_bytes + w * ORR_SCAN_STAGES * (stage + 8) > budget) --w;
-    *warps = w; *tile_rows = tr; *stage_bytes = stage;
-    *total = q_bytes + w * ORR_SCAN_STAGES * (stage + 8);
+    while (w > 1 && q_bytes + w * st * (stage + 8) > budget) --w;
+    *warps = w; *stages = st; *tile_rows = tr; *stage_bytes = stage;
+    *total = q_bytes + w * st * (stage + 8);
 }
 
 int orr_scan_smem_bytes(int dim, int* warps_out, int* tile_rows_out) {
-    int w, tr, stage, total;
-    scan_layout(dim, &w, &tr, &stage, &total);
+    int w, st, tr, stage, total;
+    scan_layout(dim, &w, &st, &tr, &stage, &total);
     if (warps_out) *warps_out = w;
     if (tile_rows_out) *tile_rows_out = tr;
     return total;
@@ -496,15 +569,18 @@ int orr_launch_scan(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& p
     a.q = sc.q;
     a.pr = pr;
     a.w_cos = (float)w.w_cos; a.w_kw = (float)w.w_kw; a.w_rec = (float)w.w_rec;
-    a.inv_decay_ticks = 1.0 / ((double)ORR_TICKS_PER_DAY * w.recency_days);
+    a.decay_per_2p20 = (float)(1048576.0 / ((double)ORR_TICKS_PER_DAY * w.recency_days));
+    a.inv_nterms = pr.n_terms > 0 ? 1.0f / (float)pr.n_terms : 0.f;
     a.now_ticks = now_ticks;
-    int warps, tr, stage, smem;
-    scan_layout(sh.dim, &warps, &tr, &stage, &smem);
-    if (warps * ORR_SCAN_STAGES * stage < 256 * 8 + 64 || smem > 227 * 1024 - 2048) {
+    int warps, stages, tr, stage, smem;
+    scan_layout(sh.dim, &warps, &stages, &tr, &stage, &smem);
+    if (warps * stages * stage < 256 * 8 + 64 || smem > 227 * 1024 - 2048) {
         orr_set_error("scan: dim %d does not fit the shared-memory ring", sh.dim);
         return ORR_E_UNSUPPORTED;
     }
     a.warps = warps;
+    a.stages = stages;
+    a.l2_hint = env_int("ORR_SCAN_L2_HINT", 1);
     a.stage_bytes = stage;
     a.n_surv = n_survivors;
     a.cta_cands = sc.cta_cands;

@@ -93,6 +93,7 @@ def test_blank_query_raises_like_the_reference():
     (64, 64, 5_000, 32, 3),           # generic-dim kernel
     (3072, 3072, 333, 10, 0),         # no query terms, ragged last tile
     (100, 100, 1_000, 1, 1),          # dim not a multiple of 128
+    (4096, 4096, 3_000, 10, 2),       # wide rows: fewer warps per CTA fit the smem ring
 ])
 def test_fused_path_matches_oracle(dim, gen_dim, n, top_k, n_terms):
     spec = synth.make_spec(dim, gen_dim=gen_dim, dup_row_ppm=2000)
