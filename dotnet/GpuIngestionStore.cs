@@ -1,0 +1,152 @@
+// GpuIngestionStore.cs — IIngestionStore (Services/IIngestionStore.cs:5-17) whose chunk rows live
+// in HBM.  Behaviour follows InMemoryIngestionStore.cs line by line; the only additions are the
+// two native calls in UpsertChunksAsync / DeleteDocumentAsync.  Source only (no .NET SDK here);
+// omni_recall_rag_b200/store.py is the tested mirror of this class.
+using System.Collections.Concurrent;
+using System.Text;
+using OmniRecall.Api.Data.Models;
+
+namespace OmniRecall.Api.Services.Gpu;
+
+public sealed class GpuIngestionStore : IIngestionStore, IDisposable
+{
+    private readonly ConcurrentDictionary<string, CosmosDocumentRecord> _documents = new();
+    private readonly ConcurrentDictionary<string, List<CosmosChunkRecord>> _chunksByDocument = new();
+    private readonly ConcurrentDictionary<ulong, CosmosChunkRecord> _chunkByRow = new();
+    private readonly ConcurrentDictionary<string, ulong[]> _rowsByDocument = new();
+    private readonly ConcurrentDictionary<string, int> _vocabulary = new(StringComparer.Ordinal);
+    private readonly object _mutate = new();
+    internal nint Handle { get; }
+    internal int Dim { get; }
+    internal int TermSlots { get; }
+
+    public GpuIngestionStore(IConfiguration configuration)
+    {
+        var cfg = new OrrConfig();
+        OrrNative.orr_config_default(ref cfg);
+        cfg.Device = configuration.GetValue("Gpu:Device", 0);
+        cfg.Dim = Dim = configuration.GetValue("Gpu:Dim", 3072);
+        cfg.TermSlots = TermSlots = configuration.GetValue("Gpu:TermSlots", 128);
+        cfg.CapacityRows = configuration.GetValue("Gpu:CapacityRows", 1L << 20);
+        OrrNative.Check(OrrNative.orr_store_create(in cfg, out var h));
+        Handle = h;
+    }
+
+    public Task<CosmosDocumentRecord> UpsertDocumentAsync(CosmosDocumentRecord document, CancellationToken ct = default)
+    {
+        _documents[document.Id] = document;
+        return Task.FromResult(document);
+    }
+
+    public unsafe Task UpsertChunksAsync(IReadOnlyList<CosmosChunkRecord> chunks, CancellationToken ct = default)
+    {
+        if (chunks.Count == 0) return Task.CompletedTask;
+        var documentId = chunks[0].DocumentId;                       // InMemoryIngestionStore.cs:22
+        var ordered = chunks.OrderBy(c => c.ChunkIndex).ToList();    // :23
+        var n = ordered.Count;
+        var emb = new float[(long)n * Dim];
+        var has = new byte[n];
+        var ticks = new long[n];
+        var offsets = new uint[n + 1];
+        var hashes = new List<ulong>();
+        var tokens = new List<string[]>(n);
+        for (var i = 0; i < n; i++)
+        {
+            var c = ordered[i];
+            if (c.Embedding is { Count: > 0 } e && e.Count == Dim)   // other widths score cosine 0 (:71-72)
+            {
+                for (var j = 0; j < Dim; j++) emb[(long)i * Dim + j] = e[j];
+                has[i] = 1;
+            }
+            ticks[i] = c.CreatedAtUtc.Ticks;
+            var toks = DistinctLowerTokens(c.Content);
+            if (toks.Length > TermSlots)
+                throw new InvalidOperationException($"chunk {c.Id} has {toks.Length} distinct tokens; Gpu:TermSlots={TermSlots}");
+            tokens.Add(toks);
+            foreach (var t in toks) hashes.Add(HashTerm(t));
+            offsets[i + 1] = (uint)hashes.Count;
+        }
+        var rows = new ulong[n];
+        var flat = hashes.Count > 0 ? hashes.ToArray() : new ulong[1];
+        lock (_mutate)
+        {
+            ForgetRows(documentId);
+            fixed (float* pe = emb) fixed (byte* ph = has) fixed (long* pt = ticks)
+            fixed (ulong* pf = flat) fixed (uint* po = offsets) fixed (ulong* pr = rows)
+                OrrNative.Check(OrrNative.orr_store_upsert_document_chunks(
+                    Handle, HashTerm("doc:" + documentId), n, pe, ph, pt, pf, po, pr));
+            _chunksByDocument[documentId] = ordered;
+            _rowsByDocument[documentId] = rows;
+            for (var i = 0; i < n; i++)
+            {
+                _chunkByRow[rows[i]] = ordered[i];
+                foreach (var t in tokens[i]) _vocabulary.AddOrUpdate(t, 1, (_, v) => v + 1);
+            }
+        }
+        return Task.CompletedTask;
+    }
+
+    public Task DeleteDocumentAsync(string documentId, CancellationToken ct = default)
+    {
+        _documents.TryRemove(documentId, out _);
+        lock (_mutate)
+        {
+            if (_chunksByDocument.TryRemove(documentId, out _))
+            {
+                ForgetRows(documentId);
+                OrrNative.Check(OrrNative.orr_store_delete_document(Handle, HashTerm("doc:" + documentId)));
+            }
+        }
+        return Task.CompletedTask;
+    }
+
+    // The remaining six methods are InMemoryIngestionStore.cs:27-48,57-76 verbatim over the host
+    // dictionaries (GetDocumentAsync, ListDocumentsAsync, GetChunksByDocumentIdAsync,
+    // GetRecentChunksAsync, GetDocumentsByIdsAsync); HealthProbeService only needs
+    // ListDocumentsAsync(1).
+    public Task<CosmosDocumentRecord?> GetDocumentAsync(string id, CancellationToken ct = default)
+        => Task.FromResult(_documents.TryGetValue(id, out var d) ? d : null);
+    public Task<IReadOnlyList<CosmosDocumentRecord>> ListDocumentsAsync(int maxCount, CancellationToken ct = default)
+        => Task.FromResult<IReadOnlyList<CosmosDocumentRecord>>(
+            _documents.Values.OrderByDescending(d => d.CreatedAtUtc).Take(Math.Max(1, maxCount)).ToList());
+    public Task<IReadOnlyList<CosmosChunkRecord>> GetChunksByDocumentIdAsync(string id, CancellationToken ct = default)
+        => Task.FromResult<IReadOnlyList<CosmosChunkRecord>>(_chunksByDocument.TryGetValue(id, out var c) ? c : []);
+    public Task<IReadOnlyList<CosmosChunkRecord>> GetRecentChunksAsync(int maxCount, CancellationToken ct = default)
+        => Task.FromResult<IReadOnlyList<CosmosChunkRecord>>(
+            _chunksByDocument.Values.SelectMany(v => v).OrderByDescending(c => c.CreatedAtUtc).Take(Math.Max(1, maxCount)).ToList());
+    public Task<IReadOnlyDictionary<string, CosmosDocumentRecord>> GetDocumentsByIdsAsync(
+        IReadOnlyCollection<string> ids, CancellationToken ct = default)
+    {
+        var set = new HashSet<string>(ids);
+        return Task.FromResult<IReadOnlyDictionary<string, CosmosDocumentRecord>>(
+            _documents.Where(kv => set.Contains(kv.Key)).ToDictionary(kv => kv.Key, kv => kv.Value));
+    }
+
+    internal CosmosChunkRecord ChunkOfRow(ulong row) => _chunkByRow[row];
+
+    /// words of the live corpus that contain `term` — the host half of Contains (RecallSearchService.cs:111)
+    internal IEnumerable<string> VocabularyWordsContaining(string term)
+        => _vocabulary.Keys.Where(w => w.Contains(term, StringComparison.Ordinal));
+
+    internal static string[] DistinctLowerTokens(string content)
+        => (content ?? string.Empty)
+            .Split((char[]?)null, StringSplitOptions.RemoveEmptyEntries | StringSplitOptions.TrimEntries)
+            .Select(t => t.ToLowerInvariant()).Distinct().ToArray();
+
+    internal static unsafe ulong HashTerm(string lower)
+    {
+        var bytes = Encoding.UTF8.GetBytes(lower);
+        fixed (byte* p = bytes) return OrrNative.orr_hash_term(p, bytes.Length);
+    }
+
+    private void ForgetRows(string documentId)
+    {
+        if (!_rowsByDocument.TryRemove(documentId, out var rows)) return;
+        foreach (var r in rows)
+            if (_chunkByRow.TryRemove(r, out var c))
+                foreach (var t in DistinctLowerTokens(c.Content))
+                    if (_vocabulary.AddOrUpdate(t, 0, (_, v) => v - 1) <= 0) _vocabulary.TryRemove(t, out _);
+    }
+
+    public void Dispose() => OrrNative.orr_store_destroy(Handle);
+}

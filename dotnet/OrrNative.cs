@@ -1,0 +1,49 @@
+// OrrNative.cs — P/Invoke binding of liborr.so (include/orr.h), ABI version 1.
+// Source only: there is no .NET SDK in the build image, so this file is not compiled here.
+using System.Runtime.InteropServices;
+
+namespace OmniRecall.Api.Services.Gpu;
+
+[StructLayout(LayoutKind.Sequential)]
+internal struct OrrConfig
+{
+    public int AbiVersion, Device, Dim, TermSlots;
+    public long CapacityRows;
+    public ulong RowBase;
+    public double WCos, WKw, WRec, RecencyDays;
+}
+
+[StructLayout(LayoutKind.Sequential)]
+internal struct OrrHit
+{
+    public ulong Row;
+    public double Score;
+    public long CreatedTicks;
+}
+
+internal static partial class OrrNative
+{
+    private const string Lib = "orr";   // liborr.so on the library path
+
+    [LibraryImport(Lib)] internal static partial void orr_config_default(ref OrrConfig cfg);
+    [LibraryImport(Lib)] internal static partial int orr_store_create(in OrrConfig cfg, out nint store);
+    [LibraryImport(Lib)] internal static partial void orr_store_destroy(nint store);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_store_upsert_document_chunks(
+        nint store, ulong docKey, int n, float* emb, byte* hasEmb, long* createdTicks,
+        ulong* termHashes, uint* termOffsets, ulong* outRows);
+    [LibraryImport(Lib)] internal static partial int orr_store_delete_document(nint store, ulong docKey);
+    [LibraryImport(Lib)] internal static partial long orr_store_count(nint store);
+    [LibraryImport(Lib)] internal static unsafe partial ulong orr_hash_term(byte* utf8Lower, int len);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_search(
+        nint store, float* q, int qDim, int nTerms, ulong* probeHash, int* probeTerm, int nProbes,
+        long nowTicks, int topK, int candidateCap, OrrHit* hits, out int nOut);
+    [LibraryImport(Lib)] internal static partial nint orr_last_error();
+
+    internal static void Check(int rc)
+    {
+        if (rc == 0) return;
+        var msg = Marshal.PtrToStringUTF8(orr_last_error()) ?? "liborr error";
+        // surfaces through the global exception handler as HTTP 500 (Program.cs:77-99)
+        throw new InvalidOperationException($"liborr {rc}: {msg}");
+    }
+}
