@@ -164,6 +164,11 @@ int  orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim
         const uint32_t* probe_offsets,
         int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
 
+/* Diagnostic for the batched path: the raw fused GEMM scores (w_cos*cos + w_rec*rec, no
+ * keyword term; fp32) of every `tile_stride`-th 128-row tile, out[b*out_ld + i]. */
+int  orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
+        int64_t now_ticks, int32_t tile_stride, float* out, int64_t out_ld);
+
 /* Merge per-shard hit lists (each already in reference order) into the global top-k
  * with the same tie chain; used after the NCCL all-gather of per-GPU candidates. */
 int  orr_merge_hits(const orr_hit* lists, const int32_t* list_len, int32_t n_lists,

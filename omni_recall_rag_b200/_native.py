@@ -70,6 +70,8 @@ _SIGNATURES = {
                                     C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "orr_search_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "orr_debug_batch_scores": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                         C.c_void_p, C.c_int64]),
     "orr_merge_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                  C.POINTER(C.c_int32)]),
     "orr_merge_hits_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

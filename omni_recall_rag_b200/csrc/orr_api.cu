@@ -36,6 +36,26 @@ struct SearchCtx {
 
 thread_local orr_timing g_timing{};
 
+// state of the batched (tcgen05) path: split planes of the store + per-call scratch
+struct BatchState {
+    std::mutex mu;                       // batched searches are serialised per store
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    void* ehi = nullptr; void* emid = nullptr;     // bf16 [capacity][dim]
+    float* inv_norm = nullptr;                     // [capacity]
+    void* rowaux = nullptr;                        // float2 [capacity padded]
+    int64_t planes_rows = 0;                       // rows whose planes are built
+    int bcap = 0, kcap = 0;
+    float* q = nullptr; void* qhi = nullptr; void* qmid = nullptr;
+    float* qscale = nullptr; float* thr = nullptr; float* kww = nullptr; int32_t* qterm = nullptr;
+    void* cand = nullptr; uint32_t* cand_count = nullptr; orr_hit* hits = nullptr; int32_t* status = nullptr;
+    OrrProbes* probes = nullptr;
+    float* dense = nullptr; size_t dense_elems = 0;
+    uint32_t* term_bits = nullptr; size_t term_bits_words = 0; void* table = nullptr;
+};
+constexpr int BATCH_CAND_CAP = 4096;
+constexpr int BATCH_TABLE_SLOTS = 16384;
+
 }  // namespace
 
 struct orr_store {
@@ -60,6 +80,7 @@ struct orr_store {
     int32_t cap_value = -1;
     std::vector<uint32_t> cap_rows;
     cudaStream_t mut_stream = nullptr;
+    std::unique_ptr<BatchState> batch;
 };
 
 namespace {
@@ -273,6 +294,15 @@ void orr_store_destroy(orr_store* s) {
     for (auto& c : s->pool) free_ctx(c.get());
     if (s->dev_ctx) free_ctx(s->dev_ctx.get());
     if (s->mut_stream) cudaStreamDestroy(s->mut_stream);
+    if (s->batch) {
+        BatchState* b = s->batch.get();
+        if (b->stream) cudaStreamSynchronize(b->stream);
+        void* ptrs[] = {b->ehi, b->emid, b->inv_norm, b->rowaux, b->q, b->qhi, b->qmid, b->qscale, b->thr, b->kww, b->qterm,
+                        b->cand, b->cand_count, b->hits, b->status, b->probes, b->dense, b->term_bits, b->table};
+        for (void* p : ptrs) cudaFree(p);
+        for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+        if (b->stream) cudaStreamDestroy(b->stream);
+    }
     cudaFree(s->d_emb); cudaFree(s->d_ticks); cudaFree(s->d_terms32); cudaFree(s->d_terms64);
     delete s;
 }
@@ -515,20 +545,262 @@ int orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim, int32_t n
     return orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, q_dim, k, M, true, st);
 }
 
+// ---- batched path ------------------------------------------------------------------------------
+static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) {
+    const int dim = s->cfg.dim;
+    const size_t cap = (size_t)s->cfg.capacity_rows;
+    if (!bs->stream) {
+        ORR_CUDA_OK(cudaStreamCreateWithFlags(&bs->stream, cudaStreamNonBlocking));
+        for (auto& e : bs->ev) ORR_CUDA_OK(cudaEventCreate(&e));
+    }
+    if (!bs->ehi) {
+        const size_t cap_pad = (cap + 127) / 128 * 128;
+        ORR_CUDA_OK(cudaMalloc(&bs->ehi, cap * dim * 2));
+        ORR_CUDA_OK(cudaMalloc(&bs->emid, cap * dim * 2));
+        ORR_CUDA_OK(cudaMalloc(&bs->inv_norm, cap * sizeof(float)));
+        ORR_CUDA_OK(cudaMalloc(&bs->rowaux, cap_pad * 8));
+        bs->planes_rows = 0;
+    }
+    if (bs->planes_rows < s->rows_used) {        // rows appended since the last batch
+        int rc = orr_batch_build_planes(s->d_emb, bs->ehi, bs->emid, bs->inv_norm, bs->planes_rows,
+                                        s->rows_used - bs->planes_rows, dim, bs->stream);
+        if (rc != ORR_OK) return rc;
+        bs->planes_rows = s->rows_used;
+    }
+    if (batch_padded > bs->bcap || k > bs->kcap) {
+        void** ptrs[] = {(void**)&bs->q, &bs->qhi, &bs->qmid, (void**)&bs->qscale, (void**)&bs->thr, (void**)&bs->kww,
+                         (void**)&bs->qterm, &bs->cand, (void**)&bs->cand_count, (void**)&bs->hits, (void**)&bs->status,
+                         (void**)&bs->probes};
+        for (void** p : ptrs) { cudaFree(*p); *p = nullptr; }
+        const size_t B = (size_t)std::max(batch_padded, bs->bcap);
+        const size_t K = (size_t)std::max(k, bs->kcap);
+        ORR_CUDA_OK(cudaMalloc(&bs->q, B * dim * sizeof(float)));
+        ORR_CUDA_OK(cudaMalloc(&bs->qhi, B * dim * 2));
+        ORR_CUDA_OK(cudaMalloc(&bs->qmid, B * dim * 2));
+        ORR_CUDA_OK(cudaMalloc(&bs->qscale, B * sizeof(float)));
+        ORR_CUDA_OK(cudaMalloc(&bs->thr, B * sizeof(float)));
+        ORR_CUDA_OK(cudaMalloc(&bs->kww, B * sizeof(float)));
+        ORR_CUDA_OK(cudaMalloc(&bs->qterm, B * ORR_BATCH_TERMS * sizeof(int32_t)));
+        ORR_CUDA_OK(cudaMalloc(&bs->cand, B * BATCH_CAND_CAP * 8));
+        ORR_CUDA_OK(cudaMalloc(&bs->cand_count, B * sizeof(uint32_t)));
+        ORR_CUDA_OK(cudaMalloc(&bs->hits, B * K * sizeof(orr_hit)));
+        ORR_CUDA_OK(cudaMalloc(&bs->status, B * 2 * sizeof(int32_t)));
+        ORR_CUDA_OK(cudaMalloc(&bs->probes, B * sizeof(OrrProbes)));
+        bs->bcap = (int)B; bs->kcap = (int)K;
+    }
+    return ORR_OK;
+}
+
+static int batch_survivors(int k) { return std::min(256, std::max(64, (k + std::max(32, k) + 31) / 32 * 32)); }
+
+// the GEMM path proper; `redo` receives the queries whose selection could not be proven safe
+static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const int32_t* n_terms,
+                           const uint64_t* probe_hash, const uint32_t* probe_offsets, int64_t now_ticks, int32_t top_k,
+                           orr_hit* out, int32_t* n_out, std::vector<int32_t>* redo) {
+    if (!s->batch) s->batch.reset(new BatchState());
+    BatchState* bs = s->batch.get();
+    std::lock_guard<std::mutex> g(bs->mu);
+    const int dim = s->cfg.dim, k = std::max(1, top_k);
+    const int bp = (batch + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
+    int rc = batch_prepare(s, bs, bp, k);
+    if (rc != ORR_OK) return rc;
+    cudaStream_t st = bs->stream;
+    const OrrShard sh = shard_view(s);
+    const OrrWeights w = weights_of(s);
+    const int64_t rows = s->rows_used;
+    const int64_t rows_pad = (rows + 127) / 128 * 128;
+    const int M = batch_survivors(k);
+
+    ORR_CUDA_OK(cudaMemcpyAsync(bs->q, q, sizeof(float) * (size_t)batch * dim, cudaMemcpyHostToDevice, st));
+    rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st);
+    if (rc != ORR_OK) return rc;
+    rc = orr_batch_build_rowaux(s->d_ticks, bs->inv_norm, bs->rowaux, rows, rows_pad, now_ticks, w, st);
+    if (rc != ORR_OK) return rc;
+
+    // ---- keyword side: distinct batch terms -> ids, bitmaps over rows, per-query id lists ----
+    bool any_terms = false;
+    for (int32_t b = 0; b < batch; ++b) any_terms |= (n_terms && n_terms[b] > 0);
+    const int64_t row_words = rows_pad / 32;
+    std::vector<OrrProbes> hp((size_t)batch);
+    if (any_terms) {
+        std::vector<uint2> table(BATCH_TABLE_SLOTS, make_uint2(0u, 0u));
+        std::vector<int32_t> qterm((size_t)bp * ORR_BATCH_TERMS, -1);
+        std::vector<float> kww((size_t)bp, 0.f);
+        uint32_t n_ids = 0;
+        for (int32_t b = 0; b < batch; ++b) {
+            const int32_t nt = n_terms[b];
+            const uint32_t p0 = probe_offsets[b];
+            rc = build_probes(nt, probe_hash + p0, nullptr, nt, &hp[(size_t)b]);
+            if (rc != ORR_OK) return rc;
+            if (nt > 0) kww[(size_t)b] = (float)(w.w_kw / (double)nt);
+            for (int32_t t = 0; t < nt; ++t) {
+                const uint32_t h = hp[(size_t)b].h32[t];
+                uint32_t pos = (h * 0x9E3779B1u) & (BATCH_TABLE_SLOTS - 1);
+                while (table[pos].x != 0u && table[pos].x != h) pos = (pos + 1) & (BATCH_TABLE_SLOTS - 1);
+                if (table[pos].x == 0u) { table[pos] = make_uint2(h, n_ids++); }
+                qterm[(size_t)b * ORR_BATCH_TERMS + t] = (int32_t)table[pos].y;
+            }
+        }
+        const size_t need = (size_t)n_ids * (size_t)row_words;
+        if (need > bs->term_bits_words) {
+            cudaFree(bs->term_bits); bs->term_bits = nullptr; bs->term_bits_words = 0;
+            ORR_CUDA_OK(cudaMalloc(&bs->term_bits, need * sizeof(uint32_t)));
+            bs->term_bits_words = need;
+        }
+        if (!bs->table) ORR_CUDA_OK(cudaMalloc(&bs->table, BATCH_TABLE_SLOTS * 8));
+        ORR_CUDA_OK(cudaMemsetAsync(bs->term_bits, 0, need * sizeof(uint32_t), st));
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table.data(), BATCH_TABLE_SLOTS * 8, cudaMemcpyHostToDevice, st));
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->qterm, qterm.data(), qterm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->kww, kww.data(), kww.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->probes, hp.data(), sizeof(OrrProbes) * (size_t)batch, cudaMemcpyHostToDevice, st));
+        ORR_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope below
+        rc = orr_batch_launch_term_bits(s->d_terms32, s->cfg.term_slots, rows, bs->table, BATCH_TABLE_SLOTS, bs->term_bits,
+                                        row_words, st);
+        if (rc != ORR_OK) return rc;
+    }
+
+    OrrBatchGemm gm{};
+    gm.qhi = bs->qhi; gm.qmid = bs->qmid; gm.ehi = bs->ehi; gm.emid = bs->emid; gm.rowaux = bs->rowaux;
+    gm.qscale = bs->qscale; gm.thr = bs->thr; gm.cand = bs->cand; gm.cand_count = bs->cand_count; gm.cand_cap = BATCH_CAND_CAP;
+    gm.term_bits = any_terms ? bs->term_bits : nullptr; gm.row_words = row_words;
+    gm.q_term_ids = any_terms ? bs->qterm : nullptr; gm.q_kw_w = any_terms ? bs->kww : nullptr;
+    gm.rows = rows; gm.dim = dim; gm.batch_padded = bp; gm.sms = s->sms;
+
+    // ---- sampling pass: dense scores of every stride-th row tile -> per-query thresholds ----
+    const int target = 4 * M;
+    const int64_t all_tiles = rows_pad / 128;
+    const int64_t want_tiles = std::max<int64_t>(8, (32 * rows / target + 127) / 128);
+    const int stride = (int)std::max<int64_t>(1, all_tiles / std::min(all_tiles, want_tiles));
+    const int64_t s_tiles = (all_tiles + stride - 1) / stride;
+    const int64_t n_s = s_tiles * 128;
+    if ((size_t)bp * (size_t)n_s > bs->dense_elems) {
+        cudaFree(bs->dense); bs->dense = nullptr; bs->dense_elems = 0;
+        ORR_CUDA_OK(cudaMalloc(&bs->dense, (size_t)bp * (size_t)n_s * sizeof(float)));
+        bs->dense_elems = (size_t)bp * (size_t)n_s;
+    }
+    gm.dense = bs->dense; gm.dense_ld = n_s; gm.tile_stride = stride;
+    ORR_CUDA_OK(cudaEventRecord(bs->ev[0], st));
+    rc = orr_batch_launch_gemm(gm, st);
+    if (rc != ORR_OK) return rc;
+    const int rstar = stride == 1 ? target : (int)std::max<int64_t>(1, (int64_t)target * n_s / rows_pad);
+    rc = orr_batch_launch_threshold(bs->dense, n_s, (int)n_s, rstar, bs->thr, batch, bp, st);
+    if (rc != ORR_OK) return rc;
+
+    // ---- main pass: every row tile, candidates above the thresholds ----
+    ORR_CUDA_OK(cudaMemsetAsync(bs->cand_count, 0, sizeof(uint32_t) * (size_t)bp, st));
+    gm.dense = nullptr; gm.dense_ld = 0; gm.tile_stride = 1;
+    ORR_CUDA_OK(cudaEventRecord(bs->ev[1], st));
+    rc = orr_batch_launch_gemm(gm, st);
+    if (rc != ORR_OK) return rc;
+    ORR_CUDA_OK(cudaEventRecord(bs->ev[2], st));
+
+    // ---- per-query finalize: survivors, exact fp64 re-score, order, bound check ----
+    const double eps = (double)ORR_BATCH_EPS * (std::fabs(w.w_cos) + std::fabs(w.w_kw) + std::fabs(w.w_rec));
+    rc = orr_batch_launch_finalize(sh, bs->q, dim, any_terms ? bs->probes : nullptr, w, now_ticks, bs->cand, bs->cand_count,
+                                   bs->thr, BATCH_CAND_CAP, M, top_k, k, eps, bs->hits, bs->status, batch, st);
+    if (rc != ORR_OK) return rc;
+    std::vector<int32_t> st_host((size_t)batch * 2);
+    ORR_CUDA_OK(cudaMemcpyAsync(st_host.data(), bs->status, sizeof(int32_t) * 2 * (size_t)batch, cudaMemcpyDeviceToHost, st));
+    ORR_CUDA_OK(cudaMemcpyAsync(out, bs->hits, sizeof(orr_hit) * (size_t)batch * k, cudaMemcpyDeviceToHost, st));
+    ORR_CUDA_OK(cudaStreamSynchronize(st));
+    float ms_sample = 0.f, ms_main = 0.f;
+    cudaEventElapsedTime(&ms_sample, bs->ev[0], bs->ev[1]);
+    cudaEventElapsedTime(&ms_main, bs->ev[1], bs->ev[2]);
+    for (int32_t b = 0; b < batch; ++b) {
+        n_out[b] = st_host[(size_t)2 * b];
+        if (st_host[(size_t)2 * b + 1] != 0) redo->push_back(b);
+    }
+    g_timing.scan_ms = ms_main;
+    g_timing.finalize_ms = ms_sample;            // sampling pass + thresholds
+    g_timing.total_device_ms = ms_sample + ms_main;
+    g_timing.path = ORR_PATH_BATCH;
+    g_timing.n_survivors = M;
+    g_timing.rows_scanned = rows;
+    return ORR_OK;
+}
+
 int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim, const int32_t* n_terms,
                      const uint64_t* probe_hash, const int32_t* probe_term, const uint32_t* probe_offsets,
                      int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
-    // Round-1 batch path: the queries run back to back through the single-query path
-    // (the tcgen05 contraction replaces this loop).
-    if (!s || batch < 0 || !out || !n_out) { orr_set_error("orr_search_batch: bad argument"); return ORR_E_INVALID; }
+    const double t0 = now_ms();
+    if (!s || batch < 0 || !out || !n_out || (batch > 0 && q_dim > 0 && !q)) { orr_set_error("orr_search_batch: bad argument"); return ORR_E_INVALID; }
+    if (batch == 0) return ORR_OK;
     const int k = std::max(1, top_k);
-    for (int32_t b = 0; b < batch; ++b) {
+    // the tcgen05 path takes: a query embedding of the store's width, dim % 64 == 0, k <= 128,
+    // <= 16 terms per query given as identity probes; anything else runs query by query
+    bool gemm_ok = (q_dim == s->cfg.dim) && (s->cfg.dim % 64 == 0) && k <= 128 && batch >= 8 && s->live_rows > 0 &&
+                   getenv("ORR_BATCH_LOOP") == nullptr;
+    if (gemm_ok && n_terms) {
+        for (int32_t b = 0; b < batch && gemm_ok; ++b) {
+            const int32_t nt = n_terms[b];
+            if (nt < 0 || nt > ORR_BATCH_TERMS) gemm_ok = false;
+            if (nt > 0) {
+                if (!probe_offsets || !probe_hash) gemm_ok = false;
+                else if ((int32_t)(probe_offsets[b + 1] - probe_offsets[b]) != nt) gemm_ok = false;
+                else if (probe_term) for (int32_t t = 0; t < nt; ++t) if (probe_term[probe_offsets[b] + t] != t) gemm_ok = false;
+            }
+        }
+    }
+    std::vector<int32_t> redo;
+    if (gemm_ok) {
+        std::shared_lock<std::shared_mutex> lock(s->mu);
+        ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+        memset(&g_timing, 0, sizeof g_timing);
+        int rc = batch_gemm_path(s, batch, q, n_terms, probe_hash, probe_offsets, now_ticks, top_k, out, n_out, &redo);
+        if (rc != ORR_OK) return rc;
+    } else {
+        for (int32_t b = 0; b < batch; ++b) redo.push_back(b);
+    }
+    const orr_timing batch_timing = g_timing;
+    for (int32_t b : redo) {                       // per-query path (exact escalation included)
         const uint32_t p0 = probe_offsets ? probe_offsets[b] : 0, p1 = probe_offsets ? probe_offsets[b + 1] : 0;
         int rc = orr_search(s, q ? q + (int64_t)b * q_dim : nullptr, q_dim, n_terms ? n_terms[b] : 0,
                             probe_hash ? probe_hash + p0 : nullptr, probe_term ? probe_term + p0 : nullptr,
                             (int32_t)(p1 - p0), now_ticks, top_k, 0, out + (int64_t)b * k, n_out + b);
         if (rc != ORR_OK) return rc;
     }
+    if (gemm_ok) {
+        g_timing = batch_timing;
+        g_timing.n_survivors = (int32_t)redo.size() | (batch_timing.n_survivors << 16);   // low half: queries re-run singly
+    }
+    g_timing.wall_ms = (float)(now_ms() - t0);
+    return ORR_OK;
+}
+
+// diagnostic: the raw fused GEMM scores (no keyword term) of every stride-th row tile
+int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t q_dim, int64_t now_ticks,
+                           int32_t tile_stride, float* out, int64_t out_ld) {
+    if (!s || !q || !out || batch < 1 || q_dim != s->cfg.dim || tile_stride < 1) { orr_set_error("orr_debug_batch_scores: bad argument"); return ORR_E_INVALID; }
+    std::shared_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (!s->batch) s->batch.reset(new BatchState());
+    BatchState* bs = s->batch.get();
+    std::lock_guard<std::mutex> g(bs->mu);
+    const int dim = s->cfg.dim;
+    const int bp = (batch + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
+    int rc = batch_prepare(s, bs, bp, 1);
+    if (rc != ORR_OK) return rc;
+    cudaStream_t st = bs->stream;
+    const int64_t rows = s->rows_used, rows_pad = (rows + 127) / 128 * 128;
+    const int64_t s_tiles = (rows_pad / 128 + tile_stride - 1) / tile_stride, n_s = s_tiles * 128;
+    if (out_ld < n_s) { orr_set_error("orr_debug_batch_scores: out_ld %lld < %lld", (long long)out_ld, (long long)n_s); return ORR_E_INVALID; }
+    ORR_CUDA_OK(cudaMemcpyAsync(bs->q, q, sizeof(float) * (size_t)batch * dim, cudaMemcpyHostToDevice, st));
+    if ((rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st)) != ORR_OK) return rc;
+    if ((rc = orr_batch_build_rowaux(s->d_ticks, bs->inv_norm, bs->rowaux, rows, rows_pad, now_ticks, weights_of(s), st)) != ORR_OK) return rc;
+    if ((size_t)bp * (size_t)n_s > bs->dense_elems) {
+        cudaFree(bs->dense); bs->dense = nullptr; bs->dense_elems = 0;
+        ORR_CUDA_OK(cudaMalloc(&bs->dense, (size_t)bp * (size_t)n_s * sizeof(float)));
+        bs->dense_elems = (size_t)bp * (size_t)n_s;
+    }
+    OrrBatchGemm gm{};
+    gm.qhi = bs->qhi; gm.qmid = bs->qmid; gm.ehi = bs->ehi; gm.emid = bs->emid; gm.rowaux = bs->rowaux;
+    gm.qscale = bs->qscale; gm.thr = bs->thr; gm.cand = bs->cand; gm.cand_count = bs->cand_count; gm.cand_cap = BATCH_CAND_CAP;
+    gm.rows = rows; gm.dim = dim; gm.batch_padded = bp; gm.sms = s->sms;
+    gm.dense = bs->dense; gm.dense_ld = n_s; gm.tile_stride = tile_stride;
+    if ((rc = orr_batch_launch_gemm(gm, st)) != ORR_OK) return rc;
+    ORR_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)out_ld * sizeof(float), bs->dense, (size_t)n_s * sizeof(float),
+                                  (size_t)n_s * sizeof(float), (size_t)batch, cudaMemcpyDeviceToHost, st));
+    ORR_CUDA_OK(cudaStreamSynchronize(st));
     return ORR_OK;
 }
 

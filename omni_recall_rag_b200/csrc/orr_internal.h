@@ -111,6 +111,37 @@ int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_
                           int dim, int slots, const orr_synth_spec& spec, uint64_t first_row,
                           int64_t local_first, int64_t n, cudaStream_t st);
 
+// ---- batched path (orr_batch.cu) ------------------------------------------------------------
+constexpr int ORR_BATCH_TERMS = 16;          // query terms the batched epilogue handles per query
+constexpr int ORR_BATCH_TILE = 128;          // queries per unit == corpus rows per unit
+struct OrrBatchGemm {
+    const void* qhi; const void* qmid;       // bf16 [batch_padded][dim]
+    const void* ehi; const void* emid;       // bf16 [rows][dim]
+    const void* rowaux;                      // float2 [rows padded to 128]
+    const float* qscale;                     // [batch_padded]
+    const float* thr;                        // [batch_padded] (main pass)
+    void* cand; uint32_t* cand_count; int32_t cand_cap;
+    float* dense; int64_t dense_ld;          // dense score output (sampling / debug) or NULL
+    const uint32_t* term_bits; int64_t row_words; const int32_t* q_term_ids; const float* q_kw_w;
+    int64_t rows; int32_t dim; int32_t batch_padded; int32_t tile_stride; int32_t sms;
+};
+int orr_batch_build_planes(const float* emb, void* hi, void* mid, float* inv_norm, int64_t first, int64_t n, int dim,
+                           cudaStream_t st);
+int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qscale, int batch, int batch_padded,
+                           int dim, cudaStream_t st);
+int orr_batch_build_rowaux(const int64_t* ticks, const float* inv_norm, void* rowaux, int64_t rows, int64_t rows_padded,
+                           int64_t now_ticks, const OrrWeights& w, cudaStream_t st);
+int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st);
+int orr_batch_launch_threshold(const float* dense, int64_t ld, int n, int rstar, float* thr, int batch, int batch_padded,
+                               cudaStream_t st);
+int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrProbes* probes, const OrrWeights& w,
+                              int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
+                              int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
+                              cudaStream_t st);
+int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows, const void* table, int table_slots,
+                               uint32_t* bits, int64_t row_words, cudaStream_t st);
+constexpr float ORR_BATCH_EPS = 2.0e-4f;     // bound on |bf16x3 GEMM score - exact score| (unit weights)
+
 // text
 uint64_t orr_hash_bytes(const char* s, int64_t n);
 #if defined(__CUDACC__)

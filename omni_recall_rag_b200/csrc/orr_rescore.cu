@@ -46,10 +46,11 @@ struct ExactArgs {
 constexpr int EX_CHUNK = 12;
 
 // fp64 ||q||^2 in the lane-strided order; all lanes return the same value
-__device__ __forceinline__ double exact_qnorm(const ExactArgs& a, int lane) {
+template <class A>
+__device__ __forceinline__ double exact_qnorm_q(const A& a, const float* q, int lane) {
     double nA = 0.0;
     const int nv4 = a.sh.dim >> 2;
-    const float4* q4 = reinterpret_cast<const float4*>(a.q);
+    const float4* q4 = reinterpret_cast<const float4*>(q);
     for (int base = 0; base < nv4; base += 32 * EX_CHUNK) {
         float4 v[EX_CHUNK];
 #pragma unroll
@@ -71,13 +72,14 @@ __device__ __forceinline__ double exact_qnorm(const ExactArgs& a, int lane) {
 }
 
 // exact fused score of one row, computed by a full warp; all lanes return the same value
-__device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int lane, double nA,
-                                            int64_t* ticks_out) {
+template <class A>
+__device__ __forceinline__ double exact_row_q(const A& a, const float* q, const OrrProbes& pr, int64_t row,
+                                              int lane, double nA, int64_t* ticks_out) {
     const int64_t ticks = a.sh.ticks[row];
     *ticks_out = ticks;
     // term hashes are fetched up front so their latency overlaps the embedding loads
     uint64_t th[4] = {0, 0, 0, 0};
-    if (a.pr.n_probes > 0) {
+    if (pr.n_probes > 0) {
         const int spl = a.sh.slots >> 5;
         const uint64_t* t64 = a.sh.terms64 + row * (int64_t)a.sh.slots;
 #pragma unroll
@@ -87,7 +89,7 @@ __device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int
     if (a.q_dim == a.sh.dim && a.q_dim > 0) {                       // :71-72 length check
         const int nv4 = a.sh.dim >> 2;
         const float4* x4 = reinterpret_cast<const float4*>(a.sh.emb + row * (int64_t)a.sh.dim);
-        const float4* q4 = reinterpret_cast<const float4*>(a.q);
+        const float4* q4 = reinterpret_cast<const float4*>(q);
         double dot = 0.0, nB = 0.0;
         for (int base = 0; base < nv4; base += 32 * EX_CHUNK) {
             float4 x[EX_CHUNK], v[EX_CHUNK];
@@ -114,19 +116,19 @@ __device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int
             cosv = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(nA), __dsqrt_rn(nB)));   // :87
     }
     double kw = 0.0;
-    if (a.pr.n_probes > 0) {                                          // :110-112
+    if (pr.n_probes > 0) {                                          // :110-112
         uint32_t m0 = 0, m1 = 0;
-        for (int p = 0; p < a.pr.n_probes; ++p) {
-            const uint64_t h = a.pr.h64[p];
+        for (int p = 0; p < pr.n_probes; ++p) {
+            const uint64_t h = pr.h64[p];
             const bool hit = (th[0] == h) | (th[1] == h) | (th[2] == h) | (th[3] == h);
             if (hit) {
-                const uint32_t t = a.pr.term[p];
+                const uint32_t t = pr.term[p];
                 if (t < 32) m0 |= 1u << t; else m1 |= 1u << (t - 32);
             }
         }
         m0 = __reduce_or_sync(FULL, m0);
         m1 = __reduce_or_sync(FULL, m1);
-        kw = __ddiv_rn((double)(__popc(m0) + __popc(m1)), (double)a.pr.n_terms);
+        kw = __ddiv_rn((double)(__popc(m0) + __popc(m1)), (double)pr.n_terms);
     }
     // RecencyScore: TimeSpan.TotalDays = ticks / 864e9; Math.Max(0, .); exp(-age/30)
     double age = __ddiv_rn((double)(a.now_ticks - ticks), 864000000000.0);
@@ -135,6 +137,11 @@ __device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int
     // ScoreChunk :66
     return __dadd_rn(__dadd_rn(__dmul_rn(cosv, a.w.w_cos), __dmul_rn(kw, a.w.w_kw)),
                      __dmul_rn(rec, a.w.w_rec));
+}
+
+__device__ __forceinline__ double exact_qnorm(const ExactArgs& a, int lane) { return exact_qnorm_q(a, a.q, lane); }
+__device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int lane, double nA, int64_t* ticks_out) {
+    return exact_row_q(a, a.q, a.pr, row, lane, nA, ticks_out);
 }
 
 // reference ordering: true if x ranks strictly before y
@@ -441,6 +448,231 @@ int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_
     while (np2 < total) np2 <<= 1;
     orr_merge_kernel<<<1, 256, np2 * sizeof(OrrExact), st>>>(lists_dev, status_dev, n_lists, stride, top_k, out_dev,
                                                             out_status_dev);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+// =====================================================================================================
+// Batched queries: threshold selection from the sampling pass, and the per-query finalize
+// (select survivors among the GEMM candidates, exact fp64 re-score, order, bound check).
+// =====================================================================================================
+namespace {
+
+__device__ OrrProbes g_no_probes;     // zero-initialised: n_probes == 0
+
+__device__ __forceinline__ uint32_t fkey(float f) {              // monotone; NaN lowest, 0 reserved
+    if (f != f) return 1u;
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+    const uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+
+// thr[b] = the rstar-th largest of dense[b][0..n): one CTA per query, MSB-first radix select
+__global__ void __launch_bounds__(256) orr_batch_threshold_kernel(const float* dense, int64_t ld, int n, int rstar,
+                                                                  float* thr, int batch) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (b >= batch) { if (tid == 0) thr[b] = INFINITY; return; }   // padding queries never produce candidates
+    if (n < rstar || rstar < 1) { if (tid == 0) thr[b] = -INFINITY; return; }
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_rem;
+    const float* x = dense + (int64_t)b * ld;
+    if (tid == 0) { s_prefix = 0; s_rem = (uint32_t)rstar; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const uint32_t pmask = pass ? (0xffffffffu << (shift + 8)) : 0u;
+        for (int i = tid; i < n; i += 256) {
+            const uint32_t k = fkey(x[i]);
+            if ((k & pmask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t rem = s_rem;
+            int d = 255;
+            for (; d > 0; --d) { if (hist[d] >= rem) break; rem -= hist[d]; }
+            s_prefix = prefix | ((uint32_t)d << shift);
+            s_rem = rem;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) thr[b] = fkey_inv(s_prefix);
+}
+
+struct BatchExact {                   // the fields exact_row_q reads
+    OrrShard sh;
+    int32_t q_dim;
+    OrrWeights w;
+    int64_t now_ticks;
+};
+
+struct BatchFinArgs {
+    BatchExact ex;
+    const float* q;                   // [B][dim]
+    const OrrProbes* probes;          // [B] or NULL
+    const uint2* cand;                // [B][cap]
+    const uint32_t* cand_count;       // [B]
+    const float* thr;                 // [B]
+    int32_t cap, n_surv, top_k, k_stride;
+    double eps;
+    orr_hit* hits;                    // [B][k_stride]
+    int32_t* status;                  // [B][2]
+};
+
+constexpr int BATCH_FIN_THREADS = 256;
+
+__global__ void __launch_bounds__(BATCH_FIN_THREADS) orr_batch_finalize_kernel(const BatchFinArgs a) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(fsm);                       // [cap pow2]
+    OrrExact* e = reinterpret_cast<OrrExact*>(fsm + (size_t)a.cap * 8);       // [256]
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t total = a.cand_count[b];
+    const int c = (int)min(total, (uint32_t)a.cap);
+    int flags = total > (uint32_t)a.cap ? 2 : 0;                             // candidate list overflowed
+    int np2 = 1;
+    while (np2 < c) np2 <<= 1;
+    const uint2* src = a.cand + (int64_t)b * a.cap;
+    for (int i = tid; i < np2; i += BATCH_FIN_THREADS) {
+        uint64_t k = 0;
+        if (i < c) { const uint2 v = src[i]; k = ((uint64_t)fkey(__uint_as_float(v.y)) << 32) | (uint64_t)(~v.x); }
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += BATCH_FIN_THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint64_t x = keys[i], y = keys[p];
+                    const bool desc = ((i & k2) == 0);
+                    if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int M = a.n_surv;
+    const int ns = min(M, c);
+    float tau = a.thr[b];                                                    // no row outside the list beats it
+    if (c > M) tau = fmaxf(tau, fkey_inv((uint32_t)(keys[M] >> 32)));
+    // exact re-score of the survivors
+    const float* q = a.q + (int64_t)b * a.ex.sh.dim;
+    const OrrProbes& pr = a.probes ? a.probes[b] : g_no_probes;
+    const bool has_q = (a.ex.q_dim == a.ex.sh.dim && a.ex.q_dim > 0);
+    const double nA = has_q ? exact_qnorm_q(a.ex, q, lane) : 0.0;
+    for (int i = warp; i < ns; i += BATCH_FIN_THREADS / 32) {
+        const int64_t row = (int64_t)(~(uint32_t)keys[i]);
+        int64_t ticks;
+        const double s = exact_row_q(a.ex, q, pr, row, lane, nA, &ticks);
+        if (lane == 0) { e[i].score = s; e[i].ticks = ticks; e[i].row = (uint64_t)row; }
+    }
+    int ep2 = 1;
+    while (ep2 < ns) ep2 <<= 1;
+    for (int i = ns + tid; i < ep2; i += BATCH_FIN_THREADS) {
+        e[i].score = __longlong_as_double(0x7ff8000000000000LL); e[i].ticks = INT64_MIN; e[i].row = ~0ull;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= ep2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < ep2; i += BATCH_FIN_THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const OrrExact x = e[i], y = e[p];
+                    const bool up = ((i & k2) == 0);
+                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int k = max(1, a.top_k);
+    const int n_out = min(k, ns);
+    for (int i = tid; i < n_out; i += BATCH_FIN_THREADS) {
+        orr_hit h; h.row = a.ex.sh.row_base + e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
+        a.hits[(int64_t)b * a.k_stride + i] = h;
+    }
+    if (tid == 0) {
+        if (tau != -INFINITY) {
+            const double sk = (ns >= k) ? e[k - 1].score : __longlong_as_double(0x7ff8000000000000LL);
+            if (!(sk - a.eps > (double)tau)) flags |= 1;                     // selection not provably safe
+        }
+        a.status[2 * b] = n_out;
+        a.status[2 * b + 1] = flags;
+    }
+}
+
+// term bitmaps: bit r of bits[t] says row r holds batch term t.  One warp per row: each lane
+// probes its words of the row's 32-bit term table in an open-addressing table of the batch's
+// distinct terms (smem), hits set bits with atomicOr.
+__global__ void __launch_bounds__(256) orr_batch_term_bits_kernel(const uint32_t* terms32, int slots, int64_t rows,
+                                                                  const uint2* table, int table_mask,
+                                                                  uint32_t* bits, int64_t row_words) {
+    extern __shared__ uint2 tab[];
+    for (int i = threadIdx.x; i <= table_mask; i += blockDim.x) tab[i] = table[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = gw; row < rows; row += W) {
+        for (int w = lane; w < slots; w += 32) {
+            const uint32_t h = __ldg(terms32 + row * slots + w);
+            if (!h) continue;
+            uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)table_mask;
+            for (;;) {
+                const uint2 ent = tab[pos];
+                if (ent.x == 0u) break;
+                if (ent.x == h) atomicOr(bits + (int64_t)ent.y * row_words + (row >> 5), 1u << (row & 31));
+                pos = (pos + 1) & (uint32_t)table_mask;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int orr_batch_launch_threshold(const float* dense, int64_t ld, int n, int rstar, float* thr, int batch, int batch_padded,
+                               cudaStream_t st) {
+    orr_batch_threshold_kernel<<<batch_padded, 256, 0, st>>>(dense, ld, n, rstar, thr, batch);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrProbes* probes, const OrrWeights& w,
+                              int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
+                              int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
+                              cudaStream_t st) {
+    if (n_surv > 256 || (cap & (cap - 1)) != 0) { orr_set_error("batch finalize: bad sizes"); return ORR_E_INTERNAL; }
+    const int smem = cap * 8 + 256 * (int)sizeof(OrrExact);
+    static bool configured = false;
+    if (!configured) {
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8 + 256 * 24));
+        configured = true;
+    }
+    BatchFinArgs a;
+    a.ex.sh = sh; a.ex.q_dim = q_dim; a.ex.w = w; a.ex.now_ticks = now_ticks;
+    a.q = q; a.probes = probes; a.cand = (const uint2*)cand; a.cand_count = cand_count; a.thr = thr;
+    a.cap = cap; a.n_surv = n_surv; a.top_k = top_k; a.k_stride = k_stride; a.eps = eps; a.hits = hits; a.status = status;
+    orr_batch_finalize_kernel<<<batch, BATCH_FIN_THREADS, smem, st>>>(a);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows, const void* table, int table_slots,
+                               uint32_t* bits, int64_t row_words, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int smem = table_slots * 8;
+    static bool configured = false;
+    if (!configured) {
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_term_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        configured = true;
+    }
+    orr_batch_term_bits_kernel<<<sms * 4, 256, smem, st>>>(terms32, slots, rows, (const uint2*)table, table_slots - 1, bits, row_words);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }

@@ -188,6 +188,45 @@ class RecallShard:
             int(now_ticks), int(top_k), C.c_void_p(out_dev_ptr), C.c_void_p(status_dev_ptr),
             C.c_void_p(stream_ptr)))
 
+    def search_batch(self, q: np.ndarray, terms: Optional[Sequence[QueryTerms]], now_ticks: int, top_k: int):
+        """orr_search_batch: q is [B, dim] in host memory; returns a list of B Hits."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B, qd = int(q.shape[0]), int(q.shape[1]) if q.ndim == 2 else 0
+        k = max(1, int(top_k))
+        out = (N.OrrHit * (k * max(B, 1)))()
+        n_out = np.zeros(max(B, 1), dtype=np.int32)
+        nt = ph = pt = po = None
+        if terms is not None:
+            nt = np.array([t.n_terms for t in terms], dtype=np.int32)
+            po = np.zeros(B + 1, dtype=np.uint32)
+            po[1:] = np.cumsum([len(t.probe_hash) for t in terms])
+            ph = np.ascontiguousarray(np.concatenate([np.asarray(t.probe_hash, dtype=np.uint64) for t in terms])
+                                      if po[-1] else np.zeros(1, dtype=np.uint64))
+            if any(t.probe_term is not None for t in terms):
+                pt = np.ascontiguousarray(np.concatenate(
+                    [np.asarray(t.probe_term if t.probe_term is not None else np.arange(len(t.probe_hash)), dtype=np.int32)
+                     for t in terms]) if po[-1] else np.zeros(1, dtype=np.int32))
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        N.check(N.lib().orr_search_batch(self._h, B, p(q) if q.size else None, qd, p(nt), p(ph), p(pt), p(po),
+                                         int(now_ticks), int(top_k), C.cast(out, C.c_void_p), p(n_out)))
+        a = np.frombuffer(out, dtype=np.dtype([("row", "<u8"), ("score", "<f8"), ("ticks", "<i8")]))
+        res = []
+        for b in range(B):
+            s = a[b * k: b * k + int(n_out[b])]
+            res.append(Hits(s["row"].copy(), s["score"].copy(), s["ticks"].copy()))
+        return res
+
+    def debug_batch_scores(self, q: np.ndarray, now_ticks: int, tile_stride: int = 1) -> np.ndarray:
+        """Raw fused GEMM scores (w_cos*cos + w_rec*rec) of every stride-th 128-row tile: [B, n]."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B = int(q.shape[0])
+        tiles = (self.rows_used + 127) // 128
+        n_s = ((tiles + tile_stride - 1) // tile_stride) * 128
+        out = np.zeros((B, n_s), dtype=np.float32)
+        N.check(N.lib().orr_debug_batch_scores(self._h, B, q.ctypes.data_as(C.c_void_p), int(q.shape[1]), int(now_ticks),
+                                               int(tile_stride), out.ctypes.data_as(C.c_void_p), n_s))
+        return out
+
     def last_timing(self) -> dict:
         t = N.OrrTiming()
         N.lib().orr_last_timing(C.byref(t))
