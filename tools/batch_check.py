@@ -11,6 +11,8 @@ from omni_recall_rag_b200 import synth
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 dim = int(sys.argv[3]) if len(sys.argv) > 3 else 768
+n_terms = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+freq = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 spec = synth.make_spec(dim)
 NOW = spec.now_ticks
 sh = orr.RecallShard(dim, rows)
@@ -33,15 +35,20 @@ print("max abs err vs fp64 numpy: %.3e  (mean %.3e)" % (err.max(), err.mean()))
 assert err.max() < 2e-4, "GEMM core wrong"
 print("pad rows -inf:", np.all(np.isneginf(got[:, rows:])) if got.shape[1] > rows else True)
 # full batched search vs single-query path
+if n_terms:
+    qs = [synth.query_host(spec, i, rows, n_terms=n_terms, frequent_terms=freq) for i in range(batch)]
+terms = [q.terms for q in qs] if n_terms else None
 for k in (10, 100):
-    t0 = time.time(); hb = sh.search_batch(Q, None, NOW, k); tb = time.time() - t0
+    sh.search_batch(Q, terms, NOW, k)
+    t0 = time.time(); hb = sh.search_batch(Q, terms, NOW, k); tb = time.time() - t0
     tm = sh.last_timing()
     bad = 0
     for b in range(min(batch, 64)):
-        h1 = sh.search(Q[b], orr.QueryTerms.none(), NOW, k)
+        h1 = sh.search(Q[b], qs[b].terms if n_terms else orr.QueryTerms.none(), NOW, k)
         if h1.rows.tolist() != hb[b].rows.tolist() or h1.scores.tolist() != hb[b].scores.tolist():
             bad += 1
-    print(f"k={k}: batch call {tb*1e3:.1f} ms, gemm main {tm['scan_ms']:.3f} ms, sample {tm['finalize_ms']:.3f} ms, "
+    qps = batch / tb
+    print(f"k={k}: {qps:.0f} QPS; batch call {tb*1e3:.1f} ms, gemm main {tm['scan_ms']:.3f} ms, sample {tm['finalize_ms']:.3f} ms, "
           f"redo={tm['n_survivors'] & 0xffff}, mismatches vs single-query path: {bad}")
     assert bad == 0
 print("batch check ok")
