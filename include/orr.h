@@ -111,6 +111,11 @@ int  orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n,
 /* DeleteDocumentAsync (InMemoryIngestionStore.cs:50-55): tombstones the rows. */
 int  orr_store_delete_document(orr_store* s, uint64_t doc_key);
 
+/* Runtime knobs.  "batch_passes": 3 (default) = the batched contraction runs bf16x3 split
+ * precision (fp32-grade screen); 1 = single bf16 pass with a proportionally deeper candidate
+ * list.  Either way the returned hits are the exact fp64 re-score, proven by the bound check. */
+int  orr_store_set_option(orr_store* s, const char* name, double value);
+
 /* Live (non-tombstoned) rows, and rows physically occupied. */
 int64_t orr_store_count(const orr_store* s);
 int64_t orr_store_rows_used(const orr_store* s);

@@ -60,6 +60,7 @@ _SIGNATURES = {
                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "orr_store_delete_document": (C.c_int, [C.c_void_p, C.c_uint64]),
     "orr_store_count": (C.c_int64, [C.c_void_p]),
+    "orr_store_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "orr_store_rows_used": (C.c_int64, [C.c_void_p]),
     "orr_hash_term": (C.c_uint64, [C.c_char_p, C.c_int32]),
     "orr_tokenize_query": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),

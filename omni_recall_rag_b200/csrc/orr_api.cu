@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "orr_internal.h"
@@ -40,7 +42,7 @@ thread_local orr_timing g_timing{};
 struct BatchState {
     std::mutex mu;                       // batched searches are serialised per store
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* ehi = nullptr; void* emid = nullptr;     // bf16 [capacity][dim]
     float* inv_norm = nullptr;                     // [capacity]
     void* rowaux = nullptr;                        // float2 [capacity padded]
@@ -54,7 +56,8 @@ struct BatchState {
     uint32_t* term_bits = nullptr; size_t term_bits_words = 0; void* table = nullptr;
 };
 constexpr int BATCH_CAND_CAP = 4096;
-constexpr int BATCH_TABLE_SLOTS = 16384;
+constexpr int BATCH_TABLE_SLOTS = 16384;       // largest smem probe table (128 KB)
+constexpr int BATCH_MAX_TERM_IDS = 12288;       // distinct terms one GEMM launch handles (table load <= 0.75)
 
 }  // namespace
 
@@ -81,6 +84,7 @@ struct orr_store {
     std::vector<uint32_t> cap_rows;
     cudaStream_t mut_stream = nullptr;
     std::unique_ptr<BatchState> batch;
+    int batch_passes = 3;            // 3 = bf16x3 split precision, 1 = bf16 screen (orr_store_set_option)
 };
 
 namespace {
@@ -274,6 +278,7 @@ int orr_store_create(const orr_config* cfg, orr_store** out) {
     std::unique_ptr<orr_store> s(new orr_store());
     s->cfg = *cfg;
     s->sms = prop.multiProcessorCount;
+    if (const char* e = getenv("ORR_BATCH_PASSES")) s->batch_passes = (atoi(e) == 1) ? 1 : 3;
     const size_t cap = (size_t)cfg->capacity_rows;
     int rc = [&]() -> int {
         ORR_CUDA_OK(cudaMalloc(&s->d_emb, cap * (size_t)cfg->dim * sizeof(float)));
@@ -305,6 +310,18 @@ void orr_store_destroy(orr_store* s) {
     }
     cudaFree(s->d_emb); cudaFree(s->d_ticks); cudaFree(s->d_terms32); cudaFree(s->d_terms64);
     delete s;
+}
+
+int orr_store_set_option(orr_store* s, const char* name, double value) {
+    if (!s || !name) { orr_set_error("orr_store_set_option: NULL argument"); return ORR_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lock(s->mu);
+    if (!strcmp(name, "batch_passes")) {
+        if (value != 1.0 && value != 3.0) { orr_set_error("batch_passes must be 1 or 3"); return ORR_E_INVALID; }
+        s->batch_passes = (int)value;
+        return ORR_OK;
+    }
+    orr_set_error("orr_store_set_option: unknown option '%s'", name);
+    return ORR_E_INVALID;
 }
 
 int64_t orr_store_count(const orr_store* s) { return s ? s->live_rows : 0; }
@@ -554,7 +571,7 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) 
         for (auto& e : bs->ev) ORR_CUDA_OK(cudaEventCreate(&e));
     }
     if (!bs->ehi) {
-        const size_t cap_pad = (cap + 127) / 128 * 128;
+        const size_t cap_pad = (cap + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
         ORR_CUDA_OK(cudaMalloc(&bs->ehi, cap * dim * 2));
         ORR_CUDA_OK(cudaMalloc(&bs->emid, cap * dim * 2));
         ORR_CUDA_OK(cudaMalloc(&bs->inv_norm, cap * sizeof(float)));
@@ -591,12 +608,22 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) 
     return ORR_OK;
 }
 
-static int batch_survivors(int k) { return std::min(256, std::max(64, (k + std::max(32, k) + 31) / 32 * 32)); }
+// rows re-scored exactly per query: the GEMM screen must keep every row whose screen score is within
+// eps of the k-th best, so the bf16-only screen (eps ~ 5.5e-3) keeps a deeper list than bf16x3 (eps ~ 1e-4)
+static int batch_survivors(int k, int passes) {
+    if (passes == 1) return std::min(ORR_BATCH_MAX_SURV, std::max(128, (4 * k + 64 + 63) / 64 * 64));
+    return std::min(256, std::max(64, (k + std::max(32, k) + 31) / 32 * 32));
+}
+static double batch_eps(const OrrWeights& w, int passes) {
+    const double base = (double)ORR_BATCH_EPS * (std::fabs(w.w_cos) + std::fabs(w.w_kw) + std::fabs(w.w_rec));
+    // bf16 operands: each product is off by < 2*2^-8 + 2^-16 relative, so |d cos| < 2^-7 by Cauchy-Schwarz
+    return passes == 1 ? base + 0.0079 * std::fabs(w.w_cos) : base;
+}
 
 // the GEMM path proper; `redo` receives the queries whose selection could not be proven safe
 static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const int32_t* n_terms,
                            const uint64_t* probe_hash, const uint32_t* probe_offsets, int64_t now_ticks, int32_t top_k,
-                           orr_hit* out, int32_t* n_out, std::vector<int32_t>* redo) {
+                           orr_hit* out, int32_t* n_out, int passes, std::vector<int32_t>* redo) {
     if (!s->batch) s->batch.reset(new BatchState());
     BatchState* bs = s->batch.get();
     std::lock_guard<std::mutex> g(bs->mu);
@@ -608,9 +635,10 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     const OrrShard sh = shard_view(s);
     const OrrWeights w = weights_of(s);
     const int64_t rows = s->rows_used;
-    const int64_t rows_pad = (rows + 127) / 128 * 128;
-    const int M = batch_survivors(k);
+    const int64_t rows_pad = (rows + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
+    const int M = batch_survivors(k, passes);
 
+    ORR_CUDA_OK(cudaEventRecord(bs->ev[3], st));
     ORR_CUDA_OK(cudaMemcpyAsync(bs->q, q, sizeof(float) * (size_t)batch * dim, cudaMemcpyHostToDevice, st));
     rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st);
     if (rc != ORR_OK) return rc;
@@ -623,7 +651,12 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     const int64_t row_words = rows_pad / 32;
     std::vector<OrrProbes> hp((size_t)batch);
     if (any_terms) {
-        std::vector<uint2> table(BATCH_TABLE_SLOTS, make_uint2(0u, 0u));
+        int64_t total_terms = 0;
+        for (int32_t b = 0; b < batch; ++b) total_terms += std::max(0, n_terms[b]);
+        if (total_terms > BATCH_MAX_TERM_IDS) { orr_set_error("batch path: %lld query terms in one launch", (long long)total_terms); return ORR_E_INTERNAL; }
+        int table_slots = 256;
+        while (table_slots < 4 * total_terms && table_slots < BATCH_TABLE_SLOTS) table_slots <<= 1;
+        std::vector<uint2> table((size_t)table_slots, make_uint2(0u, 0u));
         std::vector<int32_t> qterm((size_t)bp * ORR_BATCH_TERMS, -1);
         std::vector<float> kww((size_t)bp, 0.f);
         uint32_t n_ids = 0;
@@ -635,8 +668,8 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
             if (nt > 0) kww[(size_t)b] = (float)(w.w_kw / (double)nt);
             for (int32_t t = 0; t < nt; ++t) {
                 const uint32_t h = hp[(size_t)b].h32[t];
-                uint32_t pos = (h * 0x9E3779B1u) & (BATCH_TABLE_SLOTS - 1);
-                while (table[pos].x != 0u && table[pos].x != h) pos = (pos + 1) & (BATCH_TABLE_SLOTS - 1);
+                uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)(table_slots - 1);
+                while (table[pos].x != 0u && table[pos].x != h) pos = (pos + 1) & (uint32_t)(table_slots - 1);
                 if (table[pos].x == 0u) { table[pos] = make_uint2(h, n_ids++); }
                 qterm[(size_t)b * ORR_BATCH_TERMS + t] = (int32_t)table[pos].y;
             }
@@ -649,12 +682,12 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         }
         if (!bs->table) ORR_CUDA_OK(cudaMalloc(&bs->table, BATCH_TABLE_SLOTS * 8));
         ORR_CUDA_OK(cudaMemsetAsync(bs->term_bits, 0, need * sizeof(uint32_t), st));
-        ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table.data(), BATCH_TABLE_SLOTS * 8, cudaMemcpyHostToDevice, st));
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table.data(), (size_t)table_slots * 8, cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaMemcpyAsync(bs->qterm, qterm.data(), qterm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaMemcpyAsync(bs->kww, kww.data(), kww.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaMemcpyAsync(bs->probes, hp.data(), sizeof(OrrProbes) * (size_t)batch, cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope below
-        rc = orr_batch_launch_term_bits(s->d_terms32, s->cfg.term_slots, rows, bs->table, BATCH_TABLE_SLOTS, bs->term_bits,
+        rc = orr_batch_launch_term_bits(s->d_terms32, s->cfg.term_slots, rows, bs->table, table_slots, bs->term_bits,
                                         row_words, st);
         if (rc != ORR_OK) return rc;
     }
@@ -664,15 +697,17 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     gm.qscale = bs->qscale; gm.thr = bs->thr; gm.cand = bs->cand; gm.cand_count = bs->cand_count; gm.cand_cap = BATCH_CAND_CAP;
     gm.term_bits = any_terms ? bs->term_bits : nullptr; gm.row_words = row_words;
     gm.q_term_ids = any_terms ? bs->qterm : nullptr; gm.q_kw_w = any_terms ? bs->kww : nullptr;
-    gm.rows = rows; gm.dim = dim; gm.batch_padded = bp; gm.sms = s->sms;
+    gm.rows = rows; gm.dim = dim; gm.batch_padded = bp; gm.sms = s->sms; gm.passes = passes;
 
     // ---- sampling pass: dense scores of every stride-th row tile -> per-query thresholds ----
-    const int target = 4 * M;
-    const int64_t all_tiles = rows_pad / 128;
-    const int64_t want_tiles = std::max<int64_t>(8, (32 * rows / target + 127) / 128);
+    // thr[b] = the rstar-th best sampled score, rstar ~ ORR_BATCH_SAMPLE_HITS, chosen so that about
+    // `target` rows of the whole store pass it (cand_cap leaves 4-16x head room for the estimate's noise)
+    const int target = std::min(4 * M, BATCH_CAND_CAP / 4);
+    const int64_t all_tiles = rows_pad / ORR_BATCH_TILE;
+    const int64_t want_tiles = std::max<int64_t>(8, ((int64_t)ORR_BATCH_SAMPLE_HITS * rows / target + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE);
     const int stride = (int)std::max<int64_t>(1, all_tiles / std::min(all_tiles, want_tiles));
     const int64_t s_tiles = (all_tiles + stride - 1) / stride;
-    const int64_t n_s = s_tiles * 128;
+    const int64_t n_s = s_tiles * ORR_BATCH_TILE;
     if ((size_t)bp * (size_t)n_s > bs->dense_elems) {
         cudaFree(bs->dense); bs->dense = nullptr; bs->dense_elems = 0;
         ORR_CUDA_OK(cudaMalloc(&bs->dense, (size_t)bp * (size_t)n_s * sizeof(float)));
@@ -695,17 +730,27 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     ORR_CUDA_OK(cudaEventRecord(bs->ev[2], st));
 
     // ---- per-query finalize: survivors, exact fp64 re-score, order, bound check ----
-    const double eps = (double)ORR_BATCH_EPS * (std::fabs(w.w_cos) + std::fabs(w.w_kw) + std::fabs(w.w_rec));
+    const double eps = batch_eps(w, passes);
     rc = orr_batch_launch_finalize(sh, bs->q, dim, any_terms ? bs->probes : nullptr, w, now_ticks, bs->cand, bs->cand_count,
                                    bs->thr, BATCH_CAND_CAP, M, top_k, k, eps, bs->hits, bs->status, batch, st);
     if (rc != ORR_OK) return rc;
     std::vector<int32_t> st_host((size_t)batch * 2);
+    ORR_CUDA_OK(cudaEventRecord(bs->ev[4], st));
     ORR_CUDA_OK(cudaMemcpyAsync(st_host.data(), bs->status, sizeof(int32_t) * 2 * (size_t)batch, cudaMemcpyDeviceToHost, st));
     ORR_CUDA_OK(cudaMemcpyAsync(out, bs->hits, sizeof(orr_hit) * (size_t)batch * k, cudaMemcpyDeviceToHost, st));
+    ORR_CUDA_OK(cudaEventRecord(bs->ev[5], st));
     ORR_CUDA_OK(cudaStreamSynchronize(st));
     float ms_sample = 0.f, ms_main = 0.f;
     cudaEventElapsedTime(&ms_sample, bs->ev[0], bs->ev[1]);
     cudaEventElapsedTime(&ms_main, bs->ev[1], bs->ev[2]);
+    if (getenv("ORR_BATCH_TRACE")) {
+        float ms_prep = 0.f, ms_fin = 0.f, ms_d2h = 0.f;
+        cudaEventElapsedTime(&ms_prep, bs->ev[3], bs->ev[0]);
+        cudaEventElapsedTime(&ms_fin, bs->ev[2], bs->ev[4]);
+        cudaEventElapsedTime(&ms_d2h, bs->ev[4], bs->ev[5]);
+        fprintf(stderr, "[orr batch] B=%d k=%d passes=%d M=%d stride=%d: prep %.3f  sample %.3f  main %.3f  finalize %.3f  d2h %.3f ms\n",
+                batch, k, passes, M, stride, ms_prep, ms_sample, ms_main, ms_fin, ms_d2h);
+    }
     for (int32_t b = 0; b < batch; ++b) {
         n_out[b] = st_host[(size_t)2 * b];
         if (st_host[(size_t)2 * b + 1] != 0) redo->push_back(b);
@@ -726,6 +771,32 @@ int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
     if (!s || batch < 0 || !out || !n_out || (batch > 0 && q_dim > 0 && !q)) { orr_set_error("orr_search_batch: bad argument"); return ORR_E_INVALID; }
     if (batch == 0) return ORR_OK;
     const int k = std::max(1, top_k);
+    {   // one launch handles <= 2048 queries and <= BATCH_MAX_TERM_IDS query terms: slice larger batches
+        int64_t terms_sum = 0;
+        int32_t cut = batch;
+        for (int32_t b = 0; b < batch; ++b) {
+            terms_sum += n_terms ? std::max(0, n_terms[b]) : 0;
+            if (b >= 2048 || terms_sum > BATCH_MAX_TERM_IDS) { cut = b; break; }
+        }
+        if (cut < batch && cut > 0) {
+            for (int32_t b0 = 0; b0 < batch;) {
+                int64_t sum = 0;
+                int32_t b1 = b0;
+                while (b1 < batch && b1 - b0 < 2048) {
+                    const int64_t nt = n_terms ? std::max(0, n_terms[b1]) : 0;
+                    if (b1 > b0 && sum + nt > BATCH_MAX_TERM_IDS) break;
+                    sum += nt; ++b1;
+                }
+                int rc = orr_search_batch(s, b1 - b0, q ? q + (int64_t)b0 * q_dim : nullptr, q_dim, n_terms ? n_terms + b0 : nullptr,
+                                          probe_hash, probe_term, probe_offsets ? probe_offsets + b0 : nullptr, now_ticks, top_k,
+                                          out + (int64_t)b0 * k, n_out + b0);
+                if (rc != ORR_OK) return rc;
+                b0 = b1;
+            }
+            g_timing.wall_ms = (float)(now_ms() - t0);
+            return ORR_OK;
+        }
+    }
     // the tcgen05 path takes: a query embedding of the store's width, dim % 64 == 0, k <= 128,
     // <= 16 terms per query given as identity probes; anything else runs query by query
     bool gemm_ok = (q_dim == s->cfg.dim) && (s->cfg.dim % 64 == 0) && k <= 128 && batch >= 8 && s->live_rows > 0 &&
@@ -746,8 +817,45 @@ int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
         std::shared_lock<std::shared_mutex> lock(s->mu);
         ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
         memset(&g_timing, 0, sizeof g_timing);
-        int rc = batch_gemm_path(s, batch, q, n_terms, probe_hash, probe_offsets, now_ticks, top_k, out, n_out, &redo);
+        const int passes = s->batch_passes;
+        int rc = batch_gemm_path(s, batch, q, n_terms, probe_hash, probe_offsets, now_ticks, top_k, out, n_out, passes, &redo);
         if (rc != ORR_OK) return rc;
+        if (passes == 1 && redo.size() >= 8) {
+            // queries the bf16 screen could not prove safe go through the split-precision GEMM as a
+            // smaller batch before anything falls back to the per-query path
+            const orr_timing first = g_timing;
+            const int32_t nb = (int32_t)redo.size();
+            std::vector<float> q2((size_t)nb * q_dim);
+            std::vector<int32_t> nt2((size_t)nb, 0);
+            std::vector<uint32_t> off2((size_t)nb + 1, 0u);
+            std::vector<uint64_t> ph2;
+            for (int32_t i = 0; i < nb; ++i) {
+                const int32_t b = redo[(size_t)i];
+                memcpy(q2.data() + (size_t)i * q_dim, q + (int64_t)b * q_dim, sizeof(float) * (size_t)q_dim);
+                if (n_terms && n_terms[b] > 0) {
+                    nt2[(size_t)i] = n_terms[b];
+                    ph2.insert(ph2.end(), probe_hash + probe_offsets[b], probe_hash + probe_offsets[b + 1]);
+                }
+                off2[(size_t)i + 1] = (uint32_t)ph2.size();
+            }
+            std::vector<orr_hit> out2((size_t)nb * k);
+            std::vector<int32_t> n2((size_t)nb, 0), redo2;
+            rc = batch_gemm_path(s, nb, q2.data(), nt2.data(), ph2.empty() ? nullptr : ph2.data(), off2.data(), now_ticks,
+                                 top_k, out2.data(), n2.data(), 3, &redo2);
+            if (rc != ORR_OK) return rc;
+            std::vector<int32_t> still;
+            size_t r2 = 0;
+            for (int32_t i = 0; i < nb; ++i) {
+                const int32_t b = redo[(size_t)i];
+                if (r2 < redo2.size() && redo2[r2] == i) { still.push_back(b); ++r2; continue; }
+                memcpy(out + (int64_t)b * k, out2.data() + (size_t)i * k, sizeof(orr_hit) * (size_t)k);
+                n_out[b] = n2[(size_t)i];
+            }
+            redo.swap(still);
+            g_timing.scan_ms += first.scan_ms; g_timing.finalize_ms += first.finalize_ms;
+            g_timing.total_device_ms += first.total_device_ms;
+            g_timing.path = ORR_PATH_BATCH | ORR_PATH_ESCALATED;
+        }
     } else {
         for (int32_t b = 0; b < batch; ++b) redo.push_back(b);
     }
@@ -781,8 +889,8 @@ int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t 
     int rc = batch_prepare(s, bs, bp, 1);
     if (rc != ORR_OK) return rc;
     cudaStream_t st = bs->stream;
-    const int64_t rows = s->rows_used, rows_pad = (rows + 127) / 128 * 128;
-    const int64_t s_tiles = (rows_pad / 128 + tile_stride - 1) / tile_stride, n_s = s_tiles * 128;
+    const int64_t rows = s->rows_used, rows_pad = (rows + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
+    const int64_t s_tiles = (rows_pad / ORR_BATCH_TILE + tile_stride - 1) / tile_stride, n_s = s_tiles * ORR_BATCH_TILE;
     if (out_ld < n_s) { orr_set_error("orr_debug_batch_scores: out_ld %lld < %lld", (long long)out_ld, (long long)n_s); return ORR_E_INVALID; }
     ORR_CUDA_OK(cudaMemcpyAsync(bs->q, q, sizeof(float) * (size_t)batch * dim, cudaMemcpyHostToDevice, st));
     if ((rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st)) != ORR_OK) return rc;
@@ -796,7 +904,7 @@ int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t 
     gm.qhi = bs->qhi; gm.qmid = bs->qmid; gm.ehi = bs->ehi; gm.emid = bs->emid; gm.rowaux = bs->rowaux;
     gm.qscale = bs->qscale; gm.thr = bs->thr; gm.cand = bs->cand; gm.cand_count = bs->cand_count; gm.cand_cap = BATCH_CAND_CAP;
     gm.rows = rows; gm.dim = dim; gm.batch_padded = bp; gm.sms = s->sms;
-    gm.dense = bs->dense; gm.dense_ld = n_s; gm.tile_stride = tile_stride;
+    gm.dense = bs->dense; gm.dense_ld = n_s; gm.tile_stride = tile_stride; gm.passes = s->batch_passes;
     if ((rc = orr_batch_launch_gemm(gm, st)) != ORR_OK) return rc;
     ORR_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)out_ld * sizeof(float), bs->dense, (size_t)n_s * sizeof(float),
                                   (size_t)n_s * sizeof(float), (size_t)batch, cudaMemcpyDeviceToHost, st));

@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -33,17 +34,12 @@
 
 namespace {
 
-constexpr int BM = 128;                       // queries per unit
-constexpr int BN = 128;                       // corpus rows per unit
+constexpr int BM = 128;                       // queries (and corpus rows) staged per CTA per k-block
+constexpr int UN = ORR_BATCH_TILE;            // corpus rows per unit = UMMA N = accumulator columns (256)
 constexpr int BK = 64;                        // bf16 per k-block (128 B)
-constexpr int STAGES = 3;
 constexpr int PLANE_BYTES = BM * BK * 2;      // 16 KB
-constexpr int STAGE_BYTES = 4 * PLANE_BYTES;  // 64 KB
-constexpr int AUX_BYTES = BN * 8;             // float2 per corpus row of the unit
-constexpr int TMEM_COLS = 2 * BN;             // two accumulator buffers
-constexpr int BATCH_THREADS = 192;            // 6 warps
-
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr int TMEM_COLS = 2 * UN;             // two accumulator buffers = all 512 columns
+constexpr int BATCH_THREADS = 320;            // TMA producer, MMA issuer, 8 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -65,11 +61,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -78,16 +69,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -106,10 +87,10 @@ constexpr int ORR_BATCH_MAX_TERMS = ORR_BATCH_TERMS;
 struct BatchArgs {
     int32_t  n_row_tiles;        // row tiles this launch walks
     int32_t  row_tile_stride;    // 1 = every tile; >1 = sampling pass (tile t -> t * stride)
-    int32_t  n_qblocks;          // padded batch / 128
+    int32_t  n_qblocks;          // padded batch / 256
     int32_t  k_blocks;           // dim / 64
     int64_t  rows;               // rows in the shard
-    const float2* rowaux;        // [rows padded to 128] {w_cos * inv|e|, w_rec * rec or -inf}
+    const float2* rowaux;        // [rows padded to 256] {w_cos * inv|e|, w_rec * rec or -inf}
     const float*  qscale;        // [B padded] inv|q| (0 for padding / zero queries)
     const float*  thr;           // [B padded] candidate threshold (main pass)
     // main pass output
@@ -128,169 +109,305 @@ struct BatchArgs {
     int32_t   max_terms;
 };
 
-__global__ void __launch_bounds__(BATCH_THREADS, 1)
+// ---- cluster / cta_group::2 helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {   // same offset in CTA `cta`'s smem
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// each CTA of the pair loads its own half of the operands; completion is counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once) on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// Keyword side of one thread's half unit (4 chunks x 32 rows): the query's <= 16 term bitmaps (bit j of
+// word w = row 32w+j holds the term; one 16-byte load covers the 4 chunks) are added bit-sliced into 5
+// count planes per chunk.  Issued BEFORE the accumulator is awaited so the loads overlap the MMAs.
+struct KwPlanes { uint32_t p[UN / 64][5]; };
+__device__ __forceinline__ void kw_planes(const BatchArgs& a, int b, int64_t word0, KwPlanes& kp) {
+#pragma unroll
+    for (int c = 0; c < UN / 64; ++c)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) kp.p[c][i] = 0u;
+    const int4* ip = reinterpret_cast<const int4*>(a.q_term_ids + (int64_t)b * ORR_BATCH_MAX_TERMS);
+#pragma unroll 1
+    for (int g = 0; g < ORR_BATCH_MAX_TERMS / 4; ++g) {
+        const int4 id4 = __ldg(ip + g);
+        if (id4.x < 0) break;                                                // ids are packed front to back
+        const int id[4] = {id4.x, id4.y, id4.z, id4.w};
+        uint4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            w[i] = id[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(a.term_bits + (int64_t)id[i] * a.row_words + word0))
+                              : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+            for (int c = 0; c < UN / 64; ++c) {
+                uint32_t x = ww[c], cy;
+                cy = kp.p[c][0] & x; kp.p[c][0] ^= x; x = cy;
+                cy = kp.p[c][1] & x; kp.p[c][1] ^= x; x = cy;
+                cy = kp.p[c][2] & x; kp.p[c][2] ^= x; x = cy;
+                cy = kp.p[c][3] & x; kp.p[c][3] ^= x; x = cy;
+                kp.p[c][4] ^= x;
+            }
+        }
+    }
+}
+
+// Epilogue of one thread (= one query) over its UN/64 chunks of 32 accumulator columns.  Written for a
+// scheduler that holds only two epilogue warps: every stage is 32 independent chains, and the rare
+// work (a candidate above the threshold) sits behind ONE branch per chunk.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunks(const BatchArgs& a, uint32_t taddr, const float2* ax, int b, int64_t row0,
+                                                int t, int c_begin, float qs, float thr, float kww, const KwPlanes& kp) {
+#pragma unroll
+    for (int cc = 0; cc < UN / 64; ++cc) {
+        const int c = c_begin + cc;
+        uint32_t acc[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), acc);
+        float s[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float2 ra = ax[c * 32 + j];                               // smem broadcast
+            s[j] = fmaf(__uint_as_float(acc[j]) * qs, ra.x, ra.y);
+        }
+        if (kww != 0.f) {
+            const uint32_t c0 = kp.p[cc][0], c1 = kp.p[cc][1], c2 = kp.p[cc][2], c3 = kp.p[cc][3], c4 = kp.p[cc][4];
+            if ((c0 | c1 | c2 | c3 | c4) != 0u) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t cnt = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2) |
+                                         (((c3 >> j) & 1u) << 3) | (((c4 >> j) & 1u) << 4);
+                    s[j] = fmaf(kww, (float)cnt, s[j]);
+                }
+            }
+        }
+        if (MODE == 0) {
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) any |= (s[j] > thr);
+            if (any) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (s[j] > thr) {
+                        const uint32_t slot = atomicAdd(a.cand_count + b, 1u);
+                        if (slot < (uint32_t)a.cand_cap)
+                            a.cand[(int64_t)b * a.cand_cap + slot] =
+                                make_uint2((uint32_t)(row0 + c * 32 + j), __float_as_uint(s[j]));
+                    }
+                }
+            }
+        } else {
+            float4* dst = reinterpret_cast<float4*>(a.dense + (int64_t)b * a.dense_ld + ((int64_t)t * UN + c * 32));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+        }
+    }
+}
+
+// Unit = 256 queries x 256 corpus rows on a CTA PAIR (cta_group::2, UMMA 256x256x16): each CTA stages
+// its own 128 queries (A half) and 128 rows (B half), so a k-block costs every SM 64 KB of L2->smem
+// traffic for 2x the MMA work of a 128x128 single-CTA unit.  PASSES = 3: split precision
+// (hi.hi + hi.mid + mid.hi); PASSES = 1: bf16 screen only (wider selection margin, see orr_api.cu).
+template <int PASSES> struct GemmCfg {
+    static constexpr int PLANES = PASSES == 3 ? 4 : 2;
+    static constexpr int STAGE = PLANES * PLANE_BYTES;          // 64 KB / 32 KB per CTA
+    static constexpr int NSTAGE = PASSES == 3 ? 3 : 6;
+    static constexpr int SMEM = NSTAGE * STAGE + 2 * UN * 8 + 256 + 1024;
+};
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+template <int PASSES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BATCH_THREADS, 1)
 orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qmid,
                       const __grid_constant__ CUtensorMap map_ehi, const __grid_constant__ CUtensorMap map_emid,
                       const BatchArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* stage_mem = smem;                                         // STAGES x 64 KB, 1024-B aligned
-    float2* aux = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES);   // 2 x BN
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 2 * AUX_BYTES);
-    uint64_t* full_bar = bars;                  // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
-    uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]
-    uint64_t* aux_bar = bars + 2 * STAGES + 4;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    using C = GemmCfg<PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    // the dynamic smem base is only 16-B aligned by contract; both CTAs compute the same offset
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stage_mem = smem;                                              // NSTAGE x STAGE, 1024-B aligned
+    float2* aux = reinterpret_cast<float2*>(smem + C::NSTAGE * C::STAGE);   // 2 x UN
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE + 2 * UN * 8);
+    uint64_t* full_bar = bars;                          // [NSTAGE]  leader's copy is the live one
+    uint64_t* empty_bar = bars + C::NSTAGE;             // [NSTAGE]  per CTA (multicast commit)
+    uint64_t* tfull_bar = bars + 2 * C::NSTAGE;         // [2]       per CTA (multicast commit)
+    uint64_t* tempty_bar = bars + 2 * C::NSTAGE + 2;    // [2]       leader's copy: 16 epilogue warps of the pair
+    uint64_t* aux_full = bars + 2 * C::NSTAGE + 4;      // [2]       per CTA
+    uint64_t* aux_empty = bars + 2 * C::NSTAGE + 6;     // [2]       per CTA: 8 local epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tfull_bar[b]), 1);
-            mbar_init(smem_u32(&tempty_bar[b]), 4);
-            mbar_init(smem_u32(&aux_bar[b]), 1);
+            mbar_init(smem_u32(&tempty_bar[b]), 16);
+            mbar_init(smem_u32(&aux_full[b]), 1);
+            mbar_init(smem_u32(&aux_empty[b]), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster_sync_all();                                   // barriers of BOTH CTAs initialised, TMEM allocated
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
+    const int n_clusters = (int)gridDim.x >> 1, cid = (int)blockIdx.x >> 1;
     const int units_per_tile = a.n_qblocks;
-    const int my_tiles = (a.n_row_tiles > (int)blockIdx.x) ? (a.n_row_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my_tiles = (a.n_row_tiles > cid) ? (a.n_row_tiles - 1 - cid) / n_clusters + 1 : 0;
     const int my_units = my_tiles * units_per_tile;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (one per CTA) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int u = 0; u < my_units; ++u) {
-                const int t = blockIdx.x + (u / units_per_tile) * gridDim.x;
+                const int t = cid + (u / units_per_tile) * n_clusters;
                 const int row_tile = t * a.row_tile_stride;
                 const int qb = u % units_per_tile;
                 const int buf = u & 1;
-                // aux[buf] is free once the epilogue of unit u-2 has released its accumulator
-                mbar_wait(smem_u32(&tempty_bar[buf]), ((uint32_t)(u >> 1) & 1u) ^ 1u);
-                mbar_expect_tx(smem_u32(&aux_bar[buf]), AUX_BYTES);
-                bulk_g2s(smem_u32(aux + buf * BN), a.rowaux + (int64_t)row_tile * BN, AUX_BYTES, smem_u32(&aux_bar[buf]));
+                mbar_wait(smem_u32(&aux_empty[buf]), ((uint32_t)(u >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(smem_u32(&aux_full[buf]), UN * 8);
+                bulk_g2s(smem_u32(aux + buf * UN), a.rowaux + (int64_t)row_tile * UN, UN * 8, smem_u32(&aux_full[buf]));
+                const int qrow = qb * 256 + (int)rank * BM, erow = row_tile * UN + (int)rank * BM;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
-                    const uint32_t base = smem_u32(stage_mem + stage * STAGE_BYTES);
-                    mbar_expect_tx(fb, STAGE_BYTES);
-                    tma_load_2d(base + 0 * PLANE_BYTES, &map_qhi, kb * BK, qb * BM, fb);
-                    tma_load_2d(base + 1 * PLANE_BYTES, &map_qmid, kb * BK, qb * BM, fb);
-                    tma_load_2d(base + 2 * PLANE_BYTES, &map_ehi, kb * BK, row_tile * BN, fb);
-                    tma_load_2d(base + 3 * PLANE_BYTES, &map_emid, kb * BK, row_tile * BN, fb);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    const uint32_t fb_local = smem_u32(&full_bar[stage]);
+                    const uint32_t fb = mapa_shared(fb_local, 0);
+                    const uint32_t base = smem_u32(stage_mem + stage * C::STAGE);
+                    if (leader) mbar_expect_tx(fb_local, 2 * C::STAGE);     // both halves land on this barrier
+                    if (PASSES == 3) {
+                        tma_load_2d_pair(base + 0 * PLANE_BYTES, &map_qhi, kb * BK, qrow, fb);
+                        tma_load_2d_pair(base + 1 * PLANE_BYTES, &map_qmid, kb * BK, qrow, fb);
+                        tma_load_2d_pair(base + 2 * PLANE_BYTES, &map_ehi, kb * BK, erow, fb);
+                        tma_load_2d_pair(base + 3 * PLANE_BYTES, &map_emid, kb * BK, erow, fb);
+                    } else {
+                        tma_load_2d_pair(base + 0 * PLANE_BYTES, &map_qhi, kb * BK, qrow, fb);
+                        tma_load_2d_pair(base + 1 * PLANE_BYTES, &map_ehi, kb * BK, erow, fb);
+                    }
+                    if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        int stage = 0; uint32_t phase = 0;
-        for (int u = 0; u < my_units; ++u) {
-            const int buf = u & 1;
-            mbar_wait(smem_u32(&tempty_bar[buf]), ((uint32_t)(u >> 1) & 1u) ^ 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
-                mbar_wait(smem_u32(&full_bar[stage]), phase);
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = 0; u < my_units; ++u) {
+                const int buf = u & 1;
+                mbar_wait(smem_u32(&tempty_bar[buf]), ((uint32_t)(u >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t base = smem_u32(stage_mem + stage * STAGE_BYTES);
-                    const uint64_t qhi = umma_desc(base), qmid = umma_desc(base + PLANE_BYTES);
-                    const uint64_t ehi = umma_desc(base + 2 * PLANE_BYTES), emid = umma_desc(base + 3 * PLANE_BYTES);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * UN);
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t base = smem_u32(stage_mem + stage * C::STAGE);
+                        if (PASSES == 3) {
+                            const uint64_t qhi = umma_desc(base), qmid = umma_desc(base + PLANE_BYTES);
+                            const uint64_t ehi = umma_desc(base + 2 * PLANE_BYTES), emid = umma_desc(base + 3 * PLANE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 2);          // 16 bf16 = 32 B = 2 x 16-B units
-                        umma_bf16(tmem_d, qhi + adv, ehi + adv, (kb | k) ? 1u : 0u);
-                        umma_bf16(tmem_d, qhi + adv, emid + adv, 1u);
-                        umma_bf16(tmem_d, qmid + adv, ehi + adv, 1u);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint64_t adv = (uint64_t)(k * 2);      // 16 bf16 = 32 B = 2 x 16-B units
+                                umma_bf16_pair(tmem_d, qhi + adv, ehi + adv, IDESC2, (kb | k) ? 1u : 0u);
+                                umma_bf16_pair(tmem_d, qhi + adv, emid + adv, IDESC2, 1u);
+                                umma_bf16_pair(tmem_d, qmid + adv, ehi + adv, IDESC2, 1u);
+                            }
+                        } else {
+                            const uint64_t qhi = umma_desc(base), ehi = umma_desc(base + PLANE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint64_t adv = (uint64_t)(k * 2);
+                                umma_bf16_pair(tmem_d, qhi + adv, ehi + adv, IDESC2, (kb | k) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit_pair(smem_u32(&empty_bar[stage]));       // frees the stage in both CTAs
+                        if (kb == a.k_blocks - 1) umma_commit_pair(smem_u32(&tfull_bar[buf]));
                     }
-                    umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem stage when the MMAs retire
-                    if (kb == a.k_blocks - 1) umma_commit(smem_u32(&tfull_bar[buf]));
+                    __syncwarp();
+                    if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3;                                  // TMEM lane quarter this warp may read
+        // ===================== epilogue (warps 2..9 of each CTA: its 128 queries x 256 rows) =====================
+        // A warp may only read its own TMEM lane quarter (warp % 4); the two warps that share a
+        // quarter split the unit's 8 column chunks.  One thread = one query.
+        const int quarter = warp & 3;
+        const int c_begin = ((warp - 2) >> 2) * (UN / 64);
+        const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
         for (int u = 0; u < my_units; ++u) {
-            const int t = blockIdx.x + (u / units_per_tile) * gridDim.x;
+            const int t = cid + (u / units_per_tile) * n_clusters;
             const int row_tile = t * a.row_tile_stride;
             const int qb = u % units_per_tile;
             const int buf = u & 1;
-            const int b = qb * BM + quarter * 32 + lane;               // this thread's query
+            const int b = qb * 256 + (int)rank * BM + quarter * 32 + lane;   // this thread's query
             const float qs = a.qscale[b];
             const float thr = a.mode == 0 ? a.thr[b] : 0.f;
             const float kww = a.q_kw_w ? a.q_kw_w[b] : 0.f;
-            mbar_wait(smem_u32(&aux_bar[buf]), (uint32_t)(u >> 1) & 1u);
+            const int64_t row0 = (int64_t)row_tile * UN;
+            KwPlanes kp;
+            if (kww != 0.f) kw_planes(a, b, (row0 >> 5) + c_begin, kp);
+            mbar_wait(smem_u32(&aux_full[buf]), (uint32_t)(u >> 1) & 1u);
             mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)(u >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float2* ax = aux + buf * BN;
-            const int64_t row0 = (int64_t)row_tile * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c * 32), acc);
-                // keyword counts of this query for the 32 rows of the chunk: the query's term
-                // bitmaps (bit j = row j has the term) are added bit-sliced into 5 count planes
-                uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-                if (kww != 0.f) {
-                    const int64_t word = (row0 >> 5) + c;
-#pragma unroll 1
-                    for (int ti = 0; ti < ORR_BATCH_MAX_TERMS; ++ti) {
-                        const int id = a.q_term_ids[(int64_t)b * ORR_BATCH_MAX_TERMS + ti];
-                        if (id < 0) break;
-                        uint32_t w = __ldg(a.term_bits + (int64_t)id * a.row_words + word), cy;
-                        cy = c0 & w; c0 ^= w; w = cy;
-                        cy = c1 & w; c1 ^= w; w = cy;
-                        cy = c2 & w; c2 ^= w; w = cy;
-                        cy = c3 & w; c3 ^= w; w = cy;
-                        c4 ^= w;
-                    }
-                }
-                const uint32_t anykw = c0 | c1 | c2 | c3 | c4;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 ra = ax[c * 32 + j];                   // smem broadcast
-                    float s = __uint_as_float(acc[j]) * qs * ra.x + ra.y;
-                    if ((anykw >> j) & 1u) {
-                        const int cnt = (int)((c0 >> j) & 1u) + 2 * (int)((c1 >> j) & 1u) + 4 * (int)((c2 >> j) & 1u) +
-                                        8 * (int)((c3 >> j) & 1u) + 16 * (int)((c4 >> j) & 1u);
-                        s += kww * (float)cnt;
-                    }
-                    const int64_t row = row0 + c * 32 + j;
-                    if (a.mode == 0) {
-                        if (s > thr) {
-                            const uint32_t slot = atomicAdd(a.cand_count + b, 1u);
-                            if (slot < (uint32_t)a.cand_cap)
-                                a.cand[(int64_t)b * a.cand_cap + slot] = make_uint2((uint32_t)row, __float_as_uint(s));
-                        }
-                    } else {
-                        a.dense[(int64_t)b * a.dense_ld + ((int64_t)(t * BN) + c * 32 + j)] = s;
-                    }
-                }
-            }
+            const float2* ax = aux + buf * UN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * UN);
+            if (a.mode == 0)
+                epilogue_chunks<0>(a, taddr, ax, b, row0, t, c_begin, qs, thr, kww, kp);
+            else
+                epilogue_chunks<1>(a, taddr, ax, b, row0, t, c_begin, qs, thr, kww, kp);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&aux_empty[buf]));
+                mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+            }
         }
     }
-    __syncthreads();
+    // no CTA may leave while its peer can still signal its barriers or read its smem
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -384,8 +501,6 @@ int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int dim, in
     return ORR_OK;
 }
 
-constexpr int BATCH_SMEM = STAGES * STAGE_BYTES + 2 * AUX_BYTES + 256;
-
 }  // namespace
 
 // ---- host-side launchers ---------------------------------------------------------------------------
@@ -416,24 +531,34 @@ int orr_batch_build_rowaux(const int64_t* ticks, const float* inv_norm, void* ro
     return ORR_OK;
 }
 
-int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
-    if (g.dim % BK != 0) { orr_set_error("batch path needs dim %% 64 == 0 (dim=%d)", g.dim); return ORR_E_UNSUPPORTED; }
+template <int PASSES>
+static int launch_gemm_t(const CUtensorMap& mqh, const CUtensorMap& mqm, const CUtensorMap& meh, const CUtensorMap& mem,
+                         const BatchArgs& a, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BATCH_SMEM));
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_gemm_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<PASSES>::SMEM));
         configured = true;
     }
+    orr_batch_gemm_kernel<PASSES><<<grid, BATCH_THREADS, GemmCfg<PASSES>::SMEM, st>>>(mqh, mqm, meh, mem, a);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
+    if (g.dim % BK != 0) { orr_set_error("batch path needs dim %% 64 == 0 (dim=%d)", g.dim); return ORR_E_UNSUPPORTED; }
+    if (g.batch_padded % 256 != 0) { orr_set_error("batch path: padded batch %d not a multiple of 256", g.batch_padded); return ORR_E_INTERNAL; }
     CUtensorMap mqh, mqm, meh, mem;
     int rc;
     if ((rc = make_plane_map(&mqh, g.qhi, g.batch_padded, g.dim, BM)) != ORR_OK) return rc;
     if ((rc = make_plane_map(&mqm, g.qmid, g.batch_padded, g.dim, BM)) != ORR_OK) return rc;
-    if ((rc = make_plane_map(&meh, g.ehi, g.rows, g.dim, BN)) != ORR_OK) return rc;
-    if ((rc = make_plane_map(&mem, g.emid, g.rows, g.dim, BN)) != ORR_OK) return rc;
+    if ((rc = make_plane_map(&meh, g.ehi, g.rows, g.dim, BM)) != ORR_OK) return rc;
+    if ((rc = make_plane_map(&mem, g.emid, g.rows, g.dim, BM)) != ORR_OK) return rc;
     BatchArgs a{};
-    const int64_t all_tiles = (g.rows + BN - 1) / BN;
+    const int64_t all_tiles = (g.rows + UN - 1) / UN;
     a.row_tile_stride = g.tile_stride < 1 ? 1 : g.tile_stride;
     a.n_row_tiles = (int32_t)((all_tiles + a.row_tile_stride - 1) / a.row_tile_stride);
-    a.n_qblocks = g.batch_padded / BM;
+    a.n_qblocks = g.batch_padded / 256;
     a.k_blocks = g.dim / BK;
     a.rows = g.rows;
     a.rowaux = (const float2*)g.rowaux;
@@ -450,9 +575,8 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     a.q_term_ids = g.q_term_ids;
     a.q_kw_w = g.q_kw_w;
     a.max_terms = ORR_BATCH_MAX_TERMS;
-    int grid = g.sms < a.n_row_tiles ? g.sms : a.n_row_tiles;
-    if (grid < 1) return ORR_OK;
-    orr_batch_gemm_kernel<<<grid, BATCH_THREADS, BATCH_SMEM, st>>>(mqh, mqm, meh, mem, a);
-    ORR_CUDA_OK(cudaGetLastError());
-    return ORR_OK;
+    const int pairs = std::min<int64_t>(g.sms / 2, a.n_row_tiles);
+    if (pairs < 1) return ORR_OK;
+    return g.passes == 1 ? launch_gemm_t<1>(mqh, mqm, meh, mem, a, 2 * pairs, st)
+                         : launch_gemm_t<3>(mqh, mqm, meh, mem, a, 2 * pairs, st);
 }

@@ -113,17 +113,18 @@ int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_
 
 // ---- batched path (orr_batch.cu) ------------------------------------------------------------
 constexpr int ORR_BATCH_TERMS = 16;          // query terms the batched epilogue handles per query
-constexpr int ORR_BATCH_TILE = 128;          // queries per unit == corpus rows per unit
+constexpr int ORR_BATCH_TILE = 256;          // queries per unit == corpus rows per unit (one CTA pair)
 struct OrrBatchGemm {
     const void* qhi; const void* qmid;       // bf16 [batch_padded][dim]
     const void* ehi; const void* emid;       // bf16 [rows][dim]
-    const void* rowaux;                      // float2 [rows padded to 128]
+    const void* rowaux;                      // float2 [rows padded to ORR_BATCH_TILE]
     const float* qscale;                     // [batch_padded]
     const float* thr;                        // [batch_padded] (main pass)
     void* cand; uint32_t* cand_count; int32_t cand_cap;
     float* dense; int64_t dense_ld;          // dense score output (sampling / debug) or NULL
     const uint32_t* term_bits; int64_t row_words; const int32_t* q_term_ids; const float* q_kw_w;
     int64_t rows; int32_t dim; int32_t batch_padded; int32_t tile_stride; int32_t sms;
+    int32_t passes;                          // 3 = split precision (default), 1 = bf16 screen
 };
 int orr_batch_build_planes(const float* emb, void* hi, void* mid, float* inv_norm, int64_t first, int64_t n, int dim,
                            cudaStream_t st);
@@ -140,6 +141,8 @@ int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, con
                               cudaStream_t st);
 int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows, const void* table, int table_slots,
                                uint32_t* bits, int64_t row_words, cudaStream_t st);
+constexpr int ORR_BATCH_MAX_SURV = 1024;      // deepest per-query survivor list the finalize kernel re-scores
+constexpr int ORR_BATCH_SAMPLE_HITS = 12;     // sampled rows expected above a query's threshold
 constexpr float ORR_BATCH_EPS = 2.0e-4f;     // bound on |bf16x3 GEMM score - exact score| (unit weights)
 
 // text

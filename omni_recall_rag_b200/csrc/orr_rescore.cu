@@ -528,7 +528,7 @@ constexpr int BATCH_FIN_THREADS = 256;
 __global__ void __launch_bounds__(BATCH_FIN_THREADS) orr_batch_finalize_kernel(const BatchFinArgs a) {
     extern __shared__ __align__(16) uint8_t fsm[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(fsm);                       // [cap pow2]
-    OrrExact* e = reinterpret_cast<OrrExact*>(fsm + (size_t)a.cap * 8);       // [256]
+    OrrExact* e = reinterpret_cast<OrrExact*>(fsm + (size_t)a.cap * 8);       // [ORR_BATCH_MAX_SURV]
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t total = a.cand_count[b];
     const int c = (int)min(total, (uint32_t)a.cap);
@@ -605,28 +605,50 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS) orr_batch_finalize_kernel(c
     }
 }
 
-// term bitmaps: bit r of bits[t] says row r holds batch term t.  One warp per row: each lane
-// probes its words of the row's 32-bit term table in an open-addressing table of the batch's
-// distinct terms (smem), hits set bits with atomicOr.
-__global__ void __launch_bounds__(256) orr_batch_term_bits_kernel(const uint32_t* terms32, int slots, int64_t rows,
-                                                                  const uint2* table, int table_mask,
-                                                                  uint32_t* bits, int64_t row_words) {
+// term bitmaps: bit r of bits[t] says row r holds batch term t.  A warp takes 32 consecutive rows (one
+// output word per term): the rows' 32-bit term tables are one contiguous block, streamed with 8
+// 16-byte loads in flight per lane; every stored hash is probed in an open-addressing table of the
+// batch's distinct terms (smem) and hits set their row's bit with atomicOr (hits are sparse).
+constexpr int TERM_BITS_THREADS = 1024;
+__global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(const uint32_t* terms32, int slots, int64_t rows,
+                                                                               const uint2* table, int table_mask,
+                                                                               uint32_t* bits, int64_t row_words) {
     extern __shared__ uint2 tab[];
     for (int i = threadIdx.x; i <= table_mask; i += blockDim.x) tab[i] = table[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = gw; row < rows; row += W) {
-        for (int w = lane; w < slots; w += 32) {
-            const uint32_t h = __ldg(terms32 + row * slots + w);
-            if (!h) continue;
-            uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)table_mask;
-            for (;;) {
-                const uint2 ent = tab[pos];
-                if (ent.x == 0u) break;
-                if (ent.x == h) atomicOr(bits + (int64_t)ent.y * row_words + (row >> 5), 1u << (row & 31));
-                pos = (pos + 1) & (uint32_t)table_mask;
+    const int64_t n_blocks = (rows + 31) >> 5;
+    const int vec_per_row = slots >> 2;                                      // uint4 per row
+    for (int64_t blk = gw; blk < n_blocks; blk += W) {
+        const int rows_here = (int)min((int64_t)32, rows - (blk << 5));
+        const int n_vec = rows_here * vec_per_row;
+        const uint4* base = reinterpret_cast<const uint4*>(terms32 + (blk << 5) * slots);
+        for (int v0 = 0; v0 < n_vec; v0 += 256) {
+            uint4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int v = v0 + i * 32 + lane;
+                x[i] = v < n_vec ? __ldg(base + v) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int v = v0 + i * 32 + lane;
+                const uint32_t bit = 1u << (v / vec_per_row);
+                const uint32_t hs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t h = hs[c];
+                    if (!h) continue;
+                    uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)table_mask;
+                    for (;;) {
+                        const uint2 ent = tab[pos];
+                        if (ent.x == 0u) break;
+                        if (ent.x == h) { atomicOr(bits + (int64_t)ent.y * row_words + blk, bit); break; }
+                        pos = (pos + 1) & (uint32_t)table_mask;
+                    }
+                }
             }
         }
     }
@@ -645,11 +667,11 @@ int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, con
                               int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
                               int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
                               cudaStream_t st) {
-    if (n_surv > 256 || (cap & (cap - 1)) != 0) { orr_set_error("batch finalize: bad sizes"); return ORR_E_INTERNAL; }
-    const int smem = cap * 8 + 256 * (int)sizeof(OrrExact);
+    if (n_surv > ORR_BATCH_MAX_SURV || (cap & (cap - 1)) != 0) { orr_set_error("batch finalize: bad sizes"); return ORR_E_INTERNAL; }
+    const int smem = cap * 8 + ORR_BATCH_MAX_SURV * (int)sizeof(OrrExact);
     static bool configured = false;
     if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8 + 256 * 24));
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8 + ORR_BATCH_MAX_SURV * 24));
         configured = true;
     }
     BatchFinArgs a;
@@ -672,7 +694,9 @@ int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows,
         ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_term_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         configured = true;
     }
-    orr_batch_term_bits_kernel<<<sms * 4, 256, smem, st>>>(terms32, slots, rows, (const uint2*)table, table_slots - 1, bits, row_words);
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    orr_batch_term_bits_kernel<<<sms * per_sm, TERM_BITS_THREADS, smem, st>>>(terms32, slots, rows, (const uint2*)table,
+                                                                              table_slots - 1, bits, row_words);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }

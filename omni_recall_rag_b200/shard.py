@@ -149,6 +149,10 @@ class RecallShard:
     def fill_synthetic(self, spec: "N.OrrSynthSpec", first_row: int, n: int) -> None:
         N.check(N.lib().orr_store_fill_synthetic(self._h, C.byref(spec), first_row, n))
 
+    def set_option(self, name: str, value: float) -> None:
+        """orr_store_set_option, e.g. ("batch_passes", 1 | 3)."""
+        N.check(N.lib().orr_store_set_option(self._h, name.encode(), float(value)))
+
     @property
     def count(self) -> int:
         return int(N.lib().orr_store_count(self._h))
@@ -217,11 +221,11 @@ class RecallShard:
         return res
 
     def debug_batch_scores(self, q: np.ndarray, now_ticks: int, tile_stride: int = 1) -> np.ndarray:
-        """Raw fused GEMM scores (w_cos*cos + w_rec*rec) of every stride-th 128-row tile: [B, n]."""
+        """Raw fused GEMM scores (w_cos*cos + w_rec*rec) of every stride-th 256-row tile: [B, n]."""
         q = np.ascontiguousarray(q, dtype=np.float32)
         B = int(q.shape[0])
-        tiles = (self.rows_used + 127) // 128
-        n_s = ((tiles + tile_stride - 1) // tile_stride) * 128
+        tiles = (self.rows_used + 255) // 256
+        n_s = ((tiles + tile_stride - 1) // tile_stride) * 256
         out = np.zeros((B, n_s), dtype=np.float32)
         N.check(N.lib().orr_debug_batch_scores(self._h, B, q.ctypes.data_as(C.c_void_p), int(q.shape[1]), int(now_ticks),
                                                int(tile_stride), out.ctypes.data_as(C.c_void_p), n_s))

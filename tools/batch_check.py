@@ -32,7 +32,8 @@ rec = np.exp(-np.maximum(0, (NOW - hr.ticks) / 864e9) / 30.0)
 ref = 0.7 * cos + 0.1 * rec[None, :]
 err = np.abs(got[:, :n] - ref)
 print("max abs err vs fp64 numpy: %.3e  (mean %.3e)" % (err.max(), err.mean()))
-assert err.max() < 2e-4, "GEMM core wrong"
+passes = int(os.environ.get("ORR_BATCH_PASSES", "3"))
+assert err.max() < (2e-4 if passes == 3 else 6e-3), "GEMM core wrong"
 print("pad rows -inf:", np.all(np.isneginf(got[:, rows:])) if got.shape[1] > rows else True)
 # full batched search vs single-query path
 if n_terms:
