@@ -37,6 +37,7 @@ struct SearchCtx {
 };
 
 thread_local orr_timing g_timing{};
+thread_local int32_t g_batch_terms_built = 0;
 
 // state of the batched (tcgen05) path: split planes of the store + per-call scratch
 struct BatchState {
@@ -53,7 +54,11 @@ struct BatchState {
     void* cand = nullptr; uint32_t* cand_count = nullptr; orr_hit* hits = nullptr; int32_t* status = nullptr;
     OrrProbes* probes = nullptr;
     float* dense = nullptr; size_t dense_elems = 0;
-    uint32_t* term_bits = nullptr; size_t term_bits_words = 0; void* table = nullptr;
+    uint32_t* term_bits = nullptr; void* table = nullptr;
+    // persistent per-term row bitmaps: 32-bit term hash -> slot in term_bits[slot][row_words]
+    std::unordered_map<uint32_t, int32_t> term_slot;
+    uint64_t term_version = ~0ull; int64_t term_row_words = 0;
+    int32_t term_slots_used = 0, term_slots_cap = 0;
 };
 constexpr int BATCH_CAND_CAP = 4096;
 constexpr int BATCH_TABLE_SLOTS = 16384;       // largest smem probe table (128 KB)
@@ -654,42 +659,73 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         int64_t total_terms = 0;
         for (int32_t b = 0; b < batch; ++b) total_terms += std::max(0, n_terms[b]);
         if (total_terms > BATCH_MAX_TERM_IDS) { orr_set_error("batch path: %lld query terms in one launch", (long long)total_terms); return ORR_E_INTERNAL; }
-        int table_slots = 256;
-        while (table_slots < 4 * total_terms && table_slots < BATCH_TABLE_SLOTS) table_slots <<= 1;
-        std::vector<uint2> table((size_t)table_slots, make_uint2(0u, 0u));
+        // Term bitmaps persist across batches (keyed by the 32-bit term hash) until the store mutates:
+        // a batch only builds the bitmaps of terms it is the first to ask for.
+        if (bs->term_version != s->version || bs->term_row_words != row_words) {
+            bs->term_slot.clear(); bs->term_slots_used = 0;
+            bs->term_version = s->version; bs->term_row_words = row_words;
+        }
         std::vector<int32_t> qterm((size_t)bp * ORR_BATCH_TERMS, -1);
         std::vector<float> kww((size_t)bp, 0.f);
-        uint32_t n_ids = 0;
-        for (int32_t b = 0; b < batch; ++b) {
-            const int32_t nt = n_terms[b];
-            const uint32_t p0 = probe_offsets[b];
-            rc = build_probes(nt, probe_hash + p0, nullptr, nt, &hp[(size_t)b]);
-            if (rc != ORR_OK) return rc;
-            if (nt > 0) kww[(size_t)b] = (float)(w.w_kw / (double)nt);
-            for (int32_t t = 0; t < nt; ++t) {
-                const uint32_t h = hp[(size_t)b].h32[t];
-                uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)(table_slots - 1);
-                while (table[pos].x != 0u && table[pos].x != h) pos = (pos + 1) & (uint32_t)(table_slots - 1);
-                if (table[pos].x == 0u) { table[pos] = make_uint2(h, n_ids++); }
-                qterm[(size_t)b * ORR_BATCH_TERMS + t] = (int32_t)table[pos].y;
+        std::vector<uint32_t> distinct;
+        {
+            std::unordered_map<uint32_t, int32_t> seen;
+            for (int32_t b = 0; b < batch; ++b) {
+                const int32_t nt = n_terms[b];
+                rc = build_probes(nt, probe_hash + probe_offsets[b], nullptr, nt, &hp[(size_t)b]);
+                if (rc != ORR_OK) return rc;
+                if (nt > 0) kww[(size_t)b] = (float)(w.w_kw / (double)nt);
+                for (int32_t t = 0; t < nt; ++t)
+                    if (seen.emplace(hp[(size_t)b].h32[t], 0).second) distinct.push_back(hp[(size_t)b].h32[t]);
             }
         }
-        const size_t need = (size_t)n_ids * (size_t)row_words;
-        if (need > bs->term_bits_words) {
-            cudaFree(bs->term_bits); bs->term_bits = nullptr; bs->term_bits_words = 0;
-            ORR_CUDA_OK(cudaMalloc(&bs->term_bits, need * sizeof(uint32_t)));
-            bs->term_bits_words = need;
+        std::vector<uint32_t> missing;
+        for (uint32_t h : distinct) if (!bs->term_slot.count(h)) missing.push_back(h);
+        if ((int64_t)bs->term_slots_used + (int64_t)missing.size() > bs->term_slots_cap) {
+            // out of slots: drop the cache; grow the pool if this batch alone does not fit
+            bs->term_slot.clear(); bs->term_slots_used = 0;
+            missing = distinct;
+            if ((int64_t)distinct.size() > bs->term_slots_cap) {
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                const size_t slot_bytes = (size_t)row_words * sizeof(uint32_t);
+                const size_t have = (size_t)bs->term_slots_cap * slot_bytes;
+                size_t budget = std::min<size_t>((free_b + have) / 4, (size_t)12 << 30);
+                size_t want = std::max<size_t>(2 * distinct.size(), 4096);
+                if (want * slot_bytes > budget) want = std::max<size_t>(distinct.size(), budget / slot_bytes);
+                cudaFree(bs->term_bits); bs->term_bits = nullptr; bs->term_slots_cap = 0;
+                ORR_CUDA_OK(cudaMalloc(&bs->term_bits, want * slot_bytes));
+                bs->term_slots_cap = (int32_t)want;
+            }
         }
-        if (!bs->table) ORR_CUDA_OK(cudaMalloc(&bs->table, BATCH_TABLE_SLOTS * 8));
-        ORR_CUDA_OK(cudaMemsetAsync(bs->term_bits, 0, need * sizeof(uint32_t), st));
-        ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table.data(), (size_t)table_slots * 8, cudaMemcpyHostToDevice, st));
+        if (!missing.empty()) {
+            int table_slots = 256;
+            while (table_slots < 4 * (int64_t)missing.size() && table_slots < BATCH_TABLE_SLOTS) table_slots <<= 1;
+            std::vector<uint2> table((size_t)table_slots, make_uint2(0u, 0u));
+            const int32_t first_new = bs->term_slots_used;
+            for (uint32_t h : missing) {
+                uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)(table_slots - 1);
+                while (table[pos].x != 0u) pos = (pos + 1) & (uint32_t)(table_slots - 1);
+                table[pos] = make_uint2(h, (uint32_t)bs->term_slots_used);
+                bs->term_slot[h] = bs->term_slots_used++;
+            }
+            if (!bs->table) ORR_CUDA_OK(cudaMalloc(&bs->table, BATCH_TABLE_SLOTS * 8));
+            ORR_CUDA_OK(cudaMemsetAsync(bs->term_bits + (size_t)first_new * (size_t)row_words, 0,
+                                        missing.size() * (size_t)row_words * sizeof(uint32_t), st));
+            ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table.data(), (size_t)table_slots * 8, cudaMemcpyHostToDevice, st));
+            ORR_CUDA_OK(cudaStreamSynchronize(st));   // `table` goes out of scope
+            rc = orr_batch_launch_term_bits(s->d_terms32, s->cfg.term_slots, rows, bs->table, table_slots, bs->term_bits,
+                                            row_words, st);
+            if (rc != ORR_OK) return rc;
+        }
+        for (int32_t b = 0; b < batch; ++b)
+            for (int32_t t = 0; t < n_terms[b]; ++t)
+                qterm[(size_t)b * ORR_BATCH_TERMS + t] = bs->term_slot[hp[(size_t)b].h32[t]];
         ORR_CUDA_OK(cudaMemcpyAsync(bs->qterm, qterm.data(), qterm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaMemcpyAsync(bs->kww, kww.data(), kww.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaMemcpyAsync(bs->probes, hp.data(), sizeof(OrrProbes) * (size_t)batch, cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope below
-        rc = orr_batch_launch_term_bits(s->d_terms32, s->cfg.term_slots, rows, bs->table, table_slots, bs->term_bits,
-                                        row_words, st);
-        if (rc != ORR_OK) return rc;
+        g_batch_terms_built = (int32_t)missing.size();
     }
 
     OrrBatchGemm gm{};
@@ -748,8 +784,8 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         cudaEventElapsedTime(&ms_prep, bs->ev[3], bs->ev[0]);
         cudaEventElapsedTime(&ms_fin, bs->ev[2], bs->ev[4]);
         cudaEventElapsedTime(&ms_d2h, bs->ev[4], bs->ev[5]);
-        fprintf(stderr, "[orr batch] B=%d k=%d passes=%d M=%d stride=%d: prep %.3f  sample %.3f  main %.3f  finalize %.3f  d2h %.3f ms\n",
-                batch, k, passes, M, stride, ms_prep, ms_sample, ms_main, ms_fin, ms_d2h);
+        fprintf(stderr, "[orr batch] B=%d k=%d passes=%d M=%d stride=%d terms_built=%d: prep %.3f  sample %.3f  main %.3f  finalize %.3f  d2h %.3f ms\n",
+                batch, k, passes, M, stride, g_batch_terms_built, ms_prep, ms_sample, ms_main, ms_fin, ms_d2h);
     }
     for (int32_t b = 0; b < batch; ++b) {
         n_out[b] = st_host[(size_t)2 * b];
