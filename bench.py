@@ -17,6 +17,11 @@ shard, computes its exact local top-10, and the lists are all-gathered over NCCL
              measured HBM copy bandwidth (MEASURED_PEAKS.json).
     cpu_baseline = the C oracle (a port of the reference's C# scorer; the C# cannot run
              here) timed on this box's host cores on a bounded sample of the same corpus.
+
+--workload c3 | c5 (N=1 only) benches the batched path instead — BASELINE.json configs[2] and
+configs[4]: 5M x 768, batch 1024 top-100 (4 terms) / batch 256 top-50 (16 terms, tie-heavy) — a
+"step" is one orr_search_batch call; roofline.bound is "tensor" (useful 2*N*D*B flops of the main
+tcgen05 pass against the measured bf16 throughput).  The default line stays the headline metric.
 """
 from __future__ import annotations
 
@@ -40,6 +45,18 @@ TOP_K = 10
 N_TERMS = 4
 TERM_SLOTS = 64
 FALLBACK_HBM_GBS = 6650.0
+FALLBACK_BF16_TFLOPS = 1500.0
+# dram__bytes_read.sum + dram__bytes_write.sum of orr_scan_kernel<24,1> per launch at 1M x 3072, 4 terms,
+# from the ncu --set full capture summarised in profiles/r01_scan_kernel_first.md (12.5526 GB read + ~6.5 MB
+# written); scales linearly with rows.
+NCU_SCAN_TRAFFIC_BYTES_PER_ROW = 12559.1
+BATCH_WORKLOADS = {
+    "c3": dict(rows=5_000_000, dim=768, batch=1024, top_k=100, n_terms=4, frequent=0, dup_ppm=0,
+               name="5M chunks x 768 fp32 (truncated embeddings), batch 1024 queries, 4 terms, top-100"),
+    "c5": dict(rows=5_000_000, dim=768, batch=256, top_k=50, n_terms=16, frequent=8, dup_ppm=1000,
+               name="keyword-heavy: 5M chunks x 768, 16-term queries (8 from the 1000 most frequent tokens), "
+                    "planted duplicate rows, batch 256, top-50"),
+}
 
 
 def measured_peak():
@@ -48,6 +65,16 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback"
+
+
+def measured_tensor_peak():
+    """(burst, sustained) dense bf16 TFLOP/s."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            j = json.load(f)
+            return float(j["bf16_tflops"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured"
+    except Exception:
+        return FALLBACK_BF16_TFLOPS, FALLBACK_BF16_TFLOPS, "fallback"
 
 
 class ClockSampler:
@@ -134,6 +161,19 @@ def run_reference(args):
     from oracle import oracle_c
 
     threads = oracle_c.max_threads()
+    if args.workload != "c2":
+        wl = BATCH_WORKLOADS[args.workload]
+        sample, steps = 200_000, max(1, args.steps if args.steps != 200 else 20)
+        v, dt, n = oracle_batch_rate(wl, sample, steps, threads, 0.0)
+        print(json.dumps({
+            "impl": "reference", "metric": f"hybrid recall QPS, {wl['name']}", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wl["batch"] / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 products, f64 accumulation", "data": "synthetic", "config": batch_config(args, wl),
+            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} queries x {sample} rows x {wl['dim']}, scaled linearly to {wl['rows']} rows; C port of "
+                                       f"RecallSearchService.cs (dotnet absent)"},
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     sample = args.cpu_sample_rows
     steps = max(1, args.steps)
     from omni_recall_rag_b200 import synth
@@ -178,6 +218,132 @@ def workload_config(args):
             "value_units": "queries/s x (rows_total / 1M)"}
 
 
+def oracle_batch_rate(wl, sample_rows: int, n_queries: int, threads: int, min_seconds: float):
+    """The oracle port on the first `sample_rows` rows of the batch workload's corpus: queries/s scaled
+    linearly to the workload's row count (the scorer is a per-row loop, one query at a time)."""
+    from omni_recall_rag_b200 import synth
+    from oracle import oracle_c
+
+    spec = synth.make_spec(wl["dim"], dup_row_ppm=wl["dup_ppm"])
+    rows = synth.rows_host(spec, 0, sample_rows)
+    blob, off = oracle_c.pack_contents(synth.contents_of(rows.term_ids))
+    qs = [synth.query_host(spec, qi, wl["rows"], n_terms=wl["n_terms"], frequent_terms=wl["frequent"]) for qi in range(n_queries)]
+
+    def one(q):
+        oracle_c.search(emb=rows.emb, dim=wl["dim"], ticks=rows.ticks, content_blob=blob, content_off=off, query=q.text,
+                        qvec=q.q, now_ticks=spec.now_ticks, top_k=wl["top_k"], threads=threads)
+
+    one(qs[0])
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        one(qs[done % n_queries])
+        done += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds and done >= n_queries:
+            break
+    return (done / dt) * (sample_rows / float(wl["rows"])), dt, done
+
+
+def batch_config(args, wl):
+    return {"workload": wl["name"], "rows_total": wl["rows"], "rows_per_gpu": wl["rows"], "dim": wl["dim"], "batch": wl["batch"],
+            "top_k": wl["top_k"], "n_terms": wl["n_terms"], "parallelism": "1 GPU",
+            "split_precision_passes": args.batch_passes,
+            "l2": "bf16 planes (15.4 GB) exceed L2 (126 MB); every step is a fresh batch of queries; no flush needed"}
+
+
+def run_batch(args):
+    """--workload c3 | c5: the tcgen05 batched path through orr_search_batch (N=1)."""
+    import numpy as np
+    import torch
+
+    import omni_recall_rag_b200 as orr
+    from omni_recall_rag_b200 import _native as N
+    from omni_recall_rag_b200 import synth
+
+    wl = BATCH_WORKLOADS[args.workload]
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--workload c3/c5 is a single-GPU bench (the batched path shards like the single-query path; not benched)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: liborr has no CPU path")
+    steps = max(1, args.steps if args.steps != 200 else 20)
+    warmup = max(3, args.warmup if args.warmup != 20 else 3)
+    rows, dim, B, k = wl["rows"], wl["dim"], wl["batch"], wl["top_k"]
+    spec = synth.make_spec(dim, dup_row_ppm=wl["dup_ppm"])
+    shard = orr.RecallShard(dim, rows, device=0, term_slots=TERM_SLOTS)
+    shard.fill_synthetic(spec, 0, rows)
+    shard.set_option("batch_passes", args.batch_passes)
+    n_b = steps + warmup
+    Qs, Ts = [], []
+    for i in range(n_b):                          # every step is a fresh batch: new vectors, new terms
+        qs = [synth.query_host(spec, i * B + j, rows, n_terms=wl["n_terms"], frequent_terms=wl["frequent"]) for j in range(B)]
+        Qs.append(torch.from_numpy(np.stack([q.q for q in qs])).pin_memory())
+        Ts.append(orr.BatchTerms.pack([q.terms for q in qs]))
+
+    def one(i):
+        hits = shard.search_batch(Qs[i].numpy(), Ts[i], spec.now_ticks, k)
+        return hits, shard.last_timing()
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    dev_ms, main_ms, redo = [], [], 0
+    with ClockSampler(0) as clocks:
+        t0 = time.perf_counter()
+        for i in range(warmup, n_b):
+            hits, tm = one(i)
+            assert tm["path"] & 0xff == N.PATH_BATCH, tm
+            dev_ms.append(tm["total_device_ms"]); main_ms.append(tm["scan_ms"]); redo += tm["n_survivors"] & 0xffff
+        e2e_s = time.perf_counter() - t0
+        t_end = time.time() + 0.6                # a moment more under load for the clock samples
+        while time.time() < t_end:
+            one(warmup)
+    assert all(int(n) == k for n in hits.n_out), "short hit lists"
+    # the same batches again: every term bitmap is now cached (a service's steady state on a Zipf vocabulary)
+    warm_ms = []
+    for i in range(warmup, n_b):
+        _, tm = one(i)
+        warm_ms.append(tm["total_device_ms"])
+
+    value = steps * B / (sum(dev_ms) / 1000.0)
+    burst, sustained, peak_kind = measured_tensor_peak()
+    useful = 2.0 * rows * dim * B
+    main_avg = sum(main_ms) / len(main_ms)
+    achieved = useful / (main_avg / 1000.0) / 1.0e12
+    h2d = B * dim * 4 + B * 4 + (B + 1) * 4 + B * wl["n_terms"] * 8
+    line = {
+        "metric": f"hybrid recall QPS, {wl['name']}", "value": value, "unit": "queries/s", "n_gpus": 1, "steps": steps,
+        "warmup": warmup, "ms_per_step": sum(dev_ms) / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"bf16x{args.batch_passes} split-precision tcgen05 screen (fp32 accumulate in TMEM) + f64 exact re-rank",
+        "data": "synthetic", "config": batch_config(args, wl),
+        "e2e": {"value": steps * B / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * k * 24 + B * 8,
+                "ms_per_step": 1000.0 * e2e_s / steps},
+        "value_warm_terms": steps * B / (sum(warm_ms) / 1000.0),
+        "gpu_launches": 7 * steps,
+        "kernels_per_step": ["orr_prep_queries_kernel", "orr_build_rowaux_kernel", "orr_batch_term_bits_kernel (unseen terms only)",
+                             f"orr_batch_gemm_kernel<{args.batch_passes}> (sampling pass)", "orr_batch_threshold_kernel",
+                             f"orr_batch_gemm_kernel<{args.batch_passes}> (main pass)", "orr_batch_finalize_kernel"],
+        "roofline": {"bound": "tensor", "kernel": f"orr_batch_gemm_kernel<{args.batch_passes}> (main pass)", "achieved": achieved,
+                     "peak": sustained, "peak_kind": f"{peak_kind} cuBLAS bf16 TFLOP/s, sustained (kernel timed inside a long step); burst {burst}",
+                     "unit": "TFLOP/s", "frac": achieved / sustained, "flops_per_launch": useful,
+                     "issued_tflops": achieved * args.batch_passes, "issued_frac": achieved * args.batch_passes / sustained,
+                     "kernel_ms": main_avg, "traffic": None,
+                     "note": "achieved counts the useful 2*N*D*B flops once; the split-precision passes are not credited"},
+        "clocks": clocks.summary(),
+        "queries_rerun_singly": redo,
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle_c
+        threads = oracle_c.max_threads()
+        sample = 200_000
+        v, dt, n = oracle_batch_rate(wl, sample, 8, threads, 10.0)
+        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} queries x {sample} rows x {dim} (first rows of the same corpus) on {threads} threads "
+                                          f"({dt:.1f} s), scaled linearly to {rows} rows; C port of RecallSearchService.cs:20-119"}
+    print(json.dumps(line))
+    shard.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,9 +353,14 @@ def main():
     ap.add_argument("--rows-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--batch-passes", type=int, default=3, choices=[1, 3])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload != "c2":
+        run_batch(args)
         return
 
     import numpy as np
@@ -261,12 +432,12 @@ def main():
     for i in range(warmup):
         sr.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K)
     barrier()
-    scan_ms, fin_ms, escalated = [], [], 0
+    scan_ms, fin_ms, wall_ms, escalated = [], [], [], 0
     t0 = time.perf_counter()
     for i in range(warmup, n_q):
         hits = sr.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K)
         tm = shard.last_timing()
-        scan_ms.append(tm["scan_ms"]); fin_ms.append(tm["finalize_ms"])
+        scan_ms.append(tm["scan_ms"]); fin_ms.append(tm["finalize_ms"]); wall_ms.append(tm["wall_ms"])
         escalated += 1 if (tm["path"] & 0x100) else 0
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -298,7 +469,8 @@ def main():
         "config": workload_config(args),
         "corpus_qps": steps / (dev_ms / 1000.0),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * DIM + 12 * N_TERMS,
-                "d2h_bytes_per_step": 24 * TOP_K + 8, "ms_per_step": 1000.0 * e2e_s / steps},
+                "d2h_bytes_per_step": 24 * TOP_K + 8, "ms_per_step": 1000.0 * e2e_s / steps,
+                "c_abi_call_ms": {"median": statistics.median(wall_ms), "p99": sorted(wall_ms)[min(len(wall_ms) - 1, int(0.99 * len(wall_ms)))]}},
         "gpu_launches": launches_per_step * steps,
         "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel"] + (["orr_merge_kernel"] if world > 1 else []),
         "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel<24,1>", "achieved": achieved, "peak": peak,
@@ -306,7 +478,9 @@ def main():
                      "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
                      "bytes_per_launch": bytes_per_launch, "bytes_per_launch_emb_only": n_local * 4 * DIM,
                      "kernel_ms": scan_avg_ms, "finalize_kernel_ms": sum(fin_ms) / len(fin_ms),
-                     "traffic": None},
+                     "traffic": NCU_SCAN_TRAFFIC_BYTES_PER_ROW * n_local,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                       "(profiles/r01_scan_kernel_first.md), scaled by rows"},
         "clocks": clock_summary,
         "bound_check_escalations": escalated, "device_flags": flags_seen,
     }

@@ -35,6 +35,52 @@ class QueryTerms:
         return QueryTerms(0, np.zeros(0, dtype=np.uint64), None)
 
 
+@dataclass
+class BatchTerms:
+    """The keyword side of a query batch, packed once as the CSR orr_search_batch takes."""
+    n_terms: np.ndarray                 # int32[B]
+    probe_hash: np.ndarray              # uint64[total probes] (>= 1 element)
+    probe_term: Optional[np.ndarray]    # int32[total probes] or None (identity)
+    probe_offsets: np.ndarray           # uint32[B + 1]
+
+    @staticmethod
+    def pack(terms: Sequence[QueryTerms]) -> "BatchTerms":
+        B = len(terms)
+        nt = np.array([t.n_terms for t in terms], dtype=np.int32)
+        po = np.zeros(B + 1, dtype=np.uint32)
+        po[1:] = np.cumsum([len(t.probe_hash) for t in terms])
+        ph = np.ascontiguousarray(np.concatenate([np.asarray(t.probe_hash, dtype=np.uint64) for t in terms])
+                                  if B and po[-1] else np.zeros(1, dtype=np.uint64))
+        pt = None
+        if any(t.probe_term is not None for t in terms):
+            pt = np.ascontiguousarray(np.concatenate(
+                [np.asarray(t.probe_term if t.probe_term is not None else np.arange(len(t.probe_hash)), dtype=np.int32)
+                 for t in terms]) if po[-1] else np.zeros(1, dtype=np.int32))
+        return BatchTerms(nt, ph, pt, po)
+
+
+_HIT_DTYPE = np.dtype([("row", "<u8"), ("score", "<f8"), ("ticks", "<i8")])
+
+
+class BatchHits(Sequence):
+    """Result of orr_search_batch: hits[b] is query b's Hits; .raw is the [B, k] record array."""
+
+    def __init__(self, raw: np.ndarray, n_out: np.ndarray):
+        self.raw, self.n_out = raw, n_out
+
+    def __len__(self) -> int:
+        return int(self.n_out.shape[0])
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        s = self.raw[b, : int(self.n_out[b])]
+        return Hits(s["row"].copy(), s["score"].copy(), s["ticks"].copy())
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
 def hash_term(term_lower: str) -> int:
     b = term_lower.encode("utf-8")
     return int(N.lib().orr_hash_term(b, len(b)))
@@ -192,33 +238,25 @@ class RecallShard:
             int(now_ticks), int(top_k), C.c_void_p(out_dev_ptr), C.c_void_p(status_dev_ptr),
             C.c_void_p(stream_ptr)))
 
-    def search_batch(self, q: np.ndarray, terms: Optional[Sequence[QueryTerms]], now_ticks: int, top_k: int):
-        """orr_search_batch: q is [B, dim] in host memory; returns a list of B Hits."""
+    def search_batch(self, q: np.ndarray, terms, now_ticks: int, top_k: int) -> BatchHits:
+        """orr_search_batch: q is [B, dim] in host memory; `terms` is None, a sequence of B QueryTerms,
+        or a pre-packed BatchTerms.  Returns BatchHits (hits[b] -> Hits of query b)."""
         q = np.ascontiguousarray(q, dtype=np.float32)
         B, qd = int(q.shape[0]), int(q.shape[1]) if q.ndim == 2 else 0
         k = max(1, int(top_k))
-        out = (N.OrrHit * (k * max(B, 1)))()
+        raw = np.zeros((max(B, 1), k), dtype=_HIT_DTYPE)
         n_out = np.zeros(max(B, 1), dtype=np.int32)
-        nt = ph = pt = po = None
+        bt = None
         if terms is not None:
-            nt = np.array([t.n_terms for t in terms], dtype=np.int32)
-            po = np.zeros(B + 1, dtype=np.uint32)
-            po[1:] = np.cumsum([len(t.probe_hash) for t in terms])
-            ph = np.ascontiguousarray(np.concatenate([np.asarray(t.probe_hash, dtype=np.uint64) for t in terms])
-                                      if po[-1] else np.zeros(1, dtype=np.uint64))
-            if any(t.probe_term is not None for t in terms):
-                pt = np.ascontiguousarray(np.concatenate(
-                    [np.asarray(t.probe_term if t.probe_term is not None else np.arange(len(t.probe_hash)), dtype=np.int32)
-                     for t in terms]) if po[-1] else np.zeros(1, dtype=np.int32))
+            bt = terms if isinstance(terms, BatchTerms) else BatchTerms.pack(terms)
+            if bt.n_terms.shape[0] != B:
+                raise ValueError(f"terms describe {bt.n_terms.shape[0]} queries, q has {B}")
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        N.check(N.lib().orr_search_batch(self._h, B, p(q) if q.size else None, qd, p(nt), p(ph), p(pt), p(po),
-                                         int(now_ticks), int(top_k), C.cast(out, C.c_void_p), p(n_out)))
-        a = np.frombuffer(out, dtype=np.dtype([("row", "<u8"), ("score", "<f8"), ("ticks", "<i8")]))
-        res = []
-        for b in range(B):
-            s = a[b * k: b * k + int(n_out[b])]
-            res.append(Hits(s["row"].copy(), s["score"].copy(), s["ticks"].copy()))
-        return res
+        N.check(N.lib().orr_search_batch(self._h, B, p(q) if q.size else None, qd,
+                                         p(bt.n_terms) if bt else None, p(bt.probe_hash) if bt else None,
+                                         p(bt.probe_term) if bt else None, p(bt.probe_offsets) if bt else None,
+                                         int(now_ticks), int(top_k), p(raw), p(n_out)))
+        return BatchHits(raw[:B], n_out[:B])
 
     def debug_batch_scores(self, q: np.ndarray, now_ticks: int, tile_stride: int = 1) -> np.ndarray:
         """Raw fused GEMM scores (w_cos*cos + w_rec*rec) of every stride-th 256-row tile: [B, n]."""

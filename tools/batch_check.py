@@ -49,7 +49,7 @@ for k in (10, 100):
         if h1.rows.tolist() != hb[b].rows.tolist() or h1.scores.tolist() != hb[b].scores.tolist():
             bad += 1
     qps = batch / tb
-    print(f"k={k}: {qps:.0f} QPS; batch call {tb*1e3:.1f} ms, gemm main {tm['scan_ms']:.3f} ms, sample {tm['finalize_ms']:.3f} ms, "
+    print(f"k={k}: {qps:.0f} QPS; batch call {tb*1e3:.1f} ms, gemm main {tm['scan_ms']:.3f} ms, prep+sample+re-rank {tm['finalize_ms']:.3f} ms, "
           f"redo={tm['n_survivors'] & 0xffff}, mismatches vs single-query path: {bad}")
     assert bad == 0
 print("batch check ok")
