@@ -45,8 +45,7 @@ struct BatchState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* ehi = nullptr; void* emid = nullptr;     // bf16 [capacity][dim]
-    float* inv_norm = nullptr;                     // [capacity]
-    void* rowaux = nullptr;                        // float2 [capacity padded]
+    float* rowaux = nullptr;                       // [capacity padded] w_rec * recency of the current batch's clock
     int64_t planes_rows = 0;                       // rows whose planes are built
     int bcap = 0, kcap = 0;
     float* q = nullptr; void* qhi = nullptr; void* qmid = nullptr;
@@ -307,7 +306,7 @@ void orr_store_destroy(orr_store* s) {
     if (s->batch) {
         BatchState* b = s->batch.get();
         if (b->stream) cudaStreamSynchronize(b->stream);
-        void* ptrs[] = {b->ehi, b->emid, b->inv_norm, b->rowaux, b->q, b->qhi, b->qmid, b->qscale, b->thr, b->kww, b->qterm,
+        void* ptrs[] = {b->ehi, b->emid, b->rowaux, b->q, b->qhi, b->qmid, b->qscale, b->thr, b->kww, b->qterm,
                         b->cand, b->cand_count, b->hits, b->status, b->probes, b->dense, b->term_bits, b->table};
         for (void* p : ptrs) cudaFree(p);
         for (auto& e : b->ev) if (e) cudaEventDestroy(e);
@@ -579,13 +578,12 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) 
         const size_t cap_pad = (cap + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
         ORR_CUDA_OK(cudaMalloc(&bs->ehi, cap * dim * 2));
         ORR_CUDA_OK(cudaMalloc(&bs->emid, cap * dim * 2));
-        ORR_CUDA_OK(cudaMalloc(&bs->inv_norm, cap * sizeof(float)));
-        ORR_CUDA_OK(cudaMalloc(&bs->rowaux, cap_pad * 8));
+        ORR_CUDA_OK(cudaMalloc(&bs->rowaux, cap_pad * sizeof(float)));
         bs->planes_rows = 0;
     }
     if (bs->planes_rows < s->rows_used) {        // rows appended since the last batch
-        int rc = orr_batch_build_planes(s->d_emb, bs->ehi, bs->emid, bs->inv_norm, bs->planes_rows,
-                                        s->rows_used - bs->planes_rows, dim, bs->stream);
+        int rc = orr_batch_build_planes(s->d_emb, bs->ehi, bs->emid, bs->planes_rows, s->rows_used - bs->planes_rows, dim,
+                                        (float)s->cfg.w_cos, bs->stream);
         if (rc != ORR_OK) return rc;
         bs->planes_rows = s->rows_used;
     }
@@ -647,7 +645,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     ORR_CUDA_OK(cudaEventRecord(bs->ev[3], st));               // queries resident in HBM from here on
     rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st);
     if (rc != ORR_OK) return rc;
-    rc = orr_batch_build_rowaux(s->d_ticks, bs->inv_norm, bs->rowaux, rows, rows_pad, now_ticks, w, st);
+    rc = orr_batch_build_rowrec(s->d_ticks, bs->rowaux, rows, rows_pad, now_ticks, w, st);
     if (rc != ORR_OK) return rc;
 
     // ---- keyword side: distinct batch terms -> ids, bitmaps over rows, per-query id lists ----
@@ -693,6 +691,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
                 size_t budget = std::min<size_t>((free_b + have) / 4, (size_t)12 << 30);
                 size_t want = std::max<size_t>(2 * distinct.size(), 4096);
                 if (want * slot_bytes > budget) want = std::max<size_t>(distinct.size(), budget / slot_bytes);
+                want = std::min<size_t>(want, ORR_BATCH_MAX_TERM_SLOTS);
                 cudaFree(bs->term_bits); bs->term_bits = nullptr; bs->term_slots_cap = 0;
                 ORR_CUDA_OK(cudaMalloc(&bs->term_bits, want * slot_bytes));
                 bs->term_slots_cap = (int32_t)want;
@@ -808,18 +807,18 @@ int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
     if (!s || batch < 0 || !out || !n_out || (batch > 0 && q_dim > 0 && !q)) { orr_set_error("orr_search_batch: bad argument"); return ORR_E_INVALID; }
     if (batch == 0) return ORR_OK;
     const int k = std::max(1, top_k);
-    {   // one launch handles <= 2048 queries and <= BATCH_MAX_TERM_IDS query terms: slice larger batches
+    {   // one launch handles <= ORR_BATCH_MAX_QUERIES queries and <= BATCH_MAX_TERM_IDS query terms: slice larger batches
         int64_t terms_sum = 0;
         int32_t cut = batch;
         for (int32_t b = 0; b < batch; ++b) {
             terms_sum += n_terms ? std::max(0, n_terms[b]) : 0;
-            if (b >= 2048 || terms_sum > BATCH_MAX_TERM_IDS) { cut = b; break; }
+            if (b >= ORR_BATCH_MAX_QUERIES || terms_sum > BATCH_MAX_TERM_IDS) { cut = b; break; }
         }
         if (cut < batch && cut > 0) {
             for (int32_t b0 = 0; b0 < batch;) {
                 int64_t sum = 0;
                 int32_t b1 = b0;
-                while (b1 < batch && b1 - b0 < 2048) {
+                while (b1 < batch && b1 - b0 < ORR_BATCH_MAX_QUERIES) {
                     const int64_t nt = n_terms ? std::max(0, n_terms[b1]) : 0;
                     if (b1 > b0 && sum + nt > BATCH_MAX_TERM_IDS) break;
                     sum += nt; ++b1;
@@ -915,7 +914,7 @@ int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
 // diagnostic: the raw fused GEMM scores (no keyword term) of every stride-th row tile
 int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t q_dim, int64_t now_ticks,
                            int32_t tile_stride, float* out, int64_t out_ld) {
-    if (!s || !q || !out || batch < 1 || q_dim != s->cfg.dim || tile_stride < 1) { orr_set_error("orr_debug_batch_scores: bad argument"); return ORR_E_INVALID; }
+    if (!s || !q || !out || batch < 1 || batch > ORR_BATCH_MAX_QUERIES || q_dim != s->cfg.dim || tile_stride < 1) { orr_set_error("orr_debug_batch_scores: bad argument"); return ORR_E_INVALID; }
     std::shared_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     if (!s->batch) s->batch.reset(new BatchState());
@@ -931,7 +930,7 @@ int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t 
     if (out_ld < n_s) { orr_set_error("orr_debug_batch_scores: out_ld %lld < %lld", (long long)out_ld, (long long)n_s); return ORR_E_INVALID; }
     ORR_CUDA_OK(cudaMemcpyAsync(bs->q, q, sizeof(float) * (size_t)batch * dim, cudaMemcpyHostToDevice, st));
     if ((rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st)) != ORR_OK) return rc;
-    if ((rc = orr_batch_build_rowaux(s->d_ticks, bs->inv_norm, bs->rowaux, rows, rows_pad, now_ticks, weights_of(s), st)) != ORR_OK) return rc;
+    if ((rc = orr_batch_build_rowrec(s->d_ticks, bs->rowaux, rows, rows_pad, now_ticks, weights_of(s), st)) != ORR_OK) return rc;
     if ((size_t)bp * (size_t)n_s > bs->dense_elems) {
         cudaFree(bs->dense); bs->dense = nullptr; bs->dense_elems = 0;
         ORR_CUDA_OK(cudaMalloc(&bs->dense, (size_t)bp * (size_t)n_s * sizeof(float)));

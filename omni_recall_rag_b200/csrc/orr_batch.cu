@@ -70,29 +70,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 constexpr int ORR_BATCH_MAX_TERMS = ORR_BATCH_TERMS;
+constexpr int MAX_QBLOCKS = ORR_BATCH_MAX_QUERIES / ORR_BATCH_TILE;   // query blocks one launch walks per row tile (4)
+constexpr uint16_t NO_TERM = 0xFFFFu;
 
 struct BatchArgs {
     int32_t  n_row_tiles;        // row tiles this launch walks
     int32_t  row_tile_stride;    // 1 = every tile; >1 = sampling pass (tile t -> t * stride)
-    int32_t  n_qblocks;          // padded batch / 256
+    int32_t  n_qblocks;          // padded batch / 256  (<= MAX_QBLOCKS)
     int32_t  k_blocks;           // dim / 64
     int64_t  rows;               // rows in the shard
-    const float2* rowaux;        // [rows padded to 256] {w_cos * inv|e|, w_rec * rec or -inf}
-    const float*  qscale;        // [B padded] inv|q| (0 for padding / zero queries)
-    const float*  thr;           // [B padded] candidate threshold (main pass)
+    const float* rowrec;         // [rows padded to 256] w_rec * exp(-age/30d); -inf for tombstones and padding
+    const float* qscale;         // [B padded] inv|q| (0 for padding / zero queries)
+    const float* thr;            // [B padded] candidate threshold (main pass)
     // main pass output
     uint2*    cand;              // [B][cand_cap] (row, score bits)
     uint32_t* cand_count;        // [B]
@@ -100,13 +91,11 @@ struct BatchArgs {
     // dense output (sampling pass / debug): scores[b][dense_ld]
     float*    dense;
     int64_t   dense_ld;
-    int32_t   mode;              // 0 = main pass (threshold + append), 1 = dense store
     // keyword side: per query up to ORR_BATCH_MAX_TERMS term bitmaps over rows
-    const uint32_t* term_bits;   // [n_batch_terms][row_words] bit r%32 of word r/32 = row r has the term
+    const uint32_t* term_bits;   // [term slots][row_words] bit r%32 of word r/32 = row r has the term
     int64_t   row_words;
-    const int32_t* q_term_ids;   // [B padded][ORR_BATCH_MAX_TERMS] batch-term index or -1
+    const int32_t* q_term_ids;   // [B padded][ORR_BATCH_MAX_TERMS] term slot or -1, packed front to back
     const float*   q_kw_w;       // [B padded] w_kw / |terms_b| (0 if none)
-    int32_t   max_terms;
 };
 
 // ---- cluster / cta_group::2 helpers ---------------------------------------------------------------
@@ -125,7 +114,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default .release.cta semantics: the accumulator reads it orders are tcgen05 loads already completed by
+    // tcgen05.wait::ld + tcgen05.fence::before_thread_sync; a cluster-scope release would also drain every
+    // outstanding candidate store (a MEMBAR.GPU per unit and warp)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // each CTA of the pair loads its own half of the operands; completion is counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
@@ -146,87 +138,120 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-// Keyword side of one thread's half unit (4 chunks x 32 rows): the query's <= 16 term bitmaps (bit j of
-// word w = row 32w+j holds the term; one 16-byte load covers the 4 chunks) are added bit-sliced into 5
-// count planes per chunk.  Issued BEFORE the accumulator is awaited so the loads overlap the MMAs.
-struct KwPlanes { uint32_t p[UN / 64][5]; };
-__device__ __forceinline__ void kw_planes(const BatchArgs& a, int b, int64_t word0, KwPlanes& kp) {
-#pragma unroll
-    for (int c = 0; c < UN / 64; ++c)
-#pragma unroll
-        for (int i = 0; i < 5; ++i) kp.p[c][i] = 0u;
-    const int4* ip = reinterpret_cast<const int4*>(a.q_term_ids + (int64_t)b * ORR_BATCH_MAX_TERMS);
-#pragma unroll 1
-    for (int g = 0; g < ORR_BATCH_MAX_TERMS / 4; ++g) {
-        const int4 id4 = __ldg(ip + g);
-        if (id4.x < 0) break;                                                // ids are packed front to back
-        const int id[4] = {id4.x, id4.y, id4.z, id4.w};
-        uint4 w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            w[i] = id[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(a.term_bits + (int64_t)id[i] * a.row_words + word0))
-                              : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
-#pragma unroll
-            for (int c = 0; c < UN / 64; ++c) {
-                uint32_t x = ww[c], cy;
-                cy = kp.p[c][0] & x; kp.p[c][0] ^= x; x = cy;
-                cy = kp.p[c][1] & x; kp.p[c][1] ^= x; x = cy;
-                cy = kp.p[c][2] & x; kp.p[c][2] ^= x; x = cy;
-                cy = kp.p[c][3] & x; kp.p[c][3] ^= x; x = cy;
-                kp.p[c][4] ^= x;
-            }
-        }
-    }
+// ---- TMEM loads split into issue and wait so the load of chunk c+1 overlaps the math of chunk c ----
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// the registers are in/out operands of the wait so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
 }
 
-// Epilogue of one thread (= one query) over its UN/64 chunks of 32 accumulator columns.  Written for a
-// scheduler that holds only two epilogue warps: every stage is 32 independent chains, and the rare
-// work (a candidate above the threshold) sits behind ONE branch per chunk.
-template <int MODE>
-__device__ __forceinline__ void epilogue_chunks(const BatchArgs& a, uint32_t taddr, const float2* ax, int b, int64_t row0,
-                                                int t, int c_begin, float qs, float thr, float kww, const KwPlanes& kp) {
+// ---- keyword side -----------------------------------------------------------------------------------
+// One thread = one query; its half unit is 4 chunks x 32 rows = one 16-byte word group per term bitmap
+// (bit j of word w = row 32w+j holds the term).  A query's <= 16 term words are added bit-sliced into
+// 5 count planes per chunk; the epilogue then adds kww * 2^p to the rows whose plane-p bit is set.
+constexpr int HC = UN / 64;                   // chunks per thread per unit (4)
+struct KwPlanes { uint32_t p[HC][5]; };
+
+__device__ __forceinline__ void kw_clear(KwPlanes& kp) {
 #pragma unroll
-    for (int cc = 0; cc < UN / 64; ++cc) {
+    for (int c = 0; c < HC; ++c)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) kp.p[c][i] = 0u;
+}
+template <int DEPTH>                           // planes a carry can reach (3 is enough for the first 4 terms)
+__device__ __forceinline__ void kw_add(KwPlanes& kp, const uint4& w) {
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+        uint32_t x = ww[c], cy;
+#pragma unroll
+        for (int i = 0; i < DEPTH - 1; ++i) { cy = kp.p[c][i] & x; kp.p[c][i] ^= x; x = cy; }
+        kp.p[c][DEPTH - 1] ^= x;
+    }
+}
+__device__ __forceinline__ uint4 kw_load(const BatchArgs& a, uint32_t id, int64_t word0) {
+    return id != NO_TERM ? __ldg(reinterpret_cast<const uint4*>(a.term_bits + (int64_t)id * a.row_words + word0))
+                         : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// Epilogue of one thread (= one query) over its HC chunks of 32 accumulator columns.  The operand planes
+// hold rows scaled to w_cos / |e|, so the fused screen score is  acc * (1/|q|) + w_rec*rec  (+ keyword):
+// one FFMA per score, the row term read as broadcast float4 from smem.  The common path ends in a max
+// tree; the rare work (a candidate above the query's threshold) sits behind ONE branch per chunk.
+template <int MODE, bool HAS_KW>
+__device__ __forceinline__ void epilogue_chunks(const BatchArgs& a, uint32_t taddr, const float* rec, int b, int64_t row0,
+                                                int64_t dense_col0, int c_begin, float qs, float thr, float kww,
+                                                const KwPlanes& kp) {
+    uint32_t acc[2][32];
+    tmem_ld32_issue(taddr + (uint32_t)(c_begin * 32), acc[0]);
+#pragma unroll
+    for (int cc = 0; cc < HC; ++cc) {
         const int c = c_begin + cc;
-        uint32_t acc[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), acc);
+        uint32_t (&r)[32] = acc[cc & 1];
+        tmem_ld32_wait(r);
+        if (cc + 1 < HC) tmem_ld32_issue(taddr + (uint32_t)((c + 1) * 32), acc[(cc + 1) & 1]);
         float s[32];
+        const float4* rc4 = reinterpret_cast<const float4*>(rec + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float2 ra = ax[c * 32 + j];                               // smem broadcast
-            s[j] = fmaf(__uint_as_float(acc[j]) * qs, ra.x, ra.y);
+        for (int j = 0; j < 8; ++j) {
+            const float4 rr = rc4[j];                                       // smem broadcast
+            s[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), qs, rr.x);
+            s[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), qs, rr.y);
+            s[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), qs, rr.z);
+            s[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), qs, rr.w);
         }
-        if (kww != 0.f) {
-            const uint32_t c0 = kp.p[cc][0], c1 = kp.p[cc][1], c2 = kp.p[cc][2], c3 = kp.p[cc][3], c4 = kp.p[cc][4];
-            if ((c0 | c1 | c2 | c3 | c4) != 0u) {
+        if (HAS_KW) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t cnt = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2) |
-                                         (((c3 >> j) & 1u) << 3) | (((c4 >> j) & 1u) << 4);
-                    s[j] = fmaf(kww, (float)cnt, s[j]);
+            for (int p = 0; p < 5; ++p) {
+                const uint32_t m = kp.p[cc][p];
+                if (__any_sync(0xffffffffu, m != 0u)) {                     // warp-uniform; higher planes are almost always empty
+                    const float add = kww * (float)(1 << p);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (m & (1u << j)) s[j] += add;
                 }
             }
         }
         if (MODE == 0) {
-            bool any = false;
+            float mx = s[0];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) any |= (s[j] > thr);
-            if (any) {
+            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, s[j]);
+            if (__any_sync(0xffffffffu, mx > thr)) {                        // rare: ~1000 candidates per query and pass
+                uint32_t pass = 0u;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (s[j] > thr) {
-                        const uint32_t slot = atomicAdd(a.cand_count + b, 1u);
-                        if (slot < (uint32_t)a.cand_cap)
-                            a.cand[(int64_t)b * a.cand_cap + slot] =
-                                make_uint2((uint32_t)(row0 + c * 32 + j), __float_as_uint(s[j]));
-                    }
+                for (int j = 0; j < 32; ++j) pass |= (s[j] > thr) ? (1u << j) : 0u;
+                while (pass) {
+                    const int j = __ffs(pass) - 1;
+                    pass &= pass - 1u;
+                    float v[16];                                            // s[j] by a select tree (registers cannot be indexed)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = (j & 16) ? s[16 + i] : s[i];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (j & 8) ? v[8 + i] : v[i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = (j & 4) ? v[4 + i] : v[i];
+                    v[0] = (j & 2) ? v[2] : v[0]; v[1] = (j & 2) ? v[3] : v[1];
+                    const float sv = (j & 1) ? v[1] : v[0];
+                    const uint32_t slot = atomicAdd(a.cand_count + b, 1u);
+                    if (slot < (uint32_t)a.cand_cap)
+                        a.cand[(int64_t)b * a.cand_cap + slot] = make_uint2((uint32_t)(row0 + c * 32 + j), __float_as_uint(sv));
                 }
             }
         } else {
-            float4* dst = reinterpret_cast<float4*>(a.dense + (int64_t)b * a.dense_ld + ((int64_t)t * UN + c * 32));
+            float4* dst = reinterpret_cast<float4*>(a.dense + (int64_t)b * a.dense_ld + (dense_col0 + c * 32));
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
         }
@@ -237,15 +262,21 @@ __device__ __forceinline__ void epilogue_chunks(const BatchArgs& a, uint32_t tad
 // its own 128 queries (A half) and 128 rows (B half), so a k-block costs every SM 64 KB of L2->smem
 // traffic for 2x the MMA work of a 128x128 single-CTA unit.  PASSES = 3: split precision
 // (hi.hi + hi.mid + mid.hi); PASSES = 1: bf16 screen only (wider selection margin, see orr_api.cu).
+// MODE 0 = main pass (threshold + candidate append), 1 = dense score store (sampling pass / debug).
 template <int PASSES> struct GemmCfg {
     static constexpr int PLANES = PASSES == 3 ? 4 : 2;
     static constexpr int STAGE = PLANES * PLANE_BYTES;          // 64 KB / 32 KB per CTA
     static constexpr int NSTAGE = PASSES == 3 ? 3 : 6;
-    static constexpr int SMEM = NSTAGE * STAGE + 2 * UN * 8 + 256 + 1024;
+    static constexpr int REC_OFF = NSTAGE * STAGE;              // float rec[2][UN]
+    static constexpr int QC_OFF = REC_OFF + 2 * UN * 4;         // float3-ish: qs, thr, kww  [MAX_QBLOCKS][BM] each
+    static constexpr int ID_OFF = QC_OFF + 3 * MAX_QBLOCKS * BM * 4;          // uint16 ids [MAX_QBLOCKS][BM][16]
+    static constexpr int BAR_OFF = ID_OFF + MAX_QBLOCKS * BM * ORR_BATCH_MAX_TERMS * 2;
+    static constexpr int SMEM = BAR_OFF + 256 + 1024;           // barriers + alignment slack
 };
+static_assert(GemmCfg<3>::SMEM <= 232448 && GemmCfg<1>::SMEM <= 232448, "batched GEMM kernel exceeds 227 KB of shared memory");
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-template <int PASSES>
+template <int PASSES, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BATCH_THREADS, 1)
 orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qmid,
                       const __grid_constant__ CUtensorMap map_ehi, const __grid_constant__ CUtensorMap map_emid,
@@ -255,8 +286,12 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
     // the dynamic smem base is only 16-B aligned by contract; both CTAs compute the same offset
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_mem = smem;                                              // NSTAGE x STAGE, 1024-B aligned
-    float2* aux = reinterpret_cast<float2*>(smem + C::NSTAGE * C::STAGE);   // 2 x UN
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE + 2 * UN * 8);
+    float* rec = reinterpret_cast<float*>(smem + C::REC_OFF);               // [2][UN]
+    float* q_qs = reinterpret_cast<float*>(smem + C::QC_OFF);               // [MAX_QBLOCKS][BM]
+    float* q_thr = q_qs + MAX_QBLOCKS * BM;
+    float* q_kww = q_thr + MAX_QBLOCKS * BM;
+    uint16_t* q_ids = reinterpret_cast<uint16_t*>(smem + C::ID_OFF);        // [MAX_QBLOCKS][BM][16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
     uint64_t* full_bar = bars;                          // [NSTAGE]  leader's copy is the live one
     uint64_t* empty_bar = bars + C::NSTAGE;             // [NSTAGE]  per CTA (multicast commit)
     uint64_t* tfull_bar = bars + 2 * C::NSTAGE;         // [2]       per CTA (multicast commit)
@@ -284,8 +319,20 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                      ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
+    // this CTA's queries (128 per query block): per-query constants and term slots, staged once
+    for (int i = threadIdx.x; i < a.n_qblocks * BM; i += BATCH_THREADS) {
+        const int b = (i / BM) * 256 + (int)rank * BM + (i % BM);
+        q_qs[i] = a.qscale[b];
+        q_thr[i] = MODE == 0 ? a.thr[b] : 0.f;
+        q_kww[i] = a.q_kw_w ? a.q_kw_w[b] : 0.f;
+        if (a.q_term_ids) {
+            const int32_t* src = a.q_term_ids + (int64_t)b * ORR_BATCH_MAX_TERMS;
+#pragma unroll
+            for (int t = 0; t < ORR_BATCH_MAX_TERMS; ++t) q_ids[i * ORR_BATCH_MAX_TERMS + t] = src[t] < 0 ? NO_TERM : (uint16_t)src[t];
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();                                   // barriers of BOTH CTAs initialised, TMEM allocated
+    cluster_sync_all();                                   // barriers of BOTH CTAs initialised, TMEM allocated, queries staged
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -304,8 +351,8 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                 const int qb = u % units_per_tile;
                 const int buf = u & 1;
                 mbar_wait(smem_u32(&aux_empty[buf]), ((uint32_t)(u >> 1) & 1u) ^ 1u);
-                mbar_expect_tx(smem_u32(&aux_full[buf]), UN * 8);
-                bulk_g2s(smem_u32(aux + buf * UN), a.rowaux + (int64_t)row_tile * UN, UN * 8, smem_u32(&aux_full[buf]));
+                mbar_expect_tx(smem_u32(&aux_full[buf]), UN * 4);
+                bulk_g2s(smem_u32(rec + buf * UN), a.rowrec + (int64_t)row_tile * UN, UN * 4, smem_u32(&aux_full[buf]));
                 const int qrow = qb * 256 + (int)rank * BM, erow = row_tile * UN + (int)rank * BM;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
@@ -371,30 +418,55 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
         // A warp may only read its own TMEM lane quarter (warp % 4); the two warps that share a
         // quarter split the unit's 8 column chunks.  One thread = one query.
         const int quarter = warp & 3;
-        const int c_begin = ((warp - 2) >> 2) * (UN / 64);
+        const int c_begin = ((warp - 2) >> 2) * HC;
+        const int qloc = quarter * 32 + lane;                               // query within the CTA's 128
         const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+        const bool has_kw = a.q_term_ids != nullptr;
+        // the first 4 term words of the NEXT unit are loaded while this unit's scores are processed
+        uint4 wn[4];
+        auto prefetch_words = [&](int u) {
+            const int row_tile = (cid + (u / units_per_tile) * n_clusters) * a.row_tile_stride;
+            const int qi = (u % units_per_tile) * BM + qloc;
+            const int64_t word0 = (((int64_t)row_tile * UN) >> 5) + c_begin;
+            const uint2 id4 = *reinterpret_cast<const uint2*>(q_ids + qi * ORR_BATCH_MAX_TERMS);
+            wn[0] = kw_load(a, id4.x & 0xFFFFu, word0); wn[1] = kw_load(a, id4.x >> 16, word0);
+            wn[2] = kw_load(a, id4.y & 0xFFFFu, word0); wn[3] = kw_load(a, id4.y >> 16, word0);
+        };
+        if (has_kw && my_units > 0) prefetch_words(0);
         for (int u = 0; u < my_units; ++u) {
             const int t = cid + (u / units_per_tile) * n_clusters;
             const int row_tile = t * a.row_tile_stride;
             const int qb = u % units_per_tile;
             const int buf = u & 1;
-            const int b = qb * 256 + (int)rank * BM + quarter * 32 + lane;   // this thread's query
-            const float qs = a.qscale[b];
-            const float thr = a.mode == 0 ? a.thr[b] : 0.f;
-            const float kww = a.q_kw_w ? a.q_kw_w[b] : 0.f;
+            const int qi = qb * BM + qloc;
+            const int b = qb * 256 + (int)rank * BM + qloc;                 // this thread's query
+            const float qs = q_qs[qi], thr = q_thr[qi], kww = q_kww[qi];
             const int64_t row0 = (int64_t)row_tile * UN;
             KwPlanes kp;
-            if (kww != 0.f) kw_planes(a, b, (row0 >> 5) + c_begin, kp);
+            if (has_kw) {
+                kw_clear(kp);
+                if (kww != 0.f) {
+                    kw_add<3>(kp, wn[0]); kw_add<3>(kp, wn[1]); kw_add<3>(kp, wn[2]); kw_add<3>(kp, wn[3]);
+                    const uint2* idp = reinterpret_cast<const uint2*>(q_ids + qi * ORR_BATCH_MAX_TERMS);
+                    const int64_t word0 = (row0 >> 5) + c_begin;
+#pragma unroll 1
+                    for (int g = 1; g < ORR_BATCH_MAX_TERMS / 4; ++g) {   // queries with more than 4 terms
+                        const uint2 id4 = idp[g];
+                        if ((id4.x & 0xFFFFu) == NO_TERM) break;            // ids are packed front to back
+                        const uint4 w0 = kw_load(a, id4.x & 0xFFFFu, word0), w1 = kw_load(a, id4.x >> 16, word0);
+                        const uint4 w2 = kw_load(a, id4.y & 0xFFFFu, word0), w3 = kw_load(a, id4.y >> 16, word0);
+                        kw_add<5>(kp, w0); kw_add<5>(kp, w1); kw_add<5>(kp, w2); kw_add<5>(kp, w3);
+                    }
+                }
+                if (u + 1 < my_units) prefetch_words(u + 1);
+            }
             mbar_wait(smem_u32(&aux_full[buf]), (uint32_t)(u >> 1) & 1u);
             mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)(u >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float2* ax = aux + buf * UN;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * UN);
-            if (a.mode == 0)
-                epilogue_chunks<0>(a, taddr, ax, b, row0, t, c_begin, qs, thr, kww, kp);
-            else
-                epilogue_chunks<1>(a, taddr, ax, b, row0, t, c_begin, qs, thr, kww, kp);
+            if (has_kw) epilogue_chunks<MODE, true>(a, taddr, rec + buf * UN, b, row0, (int64_t)t * UN, c_begin, qs, thr, kww, kp);
+            else epilogue_chunks<MODE, false>(a, taddr, rec + buf * UN, b, row0, (int64_t)t * UN, c_begin, qs, thr, 0.f, kp);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
@@ -411,27 +483,41 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
     }
 }
 
-// ---- split planes of the store: x = hi + mid (+ dropped lo), bf16 each; 1/|e| per row ------------
+// ---- split planes of the store: x^ = w_cos * x / |x| = hi + mid (+ dropped lo), bf16 each ----------------
+// Rows are stored pre-scaled so the accumulator already is w_cos * cos * |q| and the epilogue needs one FFMA
+// per score.  Rows whose squared norm is 0, non-finite or overflows fp32 get all-zero planes (screen cosine 0,
+// as CosineSimilarity returns for a zero norm, RecallSearchService.cs:84-85).
 __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb, __nv_bfloat16* hi, __nv_bfloat16* mid,
-                                                               float* inv_norm, int64_t first, int64_t n, int dim) {
+                                                               int64_t first, int64_t n, int dim, float w_cos) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = gw; i < n; i += W) {
         const int64_t row = first + i;
-        const float* x = emb + row * dim;
+        const float4* x4 = reinterpret_cast<const float4*>(emb + row * dim);
         float ss = 0.f;
-        for (int c = lane; c < dim; c += 32) {
-            const float v = x[c];
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            const __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
-            hi[row * dim + c] = h;
-            mid[row * dim + c] = m;
-            ss = fmaf(v, v, ss);
+        for (int c = lane; c < dim / 4; c += 32) {
+            const float4 v = x4[c];
+            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) inv_norm[row] = (ss > 0.f && ss < 3e38f) ? rsqrtf(ss) : 0.f;
+        const float scale = (ss > 0.f && ss < 3e38f) ? w_cos * rsqrtf(ss) : 0.f;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(hi + row * dim);
+        __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(mid + row * dim);
+        for (int c = lane; c < dim / 4; c += 32) {                          // second read of the row hits L1/L2
+            const float4 v = x4[c];
+            const float e[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+            __nv_bfloat16 h[4], m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float ek = scale != 0.f ? e[k] : 0.f;                 // NaN/Inf elements of a rejected row -> 0
+                h[k] = __float2bfloat16_rn(ek);
+                m[k] = __float2bfloat16_rn(ek - __bfloat162float(h[k]));
+            }
+            h2[2 * c] = __halves2bfloat162(h[0], h[1]); h2[2 * c + 1] = __halves2bfloat162(h[2], h[3]);
+            m2[2 * c] = __halves2bfloat162(m[0], m[1]); m2[2 * c + 1] = __halves2bfloat162(m[2], m[3]);
+        }
     }
 }
 
@@ -458,23 +544,21 @@ __global__ void __launch_bounds__(128) orr_prep_queries_kernel(const float* q, _
     }
 }
 
-// per-batch row side of the fused score: {w_cos/|e|, w_rec * exp(-age/30d)}; tombstones -> -inf
-__global__ void orr_build_rowaux_kernel(const int64_t* ticks, const float* inv_norm, float2* rowaux, int64_t rows,
-                                        int64_t rows_padded, int64_t now_ticks, float w_cos, float w_rec,
-                                        float decay_per_2p20) {
+// per-batch row side of the fused score: w_rec * exp(-age/30d); tombstones and padding -> -inf
+__global__ void orr_build_rowrec_kernel(const int64_t* ticks, float* rowrec, int64_t rows, int64_t rows_padded,
+                                        int64_t now_ticks, float w_rec, float decay_per_2p20) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows_padded) return;
-    float2 v = make_float2(0.f, -INFINITY);
+    float v = -INFINITY;
     if (i < rows) {
         const int64_t tk = ticks[i];
         if (tk != ORR_DEAD_TICKS) {
             int64_t age20 = (now_ticks - tk) >> 20;
             age20 = age20 < 0 ? 0 : (age20 > 0x7fffffffLL ? 0x7fffffffLL : age20);
-            v.x = w_cos * inv_norm[i];
-            v.y = w_rec * __expf(-(float)(int32_t)age20 * decay_per_2p20);
+            v = w_rec * __expf(-(float)(int32_t)age20 * decay_per_2p20);
         }
     }
-    rowaux[i] = v;
+    rowrec[i] = v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -504,13 +588,13 @@ int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int dim, in
 }  // namespace
 
 // ---- host-side launchers ---------------------------------------------------------------------------
-int orr_batch_build_planes(const float* emb, void* hi, void* mid, float* inv_norm, int64_t first, int64_t n, int dim,
+int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first, int64_t n, int dim, float w_cos,
                            cudaStream_t st) {
     if (n <= 0) return ORR_OK;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    orr_build_planes_kernel<<<sms * 8, 256, 0, st>>>(emb, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid, inv_norm, first, n, dim);
+    orr_build_planes_kernel<<<sms * 8, 256, 0, st>>>(emb, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid, first, n, dim, w_cos);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
@@ -522,32 +606,35 @@ int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qsc
     return ORR_OK;
 }
 
-int orr_batch_build_rowaux(const int64_t* ticks, const float* inv_norm, void* rowaux, int64_t rows, int64_t rows_padded,
-                           int64_t now_ticks, const OrrWeights& w, cudaStream_t st) {
+int orr_batch_build_rowrec(const int64_t* ticks, float* rowrec, int64_t rows, int64_t rows_padded, int64_t now_ticks,
+                           const OrrWeights& w, cudaStream_t st) {
     const float decay = (float)(1048576.0 / ((double)ORR_TICKS_PER_DAY * w.recency_days));
-    orr_build_rowaux_kernel<<<(unsigned)((rows_padded + 255) / 256), 256, 0, st>>>(
-        ticks, inv_norm, (float2*)rowaux, rows, rows_padded, now_ticks, (float)w.w_cos, (float)w.w_rec, decay);
+    orr_build_rowrec_kernel<<<(unsigned)((rows_padded + 255) / 256), 256, 0, st>>>(ticks, rowrec, rows, rows_padded, now_ticks,
+                                                                                  (float)w.w_rec, decay);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
 
-template <int PASSES>
+template <int PASSES, int MODE>
 static int launch_gemm_t(const CUtensorMap& mqh, const CUtensorMap& mqm, const CUtensorMap& meh, const CUtensorMap& mem,
                          const BatchArgs& a, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_gemm_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_gemm_kernel<PASSES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmCfg<PASSES>::SMEM));
         configured = true;
     }
-    orr_batch_gemm_kernel<PASSES><<<grid, BATCH_THREADS, GemmCfg<PASSES>::SMEM, st>>>(mqh, mqm, meh, mem, a);
+    orr_batch_gemm_kernel<PASSES, MODE><<<grid, BATCH_THREADS, GemmCfg<PASSES>::SMEM, st>>>(mqh, mqm, meh, mem, a);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
 
 int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     if (g.dim % BK != 0) { orr_set_error("batch path needs dim %% 64 == 0 (dim=%d)", g.dim); return ORR_E_UNSUPPORTED; }
-    if (g.batch_padded % 256 != 0) { orr_set_error("batch path: padded batch %d not a multiple of 256", g.batch_padded); return ORR_E_INTERNAL; }
+    if (g.batch_padded % 256 != 0 || g.batch_padded > ORR_BATCH_MAX_QUERIES) {
+        orr_set_error("batch path: padded batch %d not a multiple of 256 in [256, %d]", g.batch_padded, ORR_BATCH_MAX_QUERIES);
+        return ORR_E_INTERNAL;
+    }
     CUtensorMap mqh, mqm, meh, mem;
     int rc;
     if ((rc = make_plane_map(&mqh, g.qhi, g.batch_padded, g.dim, BM)) != ORR_OK) return rc;
@@ -561,7 +648,7 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     a.n_qblocks = g.batch_padded / 256;
     a.k_blocks = g.dim / BK;
     a.rows = g.rows;
-    a.rowaux = (const float2*)g.rowaux;
+    a.rowrec = (const float*)g.rowaux;
     a.qscale = g.qscale;
     a.thr = g.thr;
     a.cand = (uint2*)g.cand;
@@ -569,14 +656,15 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     a.cand_cap = g.cand_cap;
     a.dense = g.dense;
     a.dense_ld = g.dense_ld;
-    a.mode = g.dense ? 1 : 0;
     a.term_bits = g.term_bits;
     a.row_words = g.row_words;
     a.q_term_ids = g.q_term_ids;
     a.q_kw_w = g.q_kw_w;
-    a.max_terms = ORR_BATCH_MAX_TERMS;
     const int pairs = std::min<int64_t>(g.sms / 2, a.n_row_tiles);
     if (pairs < 1) return ORR_OK;
-    return g.passes == 1 ? launch_gemm_t<1>(mqh, mqm, meh, mem, a, 2 * pairs, st)
-                         : launch_gemm_t<3>(mqh, mqm, meh, mem, a, 2 * pairs, st);
+    if (g.dense)
+        return g.passes == 1 ? launch_gemm_t<1, 1>(mqh, mqm, meh, mem, a, 2 * pairs, st)
+                             : launch_gemm_t<3, 1>(mqh, mqm, meh, mem, a, 2 * pairs, st);
+    return g.passes == 1 ? launch_gemm_t<1, 0>(mqh, mqm, meh, mem, a, 2 * pairs, st)
+                         : launch_gemm_t<3, 0>(mqh, mqm, meh, mem, a, 2 * pairs, st);
 }

@@ -114,10 +114,12 @@ int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_
 // ---- batched path (orr_batch.cu) ------------------------------------------------------------
 constexpr int ORR_BATCH_TERMS = 16;          // query terms the batched epilogue handles per query
 constexpr int ORR_BATCH_TILE = 256;          // queries per unit == corpus rows per unit (one CTA pair)
+constexpr int ORR_BATCH_MAX_QUERIES = 1024;  // queries one GEMM launch takes (their constants and term slots sit in smem)
+constexpr int ORR_BATCH_MAX_TERM_SLOTS = 65535;  // term bitmap slots are addressed with 16 bits in the kernel
 struct OrrBatchGemm {
     const void* qhi; const void* qmid;       // bf16 [batch_padded][dim]
     const void* ehi; const void* emid;       // bf16 [rows][dim]
-    const void* rowaux;                      // float2 [rows padded to ORR_BATCH_TILE]
+    const void* rowaux;                      // float [rows padded to ORR_BATCH_TILE]: w_rec * recency, -inf = dead/padding
     const float* qscale;                     // [batch_padded]
     const float* thr;                        // [batch_padded] (main pass)
     void* cand; uint32_t* cand_count; int32_t cand_cap;
@@ -126,12 +128,12 @@ struct OrrBatchGemm {
     int64_t rows; int32_t dim; int32_t batch_padded; int32_t tile_stride; int32_t sms;
     int32_t passes;                          // 3 = split precision (default), 1 = bf16 screen
 };
-int orr_batch_build_planes(const float* emb, void* hi, void* mid, float* inv_norm, int64_t first, int64_t n, int dim,
+int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first, int64_t n, int dim, float w_cos,
                            cudaStream_t st);
 int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qscale, int batch, int batch_padded,
                            int dim, cudaStream_t st);
-int orr_batch_build_rowaux(const int64_t* ticks, const float* inv_norm, void* rowaux, int64_t rows, int64_t rows_padded,
-                           int64_t now_ticks, const OrrWeights& w, cudaStream_t st);
+int orr_batch_build_rowrec(const int64_t* ticks, float* rowrec, int64_t rows, int64_t rows_padded, int64_t now_ticks,
+                           const OrrWeights& w, cudaStream_t st);
 int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st);
 int orr_batch_launch_threshold(const float* dense, int64_t ld, int n, int rstar, float* thr, int batch, int batch_padded,
                                cudaStream_t st);
