@@ -111,9 +111,11 @@ int  orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n,
 /* DeleteDocumentAsync (InMemoryIngestionStore.cs:50-55): tombstones the rows. */
 int  orr_store_delete_document(orr_store* s, uint64_t doc_key);
 
-/* Runtime knobs.  "batch_passes": 3 (default) = the batched contraction runs bf16x3 split
- * precision (fp32-grade screen); 1 = single bf16 pass with a proportionally deeper candidate
- * list.  Either way the returned hits are the exact fp64 re-score, proven by the bound check. */
+/* Runtime knobs.  "batch_passes": how the batched contraction SELECTS candidates; the returned hits are
+ * always the exact fp64 re-score, proven complete by the bound check, so every setting returns the same hits.
+ *   0 (default) = auto: one bf16 tcgen05 pass screens with a deep candidate list; queries it cannot prove
+ *                 are re-run with bf16x3 split precision (fp32-grade), then singly
+ *   1 = bf16 screen only (unproven queries run singly)      3 = bf16x3 split precision for every query */
 int  orr_store_set_option(orr_store* s, const char* name, double value);
 
 /* Live (non-tombstoned) rows, and rows physically occupied. */

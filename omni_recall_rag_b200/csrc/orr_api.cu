@@ -51,7 +51,10 @@ struct BatchState {
     float* q = nullptr; void* qhi = nullptr; void* qmid = nullptr;
     float* qscale = nullptr; float* thr = nullptr; float* kww = nullptr; int32_t* qterm = nullptr;
     void* cand = nullptr; uint32_t* cand_count = nullptr; orr_hit* hits = nullptr; int32_t* status = nullptr;
-    OrrProbes* probes = nullptr;
+    OrrBatchProbes* probes = nullptr;
+    // pinned staging of the per-call host arrays (one batched search at a time per store)
+    int32_t* h_qterm = nullptr; float* h_kww = nullptr; OrrBatchProbes* h_probes = nullptr; uint2* h_table = nullptr;
+    int32_t* h_status = nullptr;
     float* dense = nullptr; size_t dense_elems = 0;
     uint32_t* term_bits = nullptr; void* table = nullptr;
     // persistent per-term row bitmaps: 32-bit term hash -> slot in term_bits[slot][row_words]
@@ -88,7 +91,8 @@ struct orr_store {
     std::vector<uint32_t> cap_rows;
     cudaStream_t mut_stream = nullptr;
     std::unique_ptr<BatchState> batch;
-    int batch_passes = 3;            // 3 = bf16x3 split precision, 1 = bf16 screen (orr_store_set_option)
+    int batch_passes = 0;            // 0 = auto (bf16 screen, bf16x3 for what it cannot prove), 1 = screen only, 3 = bf16x3
+    std::atomic<int> batch_hold{0};  // auto mode: batches still to run bf16x3 first after a screen that mostly failed
 };
 
 namespace {
@@ -282,7 +286,7 @@ int orr_store_create(const orr_config* cfg, orr_store** out) {
     std::unique_ptr<orr_store> s(new orr_store());
     s->cfg = *cfg;
     s->sms = prop.multiProcessorCount;
-    if (const char* e = getenv("ORR_BATCH_PASSES")) s->batch_passes = (atoi(e) == 1) ? 1 : 3;
+    if (const char* e = getenv("ORR_BATCH_PASSES")) { const int v = atoi(e); s->batch_passes = (v == 1 || v == 3) ? v : 0; }
     const size_t cap = (size_t)cfg->capacity_rows;
     int rc = [&]() -> int {
         ORR_CUDA_OK(cudaMalloc(&s->d_emb, cap * (size_t)cfg->dim * sizeof(float)));
@@ -309,6 +313,7 @@ void orr_store_destroy(orr_store* s) {
         void* ptrs[] = {b->ehi, b->emid, b->rowaux, b->q, b->qhi, b->qmid, b->qscale, b->thr, b->kww, b->qterm,
                         b->cand, b->cand_count, b->hits, b->status, b->probes, b->dense, b->term_bits, b->table};
         for (void* p : ptrs) cudaFree(p);
+        cudaFreeHost(b->h_qterm); cudaFreeHost(b->h_kww); cudaFreeHost(b->h_probes); cudaFreeHost(b->h_table); cudaFreeHost(b->h_status);
         for (auto& e : b->ev) if (e) cudaEventDestroy(e);
         if (b->stream) cudaStreamDestroy(b->stream);
     }
@@ -320,8 +325,9 @@ int orr_store_set_option(orr_store* s, const char* name, double value) {
     if (!s || !name) { orr_set_error("orr_store_set_option: NULL argument"); return ORR_E_INVALID; }
     std::unique_lock<std::shared_mutex> lock(s->mu);
     if (!strcmp(name, "batch_passes")) {
-        if (value != 1.0 && value != 3.0) { orr_set_error("batch_passes must be 1 or 3"); return ORR_E_INVALID; }
+        if (value != 0.0 && value != 1.0 && value != 3.0) { orr_set_error("batch_passes must be 0 (auto), 1 or 3"); return ORR_E_INVALID; }
         s->batch_passes = (int)value;
+        s->batch_hold = 0;
         return ORR_OK;
     }
     orr_set_error("orr_store_set_option: unknown option '%s'", name);
@@ -592,6 +598,8 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) 
                          (void**)&bs->qterm, &bs->cand, (void**)&bs->cand_count, (void**)&bs->hits, (void**)&bs->status,
                          (void**)&bs->probes};
         for (void** p : ptrs) { cudaFree(*p); *p = nullptr; }
+        cudaFreeHost(bs->h_qterm); cudaFreeHost(bs->h_kww); cudaFreeHost(bs->h_probes); cudaFreeHost(bs->h_status);
+        bs->h_qterm = nullptr; bs->h_kww = nullptr; bs->h_probes = nullptr; bs->h_status = nullptr;
         const size_t B = (size_t)std::max(batch_padded, bs->bcap);
         const size_t K = (size_t)std::max(k, bs->kcap);
         ORR_CUDA_OK(cudaMalloc(&bs->q, B * dim * sizeof(float)));
@@ -605,7 +613,12 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) 
         ORR_CUDA_OK(cudaMalloc(&bs->cand_count, B * sizeof(uint32_t)));
         ORR_CUDA_OK(cudaMalloc(&bs->hits, B * K * sizeof(orr_hit)));
         ORR_CUDA_OK(cudaMalloc(&bs->status, B * 2 * sizeof(int32_t)));
-        ORR_CUDA_OK(cudaMalloc(&bs->probes, B * sizeof(OrrProbes)));
+        ORR_CUDA_OK(cudaMalloc(&bs->probes, B * sizeof(OrrBatchProbes)));
+        ORR_CUDA_OK(cudaMallocHost(&bs->h_qterm, B * ORR_BATCH_TERMS * sizeof(int32_t)));
+        ORR_CUDA_OK(cudaMallocHost(&bs->h_kww, B * sizeof(float)));
+        ORR_CUDA_OK(cudaMallocHost(&bs->h_probes, B * sizeof(OrrBatchProbes)));
+        ORR_CUDA_OK(cudaMallocHost(&bs->h_status, B * 2 * sizeof(int32_t)));
+        if (!bs->h_table) ORR_CUDA_OK(cudaMallocHost(&bs->h_table, BATCH_TABLE_SLOTS * sizeof(uint2)));
         bs->bcap = (int)B; bs->kcap = (int)K;
     }
     return ORR_OK;
@@ -652,7 +665,6 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     bool any_terms = false;
     for (int32_t b = 0; b < batch; ++b) any_terms |= (n_terms && n_terms[b] > 0);
     const int64_t row_words = rows_pad / 32;
-    std::vector<OrrProbes> hp((size_t)batch);
     if (any_terms) {
         int64_t total_terms = 0;
         for (int32_t b = 0; b < batch; ++b) total_terms += std::max(0, n_terms[b]);
@@ -663,18 +675,25 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
             bs->term_slot.clear(); bs->term_slots_used = 0;
             bs->term_version = s->version; bs->term_row_words = row_words;
         }
-        std::vector<int32_t> qterm((size_t)bp * ORR_BATCH_TERMS, -1);
-        std::vector<float> kww((size_t)bp, 0.f);
+        int32_t* qterm = bs->h_qterm;
+        float* kww = bs->h_kww;
+        OrrBatchProbes* hp = bs->h_probes;
+        std::fill(qterm, qterm + (size_t)bp * ORR_BATCH_TERMS, -1);
+        std::fill(kww, kww + bp, 0.f);
+        memset(hp, 0, sizeof(OrrBatchProbes) * (size_t)batch);
         std::vector<uint32_t> distinct;
         {
             std::unordered_map<uint32_t, int32_t> seen;
             for (int32_t b = 0; b < batch; ++b) {
                 const int32_t nt = n_terms[b];
-                rc = build_probes(nt, probe_hash + probe_offsets[b], nullptr, nt, &hp[(size_t)b]);
-                if (rc != ORR_OK) return rc;
-                if (nt > 0) kww[(size_t)b] = (float)(w.w_kw / (double)nt);
-                for (int32_t t = 0; t < nt; ++t)
-                    if (seen.emplace(hp[(size_t)b].h32[t], 0).second) distinct.push_back(hp[(size_t)b].h32[t]);
+                hp[b].n_terms = nt;
+                if (nt > 0) kww[b] = (float)(w.w_kw / (double)nt);
+                for (int32_t t = 0; t < nt; ++t) {
+                    const uint64_t h = probe_hash[probe_offsets[b] + t] ? probe_hash[probe_offsets[b] + t] : 1ULL;
+                    hp[b].h64[t] = h;
+                    const uint32_t h32 = orr_hash_low(h);
+                    if (seen.emplace(h32, 0).second) distinct.push_back(h32);
+                }
             }
         }
         std::vector<uint32_t> missing;
@@ -700,7 +719,8 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         if (!missing.empty()) {
             int table_slots = 256;
             while (table_slots < 4 * (int64_t)missing.size() && table_slots < BATCH_TABLE_SLOTS) table_slots <<= 1;
-            std::vector<uint2> table((size_t)table_slots, make_uint2(0u, 0u));
+            uint2* table = bs->h_table;
+            std::fill(table, table + table_slots, make_uint2(0u, 0u));
             const int32_t first_new = bs->term_slots_used;
             for (uint32_t h : missing) {
                 uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)(table_slots - 1);
@@ -711,19 +731,17 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
             if (!bs->table) ORR_CUDA_OK(cudaMalloc(&bs->table, BATCH_TABLE_SLOTS * 8));
             ORR_CUDA_OK(cudaMemsetAsync(bs->term_bits + (size_t)first_new * (size_t)row_words, 0,
                                         missing.size() * (size_t)row_words * sizeof(uint32_t), st));
-            ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table.data(), (size_t)table_slots * 8, cudaMemcpyHostToDevice, st));
-            ORR_CUDA_OK(cudaStreamSynchronize(st));   // `table` goes out of scope
+            ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table, (size_t)table_slots * 8, cudaMemcpyHostToDevice, st));
             rc = orr_batch_launch_term_bits(s->d_terms32, s->cfg.term_slots, rows, bs->table, table_slots, bs->term_bits,
                                             row_words, st);
             if (rc != ORR_OK) return rc;
         }
         for (int32_t b = 0; b < batch; ++b)
             for (int32_t t = 0; t < n_terms[b]; ++t)
-                qterm[(size_t)b * ORR_BATCH_TERMS + t] = bs->term_slot[hp[(size_t)b].h32[t]];
-        ORR_CUDA_OK(cudaMemcpyAsync(bs->qterm, qterm.data(), qterm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        ORR_CUDA_OK(cudaMemcpyAsync(bs->kww, kww.data(), kww.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-        ORR_CUDA_OK(cudaMemcpyAsync(bs->probes, hp.data(), sizeof(OrrProbes) * (size_t)batch, cudaMemcpyHostToDevice, st));
-        ORR_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope below
+                qterm[(size_t)b * ORR_BATCH_TERMS + t] = bs->term_slot[orr_hash_low(hp[b].h64[t])];
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->qterm, qterm, (size_t)bp * ORR_BATCH_TERMS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->kww, kww, (size_t)bp * sizeof(float), cudaMemcpyHostToDevice, st));
+        ORR_CUDA_OK(cudaMemcpyAsync(bs->probes, hp, sizeof(OrrBatchProbes) * (size_t)batch, cudaMemcpyHostToDevice, st));
         g_batch_terms_built = (int32_t)missing.size();
     }
 
@@ -769,9 +787,9 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     rc = orr_batch_launch_finalize(sh, bs->q, dim, any_terms ? bs->probes : nullptr, w, now_ticks, bs->cand, bs->cand_count,
                                    bs->thr, BATCH_CAND_CAP, M, top_k, k, eps, bs->hits, bs->status, batch, st);
     if (rc != ORR_OK) return rc;
-    std::vector<int32_t> st_host((size_t)batch * 2);
+    int32_t* st_host = bs->h_status;
     ORR_CUDA_OK(cudaEventRecord(bs->ev[4], st));
-    ORR_CUDA_OK(cudaMemcpyAsync(st_host.data(), bs->status, sizeof(int32_t) * 2 * (size_t)batch, cudaMemcpyDeviceToHost, st));
+    ORR_CUDA_OK(cudaMemcpyAsync(st_host, bs->status, sizeof(int32_t) * 2 * (size_t)batch, cudaMemcpyDeviceToHost, st));
     ORR_CUDA_OK(cudaMemcpyAsync(out, bs->hits, sizeof(orr_hit) * (size_t)batch * k, cudaMemcpyDeviceToHost, st));
     ORR_CUDA_OK(cudaEventRecord(bs->ev[5], st));
     ORR_CUDA_OK(cudaStreamSynchronize(st));
@@ -853,10 +871,16 @@ int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
         std::shared_lock<std::shared_mutex> lock(s->mu);
         ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
         memset(&g_timing, 0, sizeof g_timing);
-        const int passes = s->batch_passes;
+        // auto: screen with one bf16 pass (3x less tensor work, deeper candidate lists); queries whose selection the
+        // bound check cannot prove go through bf16x3.  A screen that fails for most of a batch (scores packed closer
+        // than the bf16 error bound) is skipped for the next 16 batches.
+        const bool automatic = s->batch_passes == 0;
+        int passes = automatic ? 1 : s->batch_passes;
+        if (automatic && s->batch_hold.load() > 0) { passes = 3; s->batch_hold.fetch_sub(1); }
         int rc = batch_gemm_path(s, batch, q, n_terms, probe_hash, probe_offsets, now_ticks, top_k, out, n_out, passes, &redo);
         if (rc != ORR_OK) return rc;
-        if (passes == 1 && redo.size() >= 8) {
+        if (automatic && passes == 1 && redo.size() * 2 > (size_t)batch) s->batch_hold = 16;
+        if (automatic && passes == 1 && redo.size() >= 8) {
             // queries the bf16 screen could not prove safe go through the split-precision GEMM as a
             // smaller batch before anything falls back to the per-query path
             const orr_timing first = g_timing;
@@ -940,7 +964,7 @@ int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t 
     gm.qhi = bs->qhi; gm.qmid = bs->qmid; gm.ehi = bs->ehi; gm.emid = bs->emid; gm.rowaux = bs->rowaux;
     gm.qscale = bs->qscale; gm.thr = bs->thr; gm.cand = bs->cand; gm.cand_count = bs->cand_count; gm.cand_cap = BATCH_CAND_CAP;
     gm.rows = rows; gm.dim = dim; gm.batch_padded = bp; gm.sms = s->sms;
-    gm.dense = bs->dense; gm.dense_ld = n_s; gm.tile_stride = tile_stride; gm.passes = s->batch_passes;
+    gm.dense = bs->dense; gm.dense_ld = n_s; gm.tile_stride = tile_stride; gm.passes = s->batch_passes == 1 ? 1 : 3;
     if ((rc = orr_batch_launch_gemm(gm, st)) != ORR_OK) return rc;
     ORR_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)out_ld * sizeof(float), bs->dense, (size_t)n_s * sizeof(float),
                                   (size_t)n_s * sizeof(float), (size_t)batch, cudaMemcpyDeviceToHost, st));

@@ -45,6 +45,19 @@ struct OrrProbes {
     uint8_t  term[ORR_MAX_QUERY_PROBES];         // query term index each probe satisfies
 };
 
+// the batched path's probes: identity (one 64-bit hash per term), <= ORR_BATCH_TERMS terms
+struct OrrBatchProbes {
+    int32_t  n_terms;
+    int32_t  reserved;
+    uint64_t h64[16];
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ int orr_probe_count(const OrrProbes& p) { return p.n_probes; }
+__device__ __forceinline__ uint32_t orr_probe_term(const OrrProbes& p, int i) { return p.term[i]; }
+__device__ __forceinline__ int orr_probe_count(const OrrBatchProbes& p) { return p.n_terms; }
+__device__ __forceinline__ uint32_t orr_probe_term(const OrrBatchProbes&, int i) { return (uint32_t)i; }
+#endif
+
 struct OrrWeights {
     double w_cos, w_kw, w_rec, recency_days;
 };
@@ -137,7 +150,7 @@ int orr_batch_build_rowrec(const int64_t* ticks, float* rowrec, int64_t rows, in
 int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st);
 int orr_batch_launch_threshold(const float* dense, int64_t ld, int n, int rstar, float* thr, int batch, int batch_padded,
                                cudaStream_t st);
-int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrProbes* probes, const OrrWeights& w,
+int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrBatchProbes* probes, const OrrWeights& w,
                               int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
                               int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
                               cudaStream_t st);

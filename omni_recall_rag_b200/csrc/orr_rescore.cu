@@ -71,15 +71,17 @@ __device__ __forceinline__ double exact_qnorm_q(const A& a, const float* q, int 
     return warp_sum_f64(nA);
 }
 
-// exact fused score of one row, computed by a full warp; all lanes return the same value
-template <class A>
-__device__ __forceinline__ double exact_row_q(const A& a, const float* q, const OrrProbes& pr, int64_t row,
+// exact fused score of one row, computed by a full warp; all lanes return the same value.
+// CHUNK = float4 loads per lane issued before the dependent fp64 chains; Q_SHARED = q lives in shared memory.
+template <class A, int CHUNK = EX_CHUNK, bool Q_SHARED = false, class P = OrrProbes>
+__device__ __forceinline__ double exact_row_q(const A& a, const float* q, const P& pr, int64_t row,
                                               int lane, double nA, int64_t* ticks_out) {
     const int64_t ticks = a.sh.ticks[row];
     *ticks_out = ticks;
     // term hashes are fetched up front so their latency overlaps the embedding loads
     uint64_t th[4] = {0, 0, 0, 0};
-    if (pr.n_probes > 0) {
+    const int n_probes = orr_probe_count(pr);
+    if (n_probes > 0) {
         const int spl = a.sh.slots >> 5;
         const uint64_t* t64 = a.sh.terms64 + row * (int64_t)a.sh.slots;
 #pragma unroll
@@ -91,22 +93,40 @@ __device__ __forceinline__ double exact_row_q(const A& a, const float* q, const 
         const float4* x4 = reinterpret_cast<const float4*>(a.sh.emb + row * (int64_t)a.sh.dim);
         const float4* q4 = reinterpret_cast<const float4*>(q);
         double dot = 0.0, nB = 0.0;
-        for (int base = 0; base < nv4; base += 32 * EX_CHUNK) {
-            float4 x[EX_CHUNK], v[EX_CHUNK];
+        for (int base = 0; base < nv4; base += 32 * CHUNK) {
+            float4 x[CHUNK];
 #pragma unroll
-            for (int j = 0; j < EX_CHUNK; ++j) {
+            for (int j = 0; j < CHUNK; ++j) {
                 const int i = base + j * 32 + lane;
-                const bool in = i < nv4;
-                x[j] = in ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[j] = in ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[j] = (i < nv4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (Q_SHARED) {
 #pragma unroll
-            for (int j = 0; j < EX_CHUNK; ++j) {
-                if (base + j * 32 + lane < nv4) {
-                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
-                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
-                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
-                    dot = __dadd_rn(dot, (double)__fmul_rn(v[j].w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
+                for (int j = 0; j < CHUNK; ++j) {
+                    const int i = base + j * 32 + lane;
+                    if (i < nv4) {
+                        const float4 v = q4[i];
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v.x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v.y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v.z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v.w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
+                    }
+                }
+            } else {
+                float4 v[CHUNK];
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) {
+                    const int i = base + j * 32 + lane;
+                    v[j] = (i < nv4) ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < CHUNK; ++j) {
+                    if (base + j * 32 + lane < nv4) {
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
+                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
+                    }
                 }
             }
         }
@@ -116,13 +136,13 @@ __device__ __forceinline__ double exact_row_q(const A& a, const float* q, const 
             cosv = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(nA), __dsqrt_rn(nB)));   // :87
     }
     double kw = 0.0;
-    if (pr.n_probes > 0) {                                          // :110-112
+    if (n_probes > 0) {                                             // :110-112
         uint32_t m0 = 0, m1 = 0;
-        for (int p = 0; p < pr.n_probes; ++p) {
+        for (int p = 0; p < n_probes; ++p) {
             const uint64_t h = pr.h64[p];
             const bool hit = (th[0] == h) | (th[1] == h) | (th[2] == h) | (th[3] == h);
             if (hit) {
-                const uint32_t t = pr.term[p];
+                const uint32_t t = orr_probe_term(pr, p);
                 if (t < 32) m0 |= 1u << t; else m1 |= 1u << (t - 32);
             }
         }
@@ -458,7 +478,7 @@ int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_
 // =====================================================================================================
 namespace {
 
-__device__ OrrProbes g_no_probes;     // zero-initialised: n_probes == 0
+__device__ OrrBatchProbes g_no_probes;     // zero-initialised: no terms
 
 __device__ __forceinline__ uint32_t fkey(float f) {              // monotone; NaN lowest, 0 reserved
     if (f != f) return 1u;
@@ -513,7 +533,7 @@ struct BatchExact {                   // the fields exact_row_q reads
 struct BatchFinArgs {
     BatchExact ex;
     const float* q;                   // [B][dim]
-    const OrrProbes* probes;          // [B] or NULL
+    const OrrBatchProbes* probes;     // [B] or NULL
     const uint2* cand;                // [B][cap]
     const uint32_t* cand_count;       // [B]
     const float* thr;                 // [B]
@@ -525,10 +545,11 @@ struct BatchFinArgs {
 
 constexpr int BATCH_FIN_THREADS = 256;
 
-__global__ void __launch_bounds__(BATCH_FIN_THREADS) orr_batch_finalize_kernel(const BatchFinArgs a) {
+__global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kernel(const BatchFinArgs a) {
     extern __shared__ __align__(16) uint8_t fsm[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(fsm);                       // [cap pow2]
     OrrExact* e = reinterpret_cast<OrrExact*>(fsm + (size_t)a.cap * 8);       // [ORR_BATCH_MAX_SURV]
+    float* qs = reinterpret_cast<float*>(fsm + (size_t)a.cap * 8 + (size_t)ORR_BATCH_MAX_SURV * sizeof(OrrExact));   // [dim]
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t total = a.cand_count[b];
     const int c = (int)min(total, (uint32_t)a.cap);
@@ -561,13 +582,15 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS) orr_batch_finalize_kernel(c
     if (c > M) tau = fmaxf(tau, fkey_inv((uint32_t)(keys[M] >> 32)));
     // exact re-score of the survivors
     const float* q = a.q + (int64_t)b * a.ex.sh.dim;
-    const OrrProbes& pr = a.probes ? a.probes[b] : g_no_probes;
+    const OrrBatchProbes& pr = a.probes ? a.probes[b] : g_no_probes;
     const bool has_q = (a.ex.q_dim == a.ex.sh.dim && a.ex.q_dim > 0);
     const double nA = has_q ? exact_qnorm_q(a.ex, q, lane) : 0.0;
+    if (has_q) for (int i = tid; i < a.ex.sh.dim; i += BATCH_FIN_THREADS) qs[i] = q[i];   // the query is re-read for every row
+    __syncthreads();
     for (int i = warp; i < ns; i += BATCH_FIN_THREADS / 32) {
         const int64_t row = (int64_t)(~(uint32_t)keys[i]);
         int64_t ticks;
-        const double s = exact_row_q(a.ex, q, pr, row, lane, nA, &ticks);
+        const double s = exact_row_q<BatchExact, 6, true, OrrBatchProbes>(a.ex, qs, pr, row, lane, nA, &ticks);
         if (lane == 0) { e[i].score = s; e[i].ticks = ticks; e[i].row = (uint64_t)row; }
     }
     int ep2 = 1;
@@ -663,15 +686,16 @@ int orr_batch_launch_threshold(const float* dense, int64_t ld, int n, int rstar,
     return ORR_OK;
 }
 
-int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrProbes* probes, const OrrWeights& w,
+int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrBatchProbes* probes, const OrrWeights& w,
                               int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
                               int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
                               cudaStream_t st) {
     if (n_surv > ORR_BATCH_MAX_SURV || (cap & (cap - 1)) != 0) { orr_set_error("batch finalize: bad sizes"); return ORR_E_INTERNAL; }
-    const int smem = cap * 8 + ORR_BATCH_MAX_SURV * (int)sizeof(OrrExact);
+    const int smem = cap * 8 + ORR_BATCH_MAX_SURV * (int)sizeof(OrrExact) + sh.dim * (int)sizeof(float);
     static bool configured = false;
     if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8 + ORR_BATCH_MAX_SURV * 24));
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         8192 * 8 + ORR_BATCH_MAX_SURV * 24 + 8192 * 4));
         configured = true;
     }
     BatchFinArgs a;

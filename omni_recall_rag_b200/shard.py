@@ -196,7 +196,7 @@ class RecallShard:
         N.check(N.lib().orr_store_fill_synthetic(self._h, C.byref(spec), first_row, n))
 
     def set_option(self, name: str, value: float) -> None:
-        """orr_store_set_option, e.g. ("batch_passes", 1 | 3)."""
+        """orr_store_set_option, e.g. ("batch_passes", 0 = auto | 1 | 3)."""
         N.check(N.lib().orr_store_set_option(self._h, name.encode(), float(value)))
 
     @property

@@ -38,7 +38,7 @@ def _check_batch(sh, rows, qs, k, what):
     return t
 
 
-@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("passes", [0, 3, 1])
 @pytest.mark.parametrize("dim,gen_dim,n,batch,top_k,n_terms,freq", [
     (768, 3072, 30_000, 64, 100, 4, 0),     # C3 in small: truncated embeddings, top-100
     (768, 3072, 20_000, 40, 50, 16, 8),     # C5 in small: 16-term queries, frequent terms, planted duplicates
@@ -196,3 +196,36 @@ def test_full_size_properties_c5_keyword_heavy_batch_256_top_50():
     """BASELINE.json configs[4]: 16-term queries, half from the 1000 most frequent tokens, planted
     duplicates (same and different timestamps) for the tie chain."""
     _properties_at_full_size(5_000_000, 768, 256, 50, 16, 8, 1000, sample=24)
+
+
+def test_auto_mode_cascades_to_split_precision_when_the_screen_cannot_prove_a_query():
+    """2000 rows packed within ~2e-3 of each other in score: the bf16 screen's error bound (5.5e-3) cannot
+    separate rank k from the survivor boundary, bf16x3 (2e-4) can.  Auto mode must cascade, still return
+    the oracle's hits, and then skip the screen for the following batches."""
+    dim, n, B, k = 128, 3_000, 32, 10
+    rng = np.random.default_rng(17)
+    base = rng.standard_normal(dim).astype(np.float32)
+    base /= np.linalg.norm(base)
+    emb = rng.standard_normal((n, dim)).astype(np.float32)
+    emb[:2000] = base + 0.1 * rng.standard_normal((2000, dim)).astype(np.float32) / np.sqrt(dim)
+    Q = (base + 0.02 * rng.standard_normal((B, dim)) / np.sqrt(dim)).astype(np.float32)
+    ticks = np.full(n, NOW - 5 * DAY, dtype=np.int64)
+    from oracle import oracle_c
+    blob, off = oracle_c.pack_contents([""] * n)
+    with orr.RecallShard(dim, n) as sh:
+        sh.upsert_document_chunks(1, emb, ticks)
+        got = sh.search_batch(Q, None, NOW, k)                       # default = auto
+        t = sh.last_timing()
+        assert t["path"] == N.PATH_BATCH | N.PATH_ESCALATED, t       # bf16 screen, then bf16x3 for the unproven queries
+        assert (t["n_survivors"] & 0xffff) <= B // 4                  # few, if any, needed the single-query path
+        for b in range(B):
+            er, es, _ = oracle_c.search(emb=emb, dim=dim, ticks=ticks, content_blob=blob, content_off=off, query="x",
+                                        qvec=Q[b], now_ticks=NOW, top_k=k)
+            assert_same_ranking(got[b].rows, got[b].scores, er, es, what=f"cascade b={b}")
+        again = sh.search_batch(Q, None, NOW, k)                      # the screen is on hold: bf16x3 directly
+        assert sh.last_timing()["path"] == N.PATH_BATCH
+        assert all(again[b].rows.tolist() == got[b].rows.tolist() for b in range(B))
+        sh.set_option("batch_passes", 1)                              # screen only: unproven queries run singly, same hits
+        single = sh.search_batch(Q, None, NOW, k)
+        assert all(single[b].rows.tolist() == got[b].rows.tolist() and single[b].scores.tolist() == got[b].scores.tolist()
+                   for b in range(B))

@@ -3,7 +3,7 @@
 set -u
 O=gpurun_out; mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_batch.py -x -q 2>&1 | tail -5
-for cfg in "c3 3" "c5 3" "c3 1" "c5 1"; do set -- $cfg
+for cfg in "c3 0" "c5 0" "c3 3" "c5 3"; do set -- $cfg
   timeout 300 python bench.py --workload $1 --batch-passes $2 --no-cpu-baseline > $O/it_$1_p$2.json 2> $O/it_$1_p$2.err || { echo "$1 p$2 FAILED"; tail -3 $O/it_$1_p$2.err; }
   python - <<PY
 import json
