@@ -213,7 +213,10 @@ def workload_config(args):
     return {"workload": f"{total} chunks x {DIM} fp32 row-major in HBM ({args.rows_per_gpu} rows/GPU), single query, "
                         f"hybrid 0.7/0.2/0.1, {N_TERMS} query terms, {TERM_SLOTS} hashed terms/chunk, top-{TOP_K}",
             "rows_total": total, "rows_per_gpu": args.rows_per_gpu, "dim": DIM, "top_k": TOP_K,
-            "parallelism": f"row-sharded x{args.gpus}, NCCL all-gather of per-GPU top-{TOP_K}" if args.gpus > 1 else "1 GPU",
+            "parallelism": (f"row-sharded x{args.gpus}, per-GPU exact top-{TOP_K}, "
+                            + ("fused peer-memory all-gather + merge kernel over NVLink (orr_xchg_allgather_merge); NCCL only "
+                               "for set-up and the timing barrier" if args.exchange == "p2p" else
+                               "NCCL all_gather_into_tensor + merge kernel")) if args.gpus > 1 else "1 GPU",
             "l2": "inputs (12.3 GB/GPU) exceed L2 (126 MB); no flush needed",
             "value_units": "queries/s x (rows_total / 1M)"}
 
@@ -360,6 +363,8 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: how the per-GPU top-k lists meet (fused peer-memory kernel, or NCCL all-gather + merge)")
     ap.add_argument("--batch-passes", type=int, default=0, choices=[0, 1, 3],
                     help="0 = auto (bf16 screen, bf16x3 cascade for unproven queries; the library default), 1, 3")
     args = ap.parse_args()
@@ -385,6 +390,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
@@ -395,7 +401,7 @@ def main():
     spec = synth.make_spec(DIM)
     shard = orr.RecallShard(DIM, n_local, device=local_rank, term_slots=TERM_SLOTS, row_base=row_base)
     shard.fill_synthetic(spec, row_base, n_local)
-    sr = sharded.ShardedRecall(shard)
+    sr = sharded.ShardedRecall(shard, exchange=args.exchange)
 
     n_q = steps + warmup
     queries = [synth.query_host(spec, qi, total_rows, n_terms=N_TERMS) for qi in range(n_q)]
@@ -468,6 +474,7 @@ def main():
     scan_avg_ms = sum(scan_ms) / len(scan_ms)
     achieved = bytes_per_launch / (scan_avg_ms / 1000.0) / 1.0e9
     launches_per_step = 2 + (1 if world > 1 else 0)
+    exchange_kernel = ["orr_xchg_merge_kernel"] if sr.exchange == "p2p" else ["orr_merge_kernel"]
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -479,7 +486,8 @@ def main():
                 "d2h_bytes_per_step": 24 * TOP_K + 8, "ms_per_step": 1000.0 * e2e_s / steps,
                 "c_abi_call_ms": {"median": statistics.median(wall_ms), "p99": sorted(wall_ms)[min(len(wall_ms) - 1, int(0.99 * len(wall_ms)))]}},
         "gpu_launches": launches_per_step * steps,
-        "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel"] + (["orr_merge_kernel"] if world > 1 else []),
+        "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel"] + (exchange_kernel if world > 1 else []),
+        "exchange": sr.exchange,
         "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel<24,1>", "achieved": achieved, "peak": peak,
                      "peak_kind": f"{peak_kind} HBM copy GB/s (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6650 GB/s",
                      "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
@@ -504,6 +512,7 @@ def main():
                       f"rows; C port of RecallSearchService.cs:20-119 (no dotnet in the image)"}
     if rank == 0:
         print(json.dumps(line))
+    sr.close()
     shard.close()
     if world > 1:
         dist.destroy_process_group()

@@ -189,6 +189,27 @@ int  orr_merge_hits_device(int32_t device, const orr_hit* lists_dev, const int32
         int32_t n_lists, int32_t list_stride, int32_t top_k,
         orr_hit* out_dev, int32_t* out_status_dev, void* cuda_stream);
 
+/* ---- fused all-gather + merge over NVLink peer memory ------------------------------------------
+ * The multi-GPU exchange step as ONE kernel per rank instead of an NCCL all-gather plus a merge kernel:
+ * every rank pushes its exact local top-k (k x 24 B + status) into every peer's exchange buffer with stores
+ * over NVLink/NVSwitch, publishes a sequence flag, waits for the other ranks' flags and merges the union with
+ * the reference tie chain.  Collective semantics: every rank calls orr_xchg_allgather_merge once per query,
+ * in the same order.  Status flag ORR_STATUS_XCHG_TIMEOUT is set if a peer did not arrive within 5 s.
+ *   one process per GPU : orr_xchg_create; exchange the 64-byte handles of orr_xchg_get_handle out of band
+ *                         (torch.distributed all_gather), orr_xchg_open_peer for every other rank (CUDA IPC)
+ *   one process, N GPUs : orr_xchg_create per GPU, orr_xchg_attach_peer (cudaDeviceEnablePeerAccess)        */
+typedef struct orr_xchg orr_xchg;
+#define ORR_XCHG_HANDLE_BYTES   64
+#define ORR_STATUS_BOUND_FAILED 1   /* status flags bit0: fp32 selection not proven, re-run through orr_search */
+#define ORR_STATUS_XCHG_TIMEOUT 4   /* status flags bit2: a peer never published its list                     */
+int  orr_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t max_top_k, orr_xchg** out);
+void orr_xchg_destroy(orr_xchg* x);
+int  orr_xchg_get_handle(orr_xchg* x, void* handle_out /* ORR_XCHG_HANDLE_BYTES */);
+int  orr_xchg_open_peer(orr_xchg* x, int32_t peer_rank, const void* handle);
+int  orr_xchg_attach_peer(orr_xchg* x, int32_t peer_rank, orr_xchg* peer);
+int  orr_xchg_allgather_merge(orr_xchg* x, const orr_hit* hits_dev, const int32_t* status_dev, int32_t top_k,
+        orr_hit* out_dev, int32_t* out_status_dev, void* cuda_stream);
+
 const char* orr_last_error(void);
 int  orr_last_timing(orr_timing* out);
 

@@ -16,6 +16,8 @@ ORR_MAX_QUERY_TERMS = 64
 ORR_MAX_QUERY_PROBES = 128
 TICKS_PER_DAY = 864_000_000_000
 
+XCHG_HANDLE_BYTES = 64
+STATUS_BOUND_FAILED, STATUS_XCHG_TIMEOUT = 1, 4
 PATH_FUSED, PATH_EXACT, PATH_SUBSET, PATH_BATCH, PATH_ESCALATED = 1, 2, 3, 4, 0x100
 
 
@@ -77,6 +79,13 @@ _SIGNATURES = {
                                  C.POINTER(C.c_int32)]),
     "orr_merge_hits_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "orr_xchg_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "orr_xchg_destroy": (None, [C.c_void_p]),
+    "orr_xchg_get_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "orr_xchg_open_peer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "orr_xchg_attach_peer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "orr_xchg_allgather_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
     "orr_last_error": (C.c_char_p, []),
     "orr_last_timing": (C.c_int, [C.POINTER(OrrTiming)]),
     "orr_synth_spec_default": (None, [C.POINTER(OrrSynthSpec), C.c_int32]),

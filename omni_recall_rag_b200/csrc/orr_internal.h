@@ -120,6 +120,21 @@ int orr_exact_select(const OrrShard& sh, OrrScratch& sc, int top_k, cudaStream_t
 int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_lists, int stride, int top_k,
                      orr_hit* out_dev, int32_t* out_status_dev, cudaStream_t st);
 
+// fused all-gather + merge over peer memory (orr_xchg.cu owns the buffers)
+constexpr int ORR_XCHG_MAX_WORLD = 16;
+constexpr int ORR_XCHG_SLOTS = 4;
+constexpr int ORR_XCHG_FLAG_TIMEOUT = 4;         // OR-ed into the merged status flags when a peer never arrived
+struct OrrXchgArgs {
+    const orr_hit* src_hits; const int32_t* src_status;     // this rank's local result (device)
+    uint8_t* peer_base[ORR_XCHG_MAX_WORLD];                  // every rank's exchange buffer; [rank] is the local one
+    size_t   slot_bytes;
+    int32_t  world, rank, kmax, top_k, slot;
+    uint32_t seq;
+    unsigned long long timeout_ns;
+    orr_hit* out; int32_t* out_status;
+};
+int orr_launch_xchg_merge(const OrrXchgArgs& a, cudaStream_t st);
+
 int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_t* terms64,
                           int dim, int slots, const orr_synth_spec& spec, uint64_t first_row,
                           int64_t local_first, int64_t n, cudaStream_t st);

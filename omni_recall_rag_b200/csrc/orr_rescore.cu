@@ -320,16 +320,15 @@ __global__ void orr_emit_sorted(const uint64_t* keys, const uint32_t* vals, cons
 // lists[G][stride] hits + status[G][2] ({n, flags}); one CTA orders the union by the reference
 // tie chain and writes the global top-k.  flags are OR-ed so a failed bound check on any
 // shard is visible to the caller.
-__global__ void __launch_bounds__(256) orr_merge_kernel(const orr_hit* lists, const int32_t* status, int n_lists,
-                                                        int stride, int top_k, orr_hit* out, int32_t* out_status) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
+__device__ __forceinline__ void merge_lists_cta(const orr_hit* lists, const int32_t* status, int n_lists, int stride,
+                                                int top_k, orr_hit* out, int32_t* out_status, int extra_flags,
+                                                OrrExact* e) {
     const int tid = threadIdx.x;
     const int total = n_lists * stride;
     int np2 = 1;
     while (np2 < total) np2 <<= 1;
     __shared__ int s_n, s_flags;
-    if (tid == 0) { s_n = 0; s_flags = 0; }
+    if (tid == 0) { s_n = 0; s_flags = extra_flags; }
     __syncthreads();
     for (int i = tid; i < np2; i += blockDim.x) {
         OrrExact v; v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull;
@@ -364,6 +363,71 @@ __global__ void __launch_bounds__(256) orr_merge_kernel(const orr_hit* lists, co
         out[i] = h;
     }
     if (tid == 0) { out_status[0] = n_out; out_status[1] = s_flags; }
+}
+
+__global__ void __launch_bounds__(256) orr_merge_kernel(const orr_hit* lists, const int32_t* status, int n_lists,
+                                                        int stride, int top_k, orr_hit* out, int32_t* out_status) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    merge_lists_cta(lists, status, n_lists, stride, top_k, out, out_status, 0, reinterpret_cast<OrrExact*>(smem_raw));
+}
+
+// ---- fused all-gather + merge over NVLink peer memory (multi-GPU) ----------------
+// Every rank owns an exchange buffer of ORR_XCHG_SLOTS slots; a slot holds hits[world][kmax], status[world][2]
+// and one arrival flag per source rank.  One CTA per rank: (1) PUSH this rank's exact local top-k and status
+// into slot[seq % SLOTS][rank] of EVERY peer with plain stores through the peer mapping, fence, then publish
+// flag = seq with a system-scope release store; (2) wait until all `world` flags of the local slot carry seq
+// (acquire loads; bounded by a timeout so a lost peer surfaces as a status flag, not a hung GPU); (3) order
+// the union with the reference tie chain, exactly like orr_merge_kernel.  No NCCL launch, no host round trip.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) orr_xchg_merge_kernel(const OrrXchgArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const size_t slot_off = (size_t)a.slot * a.slot_bytes;
+    const size_t hits_bytes = (size_t)a.kmax * sizeof(orr_hit);
+    const size_t status_off = (size_t)a.world * hits_bytes;
+    const size_t flags_off = status_off + (size_t)a.world * 2 * sizeof(int32_t);
+    // (1) push
+    const int words = min(max(1, a.top_k), a.kmax) * (int)(sizeof(orr_hit) / 8);   // the caller's list holds top_k hits
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(a.src_hits);
+    for (int p = 0; p < a.world; ++p) {
+        uint64_t* dst = reinterpret_cast<uint64_t*>(a.peer_base[p] + slot_off + (size_t)a.rank * hits_bytes);
+        for (int i = tid; i < words; i += blockDim.x) dst[i] = src[i];
+        if (tid < 2) reinterpret_cast<int32_t*>(a.peer_base[p] + slot_off + status_off)[2 * a.rank + tid] = a.src_status[tid];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < a.world) st_release_sys(reinterpret_cast<uint32_t*>(a.peer_base[tid] + slot_off + flags_off) + a.rank, a.seq);
+    // (2) wait for every source rank
+    __shared__ int s_timeout;
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    uint8_t* mine = a.peer_base[a.rank] + slot_off;
+    if (tid < a.world) {
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + flags_off) + tid;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) != a.seq) {
+            if (global_timer_ns() - t0 > a.timeout_ns) { atomicOr(&s_timeout, 1); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    // (3) merge
+    merge_lists_cta(reinterpret_cast<const orr_hit*>(mine), reinterpret_cast<const int32_t*>(mine + status_off), a.world,
+                    a.kmax, a.top_k, a.out, a.out_status, s_timeout ? ORR_XCHG_FLAG_TIMEOUT : 0,
+                    reinterpret_cast<OrrExact*>(smem_raw));
 }
 
 }  // namespace
@@ -468,6 +532,25 @@ int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_
     while (np2 < total) np2 <<= 1;
     orr_merge_kernel<<<1, 256, np2 * sizeof(OrrExact), st>>>(lists_dev, status_dev, n_lists, stride, top_k, out_dev,
                                                             out_status_dev);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+int orr_launch_xchg_merge(const OrrXchgArgs& a, cudaStream_t st) {
+    const int total = a.world * a.kmax;
+    if (a.world < 1 || a.world > ORR_XCHG_MAX_WORLD || a.kmax < 1 || total > ORR_SORT_MAX) {
+        orr_set_error("xchg merge: %d ranks x %d exceed the sorter", a.world, a.kmax);
+        return ORR_E_UNSUPPORTED;
+    }
+    static bool configured = false;
+    if (!configured) {
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ORR_SORT_MAX * (int)sizeof(OrrExact)));
+        configured = true;
+    }
+    int np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    orr_xchg_merge_kernel<<<1, 256, np2 * sizeof(OrrExact), st>>>(a);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }

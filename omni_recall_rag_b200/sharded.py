@@ -8,10 +8,14 @@ row is computed by the same deterministic function on every rank, so
 global top-k  ⊆  ∪ local top-k   and the merge (score desc, ticks desc, global row asc) gives
 exactly what the single-shard scorer would return.
 
-The only collective on the data path is the all-gather of k·24 B per rank.
+The only exchange on the data path is the all-gather of k·24 B per rank.  On GPUs the device-resident
+path does it with liborr's own fused kernel (orr_xchg_allgather_merge: every rank stores its list straight
+into its peers' HBM over NVLink and merges what arrived, one launch); `exchange="nccl"` keeps the NCCL
+all_gather_into_tensor + merge-kernel form for comparison.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, Optional, Tuple
 
 import numpy as np
@@ -52,7 +56,7 @@ class ShardedRecall:
     gather/merge logic under gloo."""
 
     def __init__(self, shard: Optional[RecallShard] = None, *, group=None,
-                 local_search: Optional[Callable[..., Hits]] = None):
+                 local_search: Optional[Callable[..., Hits]] = None, exchange: str = "p2p", max_top_k: int = 128):
         import torch.distributed as dist
 
         self.dist = dist
@@ -66,12 +70,64 @@ class ShardedRecall:
             local_search = lambda q, terms, now, k: shard.search(q, terms, now, k)  # noqa: E731
         self.local_search = local_search
         self._dev_bufs = {}
+        self._xchg = None
+        self.max_top_k = max_top_k
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange if (self.world > 1 and shard is not None) else "none"
+        if self.exchange == "p2p" and dist.get_backend(group) != "nccl":
+            self.exchange = "nccl"                       # CPU tests (gloo): there is no peer memory
+        if self.exchange == "p2p":
+            self._open_exchange()
+
+    def _open_exchange(self) -> None:
+        """One exchange buffer per rank; the 64-byte CUDA IPC handles travel over torch.distributed."""
+        import torch
+
+        L = N.lib()
+        x = C.c_void_p()
+        N.check(L.orr_xchg_create(self.shard.device, self.world, self.rank, self.max_top_k, C.byref(x)))
+        self._xchg = x
+        mine = (C.c_ubyte * N.XCHG_HANDLE_BYTES)()
+        N.check(L.orr_xchg_get_handle(x, C.cast(mine, C.c_void_p)))
+        dev = torch.device("cuda", self.shard.device)
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        allh = torch.empty((self.world, N.XCHG_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+        self.dist.all_gather_into_tensor(allh, t, group=self.group)
+        allh = allh.cpu().numpy()
+        for r in range(self.world):
+            if r != self.rank:
+                h = (C.c_ubyte * N.XCHG_HANDLE_BYTES)(*allh[r].tolist())
+                N.check(L.orr_xchg_open_peer(x, r, C.cast(h, C.c_void_p)))
+        self.dist.barrier(group=self.group)            # every rank has every peer mapped before the first push
+
+    def close(self) -> None:
+        if self._xchg is not None:
+            import torch
+
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)        # no peer may still be pushing into this rank's buffer
+            N.lib().orr_xchg_destroy(self._xchg)
+            self._xchg = None
 
     # -- host-buffer path (end-to-end: query in host memory, hits back in host memory) --------
     def search(self, q: Optional[np.ndarray], terms: QueryTerms, now_ticks: int, top_k: int) -> Hits:
         import torch
 
         k = max(1, int(top_k))
+        if (self.world > 1 and self._xchg is not None and q is not None and len(q) == self.shard.dim
+                and k <= min(self.max_top_k, 224)):
+            # GPUs: query up once, fused scan + exact re-score + peer-memory exchange on the device, hits down once
+            dev = torch.device("cuda", self.shard.device)
+            q_dev = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(dev, non_blocking=True)
+            hits_dev, status_dev = self.search_device(q_dev, terms, now_ticks, top_k)
+            hits, flags = hits_from_device(hits_dev, status_dev)
+            if flags == 0:
+                return hits
+            if flags & N.STATUS_XCHG_TIMEOUT:
+                raise RuntimeError("sharded search: a peer rank never published its hit list (exchange time-out)")
+            # a shard could not prove its fp32 selection: every rank sees the same OR-ed flag and re-runs below,
+            # where orr_search escalates to the exact path
         local = self.local_search(q, terms, now_ticks, top_k)
         if self.world == 1:
             return local
@@ -93,8 +149,9 @@ class ShardedRecall:
     def search_device(self, q_dev, terms: QueryTerms, now_ticks: int, top_k: int):
         """q_dev: torch float32 CUDA tensor [dim].  Returns (hits_dev uint8[k*24], status_dev
         int32[2] = {n_out, flags}) on the current stream: local fused scan + exact re-score
-        (orr_search_device), all_gather_into_tensor of the k·24 B candidate lists over NCCL,
-        one-CTA merge (orr_merge_hits_device)."""
+        (orr_search_device), then the exchange: the fused peer-memory all-gather + merge kernel
+        (orr_xchg_allgather_merge), or with exchange="nccl" all_gather_into_tensor of the k·24 B lists
+        followed by the one-CTA merge (orr_merge_hits_device)."""
         import torch
 
         k = max(1, int(top_k))
@@ -114,6 +171,12 @@ class ShardedRecall:
                                  b["status"].data_ptr(), stream)
         if self.world == 1:
             return b["hits"], b["status"]
+        if self._xchg is not None:
+            if k > self.max_top_k:
+                raise ValueError(f"top_k {k} > max_top_k {self.max_top_k} of the exchange buffers")
+            N.check(N.lib().orr_xchg_allgather_merge(self._xchg, b["hits"].data_ptr(), b["status"].data_ptr(), top_k,
+                                                     b["out_hits"].data_ptr(), b["out_status"].data_ptr(), stream))
+            return b["out_hits"], b["out_status"]
         self.dist.all_gather_into_tensor(b["all_hits"], b["hits"], group=self.group)
         self.dist.all_gather_into_tensor(b["all_status"], b["status"], group=self.group)
         stream = torch.cuda.current_stream(q_dev.device).cuda_stream

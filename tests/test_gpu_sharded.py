@@ -54,3 +54,86 @@ def test_virtual_ranks_on_one_gpu_match_the_single_shard_oracle(world):
     finally:
         for sh in shards:
             sh.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_peer_memory_exchange_with_virtual_ranks(world):
+    """orr_xchg_allgather_merge with `world` ranks emulated on one GPU (same-process attach, one stream per rank so
+    the ranks' one-CTA kernels can wait for each other): every rank ends with the oracle's global top-k."""
+    import ctypes as C
+    import torch
+
+    dim, total, k, kmax = 256, 9_001, 10, 16
+    spec = synth.make_spec(dim, gen_dim=dim, dup_row_ppm=20000)
+    rows = synth.rows_host(spec, 0, total)
+    L = N.lib()
+    shards, xs = [], []
+    dev = torch.device("cuda", 0)
+    try:
+        for r in range(world):
+            base, n_local = sharded.shard_rows(total, world, r)
+            sh = orr.RecallShard(dim, n_local, row_base=base)
+            sh.fill_synthetic(spec, base, n_local)
+            shards.append(sh)
+            x = C.c_void_p()
+            N.check(L.orr_xchg_create(0, world, r, kmax, C.byref(x)))
+            xs.append(x)
+        for r in range(world):
+            for p in range(world):
+                if p != r:
+                    N.check(L.orr_xchg_attach_peer(xs[r], p, xs[p]))
+        streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+        local = [torch.zeros(k * 24, dtype=torch.uint8, device=dev) for _ in range(world)]
+        status = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(world)]
+        out = [torch.zeros(k * 24, dtype=torch.uint8, device=dev) for _ in range(world)]
+        out_status = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(world)]
+        for qi in range(9):                                   # > ORR_XCHG_SLOTS queries: slots are reused
+            q = synth.query_host(spec, qi, total, n_terms=4)
+            er, es, _ = oracle_search_synth(rows, q, NOW, k)
+            q_dev = torch.from_numpy(q.q).to(dev)
+            main = torch.cuda.current_stream(dev).cuda_stream
+            for r, sh in enumerate(shards):
+                sh.search_device(q_dev.data_ptr(), q.terms, NOW, k, local[r].data_ptr(), status[r].data_ptr(), main)
+            torch.cuda.synchronize()
+            for r in range(world):
+                N.check(L.orr_xchg_allgather_merge(xs[r], local[r].data_ptr(), status[r].data_ptr(), k, out[r].data_ptr(),
+                                                   out_status[r].data_ptr(), streams[r].cuda_stream))
+            torch.cuda.synchronize()
+            for r in range(world):
+                got, flags = sharded.hits_from_device(out[r], out_status[r])
+                assert flags == 0, f"rank {r}: flags {flags}"
+                assert_same_ranking(got.rows, got.scores, er, es, what=f"xchg world={world} rank={r} q={qi}")
+    finally:
+        torch.cuda.synchronize()
+        for x in xs:
+            L.orr_xchg_destroy(x)
+        for sh in shards:
+            sh.close()
+
+
+def test_exchange_reports_a_missing_peer_instead_of_hanging():
+    """A rank whose peer never publishes gets status flag ORR_STATUS_XCHG_TIMEOUT after the time-out."""
+    import ctypes as C
+    import torch
+
+    L = N.lib()
+    dev = torch.device("cuda", 0)
+    xs = []
+    try:
+        for r in range(2):
+            x = C.c_void_p()
+            N.check(L.orr_xchg_create(0, 2, r, 4, C.byref(x)))
+            xs.append(x)
+        N.check(L.orr_xchg_attach_peer(xs[0], 1, xs[1]))
+        N.check(L.orr_xchg_attach_peer(xs[1], 0, xs[0]))
+        hits = torch.zeros(4 * 24, dtype=torch.uint8, device=dev)
+        st = torch.tensor([0, 0], dtype=torch.int32, device=dev)
+        out = torch.zeros(4 * 24, dtype=torch.uint8, device=dev)
+        out_st = torch.zeros(2, dtype=torch.int32, device=dev)
+        N.check(L.orr_xchg_allgather_merge(xs[0], hits.data_ptr(), st.data_ptr(), 4, out.data_ptr(), out_st.data_ptr(),
+                                           torch.cuda.current_stream(dev).cuda_stream))       # rank 1 never calls
+        torch.cuda.synchronize()
+        assert int(out_st.cpu()[1]) & N.STATUS_XCHG_TIMEOUT
+    finally:
+        for x in xs:
+            L.orr_xchg_destroy(x)

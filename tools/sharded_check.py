@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N tools/sharded_check.py — parity of the NCCL row-sharded path.
+"""torchrun --nproc-per-node N tools/sharded_check.py — parity of the row-sharded path (both exchanges).
 
 Each rank owns a row block of one synthetic corpus on its own GPU; every rank must return
 exactly what the CPU oracle returns for the whole corpus, through both the host-buffer path
-(ShardedRecall.search) and the device-resident path (search_device + NCCL all-gather +
-device merge)."""
+(ShardedRecall.search) and the device-resident path (search_device + the fused peer-memory
+all-gather/merge kernel, and the NCCL all-gather + device merge form), which are also timed."""
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -30,7 +31,9 @@ def main():
     base, n_local = sharded.shard_rows(total, world, rank)
     sh = orr.RecallShard(dim, n_local, device=local, row_base=base)
     sh.fill_synthetic(spec, base, n_local)
-    sr = sharded.ShardedRecall(sh)
+    sr = sharded.ShardedRecall(sh, exchange="p2p")
+    sr_nccl = sharded.ShardedRecall(sh, exchange="nccl")
+    assert sr.exchange == "p2p" and sr_nccl.exchange == "nccl"
     rows = synth.rows_host(spec, 0, total) if rank == 0 else None
     ok = 0
     for qi in range(8):
@@ -41,6 +44,10 @@ def main():
         got_dev, flags = sharded.hits_from_device(hd, sd)
         assert flags == 0
         assert got_dev.rows.tolist() == got.rows.tolist() and got_dev.scores.tolist() == got.scores.tolist()
+        hd2, sd2 = sr_nccl.search_device(torch.from_numpy(q.q).to(dev), q.terms, spec.now_ticks, k)
+        torch.cuda.synchronize()
+        got_nccl, flags2 = sharded.hits_from_device(hd2, sd2)
+        assert flags2 == 0 and got_nccl.rows.tolist() == got.rows.tolist() and got_nccl.scores.tolist() == got.scores.tolist()
         # every rank holds the same answer
         t = torch.from_numpy(got.rows.astype(np.int64)).to(dev)
         ref = t.clone()
@@ -52,7 +59,24 @@ def main():
         ok += 1
     dist.barrier()
     if rank == 0:
-        print(f"sharded parity ok: world={world}, {ok} queries, {total} x {dim}")
+        print(f"sharded parity ok: world={world}, {ok} queries, {total} x {dim}, exchanges p2p + nccl")
+    # exchange cost: the same 200 device-resident queries through each exchange (small shard => exchange-dominated)
+    q = synth.query_host(spec, 3, total, n_terms=4)
+    qd = torch.from_numpy(q.q).to(dev)
+    for name, s_ in (("p2p", sr), ("nccl", sr_nccl), ("p2p", sr), ("nccl", sr_nccl)):
+        for _ in range(20):
+            s_.search_device(qd, q.terms, spec.now_ticks, k)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            s_.search_device(qd, q.terms, spec.now_ticks, k)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 200.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"  {name:5s}: {t.item() * 1000:.1f} us per query (scan + re-score + exchange, {n_local} rows/GPU, max over ranks)")
+    sr.close()
     sh.close()
     dist.destroy_process_group()
 
