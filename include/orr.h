@@ -86,6 +86,7 @@ typedef struct orr_timing {
 #define ORR_PATH_EXACT      2   /* full fp64 scan (no-embedding mode, large k, or escalation) */
 #define ORR_PATH_SUBSET     3   /* candidate_cap > 0: exact scoring of the capped subset      */
 #define ORR_PATH_BATCH      4   /* tcgen05 batched contraction + re-rank                      */
+#define ORR_PATH_TEXT       5   /* orr_search_text: substring matching on the chunk text + exact scoring */
 #define ORR_PATH_ESCALATED  0x100 /* OR-ed in when the fused path's bound check failed        */
 
 void orr_config_default(orr_config* cfg);
@@ -107,6 +108,15 @@ void orr_store_destroy(orr_store* s);
 int  orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n,
         const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
         const uint64_t* term_hashes, const uint32_t* term_offsets, uint64_t* out_rows);
+
+/* The same, also keeping each chunk's lower-cased UTF-8 Content in HBM (text mode, orr_search_text):
+ * chunk i's text is text_lower_utf8[text_offsets[i] .. text_offsets[i+1]).  Lower-casing
+ * (ToLowerInvariant, RecallSearchService.cs:110) is the host's job.  Either every row of a store is
+ * given text or none is.  Option "text_bytes_per_row" (default 1024) sizes the arena up front. */
+int  orr_store_upsert_document_chunks_text(orr_store* s, uint64_t doc_key, int32_t n,
+        const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
+        const uint64_t* term_hashes, const uint32_t* term_offsets,
+        const char* text_lower_utf8, const uint64_t* text_offsets, uint64_t* out_rows);
 
 /* DeleteDocumentAsync (InMemoryIngestionStore.cs:50-55): tombstones the rows. */
 int  orr_store_delete_document(orr_store* s, uint64_t doc_key);
@@ -148,6 +158,18 @@ int  orr_tokenize_content(const char* utf8, int32_t len, uint64_t* out_hashes, i
  */
 int  orr_search(orr_store* s, const float* q, int32_t q_dim,
         int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+        int64_t now_ticks, int32_t top_k, int32_t candidate_cap,
+        orr_hit* out, int32_t* n_out);
+
+/* Text mode: the keyword predicate of RecallSearchService.cs:110-111 evaluated literally — for every
+ * chunk and query term, an ordinal substring search of the term in the chunk's lower-cased content kept
+ * in HBM — followed by the exact fp64 scoring of every candidate row.  No vocabulary expansion, no probe
+ * limit: this is the path for terms that are substrings of many words ("ai", "go", one letter).  Terms
+ * are the lower-cased UTF-8 bytes of the A-2 filtered query terms: term t =
+ * terms_lower_utf8[term_offsets[t] .. term_offsets[t+1]); <= 64 terms, <= 256 bytes each.  Other
+ * arguments as orr_search.  Slower than the fused scan (every row is scored in fp64). */
+int  orr_search_text(orr_store* s, const float* q, int32_t q_dim,
+        int32_t n_terms, const char* terms_lower_utf8, const uint32_t* term_offsets,
         int64_t now_ticks, int32_t top_k, int32_t candidate_cap,
         orr_hit* out, int32_t* n_out);
 

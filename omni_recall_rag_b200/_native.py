@@ -18,7 +18,7 @@ TICKS_PER_DAY = 864_000_000_000
 
 XCHG_HANDLE_BYTES = 64
 STATUS_BOUND_FAILED, STATUS_XCHG_TIMEOUT = 1, 4
-PATH_FUSED, PATH_EXACT, PATH_SUBSET, PATH_BATCH, PATH_ESCALATED = 1, 2, 3, 4, 0x100
+PATH_FUSED, PATH_EXACT, PATH_SUBSET, PATH_BATCH, PATH_TEXT, PATH_ESCALATED = 1, 2, 3, 4, 5, 0x100
 
 
 class OrrConfig(C.Structure):
@@ -60,6 +60,9 @@ _SIGNATURES = {
     "orr_store_destroy": (None, [C.c_void_p]),
     "orr_store_upsert_document_chunks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p,
                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "orr_store_upsert_document_chunks_text": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p,
+                                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p,
+                                                        C.c_void_p]),
     "orr_store_delete_document": (C.c_int, [C.c_void_p, C.c_uint64]),
     "orr_store_count": (C.c_int64, [C.c_void_p]),
     "orr_store_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
@@ -69,6 +72,8 @@ _SIGNATURES = {
     "orr_tokenize_content": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "orr_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                              C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    "orr_search_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_void_p, C.c_int64,
+                                  C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "orr_search_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "orr_search_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -34,6 +34,9 @@ struct SearchCtx {
     uint32_t* h_rows = nullptr;    // pinned [ORR_SORT_MAX]
     int32_t hits_cap = 0;
     int64_t exact_rows_cap = 0;
+    // text mode scratch
+    OrrTextTerms* d_terms = nullptr; OrrTextTerms* h_terms = nullptr;   // device / pinned
+    uint32_t* d_kw_bits = nullptr; size_t kw_bits_words = 0;
 };
 
 thread_local orr_timing g_timing{};
@@ -90,6 +93,11 @@ struct orr_store {
     int32_t cap_value = -1;
     std::vector<uint32_t> cap_rows;
     cudaStream_t mut_stream = nullptr;
+    // text mode: lower-cased UTF-8 chunk content (orr_store_upsert_document_chunks_text)
+    uint8_t* d_text = nullptr; uint64_t* d_text_off = nullptr; uint32_t* d_text_len = nullptr;
+    uint64_t text_used = 0, text_cap = 0;
+    int64_t text_rows = 0;            // rows appended WITH text; text mode needs text_rows == rows_used
+    double text_bytes_per_row = 1024.0;
     std::unique_ptr<BatchState> batch;
     int batch_passes = 0;            // 0 = auto (bf16 screen, bf16x3 for what it cannot prove), 1 = screen only, 3 = bf16x3
     std::atomic<int> batch_hold{0};  // auto mode: batches still to run bf16x3 first after a screen that mostly failed
@@ -115,6 +123,7 @@ void free_ctx(SearchCtx* c) {
     cudaFree(c->sc.scores64); cudaFree(c->sc.cub_tmp);
     cudaFree(c->sc.sort_keys[0]); cudaFree(c->sc.sort_keys[1]);
     cudaFree(c->sc.sort_vals[0]); cudaFree(c->sc.sort_vals[1]);
+    cudaFree(c->d_terms); cudaFree(c->d_kw_bits); cudaFreeHost(c->h_terms);
     cudaFreeHost(c->h_q); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_status); cudaFreeHost(c->h_rows);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -318,6 +327,7 @@ void orr_store_destroy(orr_store* s) {
         if (b->stream) cudaStreamDestroy(b->stream);
     }
     cudaFree(s->d_emb); cudaFree(s->d_ticks); cudaFree(s->d_terms32); cudaFree(s->d_terms64);
+    cudaFree(s->d_text); cudaFree(s->d_text_off); cudaFree(s->d_text_len);
     delete s;
 }
 
@@ -328,6 +338,12 @@ int orr_store_set_option(orr_store* s, const char* name, double value) {
         if (value != 0.0 && value != 1.0 && value != 3.0) { orr_set_error("batch_passes must be 0 (auto), 1 or 3"); return ORR_E_INVALID; }
         s->batch_passes = (int)value;
         s->batch_hold = 0;
+        return ORR_OK;
+    }
+    if (!strcmp(name, "text_bytes_per_row")) {
+        if (s->d_text) { orr_set_error("text_bytes_per_row must be set before the first chunk text arrives"); return ORR_E_INVALID; }
+        if (!(value >= 16.0 && value <= 1048576.0)) { orr_set_error("text_bytes_per_row out of range"); return ORR_E_INVALID; }
+        s->text_bytes_per_row = value;
         return ORR_OK;
     }
     orr_set_error("orr_store_set_option: unknown option '%s'", name);
@@ -352,11 +368,12 @@ static int tombstone_locked(orr_store* s, uint64_t doc_key) {
     return ORR_OK;
 }
 
-int orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n, const float* emb,
-                                     const uint8_t* has_emb, const int64_t* created_ticks,
-                                     const uint64_t* term_hashes, const uint32_t* term_offsets,
-                                     uint64_t* out_rows) {
+static int upsert_impl(orr_store* s, uint64_t doc_key, int32_t n, const float* emb,
+                       const uint8_t* has_emb, const int64_t* created_ticks,
+                       const uint64_t* term_hashes, const uint32_t* term_offsets,
+                       const char* text, const uint64_t* text_offsets, uint64_t* out_rows) {
     if (!s || n < 0 || (n > 0 && !created_ticks)) { orr_set_error("upsert: bad argument"); return ORR_E_INVALID; }
+    if ((text != nullptr) != (text_offsets != nullptr)) { orr_set_error("upsert: text and text_offsets go together"); return ORR_E_INVALID; }
     if (n == 0) return ORR_OK;                         // UpsertChunksAsync ignores empty batches (:19-20)
     const int dim = s->cfg.dim, slots = s->cfg.term_slots;
     for (int32_t i = 0; i < n; ++i) {
@@ -375,9 +392,48 @@ int orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n, 
         orr_set_error("upsert: store full (%lld + %d > %lld rows)", (long long)s->rows_used, n, (long long)s->cfg.capacity_rows);
         return ORR_E_OOM;
     }
+    const int64_t first = s->rows_used;
+    if (text_offsets) {
+        for (int32_t i = 0; i < n; ++i)
+            if (text_offsets[i + 1] < text_offsets[i] || text_offsets[i + 1] - text_offsets[i] > 0xffffffffull) {
+                orr_set_error("upsert: bad text offsets at chunk %d", i);
+                return ORR_E_INVALID;
+            }
+        if (s->text_rows != first) {
+            orr_set_error("upsert: chunk text must be given for every row of the store or for none (%lld of %lld rows have it)",
+                          (long long)s->text_rows, (long long)first);
+            return ORR_E_INVALID;
+        }
+        if (!s->d_text) {
+            const uint64_t cap_bytes = (uint64_t)((double)s->cfg.capacity_rows * s->text_bytes_per_row) + 4096;
+            ORR_CUDA_OK(cudaMalloc(&s->d_text, cap_bytes + 64));
+            ORR_CUDA_OK(cudaMalloc(&s->d_text_off, sizeof(uint64_t) * (size_t)s->cfg.capacity_rows));
+            ORR_CUDA_OK(cudaMalloc(&s->d_text_len, sizeof(uint32_t) * (size_t)s->cfg.capacity_rows));
+            s->text_cap = cap_bytes;
+        }
+        const uint64_t total = text_offsets[n] - text_offsets[0];
+        if (s->text_used + total > s->text_cap) {
+            orr_set_error("upsert: text arena full (%llu + %llu > %llu bytes; raise option text_bytes_per_row)",
+                          (unsigned long long)s->text_used, (unsigned long long)total, (unsigned long long)s->text_cap);
+            return ORR_E_OOM;
+        }
+    }
     int rc = tombstone_locked(s, doc_key);
     if (rc != ORR_OK) return rc;
-    const int64_t first = s->rows_used;
+    if (text_offsets) {
+        const uint64_t total = text_offsets[n] - text_offsets[0];
+        std::vector<uint64_t> off((size_t)n);
+        std::vector<uint32_t> len((size_t)n);
+        for (int32_t i = 0; i < n; ++i) {
+            off[(size_t)i] = s->text_used + (text_offsets[i] - text_offsets[0]);
+            len[(size_t)i] = (uint32_t)(text_offsets[i + 1] - text_offsets[i]);
+        }
+        if (total) ORR_CUDA_OK(cudaMemcpy(s->d_text + s->text_used, text + text_offsets[0], total, cudaMemcpyHostToDevice));
+        ORR_CUDA_OK(cudaMemcpy(s->d_text_off + first, off.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice));
+        ORR_CUDA_OK(cudaMemcpy(s->d_text_len + first, len.data(), sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+        s->text_used += total;
+        s->text_rows += n;
+    }
     if (emb) {
         ORR_CUDA_OK(cudaMemcpy(s->d_emb + first * (int64_t)dim, emb, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice));
         if (has_emb)
@@ -408,6 +464,21 @@ int orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n, 
     s->version++;
     if (out_rows) for (int32_t i = 0; i < n; ++i) out_rows[i] = s->cfg.row_base + (uint64_t)(first + i);
     return ORR_OK;
+}
+
+int orr_store_upsert_document_chunks(orr_store* s, uint64_t doc_key, int32_t n, const float* emb,
+                                     const uint8_t* has_emb, const int64_t* created_ticks,
+                                     const uint64_t* term_hashes, const uint32_t* term_offsets,
+                                     uint64_t* out_rows) {
+    return upsert_impl(s, doc_key, n, emb, has_emb, created_ticks, term_hashes, term_offsets, nullptr, nullptr, out_rows);
+}
+
+int orr_store_upsert_document_chunks_text(orr_store* s, uint64_t doc_key, int32_t n, const float* emb,
+                                          const uint8_t* has_emb, const int64_t* created_ticks,
+                                          const uint64_t* term_hashes, const uint32_t* term_offsets,
+                                          const char* text_lower_utf8, const uint64_t* text_offsets, uint64_t* out_rows) {
+    if (n > 0 && (!text_lower_utf8 || !text_offsets)) { orr_set_error("upsert_text: text and text_offsets are required"); return ORR_E_INVALID; }
+    return upsert_impl(s, doc_key, n, emb, has_emb, created_ticks, term_hashes, term_offsets, text_lower_utf8, text_offsets, out_rows);
 }
 
 int orr_store_delete_document(orr_store* s, uint64_t doc_key) {
@@ -539,6 +610,131 @@ int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, con
     g_timing.finalize_ms = fin_ms;
     g_timing.total_device_ms = scan_ms + fin_ms;
     g_timing.path = path;
+    g_timing.rows_scanned = (candidate_cap > 0) ? g_timing.n_survivors : s->rows_used;
+    g_timing.wall_ms = (float)(now_ms() - t0);
+    return ORR_OK;
+}
+
+// ---- text mode: the keyword predicate evaluated on the chunk text itself --------------------------
+int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, const char* terms_lower_utf8,
+                    const uint32_t* term_offsets, int64_t now_ticks, int32_t top_k, int32_t candidate_cap,
+                    orr_hit* out, int32_t* n_out) {
+    const double t0 = now_ms();
+    if (!s || !out || !n_out || q_dim < 0 || (q_dim > 0 && !q) || candidate_cap < 0 || n_terms < 0 ||
+        (n_terms > 0 && (!terms_lower_utf8 || !term_offsets))) {
+        orr_set_error("orr_search_text: bad argument");
+        return ORR_E_INVALID;
+    }
+    *n_out = 0;
+    if (n_terms > ORR_MAX_QUERY_TERMS) { orr_set_error("orr_search_text: %d terms > %d", n_terms, ORR_MAX_QUERY_TERMS); return ORR_E_UNSUPPORTED; }
+    int max_len = 0;
+    for (int32_t t = 0; t < n_terms; ++t) {
+        if (term_offsets[t + 1] <= term_offsets[t]) { orr_set_error("orr_search_text: term %d is empty", t); return ORR_E_INVALID; }
+        max_len = std::max<int>(max_len, (int)(term_offsets[t + 1] - term_offsets[t]));
+    }
+    if (n_terms > 0 && (max_len > ORR_TEXT_MAX_TERM_BYTES || term_offsets[n_terms] - term_offsets[0] > (uint32_t)ORR_TEXT_TERMS_BYTES)) {
+        orr_set_error("orr_search_text: terms too long (longest %d bytes, limit %d; total limit %d)", max_len,
+                      ORR_TEXT_MAX_TERM_BYTES, ORR_TEXT_TERMS_BYTES);
+        return ORR_E_UNSUPPORTED;
+    }
+    const int k = std::max(1, top_k);
+    std::shared_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    memset(&g_timing, 0, sizeof g_timing);
+    if (s->live_rows == 0) { g_timing.wall_ms = (float)(now_ms() - t0); return ORR_OK; }
+    if (n_terms > 0 && s->text_rows != s->rows_used) {
+        orr_set_error("orr_search_text: the store holds chunk text for %lld of %lld rows (use orr_store_upsert_document_chunks_text)",
+                      (long long)s->text_rows, (long long)s->rows_used);
+        return ORR_E_INVALID;
+    }
+    CtxLease lease(s);
+    int rc = lease.acquire();
+    if (rc != ORR_OK) return rc;
+    SearchCtx* c = lease.c.get();
+    const OrrShard sh = shard_view(s);
+    const int eff_q_dim = (q_dim == s->cfg.dim) ? q_dim : 0;
+    const int64_t kk = std::min<int64_t>(k, s->rows_used);
+    rc = ensure_hits(c, (int)kk);
+    if (rc != ORR_OK) return rc;
+    if (eff_q_dim > 0) {
+        memcpy(c->h_q, q, sizeof(float) * (size_t)q_dim);
+        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.q, c->h_q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream));
+    }
+    const int64_t row_words = (s->rows_used + 31) / 32;
+    std::vector<uint32_t> sub_rows;
+    if (candidate_cap > 0) {
+        if (candidate_cap > ORR_SORT_MAX) { orr_set_error("candidate_cap %d > %d", candidate_cap, ORR_SORT_MAX); return ORR_E_UNSUPPORTED; }
+        rc = capped_rows(s, candidate_cap, &sub_rows);
+        if (rc != ORR_OK) return rc;
+        memcpy(c->h_rows, sub_rows.data(), sizeof(uint32_t) * sub_rows.size());
+        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.surv_rows, c->h_rows, sizeof(uint32_t) * sub_rows.size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    ORR_CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+    OrrScratch sc = c->sc;
+    if (n_terms > 0) {
+        if (!c->d_terms) {
+            ORR_CUDA_OK(cudaMalloc(&c->d_terms, sizeof(OrrTextTerms)));
+            ORR_CUDA_OK(cudaMallocHost(&c->h_terms, sizeof(OrrTextTerms)));
+        }
+        const size_t need = (size_t)n_terms * (size_t)row_words;
+        if (need > c->kw_bits_words) {
+            cudaFree(c->d_kw_bits); c->d_kw_bits = nullptr; c->kw_bits_words = 0;
+            const size_t cap_words = (size_t)ORR_MAX_QUERY_TERMS * (size_t)((s->cfg.capacity_rows + 31) / 32);
+            const size_t alloc = std::min(cap_words, std::max(need, (size_t)8 * (size_t)((s->cfg.capacity_rows + 31) / 32)));
+            ORR_CUDA_OK(cudaMalloc(&c->d_kw_bits, alloc * sizeof(uint32_t)));
+            c->kw_bits_words = alloc;
+        }
+        OrrTextTerms* ht = c->h_terms;
+        memset(ht, 0, sizeof *ht);
+        ht->n_terms = n_terms; ht->max_len = max_len;
+        for (int32_t t = 0; t <= n_terms; ++t) ht->off[t] = (uint16_t)(term_offsets[t] - term_offsets[0]);
+        memcpy(ht->bytes, terms_lower_utf8 + term_offsets[0], term_offsets[n_terms] - term_offsets[0]);
+        ORR_CUDA_OK(cudaMemcpyAsync(c->d_terms, ht, sizeof *ht, cudaMemcpyHostToDevice, c->stream));
+        OrrTextView tv{s->d_text, s->d_text_off, s->d_text_len};
+        if (candidate_cap > 0) {
+            ORR_CUDA_OK(cudaMemsetAsync(c->d_kw_bits, 0, need * sizeof(uint32_t), c->stream));
+            rc = orr_launch_text_bits(tv, s->rows_used, c->d_terms, n_terms, max_len, c->sc.surv_rows, (int)sub_rows.size(),
+                                      c->d_kw_bits, row_words, c->stream);
+        } else {
+            rc = orr_launch_text_bits(tv, s->rows_used, c->d_terms, n_terms, max_len, nullptr, 0, c->d_kw_bits, row_words, c->stream);
+        }
+        if (rc != ORR_OK) return rc;
+        sc.kw_bits = c->d_kw_bits; sc.kw_row_words = row_words; sc.kw_terms = n_terms;
+    }
+    OrrProbes pr;
+    memset(&pr, 0, sizeof pr);
+    pr.n_terms = n_terms;                                   // the denominator; matches come from the bitmaps
+    ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+    if (candidate_cap > 0) {
+        const int32_t nl = (int32_t)sub_rows.size();
+        c->h_status[0] = nl;
+        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.sel, c->h_status, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, (int)kk, nl, false, c->stream);
+        g_timing.n_survivors = nl;
+    } else {
+        rc = ensure_exact_buffers(s, c);
+        if (rc != ORR_OK) return rc;
+        sc = c->sc;                                          // buffers may just have been allocated
+        if (n_terms > 0) { sc.kw_bits = c->d_kw_bits; sc.kw_row_words = row_words; sc.kw_terms = n_terms; }
+        rc = orr_launch_exact_scores(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, c->stream);
+        if (rc != ORR_OK) return rc;
+        rc = orr_exact_select(sh, c->sc, (int)kk, c->stream);
+    }
+    if (rc != ORR_OK) return rc;
+    ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+    ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+    ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+    ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
+    float match_ms = 0.f, fin_ms = 0.f;
+    cudaEventElapsedTime(&match_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&fin_ms, c->ev[1], c->ev[2]);
+    const int got = std::min<int>(c->h_status[0], (int)kk);
+    memcpy(out, c->h_hits, sizeof(orr_hit) * (size_t)got);
+    *n_out = got;
+    g_timing.scan_ms = match_ms;                             // substring kernel
+    g_timing.finalize_ms = fin_ms;                           // exact scoring + ordering
+    g_timing.total_device_ms = match_ms + fin_ms;
+    g_timing.path = ORR_PATH_TEXT;
     g_timing.rows_scanned = (candidate_cap > 0) ? g_timing.n_survivors : s->rows_used;
     g_timing.wall_ms = (float)(now_ms() - t0);
     return ORR_OK;

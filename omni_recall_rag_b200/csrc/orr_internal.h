@@ -84,6 +84,8 @@ struct OrrScratch {
     size_t    cub_tmp_bytes;
     uint64_t* sort_keys[2];   // exact path: key double buffer
     uint32_t* sort_vals[2];   // exact path: value double buffer
+    // text mode: per-term row bitmaps of the current query (NULL outside orr_search_text)
+    const uint32_t* kw_bits; int64_t kw_row_words; int32_t kw_terms;
 };
 
 struct OrrShard {              // device view of one shard
@@ -119,6 +121,25 @@ int orr_exact_select(const OrrShard& sh, OrrScratch& sc, int top_k, cudaStream_t
 
 int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_lists, int stride, int top_k,
                      orr_hit* out_dev, int32_t* out_status_dev, cudaStream_t st);
+
+// ---- text mode (orr_textmatch.cu): exact substring keyword matching over the chunk text kept in HBM ----
+constexpr int ORR_TEXT_MAX_TERM_BYTES = 256;     // longest query term the substring kernel takes
+constexpr int ORR_TEXT_TERMS_BYTES = 4096;       // all terms of one query
+struct OrrTextTerms {                            // device-side description of a query's terms
+    int32_t  n_terms;
+    int32_t  max_len;
+    uint16_t off[ORR_MAX_QUERY_TERMS + 1];
+    uint8_t  bytes[ORR_TEXT_TERMS_BYTES];
+};
+struct OrrTextView {
+    const uint8_t*  text;      // byte arena
+    const uint64_t* off;       // [rows] start of each row's lower-cased UTF-8 content
+    const uint32_t* len;       // [rows] byte length
+};
+// bits[t][row >> 5] bit (row & 31) = row's text contains term t.  rows_list == NULL: every row in [0, rows);
+// otherwise only the n_list listed rows (the words must have been cleared by the caller).
+int orr_launch_text_bits(const OrrTextView& tv, int64_t rows, const OrrTextTerms* terms_dev, int n_terms, int max_len,
+                         const uint32_t* rows_list, int n_list, uint32_t* bits, int64_t row_words, cudaStream_t st);
 
 // fused all-gather + merge over peer memory (orr_xchg.cu owns the buffers)
 constexpr int ORR_XCHG_MAX_WORLD = 16;

@@ -38,7 +38,22 @@ struct ExactArgs {
     OrrProbes pr;
     OrrWeights w;
     int64_t   now_ticks;
+    // text mode (orr_search_text): the keyword matches come from per-term row bitmaps produced by the
+    // substring kernel (orr_textmatch.cu) instead of the hashed term table
+    const uint32_t* kw_bits;     // [kw_terms][kw_row_words] or NULL
+    int64_t   kw_row_words;
+    int32_t   kw_terms;
 };
+template <class A> __device__ __forceinline__ const uint32_t* kw_bits_of(const A&) { return nullptr; }
+__device__ __forceinline__ const uint32_t* kw_bits_of(const ExactArgs& a) { return a.kw_bits; }
+template <class A> __device__ __forceinline__ double kw_from_bits(const A&, int64_t, int) { return 0.0; }
+__device__ __forceinline__ double kw_from_bits(const ExactArgs& a, int64_t row, int lane) {
+    int cnt = 0;
+    for (int t = lane; t < a.kw_terms; t += 32)
+        cnt += (int)((__ldg(a.kw_bits + (int64_t)t * a.kw_row_words + (row >> 5)) >> (row & 31)) & 1u);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    return __ddiv_rn((double)cnt, (double)a.kw_terms);               // :112
+}
 
 // Loads are issued in batches of EX_CHUNK float4 per lane BEFORE the dependent fp64 chains
 // so a row costs ~2 memory round trips instead of one per 128 columns; the ORDER of the fp64
@@ -136,7 +151,9 @@ __device__ __forceinline__ double exact_row_q(const A& a, const float* q, const 
             cosv = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(nA), __dsqrt_rn(nB)));   // :87
     }
     double kw = 0.0;
-    if (n_probes > 0) {                                             // :110-112
+    if (kw_bits_of(a) != nullptr) {
+        kw = kw_from_bits(a, row, lane);
+    } else if (n_probes > 0) {                                      // :110-112
         uint32_t m0 = 0, m1 = 0;
         for (int p = 0; p < n_probes; ++p) {
             const uint64_t h = pr.h64[p];
@@ -435,6 +452,7 @@ __global__ void __launch_bounds__(256) orr_xchg_merge_kernel(const OrrXchgArgs a
 static void fill_exact_args(ExactArgs& e, const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
                             const OrrWeights& w, int64_t now_ticks, int q_dim) {
     e.sh = sh; e.q = sc.q; e.q_dim = q_dim; e.pr = pr; e.w = w; e.now_ticks = now_ticks;
+    e.kw_bits = sc.kw_bits; e.kw_row_words = sc.kw_row_words; e.kw_terms = sc.kw_terms;
 }
 
 int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,

@@ -14,7 +14,7 @@ from typing import List, Optional, Protocol, Sequence
 import numpy as np
 
 from .shard import QueryTerms, hash_term
-from .store import GpuIngestionStore, _distinct_lower_tokens, _WS
+from .store import GpuIngestionStore, _distinct_lower_tokens, _WS  # noqa: F401
 from . import _native as N
 
 STOP_WORDS = frozenset(  # RecallSearchService.cs:13-18
@@ -83,11 +83,25 @@ class GpuRecallSearchService:
     per chunk, :117); `candidate_cap` defaults to the reference's 300 (:26)."""
 
     def __init__(self, store: GpuIngestionStore, embedding_client: IEmbeddingClient, *,
-                 candidate_cap: int = 300, clock=None):
+                 candidate_cap: int = 300, clock=None, keyword_mode: str = "auto"):
+        """keyword_mode: "hashed" = hashed term table + vocabulary expansion (the fused scan; raises
+        UnsupportedQueryError when a term expands to more probes than the kernels take), "text" = substring
+        search on the chunk text in HBM (orr_search_text; any term, slower), "auto" = hashed when the
+        expansion fits, else text."""
+        if keyword_mode not in ("auto", "hashed", "text"):
+            raise ValueError("keyword_mode must be auto, hashed or text")
         self.store = store
         self.embedding_client = embedding_client
         self.candidate_cap = candidate_cap
+        self.keyword_mode = keyword_mode
         self._clock = clock or _utc_now_ticks
+
+    @staticmethod
+    def filtered_terms(query: str) -> List[str]:
+        """KeywordScore's query side (:95-108): lower-cased distinct tokens minus stop words (or all of
+        them if that leaves nothing)."""
+        raw = _distinct_lower_tokens(query)
+        return [t for t in raw if t not in STOP_WORDS] or raw
 
     def query_terms(self, query: str) -> QueryTerms:
         """KeywordScore's query side (:95-108) + substring expansion over the live vocabulary
@@ -111,8 +125,17 @@ class GpuRecallSearchService:
             raise ValueError("Query is required.")  # ArgumentException (:22-23)
         query_embedding = self.embedding_client.embed(query)  # :25
         qvec = np.asarray(query_embedding.vector, dtype=np.float32)
-        hits = self.store.shard.search(qvec, self.query_terms(query), self._clock(), top_k,
-                                       candidate_cap=self.candidate_cap)  # :26-37 on the GPU
+        hits = None
+        if self.keyword_mode != "text":
+            try:
+                hits = self.store.shard.search(qvec, self.query_terms(query), self._clock(), top_k,
+                                               candidate_cap=self.candidate_cap)  # :26-37 on the GPU
+            except UnsupportedQueryError:
+                if self.keyword_mode == "hashed" or not self.store.keep_text:
+                    raise
+        if hits is None:     # a term is a substring of too many words (or text mode was asked for)
+            hits = self.store.shard.search_text(qvec, self.filtered_terms(query), self._clock(), top_k,
+                                                candidate_cap=self.candidate_cap)
         scored = [(self.store.chunk_of_row(int(r)), float(s)) for r, s in zip(hits.rows, hits.scores)]
         documents = self.store.get_documents_by_ids(list({c.document_id for c, _ in scored}))  # :39
         citations = []

@@ -167,7 +167,10 @@ class RecallShard:
     # -- mutation ---------------------------------------------------------------------------
     def upsert_document_chunks(self, doc_key: int, emb: Optional[np.ndarray], ticks: np.ndarray,
                                term_hashes: Optional[Sequence[np.ndarray]] = None,
-                               has_emb: Optional[np.ndarray] = None) -> np.ndarray:
+                               has_emb: Optional[np.ndarray] = None,
+                               texts_lower: Optional[Sequence[str]] = None) -> np.ndarray:
+        """orr_store_upsert_document_chunks(_text).  `texts_lower`: each chunk's lower-cased Content, kept in
+        HBM for text mode (search_text); give it for every chunk of the store or for none."""
         ticks = np.ascontiguousarray(ticks, dtype=np.int64)
         n = int(ticks.shape[0])
         if emb is not None:
@@ -185,8 +188,18 @@ class RecallShard:
             flat = np.ascontiguousarray(flat, dtype=np.uint64)
         out_rows = np.zeros(max(n, 1), dtype=np.uint64)
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        N.check(N.lib().orr_store_upsert_document_chunks(self._h, doc_key, n, p(emb), p(has_emb), p(ticks),
-                                                         p(flat), p(off), p(out_rows)))
+        if texts_lower is not None:
+            if len(texts_lower) != n:
+                raise ValueError(f"{len(texts_lower)} texts for {n} chunks")
+            enc = [t.encode("utf-8") for t in texts_lower]
+            toff = np.zeros(n + 1, dtype=np.uint64)
+            toff[1:] = np.cumsum([len(b) for b in enc])
+            blob = b"".join(enc) or b"\0"
+            N.check(N.lib().orr_store_upsert_document_chunks_text(self._h, doc_key, n, p(emb), p(has_emb), p(ticks),
+                                                                  p(flat), p(off), blob, p(toff), p(out_rows)))
+        else:
+            N.check(N.lib().orr_store_upsert_document_chunks(self._h, doc_key, n, p(emb), p(has_emb), p(ticks),
+                                                             p(flat), p(off), p(out_rows)))
         return out_rows[:n]
 
     def delete_document(self, doc_key: int) -> None:
@@ -224,6 +237,26 @@ class RecallShard:
             ph.ctypes.data_as(C.c_void_p) if ph.size else None,
             None if pt is None else pt.ctypes.data_as(C.c_void_p), int(ph.size),
             int(now_ticks), int(top_k), int(candidate_cap), C.cast(out, C.c_void_p), C.byref(n)))
+        return _hits_from(out, n.value)
+
+    def search_text(self, q: Optional[np.ndarray], terms_lower: Sequence[str], now_ticks: int, top_k: int,
+                    candidate_cap: int = 0) -> Hits:
+        """orr_search_text: the keyword predicate evaluated as an ordinal substring search of each (lower-cased,
+        A-2 filtered) query term in the chunk text kept in HBM; exact fp64 scoring of every candidate row."""
+        if q is None:
+            q = np.zeros(0, dtype=np.float32)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        k = max(1, int(top_k))
+        out = (N.OrrHit * k)()
+        n = C.c_int32(0)
+        enc = [t.encode("utf-8") for t in terms_lower]
+        toff = np.zeros(len(enc) + 1, dtype=np.uint32)
+        toff[1:] = np.cumsum([len(b) for b in enc])
+        blob = b"".join(enc) or b"\0"
+        N.check(N.lib().orr_search_text(
+            self._h, q.ctypes.data_as(C.c_void_p) if q.size else None, int(q.size), len(enc), blob,
+            toff.ctypes.data_as(C.c_void_p), int(now_ticks), int(top_k), int(candidate_cap),
+            C.cast(out, C.c_void_p), C.byref(n)))
         return _hits_from(out, n.value)
 
     def search_device(self, q_dev_ptr: int, terms: QueryTerms, now_ticks: int, top_k: int,

@@ -43,9 +43,13 @@ class GpuIngestionStore:
     the host (they are only needed for the <= top_k citations); embeddings, timestamps and
     hashed term sets are mirrored into HBM on every upsert."""
 
-    def __init__(self, dim: int, capacity_rows: int = 1 << 16, *, device: int = 0, term_slots: int = 128):
+    def __init__(self, dim: int, capacity_rows: int = 1 << 16, *, device: int = 0, term_slots: int = 128,
+                 keep_text: bool = True, text_bytes_per_row: int = 2048):
         self.shard = RecallShard(dim, capacity_rows, device=device, term_slots=term_slots)
         self.dim = dim
+        self.keep_text = keep_text          # lower-cased Content mirrored into HBM (text mode, orr_search_text)
+        if keep_text:
+            self.shard.set_option("text_bytes_per_row", text_bytes_per_row)
         self._lock = threading.RLock()
         self._documents: Dict[str, CosmosDocumentRecord] = {}
         self._chunks_by_document: Dict[str, List[CosmosChunkRecord]] = {}
@@ -89,7 +93,8 @@ class GpuIngestionStore:
             hashes.append(np.array([hash_term(t) for t in toks], dtype=np.uint64))
         with self._lock:
             self._forget_rows(document_id)
-            rows = self.shard.upsert_document_chunks(_doc_key(document_id), emb, ticks, hashes, has)
+            texts = [_lower_invariant(c.content or "") for c in ordered] if self.keep_text else None
+            rows = self.shard.upsert_document_chunks(_doc_key(document_id), emb, ticks, hashes, has, texts)
             self._chunks_by_document[document_id] = ordered
             self._rows_by_document[document_id] = rows
             for r, c, toks in zip(rows, ordered, tokens_per_chunk):
