@@ -121,6 +121,21 @@ int  orr_store_upsert_document_chunks_text(orr_store* s, uint64_t doc_key, int32
 /* DeleteDocumentAsync (InMemoryIngestionStore.cs:50-55): tombstones the rows. */
 int  orr_store_delete_document(orr_store* s, uint64_t doc_key);
 
+/* Squeezes tombstoned rows out (replace-by-document and delete only mark rows dead; every scan still
+ * reads them).  Live rows keep their relative order, so the reference's stable row-order tie-break is
+ * unchanged, but their ids change: new local row i was old row old_rows_out[i] (global ids, i < *n_live_out);
+ * the host remaps its row -> chunk table.  Exclusive: waits for running searches, blocks new ones. */
+int  orr_store_compact(orr_store* s, uint64_t* old_rows_out, int64_t out_cap, int64_t* n_live_out);
+
+/* Snapshot / warm load (the HBM store is volatile): orr_store_save writes the store's byte image (rows,
+ * tombstones, term tables, chunk text, document -> row table) to `path`; orr_store_load fills an EMPTY store
+ * of the same dim / term_slots and capacity >= the snapshot's rows.  Row ids are preserved, so the host's
+ * row -> CosmosChunkRecord map (which the host persists itself) stays valid.  Replaces re-ingesting every
+ * document after a restart (the Cosmos store's `SELECT TOP 300` paging cannot hydrate a scan-everything
+ * store, CosmosIngestionStore.cs:178-197). */
+int  orr_store_save(orr_store* s, const char* path);
+int  orr_store_load(orr_store* s, const char* path);
+
 /* Runtime knobs.  "batch_passes": how the batched contraction SELECTS candidates; the returned hits are
  * always the exact fp64 re-score, proven complete by the bound check, so every setting returns the same hits.
  *   0 (default) = auto: one bf16 tcgen05 pass screens with a deep candidate list; queries it cannot prove

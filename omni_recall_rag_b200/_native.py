@@ -64,6 +64,9 @@ _SIGNATURES = {
                                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p,
                                                         C.c_void_p]),
     "orr_store_delete_document": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "orr_store_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "orr_store_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "orr_store_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "orr_store_count": (C.c_int64, [C.c_void_p]),
     "orr_store_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "orr_store_rows_used": (C.c_int64, [C.c_void_p]),

@@ -740,6 +740,268 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
     return ORR_OK;
 }
 
+// ---- snapshot / warm load ----------------------------------------------
+// The HBM store is volatile; a snapshot is its byte image: header, then emb / ticks / terms32 / terms64
+// (/ text_off / text_len / text) for rows [0, rows_used) and the document -> row-run table.  Row ids are
+// preserved, so the host's row -> chunk map stays valid.  Device <-> file goes through a pinned bounce buffer.
+namespace {
+struct SnapHeader {
+    char     magic[8];           // "ORRSNAP1"
+    int32_t  abi_version, dim, term_slots, has_text;
+    int64_t  rows_used, live_rows;
+    uint64_t row_base, text_used, n_docs, n_runs;
+    double   w_cos, w_kw, w_rec, recency_days;
+};
+constexpr size_t SNAP_BOUNCE = (size_t)64 << 20;
+
+int snap_write(FILE* f, const void* dev, size_t bytes, void* bounce) {
+    const uint8_t* p = (const uint8_t*)dev;
+    while (bytes) {
+        const size_t n = std::min(bytes, SNAP_BOUNCE);
+        ORR_CUDA_OK(cudaMemcpy(bounce, p, n, cudaMemcpyDeviceToHost));
+        if (fwrite(bounce, 1, n, f) != n) { orr_set_error("snapshot: short write"); return ORR_E_INVALID; }
+        p += n; bytes -= n;
+    }
+    return ORR_OK;
+}
+int snap_read(FILE* f, void* dev, size_t bytes, void* bounce) {
+    uint8_t* p = (uint8_t*)dev;
+    while (bytes) {
+        const size_t n = std::min(bytes, SNAP_BOUNCE);
+        if (fread(bounce, 1, n, f) != n) { orr_set_error("snapshot: truncated file"); return ORR_E_INVALID; }
+        ORR_CUDA_OK(cudaMemcpy(p, bounce, n, cudaMemcpyHostToDevice));
+        p += n; bytes -= n;
+    }
+    return ORR_OK;
+}
+}  // namespace
+
+int orr_store_save(orr_store* s, const char* path) {
+    if (!s || !path) { orr_set_error("orr_store_save: NULL argument"); return ORR_E_INVALID; }
+    std::shared_lock<std::shared_mutex> lock(s->mu);           // searches may continue; mutators wait
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    FILE* f = fopen(path, "wb");
+    if (!f) { orr_set_error("orr_store_save: cannot open %s", path); return ORR_E_INVALID; }
+    void* bounce = nullptr;
+    int rc = [&]() -> int {
+        ORR_CUDA_OK(cudaMallocHost(&bounce, SNAP_BOUNCE));
+        SnapHeader h{};
+        memcpy(h.magic, "ORRSNAP1", 8);
+        h.abi_version = ORR_ABI_VERSION; h.dim = s->cfg.dim; h.term_slots = s->cfg.term_slots;
+        h.has_text = (s->d_text && s->text_rows == s->rows_used && s->rows_used > 0) ? 1 : 0;
+        h.rows_used = s->rows_used; h.live_rows = s->live_rows; h.row_base = s->cfg.row_base;
+        h.text_used = h.has_text ? s->text_used : 0;
+        h.n_docs = s->docs.size();
+        for (auto& d : s->docs) h.n_runs += d.second.size();
+        h.w_cos = s->cfg.w_cos; h.w_kw = s->cfg.w_kw; h.w_rec = s->cfg.w_rec; h.recency_days = s->cfg.recency_days;
+        if (fwrite(&h, sizeof h, 1, f) != 1) { orr_set_error("snapshot: short write"); return ORR_E_INVALID; }
+        const size_t n = (size_t)s->rows_used;
+        int r;
+        if ((r = snap_write(f, s->d_emb, n * s->cfg.dim * sizeof(float), bounce)) != ORR_OK) return r;
+        if ((r = snap_write(f, s->d_ticks, n * sizeof(int64_t), bounce)) != ORR_OK) return r;
+        if ((r = snap_write(f, s->d_terms32, n * s->cfg.term_slots * sizeof(uint32_t), bounce)) != ORR_OK) return r;
+        if ((r = snap_write(f, s->d_terms64, n * s->cfg.term_slots * sizeof(uint64_t), bounce)) != ORR_OK) return r;
+        if (h.has_text) {
+            if ((r = snap_write(f, s->d_text_off, n * sizeof(uint64_t), bounce)) != ORR_OK) return r;
+            if ((r = snap_write(f, s->d_text_len, n * sizeof(uint32_t), bounce)) != ORR_OK) return r;
+            if ((r = snap_write(f, s->d_text, (size_t)s->text_used, bounce)) != ORR_OK) return r;
+        }
+        std::vector<uint64_t> table;
+        table.reserve((size_t)(2 * h.n_docs + 2 * h.n_runs));
+        for (auto& d : s->docs) {
+            table.push_back(d.first); table.push_back((uint64_t)d.second.size());
+            for (auto& run : d.second) { table.push_back((uint64_t)run.first); table.push_back((uint64_t)run.second); }
+        }
+        if (!table.empty() && fwrite(table.data(), sizeof(uint64_t), table.size(), f) != table.size()) {
+            orr_set_error("snapshot: short write");
+            return ORR_E_INVALID;
+        }
+        return ORR_OK;
+    }();
+    cudaFreeHost(bounce);
+    if (fclose(f) != 0 && rc == ORR_OK) { orr_set_error("orr_store_save: close failed"); rc = ORR_E_INVALID; }
+    return rc;
+}
+
+int orr_store_load(orr_store* s, const char* path) {
+    if (!s || !path) { orr_set_error("orr_store_load: NULL argument"); return ORR_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (s->rows_used != 0) { orr_set_error("orr_store_load: the store is not empty"); return ORR_E_INVALID; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { orr_set_error("orr_store_load: cannot open %s", path); return ORR_E_INVALID; }
+    void* bounce = nullptr;
+    int rc = [&]() -> int {
+        SnapHeader h{};
+        if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "ORRSNAP1", 8) != 0) { orr_set_error("orr_store_load: %s is not a snapshot", path); return ORR_E_INVALID; }
+        if (h.abi_version != ORR_ABI_VERSION || h.dim != s->cfg.dim || h.term_slots != s->cfg.term_slots) {
+            orr_set_error("orr_store_load: snapshot is dim %d / %d slots / abi %d, store is dim %d / %d slots / abi %d", h.dim,
+                          h.term_slots, h.abi_version, s->cfg.dim, s->cfg.term_slots, ORR_ABI_VERSION);
+            return ORR_E_INVALID;
+        }
+        if (h.rows_used < 0 || h.rows_used > s->cfg.capacity_rows) { orr_set_error("orr_store_load: %lld rows exceed the capacity %lld", (long long)h.rows_used, (long long)s->cfg.capacity_rows); return ORR_E_OOM; }
+        ORR_CUDA_OK(cudaMallocHost(&bounce, SNAP_BOUNCE));
+        const size_t n = (size_t)h.rows_used;
+        int r;
+        if ((r = snap_read(f, s->d_emb, n * s->cfg.dim * sizeof(float), bounce)) != ORR_OK) return r;
+        if ((r = snap_read(f, s->d_ticks, n * sizeof(int64_t), bounce)) != ORR_OK) return r;
+        if ((r = snap_read(f, s->d_terms32, n * s->cfg.term_slots * sizeof(uint32_t), bounce)) != ORR_OK) return r;
+        if ((r = snap_read(f, s->d_terms64, n * s->cfg.term_slots * sizeof(uint64_t), bounce)) != ORR_OK) return r;
+        if (h.has_text) {
+            const uint64_t cap_bytes = std::max<uint64_t>((uint64_t)((double)s->cfg.capacity_rows * s->text_bytes_per_row), h.text_used) + 4096;
+            if (!s->d_text) {
+                ORR_CUDA_OK(cudaMalloc(&s->d_text, cap_bytes + 64));
+                ORR_CUDA_OK(cudaMalloc(&s->d_text_off, sizeof(uint64_t) * (size_t)s->cfg.capacity_rows));
+                ORR_CUDA_OK(cudaMalloc(&s->d_text_len, sizeof(uint32_t) * (size_t)s->cfg.capacity_rows));
+                s->text_cap = cap_bytes;
+            } else if (h.text_used > s->text_cap) { orr_set_error("orr_store_load: text arena too small"); return ORR_E_OOM; }
+            if ((r = snap_read(f, s->d_text_off, n * sizeof(uint64_t), bounce)) != ORR_OK) return r;
+            if ((r = snap_read(f, s->d_text_len, n * sizeof(uint32_t), bounce)) != ORR_OK) return r;
+            if ((r = snap_read(f, s->d_text, (size_t)h.text_used, bounce)) != ORR_OK) return r;
+            s->text_used = h.text_used; s->text_rows = h.rows_used;
+        }
+        std::vector<uint64_t> table((size_t)(2 * h.n_docs + 2 * h.n_runs));
+        if (!table.empty() && fread(table.data(), sizeof(uint64_t), table.size(), f) != table.size()) { orr_set_error("snapshot: truncated file"); return ORR_E_INVALID; }
+        s->docs.clear();
+        size_t i = 0;
+        for (uint64_t d = 0; d < h.n_docs; ++d) {
+            if (i + 2 > table.size()) { orr_set_error("snapshot: corrupt document table"); return ORR_E_INVALID; }
+            const uint64_t key = table[i++], nr = table[i++];
+            if (i + 2 * nr > table.size()) { orr_set_error("snapshot: corrupt document table"); return ORR_E_INVALID; }
+            auto& runs = s->docs[key];
+            for (uint64_t k = 0; k < nr; ++k) { runs.push_back({(int64_t)table[i], (int64_t)table[i + 1]}); i += 2; }
+        }
+        s->rows_used = h.rows_used; s->live_rows = h.live_rows;
+        s->h_ticks.clear();
+        s->version++;
+        return ORR_OK;
+    }();
+    if (bounce) cudaFreeHost(bounce);
+    fclose(f);
+    return rc;
+}
+
+// ---- compaction of tombstones ---------------------------------------------
+// Replace-by-document and delete only tombstone rows; the scan still reads them.  Compaction squeezes the
+// live rows to the front IN ORDER (so the stable row-order tie-break of the reference is unchanged) and
+// tells the host which old row every new row was.  Output segments are gathered into a bounded temp buffer
+// and copied back: output segment [o, o+m) only ever reads source rows >= o, and later segments only read
+// rows >= o+m, so the in-place move is safe.
+namespace {
+__global__ void orr_gather_rows_kernel(const uint32_t* src, const uint32_t* idx, int64_t first, int64_t m, int words_per_row,
+                                       uint32_t* tmp) {
+    const int64_t total = m * words_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / words_per_row;
+        const int w = (int)(i - r * words_per_row);
+        tmp[i] = src[(int64_t)idx[first + r] * words_per_row + w];
+    }
+}
+__global__ void orr_copy_text_kernel(const uint8_t* old_text, const uint64_t* old_off, const uint32_t* len, const uint64_t* new_off,
+                                     int64_t n, uint8_t* new_text) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = gw; r < n; r += W) {
+        const uint8_t* a = old_text + old_off[r];
+        uint8_t* b = new_text + new_off[r];
+        const uint32_t l = len[r];
+        for (uint32_t i = lane; i < l; i += 32) b[i] = a[i];
+    }
+}
+int compact_array(void* base, size_t row_bytes, const uint32_t* d_idx, int64_t n_live, void* tmp, size_t tmp_bytes, cudaStream_t st) {
+    const int words = (int)(row_bytes / 4);
+    const int64_t seg = std::max<int64_t>(1, (int64_t)(tmp_bytes / row_bytes));
+    for (int64_t o = 0; o < n_live; o += seg) {
+        const int64_t m = std::min(seg, n_live - o);
+        const int64_t total = m * words;
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+        orr_gather_rows_kernel<<<grid, 256, 0, st>>>((const uint32_t*)base, d_idx, o, m, words, (uint32_t*)tmp);
+        ORR_CUDA_OK(cudaGetLastError());
+        ORR_CUDA_OK(cudaMemcpyAsync((uint8_t*)base + (size_t)o * row_bytes, tmp, (size_t)m * row_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    return ORR_OK;
+}
+}  // namespace
+
+int orr_store_compact(orr_store* s, uint64_t* old_rows_out, int64_t out_cap, int64_t* n_live_out) {
+    if (!s || !n_live_out) { orr_set_error("orr_store_compact: NULL argument"); return ORR_E_INVALID; }
+    std::unique_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    if ((int64_t)s->h_ticks.size() < s->rows_used) {
+        const size_t have = s->h_ticks.size();
+        s->h_ticks.resize((size_t)s->rows_used);
+        ORR_CUDA_OK(cudaMemcpy(s->h_ticks.data() + have, s->d_ticks + have, sizeof(int64_t) * (s->h_ticks.size() - have), cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint32_t> idx;
+    idx.reserve((size_t)s->live_rows);
+    std::vector<int64_t> live_before((size_t)s->rows_used + 1, 0);
+    for (int64_t r = 0; r < s->rows_used; ++r) {
+        live_before[(size_t)r] = (int64_t)idx.size();
+        if (s->h_ticks[(size_t)r] != ORR_DEAD_TICKS) idx.push_back((uint32_t)r);
+    }
+    const int64_t n_live = (int64_t)idx.size();
+    *n_live_out = n_live;
+    if (old_rows_out) {
+        if (out_cap < n_live) { orr_set_error("orr_store_compact: old_rows_out holds %lld, %lld rows are live", (long long)out_cap, (long long)n_live); return ORR_E_INVALID; }
+        for (int64_t i = 0; i < n_live; ++i) old_rows_out[i] = s->cfg.row_base + idx[(size_t)i];
+    }
+    if (n_live == s->rows_used) return ORR_OK;                       // nothing to squeeze
+    cudaStream_t st = s->mut_stream;
+    uint32_t* d_idx = nullptr; void* tmp = nullptr;
+    uint8_t* new_text = nullptr; uint64_t* d_new_off = nullptr;
+    const size_t tmp_bytes = std::max<size_t>((size_t)128 << 20, (size_t)s->cfg.dim * 4 * 64);
+    int rc = [&]() -> int {
+        if (n_live > 0) {
+            ORR_CUDA_OK(cudaMalloc(&d_idx, sizeof(uint32_t) * (size_t)n_live));
+            ORR_CUDA_OK(cudaMalloc(&tmp, tmp_bytes));
+            ORR_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(uint32_t) * (size_t)n_live, cudaMemcpyHostToDevice, st));
+            int r;
+            if ((r = compact_array(s->d_emb, (size_t)s->cfg.dim * 4, d_idx, n_live, tmp, tmp_bytes, st)) != ORR_OK) return r;
+            if ((r = compact_array(s->d_ticks, 8, d_idx, n_live, tmp, tmp_bytes, st)) != ORR_OK) return r;
+            if ((r = compact_array(s->d_terms32, (size_t)s->cfg.term_slots * 4, d_idx, n_live, tmp, tmp_bytes, st)) != ORR_OK) return r;
+            if ((r = compact_array(s->d_terms64, (size_t)s->cfg.term_slots * 8, d_idx, n_live, tmp, tmp_bytes, st)) != ORR_OK) return r;
+            if (s->d_text && s->text_rows == s->rows_used) {
+                if ((r = compact_array(s->d_text_off, 8, d_idx, n_live, tmp, tmp_bytes, st)) != ORR_OK) return r;
+                if ((r = compact_array(s->d_text_len, 4, d_idx, n_live, tmp, tmp_bytes, st)) != ORR_OK) return r;
+                // squeeze the byte arena too: new offsets are the running sum of the live rows' lengths
+                std::vector<uint32_t> len((size_t)n_live);
+                ORR_CUDA_OK(cudaStreamSynchronize(st));
+                ORR_CUDA_OK(cudaMemcpy(len.data(), s->d_text_len, sizeof(uint32_t) * (size_t)n_live, cudaMemcpyDeviceToHost));
+                std::vector<uint64_t> noff((size_t)n_live);
+                uint64_t used = 0;
+                for (int64_t i = 0; i < n_live; ++i) { noff[(size_t)i] = used; used += len[(size_t)i]; }
+                ORR_CUDA_OK(cudaMalloc(&new_text, s->text_cap + 64));
+                ORR_CUDA_OK(cudaMalloc(&d_new_off, sizeof(uint64_t) * (size_t)n_live));
+                ORR_CUDA_OK(cudaMemcpyAsync(d_new_off, noff.data(), sizeof(uint64_t) * (size_t)n_live, cudaMemcpyHostToDevice, st));
+                orr_copy_text_kernel<<<148 * 8, 256, 0, st>>>(s->d_text, s->d_text_off, s->d_text_len, d_new_off, n_live, new_text);
+                ORR_CUDA_OK(cudaGetLastError());
+                ORR_CUDA_OK(cudaMemcpyAsync(s->d_text_off, d_new_off, sizeof(uint64_t) * (size_t)n_live, cudaMemcpyDeviceToDevice, st));
+                ORR_CUDA_OK(cudaStreamSynchronize(st));
+                std::swap(s->d_text, new_text);
+                s->text_used = used;
+            }
+            ORR_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        return ORR_OK;
+    }();
+    cudaFree(d_idx); cudaFree(tmp); cudaFree(new_text); cudaFree(d_new_off);
+    if (rc != ORR_OK) return rc;
+    // host bookkeeping: every run still in the table is fully live (tombstoning erases its document)
+    for (auto& d : s->docs)
+        for (auto& run : d.second) run.first = live_before[(size_t)run.first];
+    std::vector<int64_t> nt((size_t)n_live);
+    for (int64_t i = 0; i < n_live; ++i) nt[(size_t)i] = s->h_ticks[idx[(size_t)i]];
+    s->h_ticks.swap(nt);
+    if (s->text_rows == s->rows_used) s->text_rows = n_live;
+    if (n_live == 0) s->text_used = 0;
+    s->rows_used = n_live;
+    s->live_rows = n_live;
+    s->version++;
+    if (s->batch) { std::lock_guard<std::mutex> g(s->batch->mu); s->batch->planes_rows = 0; }   // bf16 planes follow the rows
+    return ORR_OK;
+}
+
 int orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim, int32_t n_terms,
                       const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
                       int64_t now_ticks, int32_t top_k, orr_hit* out_dev, int32_t* status_dev,

@@ -208,6 +208,21 @@ class RecallShard:
     def fill_synthetic(self, spec: "N.OrrSynthSpec", first_row: int, n: int) -> None:
         N.check(N.lib().orr_store_fill_synthetic(self._h, C.byref(spec), first_row, n))
 
+    def compact(self) -> np.ndarray:
+        """orr_store_compact: drops tombstoned rows; returns old_rows[new_local_row] (global ids)."""
+        out = np.zeros(max(self.rows_used, 1), dtype=np.uint64)
+        n = C.c_int64(0)
+        N.check(N.lib().orr_store_compact(self._h, out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(n)))
+        return out[: n.value].copy()
+
+    def save(self, path: str) -> None:
+        """orr_store_save: the shard's byte image (rows, tombstones, term tables, text, document table)."""
+        N.check(N.lib().orr_store_save(self._h, path.encode()))
+
+    def load(self, path: str) -> None:
+        """orr_store_load into this (empty, same dim / term_slots) shard; row ids are preserved."""
+        N.check(N.lib().orr_store_load(self._h, path.encode()))
+
     def set_option(self, name: str, value: float) -> None:
         """orr_store_set_option, e.g. ("batch_passes", 0 = auto | 1 | 3)."""
         N.check(N.lib().orr_store_set_option(self._h, name.encode(), float(value)))

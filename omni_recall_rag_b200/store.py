@@ -132,6 +132,45 @@ class GpuIngestionStore:
         with self._lock:
             return {k: v for k, v in self._documents.items() if k in wanted}
 
+    # -- maintenance: not in IIngestionStore; the HBM layout needs them -------------------------
+    def compact(self) -> int:
+        """Drops the rows that replace/delete tombstoned and remaps the host's row tables.  Returns the
+        number of rows reclaimed."""
+        with self._lock:
+            before = self.shard.rows_used
+            old_rows = self.shard.compact()
+            base = self.shard.row_base
+            new_of_old = {int(o): base + i for i, o in enumerate(old_rows)}
+            self._chunk_by_row = {new_of_old[r]: c for r, c in self._chunk_by_row.items()}
+            self._rows_by_document = {d: np.array([new_of_old[int(r)] for r in rows], dtype=np.uint64)
+                                      for d, rows in self._rows_by_document.items()}
+            return before - len(old_rows)
+
+    def save(self, directory: str) -> None:
+        """HBM image (orr_store_save) + the host-side records, so a restart does not re-ingest."""
+        import os
+        import pickle
+
+        os.makedirs(directory, exist_ok=True)
+        with self._lock:
+            self.shard.save(os.path.join(directory, "shard.orrsnap"))
+            with open(os.path.join(directory, "host.pkl"), "wb") as f:
+                pickle.dump({"documents": self._documents, "chunks": self._chunks_by_document,
+                             "rows": self._rows_by_document, "vocab": self._vocab}, f)
+
+    def load(self, directory: str) -> None:
+        import os
+        import pickle
+
+        with self._lock:
+            self.shard.load(os.path.join(directory, "shard.orrsnap"))
+            with open(os.path.join(directory, "host.pkl"), "rb") as f:
+                h = pickle.load(f)
+            self._documents, self._chunks_by_document = h["documents"], h["chunks"]
+            self._rows_by_document, self._vocab = h["rows"], h["vocab"]
+            self._chunk_by_row = {int(r): c for d, rows in self._rows_by_document.items()
+                                  for r, c in zip(rows, self._chunks_by_document[d])}
+
     # -- used by GpuRecallSearchService -------------------------------------------------------
     def chunk_of_row(self, row: int) -> CosmosChunkRecord:
         return self._chunk_by_row[int(row)]

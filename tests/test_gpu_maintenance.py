@@ -1,0 +1,189 @@
+"""Store maintenance the HBM layout needs beyond IIngestionStore: compaction of
+tombstones, snapshot / warm load, and searches running against concurrent mutations.  Needs a B200 (-m gpu)."""
+import threading
+
+import numpy as np
+import pytest
+
+import omni_recall_rag_b200 as orr
+from omni_recall_rag_b200 import _native as N
+from omni_recall_rag_b200 import recall as R
+from omni_recall_rag_b200 import store as S
+from omni_recall_rag_b200 import synth
+from oracle import oracle_c
+from tests.util import assert_same_ranking
+
+pytestmark = pytest.mark.gpu
+
+DAY = 864_000_000_000
+NOW = synth.NOW_TICKS
+WORDS = "azure kubernetes nebula vector recall chunk score index query storage blob cosmos gemini token embed".split()
+
+
+class _Emb:
+    def __init__(self, v):
+        self.v = v
+
+    def embed(self, text):
+        return R.EmbeddingResult(self.v, "Success")
+
+
+def _fill(st, rng, n_docs, dim, per_doc=5):
+    for d in range(n_docs):
+        t = NOW - int(rng.integers(1, 200)) * DAY
+        st.upsert_document(S.CosmosDocumentRecord(id=f"d{d}", file_name=f"f{d}.md", created_at_utc=t))
+        st.upsert_chunks([S.CosmosChunkRecord(id=f"d{d}:{j:04d}", document_id=f"d{d}", chunk_index=j,
+                                              content=" ".join(rng.choice(WORDS, size=12)),
+                                              embedding=rng.standard_normal(dim).astype(np.float32).tolist(), created_at_utc=t)
+                          for j in range(per_doc)])
+
+
+def _oracle_citations(st, query, qv, k, cap):
+    """The oracle over the store's LIVE chunks in the reference's candidate order (documents in insertion
+    order, chunks by index)."""
+    chunks = [c for cs in st._chunks_by_document.values() for c in cs]
+    emb = np.array([c.embedding for c in chunks], dtype=np.float32)
+    ticks = np.array([c.created_at_utc for c in chunks], dtype=np.int64)
+    blob, off = oracle_c.pack_contents([c.content for c in chunks])
+    er, es, _ = oracle_c.search(emb=emb, dim=emb.shape[1], ticks=ticks, content_blob=blob, content_off=off, query=query,
+                                qvec=np.asarray(qv, dtype=np.float32), now_ticks=NOW, top_k=k, candidate_cap=cap)
+    return [(chunks[int(r)].id, oracle_c.round4(s)) for r, s in zip(er, es)]
+
+
+def test_compaction_keeps_results_and_reclaims_rows():
+    rng = np.random.default_rng(41)
+    dim = 64
+    st = S.GpuIngestionStore(dim, 4096, term_slots=64)
+    try:
+        _fill(st, rng, 120, dim)
+        qv = rng.standard_normal(dim).astype(np.float32).tolist()
+        svc = R.GpuRecallSearchService(st, _Emb(qv), candidate_cap=0, clock=lambda: NOW)
+        for d in range(0, 120, 3):
+            st.delete_document(f"d{d}")
+        for d in range(1, 120, 6):                                  # replace: tombstones + appended rows
+            st.upsert_chunks([S.CosmosChunkRecord(id=f"d{d}:{j:04d}", document_id=f"d{d}", chunk_index=j,
+                                                  content=" ".join(rng.choice(WORDS, size=9)),
+                                                  embedding=rng.standard_normal(dim).astype(np.float32).tolist(),
+                                                  created_at_utc=NOW - 3 * DAY) for j in range(3)])
+        used_before, live = st.shard.rows_used, st.shard.count
+        assert used_before > live
+        queries = ["azure vector", "kubernetes", "we", "recall score index"]
+        before = {q: [(c.chunk_id, c.score) for c in svc.search(q, 15).citations] for q in queries}
+        text_before = [(st.chunk_of_row(int(r)).id, s) for r, s in
+                       zip(*(lambda h: (h.rows, h.scores))(st.shard.search_text(np.asarray(qv, np.float32), ["e", "or"], NOW, 15)))]
+        reclaimed = st.compact()
+        assert reclaimed == used_before - live and st.shard.rows_used == live == st.shard.count
+        for q in queries:
+            after = [(c.chunk_id, c.score) for c in svc.search(q, 15).citations]
+            assert after == before[q], q
+            # NB the oracle's candidate order is the dict order of the live documents: replaced documents keep
+            # their slot in the reference's dictionary but moved to the end of the row order here; with distinct
+            # scores the ranking is the same
+            assert after == _oracle_citations(st, q, qv, 15, 0), q
+        text_after = [(st.chunk_of_row(int(r)).id, s) for r, s in
+                      zip(*(lambda h: (h.rows, h.scores))(st.shard.search_text(np.asarray(qv, np.float32), ["e", "or"], NOW, 15)))]
+        assert text_after == text_before
+        # the batched path rebuilds its planes over the squeezed rows
+        Q = rng.standard_normal((16, dim)).astype(np.float32)
+        batch = st.shard.search_batch(Q, None, NOW, 5)
+        for b in range(16):
+            one = st.shard.search(Q[b], orr.QueryTerms.none(), NOW, 5)
+            assert one.rows.tolist() == batch[b].rows.tolist() and one.scores.tolist() == batch[b].scores.tolist()
+        # mutations keep working on the compacted store
+        st.delete_document("d1")
+        st.upsert_chunks([S.CosmosChunkRecord(id="new:0000", document_id="new", chunk_index=0, content="azure vector azure",
+                                              embedding=qv, created_at_utc=NOW - DAY)])
+        assert svc.search("azure vector", 1).citations[0].chunk_id == "new:0000"
+        assert st.compact() == 3 and st.compact() == 0
+    finally:
+        st.close()
+
+
+def test_snapshot_round_trip(tmp_path):
+    rng = np.random.default_rng(43)
+    dim = 128
+    st = S.GpuIngestionStore(dim, 2048, term_slots=64)
+    st2 = S.GpuIngestionStore(dim, 4096, term_slots=64)
+    try:
+        _fill(st, rng, 60, dim)
+        for d in (3, 17, 40):
+            st.delete_document(f"d{d}")
+        qv = rng.standard_normal(dim).astype(np.float32).tolist()
+        st.save(str(tmp_path / "snap"))
+        st2.load(str(tmp_path / "snap"))
+        assert st2.shard.rows_used == st.shard.rows_used and st2.shard.count == st.shard.count
+        for cap in (0, 300):
+            a = R.GpuRecallSearchService(st, _Emb(qv), candidate_cap=cap, clock=lambda: NOW)
+            b = R.GpuRecallSearchService(st2, _Emb(qv), candidate_cap=cap, clock=lambda: NOW)
+            for q in ["azure vector", "cosmos", "nebula gemini token", "zz"]:
+                ra, rb = a.search(q, 12), b.search(q, 12)
+                assert [(c.chunk_id, c.score, c.file_name) for c in ra.citations] == [(c.chunk_id, c.score, c.file_name) for c in rb.citations]
+        ha = st.shard.search_text(np.asarray(qv, np.float32), ["ure", "o"], NOW, 20)
+        hb = st2.shard.search_text(np.asarray(qv, np.float32), ["ure", "o"], NOW, 20)
+        assert ha.rows.tolist() == hb.rows.tolist() and ha.scores.tolist() == hb.scores.tolist()
+        hn = st2.shard.search(None, orr.QueryTerms.none(), NOW, 400)               # exact path over every row
+        assert len(hn) == st.shard.count
+        # the document -> rows table came back: delete and replace work on loaded documents
+        st2.delete_document("d5")
+        assert st2.shard.count == st.shard.count - 5
+        with pytest.raises(N.OrrError):
+            st2.shard.load(str(tmp_path / "snap" / "shard.orrsnap"))                # only into an empty store
+        with orr.RecallShard(64, 2048) as other:
+            with pytest.raises(N.OrrError):
+                other.load(str(tmp_path / "snap" / "shard.orrsnap"))                # wrong dim
+    finally:
+        st.close()
+        st2.close()
+
+
+def test_searches_run_against_concurrent_mutations():
+    """The store is a singleton shared by request threads: searches hold the shard's RW lock
+    shared, mutators exclusive.  Every search must return a well-formed, correctly ordered list of rows that
+    were live at some point, and the final state must match the oracle."""
+    rng = np.random.default_rng(47)
+    dim = 256
+    st = S.GpuIngestionStore(dim, 20000, term_slots=64)
+    try:
+        _fill(st, rng, 200, dim)
+        qv = rng.standard_normal(dim).astype(np.float32)
+        errors, done = [], threading.Event()
+
+        def searcher(seed):
+            r = np.random.default_rng(seed)
+            svc = R.GpuRecallSearchService(st, _Emb(qv.tolist()), candidate_cap=0, clock=lambda: NOW)
+            try:
+                while not done.is_set():
+                    if r.integers(0, 4) == 0:
+                        hits = st.shard.search_batch(r.standard_normal((8, dim)).astype(np.float32), None, NOW, 5)
+                        assert all(len(h) == 5 for h in hits)
+                    else:
+                        h = st.shard.search(qv, svc.query_terms("azure vector"), NOW, 10)
+                        assert len(h) == 10 and np.all(np.diff(h.scores) <= 0)
+            except Exception as e:                                     # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=searcher, args=(i,)) for i in range(4)]
+        for t in threads:
+            t.start()
+        try:
+            for i in range(150):
+                d = int(rng.integers(0, 200))
+                if i % 3 == 0:
+                    st.delete_document(f"d{d}")
+                else:
+                    st.upsert_chunks([S.CosmosChunkRecord(id=f"d{d}:{j:04d}", document_id=f"d{d}", chunk_index=j,
+                                                          content=" ".join(rng.choice(WORDS, size=10)),
+                                                          embedding=rng.standard_normal(dim).astype(np.float32).tolist(),
+                                                          created_at_utc=NOW - int(rng.integers(1, 50)) * DAY) for j in range(4)])
+                if i == 100:
+                    st.compact()
+        finally:
+            done.set()
+            for t in threads:
+                t.join(timeout=60)
+        assert not errors, errors[:2]
+        svc = R.GpuRecallSearchService(st, _Emb(qv.tolist()), candidate_cap=0, clock=lambda: NOW)
+        got = [(c.chunk_id, c.score) for c in svc.search("azure vector", 10).citations]
+        assert got == _oracle_citations(st, "azure vector", qv, 10, 0)
+    finally:
+        st.close()
