@@ -68,13 +68,24 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
         }
         var rows = new ulong[n];
         var flat = hashes.Count > 0 ? hashes.ToArray() : new ulong[1];
+        // text mode: content.ToLowerInvariant() (RecallSearchService.cs:110) as UTF-8, kept in HBM so that
+        // orr_search_text can evaluate Contains(term) literally when a term expands past the probe limit
+        var textOffsets = new ulong[n + 1];
+        using var text = new MemoryStream();
+        for (var i = 0; i < n; i++)
+        {
+            text.Write(Encoding.UTF8.GetBytes((ordered[i].Content ?? string.Empty).ToLowerInvariant()));
+            textOffsets[i + 1] = (ulong)text.Length;
+        }
+        var textBytes = text.Length > 0 ? text.ToArray() : new byte[1];
         lock (_mutate)
         {
             ForgetRows(documentId);
             fixed (float* pe = emb) fixed (byte* ph = has) fixed (long* pt = ticks)
             fixed (ulong* pf = flat) fixed (uint* po = offsets) fixed (ulong* pr = rows)
-                OrrNative.Check(OrrNative.orr_store_upsert_document_chunks(
-                    Handle, HashTerm("doc:" + documentId), n, pe, ph, pt, pf, po, pr));
+            fixed (byte* ptx = textBytes) fixed (ulong* pto = textOffsets)
+                OrrNative.Check(OrrNative.orr_store_upsert_document_chunks_text(
+                    Handle, HashTerm("doc:" + documentId), n, pe, ph, pt, pf, po, ptx, pto, pr));
             _chunksByDocument[documentId] = ordered;
             _rowsByDocument[documentId] = rows;
             for (var i = 0; i < n; i++)
@@ -123,6 +134,33 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
     }
 
     internal CosmosChunkRecord ChunkOfRow(ulong row) => _chunkByRow[row];
+
+    /// Maintenance the HBM layout needs (not part of IIngestionStore): squeeze out the rows that replace /
+    /// delete tombstoned and remap the host's row tables.  Run from a background service when
+    /// rows_used - count grows (every scan still reads tombstoned rows).
+    public unsafe long Compact()
+    {
+        lock (_mutate)
+        {
+            var before = OrrNative.orr_store_rows_used(Handle);
+            var old = new ulong[Math.Max(1, before)];
+            long nLive;
+            fixed (ulong* po = old) OrrNative.Check(OrrNative.orr_store_compact(Handle, po, old.Length, out nLive));
+            var newOfOld = new Dictionary<ulong, ulong>();
+            for (long i = 0; i < nLive; i++) newOfOld[old[i]] = (ulong)i;
+            var remapped = _chunkByRow.ToDictionary(kv => newOfOld[kv.Key], kv => kv.Value);
+            _chunkByRow.Clear();
+            foreach (var kv in remapped) _chunkByRow[kv.Key] = kv.Value;
+            foreach (var d in _rowsByDocument.Keys.ToList())
+                _rowsByDocument[d] = _rowsByDocument[d].Select(r => newOfOld[r]).ToArray();
+            return before - nLive;
+        }
+    }
+
+    /// Snapshot / warm load of the HBM image; the host records (documents, chunks, row tables) are
+    /// serialised beside it by the caller (e.g. System.Text.Json) — see omni_recall_rag_b200/store.py.
+    public void SaveShard(string path) { lock (_mutate) OrrNative.Check(OrrNative.orr_store_save(Handle, path)); }
+    public void LoadShard(string path) { lock (_mutate) OrrNative.Check(OrrNative.orr_store_load(Handle, path)); }
 
     /// words of the live corpus that contain `term` — the host half of Contains (RecallSearchService.cs:111)
     internal IEnumerable<string> VocabularyWordsContaining(string term)

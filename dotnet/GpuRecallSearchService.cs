@@ -43,11 +43,30 @@ public sealed class GpuRecallSearchService(GpuIngestionStore store, IEmbeddingCl
         int nOut;
         unsafe
         {
-            var ph = probeHash.Count > 0 ? probeHash.ToArray() : new ulong[1];
-            var pt = probeTerm.Count > 0 ? probeTerm.ToArray() : new int[1];
-            fixed (float* pq = q) fixed (ulong* pph = ph) fixed (int* ppt = pt) fixed (OrrHit* pout = hits)
-                OrrNative.Check(OrrNative.orr_search(store.Handle, q.Length > 0 ? pq : null, q.Length, terms.Length,
-                    pph, ppt, probeHash.Count, DateTime.UtcNow.Ticks, topK, cap, pout, out nOut));
+            if (terms.Length <= 64 && probeHash.Count <= 128)          // ORR_MAX_QUERY_TERMS / ORR_MAX_QUERY_PROBES
+            {
+                var ph = probeHash.Count > 0 ? probeHash.ToArray() : new ulong[1];
+                var pt = probeTerm.Count > 0 ? probeTerm.ToArray() : new int[1];
+                fixed (float* pq = q) fixed (ulong* pph = ph) fixed (int* ppt = pt) fixed (OrrHit* pout = hits)
+                    OrrNative.Check(OrrNative.orr_search(store.Handle, q.Length > 0 ? pq : null, q.Length, terms.Length,
+                        pph, ppt, probeHash.Count, DateTime.UtcNow.Ticks, topK, cap, pout, out nOut));
+            }
+            else
+            {
+                // a term is a substring of too many vocabulary words ("ai", "go", one letter): evaluate
+                // Contains on the chunk text in HBM instead (slower: every candidate row is scored in fp64)
+                var offs = new uint[terms.Length + 1];
+                using var blob = new MemoryStream();
+                for (var i = 0; i < terms.Length; i++)
+                {
+                    blob.Write(System.Text.Encoding.UTF8.GetBytes(terms[i]));
+                    offs[i + 1] = (uint)blob.Length;
+                }
+                var tb = blob.Length > 0 ? blob.ToArray() : new byte[1];
+                fixed (float* pq = q) fixed (byte* ptb = tb) fixed (uint* po = offs) fixed (OrrHit* pout = hits)
+                    OrrNative.Check(OrrNative.orr_search_text(store.Handle, q.Length > 0 ? pq : null, q.Length, terms.Length,
+                        ptb, po, DateTime.UtcNow.Ticks, topK, cap, pout, out nOut));
+            }
         }
 
         var scored = hits.Take(nOut).Select(h => (Chunk: store.ChunkOfRow(h.Row), h.Score)).ToList();

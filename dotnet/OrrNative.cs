@@ -31,12 +31,38 @@ internal static partial class OrrNative
     [LibraryImport(Lib)] internal static unsafe partial int orr_store_upsert_document_chunks(
         nint store, ulong docKey, int n, float* emb, byte* hasEmb, long* createdTicks,
         ulong* termHashes, uint* termOffsets, ulong* outRows);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_store_upsert_document_chunks_text(
+        nint store, ulong docKey, int n, float* emb, byte* hasEmb, long* createdTicks,
+        ulong* termHashes, uint* termOffsets, byte* textLowerUtf8, ulong* textOffsets, ulong* outRows);
     [LibraryImport(Lib)] internal static partial int orr_store_delete_document(nint store, ulong docKey);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_store_compact(nint store, ulong* oldRowsOut, long outCap, out long nLive);
+    [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] internal static partial int orr_store_save(nint store, string path);
+    [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] internal static partial int orr_store_load(nint store, string path);
+    [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] internal static partial int orr_store_set_option(nint store, string name, double value);
+    [LibraryImport(Lib)] internal static partial long orr_store_rows_used(nint store);
     [LibraryImport(Lib)] internal static partial long orr_store_count(nint store);
     [LibraryImport(Lib)] internal static unsafe partial ulong orr_hash_term(byte* utf8Lower, int len);
     [LibraryImport(Lib)] internal static unsafe partial int orr_search(
         nint store, float* q, int qDim, int nTerms, ulong* probeHash, int* probeTerm, int nProbes,
         long nowTicks, int topK, int candidateCap, OrrHit* hits, out int nOut);
+    // text mode: KeywordScore's Contains evaluated on the chunk text kept in HBM (no probe limit)
+    [LibraryImport(Lib)] internal static unsafe partial int orr_search_text(
+        nint store, float* q, int qDim, int nTerms, byte* termsLowerUtf8, uint* termOffsets,
+        long nowTicks, int topK, int candidateCap, OrrHit* hits, out int nOut);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_search_batch(
+        nint store, int batch, float* q, int qDim, int* nTerms, ulong* probeHash, int* probeTerm, uint* probeOffsets,
+        long nowTicks, int topK, OrrHit* hits, int* nOut);
+    // one host process driving several GPUs: per-GPU stores + the fused peer-memory all-gather/merge
+    [LibraryImport(Lib)] internal static unsafe partial int orr_search_device(
+        nint store, float* qDev, int qDim, int nTerms, ulong* probeHash, int* probeTerm, int nProbes,
+        long nowTicks, int topK, OrrHit* outDev, int* statusDev, nint cudaStream);
+    [LibraryImport(Lib)] internal static partial int orr_xchg_create(int device, int world, int rank, int maxTopK, out nint xchg);
+    [LibraryImport(Lib)] internal static partial int orr_xchg_attach_peer(nint xchg, int peerRank, nint peer);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_xchg_allgather_merge(
+        nint xchg, OrrHit* hitsDev, int* statusDev, int topK, OrrHit* outDev, int* outStatusDev, nint cudaStream);
+    [LibraryImport(Lib)] internal static partial void orr_xchg_destroy(nint xchg);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_merge_hits(
+        OrrHit* lists, int* listLen, int nLists, int listStride, int topK, OrrHit* hits, out int nOut);
     [LibraryImport(Lib)] internal static partial nint orr_last_error();
 
     internal static void Check(int rc)
