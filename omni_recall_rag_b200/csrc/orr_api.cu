@@ -98,6 +98,7 @@ struct orr_store {
     uint64_t text_used = 0, text_cap = 0;
     int64_t text_rows = 0;            // rows appended WITH text; text mode needs text_rows == rows_used
     double text_bytes_per_row = 1024.0;
+    bool synth_text = false;          // option "synth_text": orr_store_fill_synthetic also writes the chunk text
     std::unique_ptr<BatchState> batch;
     int batch_passes = 0;            // 0 = auto (bf16 screen, bf16x3 for what it cannot prove), 1 = screen only, 3 = bf16x3
     std::atomic<int> batch_hold{0};  // auto mode: batches still to run bf16x3 first after a screen that mostly failed
@@ -340,6 +341,7 @@ int orr_store_set_option(orr_store* s, const char* name, double value) {
         s->batch_hold = 0;
         return ORR_OK;
     }
+    if (!strcmp(name, "synth_text")) { s->synth_text = value != 0.0; return ORR_OK; }
     if (!strcmp(name, "text_bytes_per_row")) {
         if (s->d_text) { orr_set_error("text_bytes_per_row must be set before the first chunk text arrives"); return ORR_E_INVALID; }
         if (!(value >= 16.0 && value <= 1048576.0)) { orr_set_error("text_bytes_per_row out of range"); return ORR_E_INVALID; }
@@ -352,6 +354,16 @@ int orr_store_set_option(orr_store* s, const char* name, double value) {
 
 int64_t orr_store_count(const orr_store* s) { return s ? s->live_rows : 0; }
 int64_t orr_store_rows_used(const orr_store* s) { return s ? s->rows_used : 0; }
+
+static int ensure_text_arena(orr_store* s) {
+    if (s->d_text) return ORR_OK;
+    const uint64_t cap_bytes = (uint64_t)((double)s->cfg.capacity_rows * s->text_bytes_per_row) + 4096;
+    ORR_CUDA_OK(cudaMalloc(&s->d_text, cap_bytes + 64));
+    ORR_CUDA_OK(cudaMalloc(&s->d_text_off, sizeof(uint64_t) * (size_t)s->cfg.capacity_rows));
+    ORR_CUDA_OK(cudaMalloc(&s->d_text_len, sizeof(uint32_t) * (size_t)s->cfg.capacity_rows));
+    s->text_cap = cap_bytes;
+    return ORR_OK;
+}
 
 static int tombstone_locked(orr_store* s, uint64_t doc_key) {
     auto it = s->docs.find(doc_key);
@@ -404,13 +416,8 @@ static int upsert_impl(orr_store* s, uint64_t doc_key, int32_t n, const float* e
                           (long long)s->text_rows, (long long)first);
             return ORR_E_INVALID;
         }
-        if (!s->d_text) {
-            const uint64_t cap_bytes = (uint64_t)((double)s->cfg.capacity_rows * s->text_bytes_per_row) + 4096;
-            ORR_CUDA_OK(cudaMalloc(&s->d_text, cap_bytes + 64));
-            ORR_CUDA_OK(cudaMalloc(&s->d_text_off, sizeof(uint64_t) * (size_t)s->cfg.capacity_rows));
-            ORR_CUDA_OK(cudaMalloc(&s->d_text_len, sizeof(uint32_t) * (size_t)s->cfg.capacity_rows));
-            s->text_cap = cap_bytes;
-        }
+        int rc0 = ensure_text_arena(s);
+        if (rc0 != ORR_OK) return rc0;
         const uint64_t total = text_offsets[n] - text_offsets[0];
         if (s->text_used + total > s->text_cap) {
             orr_set_error("upsert: text arena full (%llu + %llu > %llu bytes; raise option text_bytes_per_row)",
@@ -498,10 +505,19 @@ int orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t 
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     if (s->rows_used + n > s->cfg.capacity_rows) { orr_set_error("fill_synthetic: store full"); return ORR_E_OOM; }
+    const bool with_text = s->synth_text && s->text_rows == s->rows_used;
+    const uint64_t text_len = spec->terms_per_chunk > 0 ? (uint64_t)(9 * spec->terms_per_chunk - 1) : 0;
+    if (with_text) {
+        int rc0 = ensure_text_arena(s);
+        if (rc0 != ORR_OK) return rc0;
+        if (s->text_used + text_len * (uint64_t)n > s->text_cap) { orr_set_error("fill_synthetic: text arena full (raise text_bytes_per_row)"); return ORR_E_OOM; }
+    }
     int rc = orr_launch_synth_fill(s->d_emb, s->d_ticks, s->d_terms32, s->d_terms64, s->cfg.dim, s->cfg.term_slots,
-                                   *spec, first_row, s->rows_used, n, s->mut_stream);
+                                   *spec, first_row, s->rows_used, n, with_text ? s->d_text : nullptr, s->d_text_off,
+                                   s->d_text_len, s->text_used, s->mut_stream);
     if (rc != ORR_OK) return rc;
     ORR_CUDA_OK(cudaStreamSynchronize(s->mut_stream));
+    if (with_text) { s->text_used += text_len * (uint64_t)n; s->text_rows += n; }
     s->rows_used += n;
     s->live_rows += n;
     s->version++;
@@ -661,6 +677,7 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
         ORR_CUDA_OK(cudaMemcpyAsync(c->sc.q, c->h_q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream));
     }
     const int64_t row_words = (s->rows_used + 31) / 32;
+    bool escalated = false;
     std::vector<uint32_t> sub_rows;
     if (candidate_cap > 0) {
         if (candidate_cap > ORR_SORT_MAX) { orr_set_error("candidate_cap %d > %d", candidate_cap, ORR_SORT_MAX); return ORR_E_UNSUPPORTED; }
@@ -712,13 +729,29 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
         rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, (int)kk, nl, false, c->stream);
         g_timing.n_survivors = nl;
     } else {
-        rc = ensure_exact_buffers(s, c);
-        if (rc != ORR_OK) return rc;
-        sc = c->sc;                                          // buffers may just have been allocated
-        if (n_terms > 0) { sc.kw_bits = c->d_kw_bits; sc.kw_row_words = row_words; sc.kw_terms = n_terms; }
-        rc = orr_launch_exact_scores(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, c->stream);
-        if (rc != ORR_OK) return rc;
-        rc = orr_exact_select(sh, c->sc, (int)kk, c->stream);
+        // every row is a candidate: the fused scan selects with the bitmaps as its keyword side (<= 32 terms),
+        // K3 re-scores exactly and proves the selection; otherwise (or when the proof fails) the full fp64 pass
+        bool fused = eff_q_dim > 0 && k <= ORR_FUSED_MAX_K && n_terms <= 32;
+        if (fused) {
+            const int M = survivors_for(k);
+            rc = orr_launch_scan(sh, sc, pr, weights_of(s), now_ticks, M, s->sms, c->stream);
+            if (rc != ORR_OK) return rc;
+            rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, k, M, true, c->stream);
+            if (rc != ORR_OK) return rc;
+            ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+            ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
+            g_timing.n_survivors = M;
+            if (c->h_status[1] & 1) { fused = false; escalated = true; }
+        }
+        if (!fused) {
+            rc = ensure_exact_buffers(s, c);
+            if (rc != ORR_OK) return rc;
+            sc = c->sc;                                      // buffers may just have been allocated
+            if (n_terms > 0) { sc.kw_bits = c->d_kw_bits; sc.kw_row_words = row_words; sc.kw_terms = n_terms; }
+            rc = orr_launch_exact_scores(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, c->stream);
+            if (rc != ORR_OK) return rc;
+            rc = orr_exact_select(sh, c->sc, (int)kk, c->stream);
+        }
     }
     if (rc != ORR_OK) return rc;
     ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
@@ -732,9 +765,9 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
     memcpy(out, c->h_hits, sizeof(orr_hit) * (size_t)got);
     *n_out = got;
     g_timing.scan_ms = match_ms;                             // substring kernel
-    g_timing.finalize_ms = fin_ms;                           // exact scoring + ordering
+    g_timing.finalize_ms = fin_ms;                           // fused scan + K3 (or the full fp64 pass) + ordering
     g_timing.total_device_ms = match_ms + fin_ms;
-    g_timing.path = ORR_PATH_TEXT;
+    g_timing.path = ORR_PATH_TEXT | (escalated ? ORR_PATH_ESCALATED : 0);
     g_timing.rows_scanned = (candidate_cap > 0) ? g_timing.n_survivors : s->rows_used;
     g_timing.wall_ms = (float)(now_ms() - t0);
     return ORR_OK;

@@ -158,7 +158,8 @@ int orr_launch_xchg_merge(const OrrXchgArgs& a, cudaStream_t st);
 
 int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_t* terms64,
                           int dim, int slots, const orr_synth_spec& spec, uint64_t first_row,
-                          int64_t local_first, int64_t n, cudaStream_t st);
+                          int64_t local_first, int64_t n, uint8_t* text, uint64_t* text_off, uint32_t* text_len,
+                          uint64_t text_base, cudaStream_t st);
 
 // ---- batched path (orr_batch.cu) ------------------------------------------------------------
 constexpr int ORR_BATCH_TERMS = 16;          // query terms the batched epilogue handles per query

@@ -145,11 +145,15 @@ struct ScanArgs {
     float*    cta_floor;         // [grid]
     int32_t*  sel;               // {n_surv_out, tau_bits, ticket, ...}
     uint32_t* surv_rows;
+    // text mode: up to 32 query terms whose matches come from row bitmaps (orr_textmatch.cu) instead of probes
+    const uint32_t* bm_bits;     // [n_bm][bm_row_words] or NULL
+    int64_t   bm_row_words;
+    int32_t   n_bm;
 };
 
 // ---- the per-row fp32 epilogue ---------------------------------------------------------
 __device__ __forceinline__ float fuse_row(const ScanArgs& a, float dot, float nb, float inv_qn,
-                                          int64_t ticks, const uint32_t* th, int spl) {
+                                          int64_t ticks, const uint32_t* th, int spl, int bm_matches) {
     if (ticks == ORR_DEAD_TICKS) return -INFINITY;                 // tombstone
     // cosine (RecallSearchService.cs:84-87); zero row => 0
     float cosv = 0.f;
@@ -162,7 +166,7 @@ __device__ __forceinline__ float fuse_row(const ScanArgs& a, float dot, float nb
         force = true;                                              // NaN
     }
     // keyword (:110-112): which query terms does the chunk's hashed term set contain
-    float kw = 0.f;
+    float kw = (float)bm_matches * a.inv_nterms;                    // terms matched through row bitmaps
     if (a.pr.n_probes > 0) {
         uint32_t m0 = 0, m1 = 0;
         for (int p = 0; p < a.pr.n_probes; ++p) {
@@ -177,7 +181,7 @@ __device__ __forceinline__ float fuse_row(const ScanArgs& a, float dot, float nb
         }
         m0 = __reduce_or_sync(FULL, m0);
         if (a.pr.n_terms > 32) m1 = __reduce_or_sync(FULL, m1);
-        kw = (float)(__popc(m0) + __popc(m1)) * a.inv_nterms;
+        kw = (float)(__popc(m0) + __popc(m1) + bm_matches) * a.inv_nterms;
     }
     // recency (:115-119): age in units of 2^20 ticks (0.1 s) fits int32 for ~7 years, beyond
     // which exp(-age/30d) < 1e-37; selection-grade only, K3 recomputes it in fp64
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
     uint32_t pth[TR][4];                       // pending tile: this lane's term words
     int64_t ptk = 0, pr0 = 0;
     int pnr = 0;
+    uint32_t pbw = 0u;                         // pending tile: lane t's bitmap word of bitmap term t
 #pragma unroll
     for (int r = 0; r < TR; ++r) { pd[r] = pn[r] = 0.f; pth[r][0] = pth[r][1] = pth[r][2] = pth[r][3] = 0u; }
 
@@ -285,7 +290,8 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
                 const float dot = warp_sum(pd[r]);
                 const float nb = warp_sum(pn[r]);
                 const int64_t ticks = __shfl_sync(FULL, ptk, r);
-                const float s = fuse_row(a, dot, nb, inv_qn, ticks, pth[r], spl);
+                const int bm = a.n_bm ? __popc(__ballot_sync(FULL, (pbw >> ((uint32_t)(pr0 + r) & 31u)) & 1u)) : 0;
+                const float s = fuse_row(a, dot, nb, inv_qn, ticks, pth[r], spl, bm);
                 if (s > wmin) {                                          // warp-uniform
                     if (lane == wmin_lane) { es = s; er = (uint32_t)(pr0 + r); }
                     const uint32_t k = order_key(es);
@@ -306,6 +312,8 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
         // this tile's per-row scalars straight from global; consumed one iteration later
         int64_t tk = 0;
         if (lane < nr) tk = ldg_nc_s64(a.sh.ticks + r0 + lane);
+        uint32_t bw = 0u;                      // TR divides 32: a tile's rows share one bitmap word
+        if (lane < a.n_bm) bw = ldg_nc_u32(a.bm_bits + (int64_t)lane * a.bm_row_words + (r0 >> 5));
         uint32_t th[TR][4];
 #pragma unroll
         for (int r = 0; r < TR; ++r) { th[r][0] = th[r][1] = th[r][2] = th[r][3] = 0u; }
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
             pd[r] = cd[r]; pn[r] = cn[r];
             pth[r][0] = th[r][0]; pth[r][1] = th[r][1]; pth[r][2] = th[r][2]; pth[r][3] = th[r][3];
         }
-        ptk = tk; pr0 = r0; pnr = nr;
+        ptk = tk; pr0 = r0; pnr = nr; pbw = bw;
         if (!PIPE) { finish_pending(); pnr = 0; }                        // this tile, immediately
         if (++stage == a.stages) { stage = 0; parity ^= 1u; }
     }
@@ -587,6 +595,11 @@ int orr_launch_scan(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& p
     a.cta_floor = sc.cta_floor;
     a.sel = sc.sel;
     a.surv_rows = sc.surv_rows;
+    a.bm_bits = nullptr; a.bm_row_words = 0; a.n_bm = 0;
+    if (sc.kw_bits) {
+        if (sc.kw_terms < 1 || sc.kw_terms > 32 || pr.n_probes > 0) { orr_set_error("scan: bitmap terms must be 1..32 and exclusive of probes"); return ORR_E_INTERNAL; }
+        a.bm_bits = sc.kw_bits; a.bm_row_words = sc.kw_row_words; a.n_bm = sc.kw_terms;
+    }
     if (sh.dim == 3072) return launch_t<24, 1>(a, grid, smem, st);
     if (sh.dim == 1536) return launch_t<12, 2>(a, grid, smem, st);
     if (sh.dim == 768) return launch_t<6, 4>(a, grid, smem, st);

@@ -28,10 +28,13 @@ struct FillArgs {
     uint64_t first_row;       // global synthetic row id of the first generated row
     int64_t  local_first;     // local row index it lands in
     int64_t  n;
+    // optional chunk text (text mode): the tokens "t%07d" joined by single spaces, 9*tpc-1 bytes per row
+    uint8_t* text; uint64_t* text_off; uint32_t* text_len; uint64_t text_base;
 };
 
 // one warp per row: the lanes split the columns; lane 0 draws the terms and the timestamp
 __global__ void __launch_bounds__(256) orr_synth_fill_kernel(const FillArgs a) {
+    __shared__ uint32_t s_ids[8][128];
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -56,16 +59,34 @@ __global__ void __launch_bounds__(256) orr_synth_fill_kernel(const FillArgs a) {
             const long long v = zero ? 0 : orr_synth_component(a.spec.seed, crow, (uint32_t)c);
             out[c] = orr_synth_scaled(v, scale);
         }
+        const int tpc = a.spec.terms_per_chunk;
+        uint32_t* ids = s_ids[threadIdx.x >> 5];
+        __syncwarp();
         if (lane == 0) {
             a.ticks[lrow] = orr_synth_row_ticks(a.spec.seed, row, a.spec.now_ticks, a.spec.dup_row_ppm);
-            uint32_t ids[128];
-            const int tpc = a.spec.terms_per_chunk;
             orr_synth_chunk_terms(a.spec.seed, crow, tpc, ids);
-            for (int s = 0; s < a.slots; ++s) {
-                uint64_t h = 0;
-                if (s < tpc) h = synth_term_hash(ids[s]);
-                a.terms64[lrow * (int64_t)a.slots + s] = h;
-                a.terms32[lrow * (int64_t)a.slots + s] = h ? orr_hash_low(h) : 0u;
+        }
+        __syncwarp();
+        for (int s = lane; s < a.slots; s += 32) {
+            uint64_t h = 0;
+            if (s < tpc) h = synth_term_hash(ids[s]);
+            a.terms64[lrow * (int64_t)a.slots + s] = h;
+            a.terms32[lrow * (int64_t)a.slots + s] = h ? orr_hash_low(h) : 0u;
+        }
+        if (a.text) {
+            const uint32_t len = tpc > 0 ? (uint32_t)(9 * tpc - 1) : 0u;
+            const uint64_t off = a.text_base + (uint64_t)i * len;
+            if (lane == 0) { a.text_off[lrow] = off; a.text_len[lrow] = len; }
+            for (uint32_t p = lane; p < len; p += 32) {
+                const uint32_t tok = p / 9u, c = p - tok * 9u;          // c: 0 't', 1..7 digits, 8 space
+                uint8_t ch = ' ';
+                if (c == 0) ch = 't';
+                else if (c < 8) {
+                    uint32_t v = ids[tok];
+                    for (uint32_t d = 7; d > c; --d) v /= 10u;
+                    ch = (uint8_t)('0' + v % 10u);
+                }
+                a.text[off + p] = ch;
             }
         }
     }
@@ -75,9 +96,10 @@ __global__ void __launch_bounds__(256) orr_synth_fill_kernel(const FillArgs a) {
 
 int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_t* terms64,
                           int dim, int slots, const orr_synth_spec& spec, uint64_t first_row,
-                          int64_t local_first, int64_t n, cudaStream_t st) {
+                          int64_t local_first, int64_t n, uint8_t* text, uint64_t* text_off, uint32_t* text_len,
+                          uint64_t text_base, cudaStream_t st) {
     if (n <= 0) return ORR_OK;
-    FillArgs a{emb, ticks, terms32, terms64, dim, slots, spec, first_row, local_first, n};
+    FillArgs a{emb, ticks, terms32, terms64, dim, slots, spec, first_row, local_first, n, text, text_off, text_len, text_base};
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

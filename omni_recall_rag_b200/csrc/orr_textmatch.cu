@@ -14,17 +14,30 @@ namespace {
 
 constexpr int TM_THREADS = 256;
 constexpr int TM_WIN = 1024;                                  // text bytes staged per warp and window
-constexpr int TM_BUF = TM_WIN + ORR_TEXT_MAX_TERM_BYTES + 32; // window + overlap + alignment slack
+constexpr int TM_BUF = TM_WIN + ORR_TEXT_MAX_TERM_BYTES + 64; // window + overlap + alignment / look-ahead slack
 
 __global__ void __launch_bounds__(TM_THREADS) orr_text_bits_kernel(const OrrTextView tv, int64_t rows,
                                                                    const OrrTextTerms* terms_g, const uint32_t* rows_list,
                                                                    int n_list, uint32_t* bits, int64_t row_words) {
     __shared__ OrrTextTerms tt;
     __shared__ __align__(16) uint8_t wbuf[TM_THREADS / 32][TM_BUF];
+    // per term: its first min(8, len) bytes as a little-endian word + mask, so one 64-bit compare per
+    // (position, term) decides almost every case; longer terms verify their tail byte by byte
+    __shared__ uint64_t t_pat[ORR_MAX_QUERY_TERMS], t_msk[ORR_MAX_QUERY_TERMS];
+    __shared__ int t_len[ORR_MAX_QUERY_TERMS];
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(terms_g);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&tt);
         for (int i = threadIdx.x; i < (int)(sizeof(OrrTextTerms) / 4); i += TM_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < tt.n_terms) {
+        const int t = threadIdx.x, o = tt.off[t], tl = tt.off[t + 1] - o;
+        uint64_t pat = 0ull;
+        for (int i = 0; i < min(tl, 8); ++i) pat |= (uint64_t)tt.bytes[o + i] << (8 * i);
+        t_pat[t] = pat;
+        t_msk[t] = tl >= 8 ? ~0ull : ((1ull << (8 * tl)) - 1ull);
+        t_len[t] = tl;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -56,13 +69,23 @@ __global__ void __launch_bounds__(TM_THREADS) orr_text_bits_kernel(const OrrText
                 const uint8_t* tx = buf + head;
                 const int starts = min(want, TM_WIN);         // start positions owned by this window
                 for (int p = lane; p < starts; p += 32) {
-                    const uint8_t c = tx[p];
+                    // the 8 text bytes at p as one word: three aligned 32-bit smem loads + two funnel shifts
+                    const int at = head + p;
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(buf + (at & ~3));
+                    const uint32_t sh = (uint32_t)(at & 3) * 8u;
+                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+                    const uint64_t w = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | (uint64_t)__funnelshift_r(w0, w1, sh);
                     for (int t = 0; t < T; ++t) {
-                        const int o = tt.off[t], tl = tt.off[t + 1] - o;
-                        if (c != tt.bytes[o] || p + tl > want || ((found >> t) & 1ull)) continue;
-                        int i = 1;
-                        while (i < tl && tx[p + i] == tt.bytes[o + i]) ++i;
-                        if (i == tl) found |= 1ull << t;
+                        if (((w ^ t_pat[t]) & t_msk[t]) != 0ull) continue;
+                        const int tl = t_len[t];
+                        if (tl == 0 || p + tl > want) continue;                // bytes past `want` belong to no one
+                        if (tl > 8) {
+                            const int o = tt.off[t];
+                            int i = 8;
+                            while (i < tl && tx[p + i] == tt.bytes[o + i]) ++i;
+                            if (i < tl) continue;
+                        }
+                        found |= 1ull << t;
                     }
                 }
             }

@@ -154,3 +154,29 @@ def test_text_mode_needs_text_for_every_row():
         with pytest.raises(N.OrrError):                                                  # mixing is refused
             sh.upsert_document_chunks(2, None, np.array([NOW - DAY]), None, None, texts_lower=["abc"])
         assert len(sh.search_text(None, [], NOW, 3)) == 1                                # no terms: nothing to match
+
+
+def test_synthetic_text_fill_and_prefix_terms_match_the_oracle():
+    """The device-side synthetic fill can also write the chunk text (option synth_text): text mode over it
+    equals the oracle, including prefix terms that are substrings of thousands of vocabulary tokens, and
+    equals the fused hashed path for whole-token terms."""
+    dim, n = 256, 20_000
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=24, dup_row_ppm=5000)
+    rows = synth.rows_host(spec, 0, n)
+    contents = synth.contents_of(rows.term_ids)
+    blob, off = oracle_c.pack_contents(contents)
+    with orr.RecallShard(dim, n) as sh:
+        sh.set_option("synth_text", 1)
+        sh.set_option("text_bytes_per_row", 256)
+        sh.fill_synthetic(spec, 0, n)
+        for qi, terms in enumerate([["t00000"], ["t0000012", "00"], ["7", "t1", "zz"]]):
+            q = synth.query_host(spec, qi, n, n_terms=0)
+            got = sh.search_text(q.q, terms, NOW, 25)
+            er, es, _ = oracle_c.search(emb=rows.emb, dim=dim, ticks=rows.ticks, content_blob=blob, content_off=off,
+                                        query=" ".join(terms), qvec=q.q, now_ticks=NOW, top_k=25)
+            assert_same_ranking(got.rows, got.scores, er, es, what=f"synthetic text terms={terms}")
+        for qi in range(4):
+            q = synth.query_host(spec, qi, n, n_terms=4, frequent_terms=2)
+            a = sh.search(q.q, q.terms, NOW, 10)
+            b = sh.search_text(q.q, q.text.split(), NOW, 10)
+            assert a.rows.tolist() == b.rows.tolist() and a.scores.tolist() == b.scores.tolist()
