@@ -199,6 +199,10 @@ int  orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim,
         int64_t now_ticks, int32_t top_k,
         orr_hit* out_dev, int32_t* status_dev, void* cuda_stream);
 
+/* CUDA-event durations of the LAST orr_search_device call on this store (scan_ms = K1, finalize_ms = K3);
+ * waits for that call's kernels to finish. */
+int  orr_search_device_timing(orr_store* s, orr_timing* out);
+
 /* Batched queries (tcgen05 contraction + exact re-rank).  q is batch x q_dim row-major
  * in HOST memory; terms are a CSR over queries: query b owns probes
  * [probe_offsets[b], probe_offsets[b+1]) and n_terms[b] terms.  out is

@@ -88,6 +88,8 @@ struct orr_store {
     std::vector<std::unique_ptr<SearchCtx>> pool;
     std::mutex dev_mu;
     std::unique_ptr<SearchCtx> dev_ctx;                                             // orr_search_device scratch
+    bool dev_timing_valid = false;
+    int64_t dev_rows = 0;
     std::mutex cap_mu;
     uint64_t cap_version = ~0ull;
     int32_t cap_value = -1;
@@ -119,6 +121,7 @@ OrrWeights weights_of(const orr_store* s) {
 void free_ctx(SearchCtx* c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
+    else cudaDeviceSynchronize();
     cudaFree(c->sc.q); cudaFree(c->sc.cta_cands); cudaFree(c->sc.cta_floor); cudaFree(c->sc.surv_rows);
     cudaFree(c->sc.exact); cudaFree(c->sc.sel); cudaFree(c->sc.hits); cudaFree(c->sc.status);
     cudaFree(c->sc.scores64); cudaFree(c->sc.cub_tmp);
@@ -146,10 +149,8 @@ int make_ctx(orr_store* s, std::unique_ptr<SearchCtx>& out, bool own_stream) {
     std::unique_ptr<SearchCtx> c(new SearchCtx());
     const int dim = s->cfg.dim;
     int rc = [&]() -> int {
-        if (own_stream) {
-            ORR_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-            for (auto& e : c->ev) ORR_CUDA_OK(cudaEventCreate(&e));
-        }
+        if (own_stream) ORR_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev) ORR_CUDA_OK(cudaEventCreate(&e));
         ORR_CUDA_OK(cudaMalloc(&c->sc.q, sizeof(float) * (size_t)dim));
         ORR_CUDA_OK(cudaMalloc(&c->sc.cta_cands, sizeof(uint2) * (size_t)s->sms * ORR_MAX_SURVIVORS));
         ORR_CUDA_OK(cudaMalloc(&c->sc.cta_floor, sizeof(float) * (size_t)s->sms));
@@ -1058,9 +1059,33 @@ int orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim, int32_t n
     sc.status = status_dev;
     const OrrShard sh = shard_view(s);
     const int M = survivors_for(k);
+    SearchCtx* c = s->dev_ctx.get();
+    ORR_CUDA_OK(cudaEventRecord(c->ev[0], st));
     rc = orr_launch_scan(sh, sc, pr, weights_of(s), now_ticks, M, s->sms, st);
     if (rc != ORR_OK) return rc;
-    return orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, q_dim, k, M, true, st);
+    ORR_CUDA_OK(cudaEventRecord(c->ev[1], st));
+    rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, q_dim, k, M, true, st);
+    if (rc != ORR_OK) return rc;
+    ORR_CUDA_OK(cudaEventRecord(c->ev[2], st));
+    s->dev_timing_valid = true;
+    s->dev_rows = s->rows_used;
+    return ORR_OK;
+}
+
+int orr_search_device_timing(orr_store* s, orr_timing* out) {
+    if (!s || !out) { orr_set_error("orr_search_device_timing: NULL argument"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> g(s->dev_mu);
+    memset(out, 0, sizeof *out);
+    if (!s->dev_ctx || !s->dev_timing_valid) { orr_set_error("orr_search_device_timing: no orr_search_device call yet"); return ORR_E_INVALID; }
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    SearchCtx* c = s->dev_ctx.get();
+    ORR_CUDA_OK(cudaEventSynchronize(c->ev[2]));
+    ORR_CUDA_OK(cudaEventElapsedTime(&out->scan_ms, c->ev[0], c->ev[1]));
+    ORR_CUDA_OK(cudaEventElapsedTime(&out->finalize_ms, c->ev[1], c->ev[2]));
+    out->total_device_ms = out->scan_ms + out->finalize_ms;
+    out->path = ORR_PATH_FUSED;
+    out->rows_scanned = s->dev_rows;
+    return ORR_OK;
 }
 
 // ---- batched path ------------------------------------------------------------------------------

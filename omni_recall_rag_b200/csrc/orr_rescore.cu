@@ -389,18 +389,20 @@ __global__ void __launch_bounds__(256) orr_merge_kernel(const orr_hit* lists, co
 }
 
 // ---- fused all-gather + merge over NVLink peer memory (multi-GPU) ----------------
-// Every rank owns an exchange buffer of ORR_XCHG_SLOTS slots; a slot holds hits[world][kmax], status[world][2]
-// and one arrival flag per source rank.  One CTA per rank: (1) PUSH this rank's exact local top-k and status
-// into slot[seq % SLOTS][rank] of EVERY peer with plain stores through the peer mapping, fence, then publish
-// flag = seq with a system-scope release store; (2) wait until all `world` flags of the local slot carry seq
-// (acquire loads; bounded by a timeout so a lost peer surfaces as a status flag, not a hung GPU); (3) order
-// the union with the reference tie chain, exactly like orr_merge_kernel.  No NCCL launch, no host round trip.
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Every rank owns an exchange buffer of ORR_XCHG_SLOTS slots; a slot holds, per source rank, the rank's hit
+// list and status as LL words: each 4 bytes of payload travel in one 8-byte {data, seq} store, so the flag
+// arrives WITH the data and no fence or separate flag round trip is needed (8-byte stores are single NVLink
+// transactions).  One CTA per rank: (1) PUSH the k x 24 B + 8 B of this rank into slot[seq % SLOTS][rank] of
+// EVERY peer, all stores in flight at once; (2) PULL: spin on each expected word of the local slot until its
+// tag is seq (bounded by a timeout so a lost peer surfaces as a status flag, not a hung GPU) and unpack into
+// shared memory; (3) order the union with the reference tie chain, exactly like orr_merge_kernel.
+// No NCCL launch, no host round trip, one NVLink store latency.
+__device__ __forceinline__ void st_ll(uint2* p, uint32_t data, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -412,39 +414,45 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __global__ void __launch_bounds__(256) orr_xchg_merge_kernel(const OrrXchgArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x;
+    const int k = min(max(1, a.top_k), a.kmax);
+    const int words = k * 6 + 2;                                   // k hits (6 words each) + {n, flags}
+    const int words_max = a.kmax * 6 + 2;                          // LL words reserved per source rank
     const size_t slot_off = (size_t)a.slot * a.slot_bytes;
-    const size_t hits_bytes = (size_t)a.kmax * sizeof(orr_hit);
-    const size_t status_off = (size_t)a.world * hits_bytes;
-    const size_t flags_off = status_off + (size_t)a.world * 2 * sizeof(int32_t);
-    // (1) push
-    const int words = min(max(1, a.top_k), a.kmax) * (int)(sizeof(orr_hit) / 8);   // the caller's list holds top_k hits
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(a.src_hits);
-    for (int p = 0; p < a.world; ++p) {
-        uint64_t* dst = reinterpret_cast<uint64_t*>(a.peer_base[p] + slot_off + (size_t)a.rank * hits_bytes);
-        for (int i = tid; i < words; i += blockDim.x) dst[i] = src[i];
-        if (tid < 2) reinterpret_cast<int32_t*>(a.peer_base[p] + slot_off + status_off)[2 * a.rank + tid] = a.src_status[tid];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < a.world) st_release_sys(reinterpret_cast<uint32_t*>(a.peer_base[tid] + slot_off + flags_off) + a.rank, a.seq);
-    // (2) wait for every source rank
+    // smem: gathered hits [world][k] + status [world][2], then the sort array
+    uint32_t* g_hits = reinterpret_cast<uint32_t*>(smem_raw);
+    int32_t* g_status = reinterpret_cast<int32_t*>(g_hits + (size_t)a.world * k * 6);
+    OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw + (((size_t)a.world * (k * 24 + 8)) + 15) / 16 * 16);
     __shared__ int s_timeout;
     if (tid == 0) s_timeout = 0;
-    __syncthreads();
-    uint8_t* mine = a.peer_base[a.rank] + slot_off;
-    if (tid < a.world) {
-        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + flags_off) + tid;
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(flag) != a.seq) {
-            if (global_timer_ns() - t0 > a.timeout_ns) { atomicOr(&s_timeout, 1); break; }
-            __nanosleep(64);
-        }
+    // (1) push: word i of this rank -> every peer
+    const uint32_t* src_h = reinterpret_cast<const uint32_t*>(a.src_hits);
+    for (int idx = tid; idx < words * a.world; idx += blockDim.x) {
+        const int p = idx / words, i = idx - p * words;
+        const uint32_t v = i < k * 6 ? src_h[i] : (uint32_t)a.src_status[i - k * 6];
+        st_ll(reinterpret_cast<uint2*>(a.peer_base[p] + slot_off) + (size_t)a.rank * words_max + i, v, a.seq);
     }
     __syncthreads();
+    // (2) pull: every expected word of the local slot
+    const uint2* mine = reinterpret_cast<const uint2*>(a.peer_base[a.rank] + slot_off);
+    const unsigned long long t0 = global_timer_ns();
+    for (int idx = tid; idx < words * a.world; idx += blockDim.x) {
+        const int r = idx / words, i = idx - r * words;
+        const uint2* w = mine + (size_t)r * words_max + i;
+        uint2 v = ld_ll(w);
+        while (v.y != a.seq) {
+            if (global_timer_ns() - t0 > a.timeout_ns) { atomicOr(&s_timeout, 1); v.x = 0u; break; }
+            __nanosleep(32);
+            v = ld_ll(w);
+        }
+        if (i < k * 6) g_hits[(size_t)r * k * 6 + i] = v.x;
+        else g_status[2 * r + (i - k * 6)] = (int32_t)v.x;
+    }
+    __syncthreads();
+    if (s_timeout && tid < a.world) g_status[2 * tid] = 0;        // incomplete exchange: return nothing, flag it
+    __syncthreads();
     // (3) merge
-    merge_lists_cta(reinterpret_cast<const orr_hit*>(mine), reinterpret_cast<const int32_t*>(mine + status_off), a.world,
-                    a.kmax, a.top_k, a.out, a.out_status, s_timeout ? ORR_XCHG_FLAG_TIMEOUT : 0,
-                    reinterpret_cast<OrrExact*>(smem_raw));
+    merge_lists_cta(reinterpret_cast<const orr_hit*>(g_hits), g_status, a.world, k, a.top_k, a.out, a.out_status,
+                    s_timeout ? ORR_XCHG_FLAG_TIMEOUT : 0, e);
 }
 
 }  // namespace
@@ -563,12 +571,14 @@ int orr_launch_xchg_merge(const OrrXchgArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         ORR_CUDA_OK(cudaFuncSetAttribute(orr_xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ORR_SORT_MAX * (int)sizeof(OrrExact)));
+                                         2 * ORR_SORT_MAX * (int)sizeof(OrrExact) + 1024));
         configured = true;
     }
+    const int k = std::min(std::max(1, a.top_k), a.kmax);
     int np2 = 1;
-    while (np2 < total) np2 <<= 1;
-    orr_xchg_merge_kernel<<<1, 256, np2 * sizeof(OrrExact), st>>>(a);
+    while (np2 < a.world * k) np2 <<= 1;
+    const size_t smem = ((size_t)a.world * (k * 24 + 8) + 15) / 16 * 16 + (size_t)np2 * sizeof(OrrExact);
+    orr_xchg_merge_kernel<<<1, 256, smem, st>>>(a);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }

@@ -34,7 +34,8 @@ int orr_xchg_create(int32_t device, int32_t world, int32_t rank, int32_t max_top
     ORR_CUDA_OK(cudaSetDevice(device));
     std::unique_ptr<orr_xchg> x(new orr_xchg());
     x->device = device; x->world = world; x->rank = rank; x->kmax = max_top_k;
-    const size_t raw = (size_t)world * max_top_k * sizeof(orr_hit) + (size_t)world * 2 * sizeof(int32_t) + (size_t)world * sizeof(uint32_t);
+    // per source rank: max_top_k hits (6 words each) + 2 status words, every word an 8-byte {data, seq} LL store
+    const size_t raw = (size_t)world * ((size_t)max_top_k * 6 + 2) * 8;
     x->slot_bytes = (raw + 127) / 128 * 128;
     x->bytes = x->slot_bytes * ORR_XCHG_SLOTS;
     ORR_CUDA_OK(cudaMalloc(&x->local, x->bytes));

@@ -317,6 +317,12 @@ class RecallShard:
                                                int(tile_stride), out.ctypes.data_as(C.c_void_p), n_s))
         return out
 
+    def last_device_timing(self) -> dict:
+        """CUDA-event durations of the last search_device call (waits for it)."""
+        t = N.OrrTiming()
+        N.check(N.lib().orr_search_device_timing(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in N.OrrTiming._fields_}
+
     def last_timing(self) -> dict:
         t = N.OrrTiming()
         N.lib().orr_last_timing(C.byref(t))

@@ -101,6 +101,10 @@ class ShardedRecall:
                 N.check(L.orr_xchg_open_peer(x, r, C.cast(h, C.c_void_p)))
         self.dist.barrier(group=self.group)            # every rank has every peer mapped before the first push
 
+    def last_timing(self) -> dict:
+        """Kernel durations (CUDA events) of this rank's part of the last search()."""
+        return dict(getattr(self, "_last_timing", {}))
+
     def close(self) -> None:
         if self._xchg is not None:
             import torch
@@ -122,6 +126,7 @@ class ShardedRecall:
             q_dev = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(dev, non_blocking=True)
             hits_dev, status_dev = self.search_device(q_dev, terms, now_ticks, top_k)
             hits, flags = hits_from_device(hits_dev, status_dev)
+            self._last_timing = self.shard.last_device_timing()
             if flags == 0:
                 return hits
             if flags & N.STATUS_XCHG_TIMEOUT:
@@ -129,6 +134,7 @@ class ShardedRecall:
             # a shard could not prove its fp32 selection: every rank sees the same OR-ed flag and re-runs below,
             # where orr_search escalates to the exact path
         local = self.local_search(q, terms, now_ticks, top_k)
+        self._last_timing = self.shard.last_timing() if self.shard is not None else {}
         if self.world == 1:
             return local
         mine = torch.from_numpy(_pack(local, k))
