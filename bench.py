@@ -468,6 +468,15 @@ def main():
     assert got.rows.tolist() == hits.rows.tolist() and got.scores.tolist() == hits.scores.tolist(), "device/host paths disagree"
     flags_seen |= flags
 
+    # per-rank scan kernel time: the exchange makes every query wait for the slowest shard
+    scan_avg_local = sum(scan_ms) / len(scan_ms)
+    per_rank_scan = [scan_avg_local]
+    if world > 1:
+        tl = torch.tensor([scan_avg_local], dtype=torch.float64, device=dev)
+        tg = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(tg, tl)
+        per_rank_scan = [round(float(x), 4) for x in tg.cpu().tolist()]
+
     scale = total_rows / 1.0e6
     value = steps / (dev_ms / 1000.0) * scale
     e2e_value = steps / e2e_s * scale
@@ -489,7 +498,7 @@ def main():
                 "call_ms": {"what": "orr_search wall clock" if world == 1 else "ShardedRecall.search wall clock", "median": statistics.median(wall_ms), "p99": sorted(wall_ms)[min(len(wall_ms) - 1, int(0.99 * len(wall_ms)))]}},
         "gpu_launches": launches_per_step * steps,
         "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel"] + (exchange_kernel if world > 1 else []),
-        "exchange": sr.exchange,
+        "exchange": sr.exchange, "per_rank_scan_kernel_ms": per_rank_scan,
         "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel<24,1>", "achieved": achieved, "peak": peak,
                      "peak_kind": f"{peak_kind} HBM copy GB/s (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6650 GB/s",
                      "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
