@@ -230,6 +230,12 @@ int  orr_merge_hits_device(int32_t device, const orr_hit* lists_dev, const int32
         int32_t n_lists, int32_t list_stride, int32_t top_k,
         orr_hit* out_dev, int32_t* out_status_dev, void* cuda_stream);
 
+/* Batched form for row-sharded orr_search_batch: lists_dev is the all-gathered [n_lists][batch][k] hit array
+ * (every shard's answer to every query), n_dev the [n_lists][batch] valid counts; one CTA per query writes the
+ * global top-k to out_dev[batch][k] / n_out_dev[batch]. */
+int  orr_merge_hits_batch_device(int32_t device, const orr_hit* lists_dev, const int32_t* n_dev, int32_t n_lists,
+        int32_t batch, int32_t k, orr_hit* out_dev, int32_t* n_out_dev, void* cuda_stream);
+
 /* ---- fused all-gather + merge over NVLink peer memory ------------------------------------------
  * The multi-GPU exchange step as ONE kernel per rank instead of an NCCL all-gather plus a merge kernel:
  * every rank pushes its exact local top-k (k x 24 B + status) into every peer's exchange buffer with stores

@@ -88,6 +88,8 @@ _SIGNATURES = {
                                  C.POINTER(C.c_int32)]),
     "orr_merge_hits_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "orr_merge_hits_batch_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
     "orr_xchg_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "orr_xchg_destroy": (None, [C.c_void_p]),
     "orr_xchg_get_handle": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1520,6 +1520,13 @@ int orr_merge_hits_device(int32_t device, const orr_hit* lists_dev, const int32_
                             (cudaStream_t)cuda_stream);
 }
 
+int orr_merge_hits_batch_device(int32_t device, const orr_hit* lists_dev, const int32_t* n_dev, int32_t n_lists, int32_t batch,
+                                int32_t k, orr_hit* out_dev, int32_t* n_out_dev, void* cuda_stream) {
+    if (!lists_dev || !n_dev || !out_dev || !n_out_dev) { orr_set_error("orr_merge_hits_batch_device: NULL argument"); return ORR_E_INVALID; }
+    ORR_CUDA_OK(cudaSetDevice(device));
+    return orr_launch_merge_batch(lists_dev, n_dev, n_lists, batch, k, out_dev, n_out_dev, (cudaStream_t)cuda_stream);
+}
+
 int orr_last_timing(orr_timing* out) {
     if (!out) return ORR_E_INVALID;
     *out = g_timing;

@@ -156,6 +156,9 @@ struct OrrXchgArgs {
 };
 int orr_launch_xchg_merge(const OrrXchgArgs& a, cudaStream_t st);
 
+int orr_launch_merge_batch(const orr_hit* lists_dev, const int32_t* n_dev, int n_lists, int batch, int k, orr_hit* out_dev,
+                           int32_t* n_out_dev, cudaStream_t st);
+
 int orr_launch_synth_fill(float* emb, int64_t* ticks, uint32_t* terms32, uint64_t* terms64,
                           int dim, int slots, const orr_synth_spec& spec, uint64_t first_row,
                           int64_t local_first, int64_t n, uint8_t* text, uint64_t* text_off, uint32_t* text_len,

@@ -388,6 +388,53 @@ __global__ void __launch_bounds__(256) orr_merge_kernel(const orr_hit* lists, co
     merge_lists_cta(lists, status, n_lists, stride, top_k, out, out_status, 0, reinterpret_cast<OrrExact*>(smem_raw));
 }
 
+// batched form (row-sharded orr_search_batch): one CTA per query merges the query's n_lists gathered lists.
+// lists[l][b][k], n[l][b] -> out[b][k], n_out[b]
+__global__ void __launch_bounds__(128) orr_merge_batch_kernel(const orr_hit* lists, const int32_t* n, int n_lists, int batch,
+                                                              int k, orr_hit* out, int32_t* n_out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int total = n_lists * k;
+    int np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    __shared__ int s_n;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int i = tid; i < np2; i += blockDim.x) {
+        OrrExact v; v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull;
+        if (i < total) {
+            const int l = i / k, j = i - l * k;
+            if (j < n[(int64_t)l * batch + b]) {
+                const orr_hit h = lists[((int64_t)l * batch + b) * k + j];
+                v.score = h.score; v.ticks = h.created_ticks; v.row = h.row;
+                atomicAdd(&s_n, 1);
+            }
+        }
+        e[i] = v;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const OrrExact x = e[i], y = e[p];
+                    const bool up = ((i & k2) == 0);
+                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int m = min(k, s_n);
+    for (int i = tid; i < m; i += blockDim.x) {
+        orr_hit h; h.row = e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
+        out[(int64_t)b * k + i] = h;
+    }
+    if (tid == 0) n_out[b] = m;
+}
+
 // ---- fused all-gather + merge over NVLink peer memory (multi-GPU) ----------------
 // Every rank owns an exchange buffer of ORR_XCHG_SLOTS slots; a slot holds, per source rank, the rank's hit
 // list and status as LL words: each 4 bytes of payload travel in one 8-byte {data, seq} store, so the flag
@@ -558,6 +605,23 @@ int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_
     while (np2 < total) np2 <<= 1;
     orr_merge_kernel<<<1, 256, np2 * sizeof(OrrExact), st>>>(lists_dev, status_dev, n_lists, stride, top_k, out_dev,
                                                             out_status_dev);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+int orr_launch_merge_batch(const orr_hit* lists_dev, const int32_t* n_dev, int n_lists, int batch, int k, orr_hit* out_dev,
+                           int32_t* n_out_dev, cudaStream_t st) {
+    const int total = n_lists * k;
+    if (n_lists < 1 || k < 1 || batch < 0 || total > ORR_SORT_MAX) { orr_set_error("batch merge: %d lists x %d exceed the sorter", n_lists, k); return ORR_E_UNSUPPORTED; }
+    if (batch == 0) return ORR_OK;
+    static bool configured = false;
+    if (!configured) {
+        ORR_CUDA_OK(cudaFuncSetAttribute(orr_merge_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ORR_SORT_MAX * (int)sizeof(OrrExact)));
+        configured = true;
+    }
+    int np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    orr_merge_batch_kernel<<<batch, 128, np2 * sizeof(OrrExact), st>>>(lists_dev, n_dev, n_lists, batch, k, out_dev, n_out_dev);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }

@@ -21,7 +21,7 @@ from typing import Callable, Optional, Tuple
 import numpy as np
 
 from . import _native as N
-from .shard import Hits, QueryTerms, RecallShard, merge_hits
+from .shard import BatchHits, Hits, QueryTerms, RecallShard, merge_hits, _HIT_DTYPE
 
 HIT_BYTES = 24  # sizeof(orr_hit)
 
@@ -150,6 +150,33 @@ class ShardedRecall:
             self.dist.all_gather(parts, mine, group=self.group)
             gathered = np.stack([p.numpy() for p in parts])
         return merge_hits([_unpack(gathered[r], k) for r in range(self.world)], top_k)
+
+    # -- batched queries over the sharded corpus -------------------------------------------------------
+    def search_batch(self, q: np.ndarray, terms, now_ticks: int, top_k: int) -> BatchHits:
+        """Every rank runs orr_search_batch (tcgen05 contraction + exact re-rank) on its shard; the B x k x 24 B
+        answers are all-gathered (a bandwidth-type exchange: NCCL) and merged per query on the device
+        (orr_merge_hits_batch_device, one CTA per query) with the reference tie chain."""
+        import torch
+
+        local = self.shard.search_batch(q, terms, now_ticks, top_k)
+        if self.world == 1:
+            return local
+        B, k = len(local), max(1, int(top_k))
+        if self.dist.get_backend(self.group) != "nccl":
+            raise RuntimeError("sharded search_batch needs the nccl backend (device merge)")
+        dev = torch.device("cuda", self.shard.device)
+        mine = torch.from_numpy(local.raw.view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
+        mine_n = torch.from_numpy(np.ascontiguousarray(local.n_out, dtype=np.int32)).to(dev, non_blocking=True)
+        allh = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=dev)
+        alln = torch.empty(self.world * B, dtype=torch.int32, device=dev)
+        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
+        self.dist.all_gather_into_tensor(alln, mine_n, group=self.group)
+        out = torch.empty(B * k * HIT_BYTES, dtype=torch.uint8, device=dev)
+        out_n = torch.empty(B, dtype=torch.int32, device=dev)
+        N.check(N.lib().orr_merge_hits_batch_device(self.shard.device, allh.data_ptr(), alln.data_ptr(), self.world, B, k,
+                                                    out.data_ptr(), out_n.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        raw = np.frombuffer(out.cpu().numpy().tobytes(), dtype=_HIT_DTYPE).reshape(B, k).copy()
+        return BatchHits(raw, out_n.cpu().numpy())
 
     # -- device-resident path (query and hits stay in HBM; nothing synchronises the host) -----
     def search_device(self, q_dev, terms: QueryTerms, now_ticks: int, top_k: int):

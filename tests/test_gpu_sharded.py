@@ -137,3 +137,42 @@ def test_exchange_reports_a_missing_peer_instead_of_hanging():
     finally:
         for x in xs:
             L.orr_xchg_destroy(x)
+
+
+def test_batched_search_over_virtual_shards_merges_to_the_oracle():
+    """Row-sharded orr_search_batch: every shard answers every query, the [shards][B][k] lists are merged per
+    query on the device (orr_merge_hits_batch_device) -> the oracle's global top-k for each query."""
+    import torch
+
+    dim, total, k, B, world = 128, 12_003, 20, 24, 3
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=16, dup_row_ppm=20000)
+    rows = synth.rows_host(spec, 0, total)
+    qs = [synth.query_host(spec, qi, total, n_terms=3, frequent_terms=1) for qi in range(B)]
+    Q = np.stack([q.q for q in qs])
+    dev = torch.device("cuda", 0)
+    shards = []
+    try:
+        raws, ns = [], []
+        for r in range(world):
+            base, n_local = sharded.shard_rows(total, world, r)
+            sh = orr.RecallShard(dim, n_local, row_base=base)
+            sh.fill_synthetic(spec, base, n_local)
+            shards.append(sh)
+            got = sh.search_batch(Q, [q.terms for q in qs], NOW, k)
+            assert sh.last_timing()["path"] & 0xff == N.PATH_BATCH
+            raws.append(got.raw.copy()); ns.append(got.n_out.astype(np.int32))
+        allh = torch.from_numpy(np.stack(raws).view(np.uint8).reshape(-1)).to(dev)
+        alln = torch.from_numpy(np.stack(ns).reshape(-1)).to(dev)
+        out = torch.zeros(B * k * 24, dtype=torch.uint8, device=dev)
+        out_n = torch.zeros(B, dtype=torch.int32, device=dev)
+        N.check(N.lib().orr_merge_hits_batch_device(0, allh.data_ptr(), alln.data_ptr(), world, B, k, out.data_ptr(),
+                                                    out_n.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        torch.cuda.synchronize()
+        a = np.frombuffer(out.cpu().numpy().tobytes(), dtype=np.dtype([("row", "<u8"), ("score", "<f8"), ("ticks", "<i8")])).reshape(B, k)
+        assert out_n.cpu().tolist() == [k] * B
+        for b, q in enumerate(qs):
+            er, es, _ = oracle_search_synth(rows, q, NOW, k)
+            assert_same_ranking(a[b]["row"], a[b]["score"], er, es, what=f"sharded batch b={b}")
+    finally:
+        for sh in shards:
+            sh.close()

@@ -60,6 +60,16 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"sharded parity ok: world={world}, {ok} queries, {total} x {dim}, exchanges p2p + nccl")
+    # batched queries over the sharded corpus: all-gather of the B x k answers + per-query device merge
+    B, kb = 32, 20
+    qs = [synth.query_host(spec, 100 + i, total, n_terms=4) for i in range(B)]
+    Q = np.stack([q.q for q in qs])
+    gotb = sr.search_batch(Q, [q.terms for q in qs], spec.now_ticks, kb)
+    if rank == 0:
+        for b in range(0, B, 3):
+            er, es, _ = oracle_search_synth(rows, qs[b], spec.now_ticks, kb)
+            assert_same_ranking(gotb[b].rows, gotb[b].scores, er, es, what=f"sharded batch x{world} b={b}")
+        print(f"sharded batch parity ok: {B} queries, top-{kb}")
     # exchange cost: the same 200 device-resident queries through each exchange (small shard => exchange-dominated)
     q = synth.query_host(spec, 3, total, n_terms=4)
     qd = torch.from_numpy(q.q).to(dev)
