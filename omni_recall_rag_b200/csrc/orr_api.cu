@@ -1224,7 +1224,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
                 const size_t slot_bytes = (size_t)row_words * sizeof(uint32_t);
                 const size_t have = (size_t)bs->term_slots_cap * slot_bytes;
                 size_t budget = std::min<size_t>((free_b + have) / 4, (size_t)12 << 30);
-                size_t want = std::max<size_t>(2 * distinct.size(), 4096);
+                size_t want = std::max<size_t>(8 * distinct.size(), 16384);   // room for several batches before the pool recycles
                 if (want * slot_bytes > budget) want = std::max<size_t>(distinct.size(), budget / slot_bytes);
                 want = std::min<size_t>(want, ORR_BATCH_MAX_TERM_SLOTS);
                 cudaFree(bs->term_bits); bs->term_bits = nullptr; bs->term_slots_cap = 0;

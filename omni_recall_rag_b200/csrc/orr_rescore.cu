@@ -808,20 +808,27 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
 // 16-byte loads in flight per lane; every stored hash is probed in an open-addressing table of the
 // batch's distinct terms (smem) and hits set their row's bit with atomicOr (hits are sparse).
 constexpr int TERM_BITS_THREADS = 1024;
+constexpr int TERM_ACC = 64;                  // per-warp accumulator entries (direct-mapped by slot)
 __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(const uint32_t* terms32, int slots, int64_t rows,
                                                                                const uint2* table, int table_mask,
                                                                                uint32_t* bits, int64_t row_words) {
     extern __shared__ uint2 tab[];
+    // Zipf vocabularies: a handful of terms hit in most rows, i.e. up to 32 times per output word.  Each warp owns
+    // its 32-row block's words, so it first ORs hits into a small shared accumulator ({slot + 1, bits}, claimed by
+    // CAS) and flushes one atomic per (term, block); only accumulator conflicts go to global memory directly.
+    __shared__ uint2 acc_all[TERM_BITS_THREADS / 32][TERM_ACC];
     for (int i = threadIdx.x; i <= table_mask; i += blockDim.x) tab[i] = table[i];
+    for (int i = threadIdx.x; i < (TERM_BITS_THREADS / 32) * TERM_ACC; i += blockDim.x) (&acc_all[0][0])[i] = make_uint2(0u, 0u);
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(acc_all[threadIdx.x >> 5]);
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_blocks = (rows + 31) >> 5;
-    const int vec_per_row = slots >> 2;                                      // uint4 per row
+    const int vec_shift = 31 - __clz(slots >> 2);                            // uint4 per row = 8, 16 or 32
     for (int64_t blk = gw; blk < n_blocks; blk += W) {
         const int rows_here = (int)min((int64_t)32, rows - (blk << 5));
-        const int n_vec = rows_here * vec_per_row;
+        const int n_vec = rows_here << vec_shift;
         const uint4* base = reinterpret_cast<const uint4*>(terms32 + (blk << 5) * slots);
         for (int v0 = 0; v0 < n_vec; v0 += 256) {
             uint4 x[8];
@@ -833,7 +840,7 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int v = v0 + i * 32 + lane;
-                const uint32_t bit = 1u << (v / vec_per_row);
+                const uint32_t bit = 1u << (v >> vec_shift);
                 const uint32_t hs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -843,12 +850,27 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
                     for (;;) {
                         const uint2 ent = tab[pos];
                         if (ent.x == 0u) break;
-                        if (ent.x == h) { atomicOr(bits + (int64_t)ent.y * row_words + blk, bit); break; }
+                        if (ent.x == h) {
+                            uint32_t* e = acc + 2 * (ent.y & (TERM_ACC - 1));
+                            const uint32_t cur = atomicCAS(e, 0u, ent.y + 1u);
+                            if (cur == 0u || cur == ent.y + 1u) atomicOr(e + 1, bit);
+                            else atomicOr(bits + (int64_t)ent.y * row_words + blk, bit);
+                            break;
+                        }
                         pos = (pos + 1) & (uint32_t)table_mask;
                     }
                 }
             }
         }
+        __syncwarp();
+        for (int j = lane; j < TERM_ACC; j += 32) {
+            const uint32_t sl = acc[2 * j];
+            if (sl) {
+                atomicOr(bits + (int64_t)(sl - 1u) * row_words + blk, acc[2 * j + 1]);
+                acc[2 * j] = 0u; acc[2 * j + 1] = 0u;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -893,7 +915,7 @@ int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows,
         ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_term_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         configured = true;
     }
-    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    const int per_sm = smem <= 90 * 1024 ? 2 : 1;
     orr_batch_term_bits_kernel<<<sms * per_sm, TERM_BITS_THREADS, smem, st>>>(terms32, slots, rows, (const uint2*)table,
                                                                               table_slots - 1, bits, row_words);
     ORR_CUDA_OK(cudaGetLastError());
