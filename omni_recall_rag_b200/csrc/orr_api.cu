@@ -60,7 +60,7 @@ struct BatchState {
     int32_t* h_status = nullptr;
     float* dense = nullptr; size_t dense_elems = 0;
     uint32_t* term_bits = nullptr; void* table = nullptr;
-    // persistent per-term row bitmaps: 32-bit term hash -> slot in term_bits[slot][row_words]
+    // persistent per-term row bitmaps: 32-bit term hash -> slot in the tile-major term_bits[tile][slot][8 words]
     std::unordered_map<uint32_t, int32_t> term_slot;
     uint64_t term_version = ~0ull; int64_t term_row_words = 0;
     int32_t term_slots_used = 0, term_slots_cap = 0;
@@ -1221,7 +1221,8 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
             if ((int64_t)distinct.size() > bs->term_slots_cap) {
                 size_t free_b = 0, total_b = 0;
                 cudaMemGetInfo(&free_b, &total_b);
-                const size_t slot_bytes = (size_t)row_words * sizeof(uint32_t);
+                // sized for the store's CAPACITY (32 B per slot and 256-row tile), so appended rows never outgrow it
+                const size_t slot_bytes = (size_t)((s->cfg.capacity_rows + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE) * 32;
                 const size_t have = (size_t)bs->term_slots_cap * slot_bytes;
                 size_t budget = std::min<size_t>((free_b + have) / 4, (size_t)12 << 30);
                 size_t want = std::max<size_t>(8 * distinct.size(), 16384);   // room for several batches before the pool recycles
@@ -1245,11 +1246,9 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
                 bs->term_slot[h] = bs->term_slots_used++;
             }
             if (!bs->table) ORR_CUDA_OK(cudaMalloc(&bs->table, BATCH_TABLE_SLOTS * 8));
-            ORR_CUDA_OK(cudaMemsetAsync(bs->term_bits + (size_t)first_new * (size_t)row_words, 0,
-                                        missing.size() * (size_t)row_words * sizeof(uint32_t), st));
             ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table, (size_t)table_slots * 8, cudaMemcpyHostToDevice, st));
             rc = orr_batch_launch_term_bits(s->d_terms32, s->cfg.term_slots, rows, bs->table, table_slots, bs->term_bits,
-                                            row_words, st);
+                                            bs->term_slots_cap, first_new, (int)missing.size(), st);
             if (rc != ORR_OK) return rc;
         }
         for (int32_t b = 0; b < batch; ++b)
@@ -1264,7 +1263,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     OrrBatchGemm gm{};
     gm.qhi = bs->qhi; gm.qmid = bs->qmid; gm.ehi = bs->ehi; gm.emid = bs->emid; gm.rowaux = bs->rowaux;
     gm.qscale = bs->qscale; gm.thr = bs->thr; gm.cand = bs->cand; gm.cand_count = bs->cand_count; gm.cand_cap = BATCH_CAND_CAP;
-    gm.term_bits = any_terms ? bs->term_bits : nullptr; gm.row_words = row_words;
+    gm.term_bits = any_terms ? bs->term_bits : nullptr; gm.slot_cap = bs->term_slots_cap;
     gm.q_term_ids = any_terms ? bs->qterm : nullptr; gm.q_kw_w = any_terms ? bs->kww : nullptr;
     gm.rows = rows; gm.dim = dim; gm.batch_padded = bp; gm.sms = s->sms; gm.passes = passes;
 

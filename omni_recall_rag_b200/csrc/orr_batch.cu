@@ -92,8 +92,10 @@ struct BatchArgs {
     float*    dense;
     int64_t   dense_ld;
     // keyword side: per query up to ORR_BATCH_MAX_TERMS term bitmaps over rows
-    const uint32_t* term_bits;   // [term slots][row_words] bit r%32 of word r/32 = row r has the term
-    int64_t   row_words;
+    // tile-major: term_bits[row tile][slot][8 words] — the 256 rows of one tile for every term slot are one
+    // contiguous slot_cap x 32 B region, read once per tile and shared by all queries of the batch
+    const uint32_t* term_bits;   // bit j of word w = row 256*tile + 32*w + j holds the term
+    int64_t   slot_cap;          // term slots per row tile (the pool's capacity)
     const int32_t* q_term_ids;   // [B padded][ORR_BATCH_MAX_TERMS] term slot or -1, packed front to back
     const float*   q_kw_w;       // [B padded] w_kw / |terms_b| (0 if none)
 };
@@ -183,8 +185,9 @@ __device__ __forceinline__ void kw_add(KwPlanes& kp, const uint4& w) {
         kp.p[c][DEPTH - 1] ^= x;
     }
 }
-__device__ __forceinline__ uint4 kw_load(const BatchArgs& a, uint32_t id, int64_t word0) {
-    return id != NO_TERM ? __ldg(reinterpret_cast<const uint4*>(a.term_bits + (int64_t)id * a.row_words + word0))
+// `tile_half` = 2 * row tile + (0 | 1): the thread's 128-row half of the tile = 4 of the slot's 8 words
+__device__ __forceinline__ uint4 kw_load(const BatchArgs& a, uint32_t id, int64_t tile_half) {
+    return id != NO_TERM ? __ldg(reinterpret_cast<const uint4*>(a.term_bits) + ((tile_half >> 1) * a.slot_cap + id) * 2 + (tile_half & 1))
                          : make_uint4(0u, 0u, 0u, 0u);
 }
 
@@ -428,7 +431,7 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
         auto prefetch_words = [&](int u) {
             const int row_tile = (cid + (u / units_per_tile) * n_clusters) * a.row_tile_stride;
             const int qi = (u % units_per_tile) * BM + qloc;
-            const int64_t word0 = (((int64_t)row_tile * UN) >> 5) + c_begin;
+            const int64_t word0 = (int64_t)row_tile * 2 + (c_begin / HC);
             const uint2 id4 = *reinterpret_cast<const uint2*>(q_ids + qi * ORR_BATCH_MAX_TERMS);
             wn[0] = kw_load(a, id4.x & 0xFFFFu, word0); wn[1] = kw_load(a, id4.x >> 16, word0);
             wn[2] = kw_load(a, id4.y & 0xFFFFu, word0); wn[3] = kw_load(a, id4.y >> 16, word0);
@@ -449,7 +452,7 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                 if (kww != 0.f) {
                     kw_add<3>(kp, wn[0]); kw_add<3>(kp, wn[1]); kw_add<3>(kp, wn[2]); kw_add<3>(kp, wn[3]);
                     const uint2* idp = reinterpret_cast<const uint2*>(q_ids + qi * ORR_BATCH_MAX_TERMS);
-                    const int64_t word0 = (row0 >> 5) + c_begin;
+                    const int64_t word0 = (int64_t)row_tile * 2 + (c_begin / HC);
 #pragma unroll 1
                     for (int g = 1; g < ORR_BATCH_MAX_TERMS / 4; ++g) {   // queries with more than 4 terms
                         const uint2 id4 = idp[g];
@@ -657,7 +660,7 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     a.dense = g.dense;
     a.dense_ld = g.dense_ld;
     a.term_bits = g.term_bits;
-    a.row_words = g.row_words;
+    a.slot_cap = g.slot_cap;
     a.q_term_ids = g.q_term_ids;
     a.q_kw_w = g.q_kw_w;
     const int pairs = std::min<int64_t>(g.sms / 2, a.n_row_tiles);

@@ -177,7 +177,7 @@ struct OrrBatchGemm {
     const float* thr;                        // [batch_padded] (main pass)
     void* cand; uint32_t* cand_count; int32_t cand_cap;
     float* dense; int64_t dense_ld;          // dense score output (sampling / debug) or NULL
-    const uint32_t* term_bits; int64_t row_words; const int32_t* q_term_ids; const float* q_kw_w;
+    const uint32_t* term_bits; int64_t slot_cap; const int32_t* q_term_ids; const float* q_kw_w;   // tile-major bitmaps
     int64_t rows; int32_t dim; int32_t batch_padded; int32_t tile_stride; int32_t sms;
     int32_t passes;                          // 3 = split precision (default), 1 = bf16 screen
 };
@@ -194,8 +194,9 @@ int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, con
                               int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
                               int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
                               cudaStream_t st);
+// bits is tile-major [row tile][slot_cap][8 words]; slots [first_new, first_new + n_new) are cleared first
 int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows, const void* table, int table_slots,
-                               uint32_t* bits, int64_t row_words, cudaStream_t st);
+                               uint32_t* bits, int64_t slot_cap, int first_new, int n_new, cudaStream_t st);
 constexpr int ORR_BATCH_MAX_SURV = 1024;      // deepest per-query survivor list the finalize kernel re-scores
 constexpr int ORR_BATCH_SAMPLE_HITS = 12;     // sampled rows expected above a query's threshold
 constexpr float ORR_BATCH_EPS = 2.0e-4f;     // bound on |bf16x3 GEMM score - exact score| (unit weights)

@@ -811,7 +811,7 @@ constexpr int TERM_BITS_THREADS = 1024;
 constexpr int TERM_ACC = 64;                  // per-warp accumulator entries (direct-mapped by slot)
 __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(const uint32_t* terms32, int slots, int64_t rows,
                                                                                const uint2* table, int table_mask,
-                                                                               uint32_t* bits, int64_t row_words) {
+                                                                               uint32_t* bits, int64_t slot_cap) {
     extern __shared__ uint2 tab[];
     // Zipf vocabularies: a handful of terms hit in most rows, i.e. up to 32 times per output word.  Each warp owns
     // its 32-row block's words, so it first ORs hits into a small shared accumulator ({slot + 1, bits}, claimed by
@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
                             uint32_t* e = acc + 2 * (ent.y & (TERM_ACC - 1));
                             const uint32_t cur = atomicCAS(e, 0u, ent.y + 1u);
                             if (cur == 0u || cur == ent.y + 1u) atomicOr(e + 1, bit);
-                            else atomicOr(bits + (int64_t)ent.y * row_words + blk, bit);
+                            else atomicOr(bits + (((blk >> 3) * slot_cap + ent.y) << 3) + (blk & 7), bit);
                             break;
                         }
                         pos = (pos + 1) & (uint32_t)table_mask;
@@ -866,11 +866,20 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
         for (int j = lane; j < TERM_ACC; j += 32) {
             const uint32_t sl = acc[2 * j];
             if (sl) {
-                atomicOr(bits + (int64_t)(sl - 1u) * row_words + blk, acc[2 * j + 1]);
+                atomicOr(bits + (((blk >> 3) * slot_cap + (sl - 1u)) << 3) + (blk & 7), acc[2 * j + 1]);
                 acc[2 * j] = 0u; acc[2 * j + 1] = 0u;
             }
         }
         __syncwarp();
+    }
+}
+
+// clears slots [first, first + n) of every row tile (n x 32 contiguous bytes per tile)
+__global__ void orr_batch_clear_slots_kernel(uint4* bits, int64_t slot_cap, int first, int n, int64_t n_tiles) {
+    const int64_t total = n_tiles * n * 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tile = i / (2 * n), r = i - tile * 2 * n;
+        bits[(tile * slot_cap + first) * 2 + r] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -905,10 +914,15 @@ int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, con
 }
 
 int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows, const void* table, int table_slots,
-                               uint32_t* bits, int64_t row_words, cudaStream_t st) {
+                               uint32_t* bits, int64_t slot_cap, int first_new, int n_new, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n_tiles = (rows + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE;
+    if (n_new > 0 && n_tiles > 0) {
+        orr_batch_clear_slots_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(bits), slot_cap, first_new, n_new, n_tiles);
+        ORR_CUDA_OK(cudaGetLastError());
+    }
     const int smem = table_slots * 8;
     static bool configured = false;
     if (!configured) {
@@ -917,7 +931,7 @@ int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows,
     }
     const int per_sm = smem <= 90 * 1024 ? 2 : 1;
     orr_batch_term_bits_kernel<<<sms * per_sm, TERM_BITS_THREADS, smem, st>>>(terms32, slots, rows, (const uint2*)table,
-                                                                              table_slots - 1, bits, row_words);
+                                                                              table_slots - 1, bits, slot_cap);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
