@@ -257,6 +257,32 @@ int  orr_xchg_attach_peer(orr_xchg* x, int32_t peer_rank, orr_xchg* peer);
 int  orr_xchg_allgather_merge(orr_xchg* x, const orr_hit* hits_dev, const int32_t* status_dev, int32_t top_k,
         orr_hit* out_dev, int32_t* out_status_dev, void* cuda_stream);
 
+/* ---- one host process, N GPUs (the .NET deployment of the row-sharded layout) ----------------------
+ * An orr_cluster owns one orr_store per device (global row id = shard << 40 | local row), their exchange
+ * buffers attached to each other, and one stream per device.  orr_cluster_search issues, from the calling
+ * thread and without NCCL, for every device: query -> HBM, orr_search_device, orr_xchg_allgather_merge; then
+ * reads the merged hits from device 0.  A document lives on one shard (the one that already holds it, else the
+ * emptiest), so replace / delete touch one GPU.  Queries without an embedding, of another width, or with
+ * top_k > max_top_k run shard by shard through orr_search and are merged on the host.  One search or
+ * mutation at a time per cluster (a query saturates every GPU's HBM anyway). */
+typedef struct orr_cluster orr_cluster;
+struct orr_synth_spec;
+int  orr_cluster_create(const orr_config* cfg /* per shard; device and row_base are overwritten */,
+        const int32_t* devices, int32_t n_devices, int32_t max_top_k, orr_cluster** out);
+void orr_cluster_destroy(orr_cluster* c);
+int32_t    orr_cluster_size(const orr_cluster* c);
+orr_store* orr_cluster_shard(orr_cluster* c, int32_t i);      /* borrowed: options, snapshot, compaction per shard */
+int64_t    orr_cluster_count(const orr_cluster* c);
+int  orr_cluster_upsert_document_chunks(orr_cluster* c, uint64_t doc_key, int32_t n,
+        const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
+        const uint64_t* term_hashes, const uint32_t* term_offsets,
+        const char* text_lower_utf8 /* or NULL */, const uint64_t* text_offsets, uint64_t* out_rows);
+int  orr_cluster_delete_document(orr_cluster* c, uint64_t doc_key);
+int  orr_cluster_fill_synthetic(orr_cluster* c, const struct orr_synth_spec* spec, uint64_t first_row, int64_t n_per_shard);
+int  orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim,
+        int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+        int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
+
 const char* orr_last_error(void);
 int  orr_last_timing(orr_timing* out);
 

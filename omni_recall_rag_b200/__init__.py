@@ -11,6 +11,7 @@ fchchen/omni-recall-rag's POST /api/recall/search).
 There is no CPU fallback anywhere in this package.
 """
 from . import _native  # noqa: F401
+from .cluster import RecallCluster  # noqa: F401
 from .shard import BatchHits, BatchTerms, Hits, QueryTerms, RecallShard, hash_term, merge_hits, tokenize_content, tokenize_query  # noqa: F401
 
-__all__ = ["BatchHits", "BatchTerms", "Hits", "QueryTerms", "RecallShard", "hash_term", "merge_hits", "tokenize_content", "tokenize_query"]
+__all__ = ["RecallCluster", "BatchHits", "BatchTerms", "Hits", "QueryTerms", "RecallShard", "hash_term", "merge_hits", "tokenize_content", "tokenize_query"]

@@ -97,6 +97,17 @@ _SIGNATURES = {
     "orr_xchg_attach_peer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "orr_xchg_allgather_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
+    "orr_cluster_create": (C.c_int, [C.POINTER(OrrConfig), C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "orr_cluster_destroy": (None, [C.c_void_p]),
+    "orr_cluster_size": (C.c_int32, [C.c_void_p]),
+    "orr_cluster_shard": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "orr_cluster_count": (C.c_int64, [C.c_void_p]),
+    "orr_cluster_upsert_document_chunks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
+    "orr_cluster_delete_document": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "orr_cluster_fill_synthetic": (C.c_int, [C.c_void_p, C.POINTER(OrrSynthSpec), C.c_uint64, C.c_int64]),
+    "orr_cluster_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "orr_last_error": (C.c_char_p, []),
     "orr_last_timing": (C.c_int, [C.POINTER(OrrTiming)]),
     "orr_synth_spec_default": (None, [C.POINTER(OrrSynthSpec), C.c_int32]),

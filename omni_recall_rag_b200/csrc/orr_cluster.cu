@@ -1,0 +1,193 @@
+// orr_cluster.cu — one host process driving the GPUs of a box ("single process, one
+// stream per device").  The .NET API is a single process, so its multi-GPU form is not one rank per GPU but
+// one orr_cluster: N orr_store shards (one per device), N exchange buffers attached to each other
+// (cudaDeviceEnablePeerAccess), and per query
+//     for every device d:  q -> HBM(d) ; orr_search_device(d) ; orr_xchg_allgather_merge(d)      (all async)
+//     device 0:            merged hits -> pinned host ; synchronise stream 0
+// i.e. 3 kernels per device, all launched from the calling thread, no NCCL, no host thread per GPU.
+// Built on the public C ABI only (orr_store_*, orr_search_device, orr_xchg_*).
+#include <algorithm>
+#include <cstring>
+
+#include "orr_internal.h"
+
+namespace {
+constexpr int CLUSTER_MAX = ORR_XCHG_MAX_WORLD;
+constexpr int CLUSTER_ROW_SHIFT = 40;          // global row id = shard << 40 | local row
+}
+
+struct orr_cluster {
+    int n = 0;
+    int dim = 0;
+    int max_k = 0;
+    int devices[CLUSTER_MAX] = {};
+    orr_store* store[CLUSTER_MAX] = {};
+    orr_xchg* xchg[CLUSTER_MAX] = {};
+    cudaStream_t stream[CLUSTER_MAX] = {};
+    float* d_q[CLUSTER_MAX] = {};
+    orr_hit* d_hits[CLUSTER_MAX] = {};
+    int32_t* d_status[CLUSTER_MAX] = {};
+    orr_hit* d_out[CLUSTER_MAX] = {};
+    int32_t* d_out_status[CLUSTER_MAX] = {};
+    float* h_q = nullptr;                       // pinned
+    orr_hit* h_out = nullptr;                   // pinned
+    int32_t* h_status = nullptr;                // pinned
+    std::unordered_map<uint64_t, int> doc_shard;
+    std::mutex mu;                              // one search / mutation at a time per cluster
+};
+
+extern "C" {
+
+void orr_cluster_destroy(orr_cluster* c) {
+    if (!c) return;
+    for (int d = 0; d < c->n; ++d) {
+        cudaSetDevice(c->devices[d]);
+        if (c->stream[d]) cudaStreamSynchronize(c->stream[d]);
+    }
+    for (int d = 0; d < c->n; ++d) {
+        cudaSetDevice(c->devices[d]);
+        if (c->xchg[d]) orr_xchg_destroy(c->xchg[d]);
+        cudaFree(c->d_q[d]); cudaFree(c->d_hits[d]); cudaFree(c->d_status[d]); cudaFree(c->d_out[d]); cudaFree(c->d_out_status[d]);
+        if (c->stream[d]) cudaStreamDestroy(c->stream[d]);
+        if (c->store[d]) orr_store_destroy(c->store[d]);
+    }
+    cudaFreeHost(c->h_q); cudaFreeHost(c->h_out); cudaFreeHost(c->h_status);
+    delete c;
+}
+
+int orr_cluster_create(const orr_config* cfg, const int32_t* devices, int32_t n_devices, int32_t max_top_k, orr_cluster** out) {
+    if (!cfg || !devices || !out || n_devices < 1 || n_devices > CLUSTER_MAX || max_top_k < 1 || max_top_k > ORR_FUSED_MAX_K ||
+        (int64_t)n_devices * max_top_k > ORR_SORT_MAX) {
+        orr_set_error("orr_cluster_create: bad argument (%d devices, max_top_k %d)", n_devices, max_top_k);
+        return ORR_E_INVALID;
+    }
+    *out = nullptr;
+    std::unique_ptr<orr_cluster, void (*)(orr_cluster*)> c(new orr_cluster(), orr_cluster_destroy);
+    c->n = n_devices; c->dim = cfg->dim; c->max_k = max_top_k;
+    for (int d = 0; d < n_devices; ++d) {
+        c->devices[d] = devices[d];
+        orr_config sc = *cfg;
+        sc.device = devices[d];
+        sc.row_base = (uint64_t)d << CLUSTER_ROW_SHIFT;
+        int rc = orr_store_create(&sc, &c->store[d]);
+        if (rc != ORR_OK) return rc;
+        ORR_CUDA_OK(cudaSetDevice(devices[d]));
+        ORR_CUDA_OK(cudaStreamCreateWithFlags(&c->stream[d], cudaStreamNonBlocking));
+        ORR_CUDA_OK(cudaMalloc(&c->d_q[d], sizeof(float) * (size_t)cfg->dim));
+        ORR_CUDA_OK(cudaMalloc(&c->d_hits[d], sizeof(orr_hit) * (size_t)max_top_k));
+        ORR_CUDA_OK(cudaMalloc(&c->d_status[d], sizeof(int32_t) * 2));
+        ORR_CUDA_OK(cudaMalloc(&c->d_out[d], sizeof(orr_hit) * (size_t)max_top_k));
+        ORR_CUDA_OK(cudaMalloc(&c->d_out_status[d], sizeof(int32_t) * 2));
+        rc = orr_xchg_create(devices[d], n_devices, d, max_top_k, &c->xchg[d]);
+        if (rc != ORR_OK) return rc;
+    }
+    for (int d = 0; d < n_devices; ++d)
+        for (int p = 0; p < n_devices; ++p)
+            if (p != d) { int rc = orr_xchg_attach_peer(c->xchg[d], p, c->xchg[p]); if (rc != ORR_OK) return rc; }
+    ORR_CUDA_OK(cudaMallocHost(&c->h_q, sizeof(float) * (size_t)cfg->dim));
+    ORR_CUDA_OK(cudaMallocHost(&c->h_out, sizeof(orr_hit) * (size_t)max_top_k));
+    ORR_CUDA_OK(cudaMallocHost(&c->h_status, sizeof(int32_t) * 2));
+    *out = c.release();
+    return ORR_OK;
+}
+
+int32_t orr_cluster_size(const orr_cluster* c) { return c ? c->n : 0; }
+orr_store* orr_cluster_shard(orr_cluster* c, int32_t i) { return (c && i >= 0 && i < c->n) ? c->store[i] : nullptr; }
+
+int64_t orr_cluster_count(const orr_cluster* c) {
+    int64_t n = 0;
+    if (c) for (int d = 0; d < c->n; ++d) n += orr_store_count(c->store[d]);
+    return n;
+}
+
+// replace-by-document: a document lives on ONE shard (so replace/delete touch one GPU): the shard that already
+// holds it, else the one with the fewest rows in use
+int orr_cluster_upsert_document_chunks(orr_cluster* c, uint64_t doc_key, int32_t n, const float* emb, const uint8_t* has_emb,
+                                       const int64_t* created_ticks, const uint64_t* term_hashes, const uint32_t* term_offsets,
+                                       const char* text_lower_utf8, const uint64_t* text_offsets, uint64_t* out_rows) {
+    if (!c) { orr_set_error("orr_cluster_upsert_document_chunks: NULL cluster"); return ORR_E_INVALID; }
+    if (n == 0) return ORR_OK;
+    std::lock_guard<std::mutex> g(c->mu);
+    int shard = -1;
+    auto it = c->doc_shard.find(doc_key);
+    if (it != c->doc_shard.end()) shard = it->second;
+    else {
+        int64_t best = INT64_MAX;
+        for (int d = 0; d < c->n; ++d) {
+            const int64_t used = orr_store_rows_used(c->store[d]);
+            if (used < best) { best = used; shard = d; }
+        }
+    }
+    int rc = text_lower_utf8
+        ? orr_store_upsert_document_chunks_text(c->store[shard], doc_key, n, emb, has_emb, created_ticks, term_hashes, term_offsets,
+                                                text_lower_utf8, text_offsets, out_rows)
+        : orr_store_upsert_document_chunks(c->store[shard], doc_key, n, emb, has_emb, created_ticks, term_hashes, term_offsets, out_rows);
+    if (rc == ORR_OK) c->doc_shard[doc_key] = shard;
+    return rc;
+}
+
+int orr_cluster_delete_document(orr_cluster* c, uint64_t doc_key) {
+    if (!c) { orr_set_error("orr_cluster_delete_document: NULL cluster"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->doc_shard.find(doc_key);
+    if (it == c->doc_shard.end()) return ORR_OK;
+    const int rc = orr_store_delete_document(c->store[it->second], doc_key);
+    if (rc == ORR_OK) c->doc_shard.erase(it);
+    return rc;
+}
+
+// bench/test: rows [first_row + d * n_per_shard, ...) of the synthetic corpus on shard d
+int orr_cluster_fill_synthetic(orr_cluster* c, const orr_synth_spec* spec, uint64_t first_row, int64_t n_per_shard) {
+    if (!c || !spec) { orr_set_error("orr_cluster_fill_synthetic: NULL argument"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> g(c->mu);
+    for (int d = 0; d < c->n; ++d) {
+        const int rc = orr_store_fill_synthetic(c->store[d], spec, first_row + (uint64_t)d * (uint64_t)n_per_shard, n_per_shard);
+        if (rc != ORR_OK) return rc;
+    }
+    return ORR_OK;
+}
+
+int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
+                       const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
+    if (!c || !out || !n_out || q_dim < 0 || (q_dim > 0 && !q)) { orr_set_error("orr_cluster_search: bad argument"); return ORR_E_INVALID; }
+    *n_out = 0;
+    const int k = std::max(1, top_k);
+    std::lock_guard<std::mutex> g(c->mu);
+    bool fused = q_dim == c->dim && k <= c->max_k;
+    if (fused) {
+        memcpy(c->h_q, q, sizeof(float) * (size_t)q_dim);
+        for (int d = 0; d < c->n; ++d) {
+            ORR_CUDA_OK(cudaSetDevice(c->devices[d]));
+            ORR_CUDA_OK(cudaMemcpyAsync(c->d_q[d], c->h_q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream[d]));
+            int rc = orr_search_device(c->store[d], c->d_q[d], q_dim, n_terms, probe_hash, probe_term, n_probes, now_ticks, top_k,
+                                       c->d_hits[d], c->d_status[d], c->stream[d]);
+            if (rc != ORR_OK) return rc;
+            rc = orr_xchg_allgather_merge(c->xchg[d], c->d_hits[d], c->d_status[d], top_k, c->d_out[d], c->d_out_status[d], c->stream[d]);
+            if (rc != ORR_OK) return rc;
+        }
+        ORR_CUDA_OK(cudaSetDevice(c->devices[0]));
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->d_out_status[0], sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream[0]));
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_out, c->d_out[0], sizeof(orr_hit) * (size_t)k, cudaMemcpyDeviceToHost, c->stream[0]));
+        ORR_CUDA_OK(cudaStreamSynchronize(c->stream[0]));
+        if (c->h_status[1] & ORR_STATUS_XCHG_TIMEOUT) { orr_set_error("orr_cluster_search: a shard never published its list"); return ORR_E_CUDA; }
+        if (c->h_status[1] == 0) {
+            const int got = std::min(c->h_status[0], k);
+            memcpy(out, c->h_out, sizeof(orr_hit) * (size_t)got);
+            *n_out = got;
+            return ORR_OK;
+        }
+        // a shard could not prove its fp32 selection: fall through to the per-shard host path (which escalates)
+        for (int d = 0; d < c->n; ++d) { ORR_CUDA_OK(cudaSetDevice(c->devices[d])); ORR_CUDA_OK(cudaStreamSynchronize(c->stream[d])); }
+    }
+    // no query embedding, a query of another width, k beyond the fused path: per-shard orr_search + host merge
+    std::vector<orr_hit> lists((size_t)c->n * k);
+    std::vector<int32_t> lens((size_t)c->n, 0);
+    for (int d = 0; d < c->n; ++d) {
+        const int rc = orr_search(c->store[d], q, q_dim, n_terms, probe_hash, probe_term, n_probes, now_ticks, top_k, 0,
+                                  lists.data() + (size_t)d * k, &lens[(size_t)d]);
+        if (rc != ORR_OK) return rc;
+    }
+    return orr_merge_hits(lists.data(), lens.data(), c->n, k, top_k, out, n_out);
+}
+
+}  // extern "C"

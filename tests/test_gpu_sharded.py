@@ -176,3 +176,39 @@ def test_batched_search_over_virtual_shards_merges_to_the_oracle():
     finally:
         for sh in shards:
             sh.close()
+
+
+def test_single_process_cluster_matches_the_oracle():
+    """orr_cluster_*: one process, several shards (here all on GPU 0), fused scan + peer-memory exchange per shard.
+    Synthetic corpus split contiguously over the shards -> the oracle's global ranking (global row ids are
+    shard << 40 | local row); then document mutations routed to one shard each."""
+    dim, per, world, k = 256, 3_000, 3, 10
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=16, dup_row_ppm=20000)
+    rows = synth.rows_host(spec, 0, per * world)
+    with orr.RecallCluster(dim, per + 64, [0] * world, max_top_k=32) as cl:
+        cl.fill_synthetic(spec, 0, per)
+        assert cl.count == per * world
+        to_global = lambda r: ((int(r) // per) << 40) | (int(r) % per)
+        for qi in range(8):
+            q = synth.query_host(spec, qi, per * world, n_terms=3)
+            got = cl.search(q.q, q.terms, NOW, k)
+            er, es, _ = oracle_search_synth(rows, q, NOW, k)
+            assert_same_ranking(got.rows, got.scores, [to_global(r) for r in er], es, what=f"cluster q={qi}")
+        # no embedding -> per-shard exact path + host merge
+        q = synth.query_host(spec, 3, per * world, n_terms=3, frequent_terms=1)
+        got = cl.search(None, q.terms, NOW, k)
+        q0 = synth.HostQuery(np.zeros(0, np.float32), q.term_ids, q.text, q.terms)
+        er, es, _ = oracle_search_synth(rows, q0, NOW, k)
+        assert [int(r) for r in got.rows] == [to_global(r) for r in er]
+        # mutations: a new document lands on one shard, wins, and disappears again
+        q = synth.query_host(spec, 5, per * world, n_terms=2)
+        new_rows = cl.upsert_document_chunks(77, q.q[None, :].copy(), np.array([NOW - 864_000_000_000]),
+                                             [np.asarray(q.terms.probe_hash, dtype=np.uint64)])
+        assert cl.search(q.q, q.terms, NOW, 3).rows[0] == new_rows[0]
+        cl.upsert_document_chunks(77, -q.q[None, :].copy(), np.array([NOW - 864_000_000_000]))   # replace: same shard
+        assert cl.count == per * world + 1
+        cl.delete_document(77)
+        assert cl.count == per * world
+        got = cl.search(q.q, q.terms, NOW, k)
+        er, es, _ = oracle_search_synth(rows, q, NOW, k)
+        assert_same_ranking(got.rows, got.scores, [to_global(r) for r in er], es, what="cluster after delete")
