@@ -61,6 +61,17 @@ internal static partial class OrrNative
     [LibraryImport(Lib)] internal static unsafe partial int orr_xchg_allgather_merge(
         nint xchg, OrrHit* hitsDev, int* statusDev, int topK, OrrHit* outDev, int* outStatusDev, nint cudaStream);
     [LibraryImport(Lib)] internal static partial void orr_xchg_destroy(nint xchg);
+    // the whole box from this one process: one shard per GPU, fused peer-memory all-gather + merge per query
+    [LibraryImport(Lib)] internal static unsafe partial int orr_cluster_create(in OrrConfig cfg, int* devices, int nDevices, int maxTopK, out nint cluster);
+    [LibraryImport(Lib)] internal static partial void orr_cluster_destroy(nint cluster);
+    [LibraryImport(Lib)] internal static partial long orr_cluster_count(nint cluster);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_cluster_upsert_document_chunks(
+        nint cluster, ulong docKey, int n, float* emb, byte* hasEmb, long* createdTicks,
+        ulong* termHashes, uint* termOffsets, byte* textLowerUtf8, ulong* textOffsets, ulong* outRows);
+    [LibraryImport(Lib)] internal static partial int orr_cluster_delete_document(nint cluster, ulong docKey);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_cluster_search(
+        nint cluster, float* q, int qDim, int nTerms, ulong* probeHash, int* probeTerm, int nProbes,
+        long nowTicks, int topK, OrrHit* hits, out int nOut);
     [LibraryImport(Lib)] internal static unsafe partial int orr_merge_hits(
         OrrHit* lists, int* listLen, int nLists, int listStride, int topK, OrrHit* hits, out int nOut);
     [LibraryImport(Lib)] internal static partial nint orr_last_error();

@@ -621,12 +621,7 @@ int orr_batch_build_rowrec(const int64_t* ticks, float* rowrec, int64_t rows, in
 template <int PASSES, int MODE>
 static int launch_gemm_t(const CUtensorMap& mqh, const CUtensorMap& mqm, const CUtensorMap& meh, const CUtensorMap& mem,
                          const BatchArgs& a, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_gemm_kernel<PASSES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<PASSES>::SMEM));
-        configured = true;
-    }
+    ORR_SMEM_OPT_IN((orr_batch_gemm_kernel<PASSES, MODE>), GemmCfg<PASSES>::SMEM);
     orr_batch_gemm_kernel<PASSES, MODE><<<grid, BATCH_THREADS, GemmCfg<PASSES>::SMEM, st>>>(mqh, mqm, meh, mem, a);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;

@@ -26,6 +26,19 @@ void orr_set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs
+// (orr_cluster) must opt in on each of them.  One bit per device ordinal and call site.
+#define ORR_SMEM_OPT_IN(func, bytes)                                                                        \
+    do {                                                                                                    \
+        static std::atomic<uint64_t> _done{0};                                                              \
+        int _dev = 0;                                                                                       \
+        cudaGetDevice(&_dev);                                                                               \
+        if (!((_done.load(std::memory_order_relaxed) >> (_dev & 63)) & 1ull)) {                             \
+            ORR_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _done.fetch_or(1ull << (_dev & 63));                                                            \
+        }                                                                                                   \
+    } while (0)
+
 // ---- constants ----------------------------------------------------------------------------
 constexpr int64_t ORR_DEAD_TICKS = INT64_MIN;   // tombstone marker in the ticks column
 constexpr int ORR_SCAN_WARPS = 8;               // consumer warps per scan CTA

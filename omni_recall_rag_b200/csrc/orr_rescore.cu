@@ -513,12 +513,7 @@ static void fill_exact_args(ExactArgs& e, const OrrShard& sh, const OrrScratch& 
 int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
                        const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
                        int n_listed_max, bool check_bound, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ORR_SORT_MAX * (int)sizeof(OrrExact)));
-        configured = true;
-    }
+    ORR_SMEM_OPT_IN((orr_rescore_kernel), ORR_SORT_MAX * (int)sizeof(OrrExact));
     if (n_listed_max < 1) n_listed_max = 1;
     if (n_listed_max > ORR_SORT_MAX) { orr_set_error("rescore: %d rows exceed the sorter", n_listed_max); return ORR_E_INTERNAL; }
     RescoreArgs a;
@@ -595,12 +590,7 @@ int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_
         orr_set_error("merge: %d lists x %d exceed the sorter", n_lists, stride);
         return ORR_E_UNSUPPORTED;
     }
-    static bool configured = false;
-    if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ORR_SORT_MAX * (int)sizeof(OrrExact)));
-        configured = true;
-    }
+    ORR_SMEM_OPT_IN((orr_merge_kernel), ORR_SORT_MAX * (int)sizeof(OrrExact));
     int np2 = 1;
     while (np2 < total) np2 <<= 1;
     orr_merge_kernel<<<1, 256, np2 * sizeof(OrrExact), st>>>(lists_dev, status_dev, n_lists, stride, top_k, out_dev,
@@ -614,11 +604,7 @@ int orr_launch_merge_batch(const orr_hit* lists_dev, const int32_t* n_dev, int n
     const int total = n_lists * k;
     if (n_lists < 1 || k < 1 || batch < 0 || total > ORR_SORT_MAX) { orr_set_error("batch merge: %d lists x %d exceed the sorter", n_lists, k); return ORR_E_UNSUPPORTED; }
     if (batch == 0) return ORR_OK;
-    static bool configured = false;
-    if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_merge_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ORR_SORT_MAX * (int)sizeof(OrrExact)));
-        configured = true;
-    }
+    ORR_SMEM_OPT_IN((orr_merge_batch_kernel), ORR_SORT_MAX * (int)sizeof(OrrExact));
     int np2 = 1;
     while (np2 < total) np2 <<= 1;
     orr_merge_batch_kernel<<<batch, 128, np2 * sizeof(OrrExact), st>>>(lists_dev, n_dev, n_lists, batch, k, out_dev, n_out_dev);
@@ -632,12 +618,7 @@ int orr_launch_xchg_merge(const OrrXchgArgs& a, cudaStream_t st) {
         orr_set_error("xchg merge: %d ranks x %d exceed the sorter", a.world, a.kmax);
         return ORR_E_UNSUPPORTED;
     }
-    static bool configured = false;
-    if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         2 * ORR_SORT_MAX * (int)sizeof(OrrExact) + 1024));
-        configured = true;
-    }
+    ORR_SMEM_OPT_IN((orr_xchg_merge_kernel), 2 * ORR_SORT_MAX * (int)sizeof(OrrExact) + 1024);
     const int k = std::min(std::max(1, a.top_k), a.kmax);
     int np2 = 1;
     while (np2 < a.world * k) np2 <<= 1;
@@ -898,12 +879,7 @@ int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, con
                               cudaStream_t st) {
     if (n_surv > ORR_BATCH_MAX_SURV || (cap & (cap - 1)) != 0) { orr_set_error("batch finalize: bad sizes"); return ORR_E_INTERNAL; }
     const int smem = cap * 8 + ORR_BATCH_MAX_SURV * (int)sizeof(OrrExact) + sh.dim * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         8192 * 8 + ORR_BATCH_MAX_SURV * 24 + 8192 * 4));
-        configured = true;
-    }
+    ORR_SMEM_OPT_IN((orr_batch_finalize_kernel), 8192 * 8 + ORR_BATCH_MAX_SURV * 24 + 8192 * 4);
     BatchFinArgs a;
     a.ex.sh = sh; a.ex.q_dim = q_dim; a.ex.w = w; a.ex.now_ticks = now_ticks;
     a.q = q; a.probes = probes; a.cand = (const uint2*)cand; a.cand_count = cand_count; a.thr = thr;
@@ -924,11 +900,7 @@ int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows,
         ORR_CUDA_OK(cudaGetLastError());
     }
     const int smem = table_slots * 8;
-    static bool configured = false;
-    if (!configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_batch_term_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        configured = true;
-    }
+    ORR_SMEM_OPT_IN((orr_batch_term_bits_kernel), 128 * 1024);
     const int per_sm = smem <= 90 * 1024 ? 2 : 1;
     orr_batch_term_bits_kernel<<<sms * per_sm, TERM_BITS_THREADS, smem, st>>>(terms32, slots, rows, (const uint2*)table,
                                                                               table_slots - 1, bits, slot_cap);

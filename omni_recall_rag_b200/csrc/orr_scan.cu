@@ -518,12 +518,8 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
 
 template <int NV, int TR, bool PIPE>
 int launch_p(const ScanArgs& args, int grid, int smem, cudaStream_t st) {
-    static int configured = 0;                 // largest dynamic smem opted into so far
-    if (smem > configured) {
-        ORR_CUDA_OK(cudaFuncSetAttribute(orr_scan_kernel<NV, TR, PIPE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    // opt in to the largest ring any dim needs (per device, once): the kernel is launched with `smem` <= that
+    ORR_SMEM_OPT_IN((orr_scan_kernel<NV, TR, PIPE>), 227 * 1024 - 2048);
     orr_scan_kernel<NV, TR, PIPE><<<grid, args.warps * 32, smem, st>>>(args);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
