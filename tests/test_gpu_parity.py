@@ -301,3 +301,44 @@ def test_full_size_properties_1m_x_3072():
                 assert exact.scores[:10].tolist() == got.scores.tolist()
                 checked += 1
         assert checked >= 5
+
+
+def test_error_codes_and_limits():
+    """The C ABI reports bad input as ORR_E_* codes with a message, never by aborting."""
+    import ctypes as C
+
+    L = N.lib()
+    cfg = N.OrrConfig()
+    L.orr_config_default(C.byref(cfg))
+    h = C.c_void_p()
+    for field, bad, code in [("dim", 6, N.ORR_E_UNSUPPORTED), ("term_slots", 48, N.ORR_E_UNSUPPORTED),
+                             ("capacity_rows", 0, N.ORR_E_INVALID), ("abi_version", 99, N.ORR_E_INVALID),
+                             ("device", 99, N.ORR_E_CUDA), ("recency_days", 0.0, N.ORR_E_INVALID)]:
+        c2 = N.OrrConfig()
+        L.orr_config_default(C.byref(c2))
+        setattr(c2, field, bad)
+        assert L.orr_store_create(C.byref(c2), C.byref(h)) == code, field
+        assert L.orr_last_error()
+    with orr.RecallShard(8, 4, term_slots=32) as sh:
+        emb = np.eye(8, dtype=np.float32)[:3]
+        sh.upsert_document_chunks(1, emb, np.array([NOW, NOW, NOW]))
+        with pytest.raises(N.OrrError) as e:                         # store full
+            sh.upsert_document_chunks(2, emb, np.array([NOW, NOW, NOW]))
+        assert e.value.code == N.ORR_E_OOM
+        with pytest.raises(N.OrrError) as e:                         # more distinct terms than slots
+            sh.upsert_document_chunks(3, emb[:1], np.array([NOW]), [np.arange(1, 40, dtype=np.uint64)])
+        assert e.value.code == N.ORR_E_UNSUPPORTED
+        with pytest.raises(N.OrrError) as e:                         # reserved ticks value
+            sh.upsert_document_chunks(4, emb[:1], np.array([np.iinfo(np.int64).min]))
+        assert e.value.code == N.ORR_E_INVALID
+        q = np.ones(8, dtype=np.float32)
+        with pytest.raises(N.OrrError) as e:
+            sh.search(q, orr.QueryTerms(2, np.array([1, 2, 3], dtype=np.uint64), np.array([0, 1, 5], dtype=np.int32)), NOW, 3)
+        assert e.value.code == N.ORR_E_INVALID                       # probe_term out of range
+        with pytest.raises(N.OrrError):
+            sh.search(q, orr.QueryTerms.none(), NOW, 3, candidate_cap=5000)
+        with pytest.raises(N.OrrError):
+            sh.set_option("no_such_option", 1)
+        with pytest.raises(N.OrrError):
+            sh.search_text(q, ["x" * 300], NOW, 3)                   # term longer than the substring kernel takes
+        assert sh.count == 3 and len(sh.search(q, orr.QueryTerms.none(), NOW, 3)) == 3   # the store survived all of it
