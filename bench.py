@@ -22,6 +22,11 @@ shard, computes its exact local top-10, and the lists are all-gathered over NCCL
 configs[4]: 5M x 768, batch 1024 top-100 (4 terms) / batch 256 top-50 (16 terms, tie-heavy) — a
 "step" is one orr_search_batch call; roofline.bound is "tensor" (useful 2*N*D*B flops of the main
 tcgen05 pass against the measured bf16 throughput).  The default line stays the headline metric.
+
+--workload c1 (N=1) is BASELINE.json configs[0], the reference's own CPU-runnable case, in full: 10k x 3072,
+single query, top-10, with the reference's 300-most-recent pre-selection (InMemoryIngestionStore.cs:57-65,
+candidate_cap=300 — the line's value) and over all rows (cap=0, under "all_rows"); the CPU port runs the
+whole workload (no sampling) on 1 thread (the reference's own execution) and on all threads.
 """
 from __future__ import annotations
 
@@ -161,6 +166,8 @@ def run_reference(args):
     from oracle import oracle_c
 
     threads = oracle_c.max_threads()
+    if args.workload == "c1":
+        raise SystemExit("--impl reference --workload c1: the c1 line times the CPU port itself (cpu_baseline); use --workload c1")
     if args.workload != "c2":
         wl = BATCH_WORKLOADS[args.workload]
         sample, steps = 200_000, max(1, args.steps if args.steps != 200 else 20)
@@ -253,6 +260,92 @@ def batch_config(args, wl):
             "top_k": wl["top_k"], "n_terms": wl["n_terms"], "parallelism": "1 GPU",
             "split_precision_passes": args.batch_passes,
             "l2": "bf16 planes (15.4 GB) exceed L2 (126 MB); every step is a fresh batch of queries; no flush needed"}
+
+
+def run_c1(args):
+    """--workload c1: 10k x 3072, single query, top-10 — candidate_cap=300 (the reference's behaviour) and all rows."""
+    import numpy as np
+    import torch
+
+    import omni_recall_rag_b200 as orr
+    from omni_recall_rag_b200 import _native as N  # noqa: F401
+    from omni_recall_rag_b200 import synth
+
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--workload c1 is a single-GPU bench")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: liborr has no CPU path")
+    rows_n = 10_000
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    spec = synth.make_spec(DIM)
+    shard = orr.RecallShard(DIM, rows_n, device=0, term_slots=TERM_SLOTS)
+    shard.fill_synthetic(spec, 0, rows_n)
+    n_q = steps + warmup
+    queries = [synth.query_host(spec, qi, rows_n, n_terms=N_TERMS) for qi in range(n_q)]
+    q_pinned = [torch.from_numpy(q.q).pin_memory() for q in queries]
+    res = {}
+    with ClockSampler(0) as clocks:
+        for cap in (300, 0):
+            for i in range(warmup):
+                shard.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K, candidate_cap=cap)
+            torch.cuda.synchronize()
+            dev_ms, wall = [], []
+            t0 = time.perf_counter()
+            for i in range(warmup, n_q):
+                shard.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K, candidate_cap=cap)
+                tm = shard.last_timing()
+                dev_ms.append(tm["total_device_ms"]); wall.append(tm["wall_ms"])
+            e2e_s = time.perf_counter() - t0
+            res[cap] = dict(qps_device=steps / (sum(dev_ms) / 1000.0), qps_e2e=steps / e2e_s, device_ms=sum(dev_ms) / steps,
+                            call_ms_median=statistics.median(wall), call_ms_p99=sorted(wall)[min(len(wall) - 1, int(0.99 * len(wall)))],
+                            path=tm["path"])
+    peak, peak_kind = measured_peak()
+    bytes_all = rows_n * (4 * DIM + 8 + 4 * TERM_SLOTS)
+    line = {
+        "metric": "hybrid recall QPS at 10k x 3072 fp32, top-10 (the reference's own CPU-runnable case)", "value": res[300]["qps_device"],
+        "unit": "queries/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": res[300]["device_ms"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 scan select + f64 exact re-score", "data": "synthetic",
+        "config": {"workload": "InMemory-store shape: 10000 chunks x 3072 fp32, single query, hybrid 0.7/0.2/0.1, 4 query terms, top-10, "
+                               "scored over the 300 most recent chunks (candidate_cap=300, the reference's GetRecentChunksAsync cut)",
+                   "rows_total": rows_n, "dim": DIM, "top_k": TOP_K, "candidate_cap": 300, "parallelism": "1 GPU",
+                   "l2": "the 123 MB corpus fits L2 (126 MB): latency-bound, no flush (steady state of a small store)"},
+        "e2e": {"value": res[300]["qps_e2e"], "unit": "queries/s", "h2d_bytes_per_step": 4 * DIM + 12 * N_TERMS,
+                "d2h_bytes_per_step": 24 * TOP_K + 8, "call_ms": {"median": res[300]["call_ms_median"], "p99": res[300]["call_ms_p99"]}},
+        "all_rows": {"candidate_cap": 0, "value": res[0]["qps_device"], "e2e": res[0]["qps_e2e"], "device_ms": res[0]["device_ms"],
+                     "call_ms": {"median": res[0]["call_ms_median"], "p99": res[0]["call_ms_p99"]}},
+        "gpu_launches": 2 * steps * 2,
+        "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel (all rows, cap=0)", "achieved": bytes_all / (res[0]["device_ms"] / 1000.0) / 1.0e9,
+                     "peak": peak, "unit": "GB/s", "frac": bytes_all / (res[0]["device_ms"] / 1000.0) / 1.0e9 / peak, "traffic": None,
+                     "note": "a 125 MB pass is launch/latency-bound (and L2-resident), not a bandwidth measurement; the headline roofline is the c2 line"},
+        "clocks": clocks.summary(),
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle_c
+        threads = oracle_c.max_threads()
+        rows = synth.rows_host(spec, 0, rows_n)
+        blob, off = oracle_c.pack_contents(synth.contents_of(rows.term_ids))
+        cpu = {}
+        for cap in (300, 0):
+            for th in (1, threads):
+                nq = 0
+                t0 = time.perf_counter()
+                while True:
+                    q = queries[nq % n_q]
+                    oracle_c.search(emb=rows.emb, dim=DIM, ticks=rows.ticks, content_blob=blob, content_off=off, query=q.text, qvec=q.q,
+                                    now_ticks=spec.now_ticks, top_k=TOP_K, candidate_cap=cap, threads=th)
+                    nq += 1
+                    dt = time.perf_counter() - t0
+                    if dt >= 3.0 and nq >= 8:
+                        break
+                cpu[(cap, th)] = nq / dt
+        line["cpu_baseline"] = {"value": cpu[(300, 1)], "unit": "queries/s", "cores": 1, "kind": "port",
+                                "value_all_threads": cpu[(300, threads)], "threads": threads,
+                                "all_rows_1_thread": cpu[(0, 1)], "all_rows_all_threads": cpu[(0, threads)],
+                                "sample": "the whole workload (10000 rows, no sampling), >= 3 s per figure; 1 thread is the reference's own "
+                                          "sequential execution of a request; C port of RecallSearchService.cs:20-119 + "
+                                          "InMemoryIngestionStore.cs:57-65 (no dotnet in the image)"}
+    print(json.dumps(line))
+    shard.close()
 
 
 def run_batch(args):
@@ -362,7 +455,7 @@ def main():
     ap.add_argument("--rows-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the per-GPU top-k lists meet (fused peer-memory kernel, or NCCL all-gather + merge)")
     ap.add_argument("--batch-passes", type=int, default=0, choices=[0, 1, 3],
@@ -370,6 +463,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "c1":
+        run_c1(args)
         return
     if args.workload != "c2":
         run_batch(args)

@@ -49,7 +49,8 @@ struct BatchState {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* ehi = nullptr; void* emid = nullptr;     // bf16 [capacity][dim]
     float* rowaux = nullptr;                       // [capacity padded] w_rec * recency of the current batch's clock
-    int64_t planes_rows = 0;                       // rows whose planes are built
+    int64_t planes_rows = 0;                       // rows whose hi plane is built
+    int64_t mid_rows = 0;                          // rows whose mid plane is built (allocated on the first bf16x3 pass)
     int bcap = 0, kcap = 0;
     float* q = nullptr; void* qhi = nullptr; void* qmid = nullptr;
     float* qscale = nullptr; float* thr = nullptr; float* kww = nullptr; int32_t* qterm = nullptr;
@@ -1032,7 +1033,7 @@ int orr_store_compact(orr_store* s, uint64_t* old_rows_out, int64_t out_cap, int
     s->rows_used = n_live;
     s->live_rows = n_live;
     s->version++;
-    if (s->batch) { std::lock_guard<std::mutex> g(s->batch->mu); s->batch->planes_rows = 0; }   // bf16 planes follow the rows
+    if (s->batch) { std::lock_guard<std::mutex> g(s->batch->mu); s->batch->planes_rows = 0; s->batch->mid_rows = 0; }   // bf16 planes follow the rows
     return ORR_OK;
 }
 
@@ -1089,7 +1090,7 @@ int orr_search_device_timing(orr_store* s, orr_timing* out) {
 }
 
 // ---- batched path ------------------------------------------------------------------------------
-static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) {
+static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k, bool need_mid) {
     const int dim = s->cfg.dim;
     const size_t cap = (size_t)s->cfg.capacity_rows;
     if (!bs->stream) {
@@ -1099,15 +1100,25 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k) 
     if (!bs->ehi) {
         const size_t cap_pad = (cap + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
         ORR_CUDA_OK(cudaMalloc(&bs->ehi, cap * dim * 2));
-        ORR_CUDA_OK(cudaMalloc(&bs->emid, cap * dim * 2));
         ORR_CUDA_OK(cudaMalloc(&bs->rowaux, cap_pad * sizeof(float)));
         bs->planes_rows = 0;
     }
     if (bs->planes_rows < s->rows_used) {        // rows appended since the last batch
-        int rc = orr_batch_build_planes(s->d_emb, bs->ehi, bs->emid, bs->planes_rows, s->rows_used - bs->planes_rows, dim,
+        int rc = orr_batch_build_planes(s->d_emb, bs->ehi, nullptr, bs->planes_rows, s->rows_used - bs->planes_rows, dim,
                                         (float)s->cfg.w_cos, bs->stream);
         if (rc != ORR_OK) return rc;
         bs->planes_rows = s->rows_used;
+    }
+    // the mid plane (the other half of the split) costs as much HBM as the hi plane and is only read by bf16x3
+    // passes: it is allocated and built the first time one runs (auto mode: the first cascade)
+    if (need_mid) {
+        if (!bs->emid) { ORR_CUDA_OK(cudaMalloc(&bs->emid, cap * dim * 2)); bs->mid_rows = 0; }
+        if (bs->mid_rows < s->rows_used) {
+            int rc = orr_batch_build_planes(s->d_emb, nullptr, bs->emid, bs->mid_rows, s->rows_used - bs->mid_rows, dim,
+                                            (float)s->cfg.w_cos, bs->stream);
+            if (rc != ORR_OK) return rc;
+            bs->mid_rows = s->rows_used;
+        }
     }
     if (batch_padded > bs->bcap || k > bs->kcap) {
         void** ptrs[] = {(void**)&bs->q, &bs->qhi, &bs->qmid, (void**)&bs->qscale, (void**)&bs->thr, (void**)&bs->kww,
@@ -1161,7 +1172,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     std::lock_guard<std::mutex> g(bs->mu);
     const int dim = s->cfg.dim, k = std::max(1, top_k);
     const int bp = (batch + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
-    int rc = batch_prepare(s, bs, bp, k);
+    int rc = batch_prepare(s, bs, bp, k, passes == 3);
     if (rc != ORR_OK) return rc;
     cudaStream_t st = bs->stream;
     const OrrShard sh = shard_view(s);
@@ -1235,7 +1246,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         }
         if (!missing.empty()) {
             int table_slots = 256;
-            while (table_slots < 4 * (int64_t)missing.size() && table_slots < BATCH_TABLE_SLOTS) table_slots <<= 1;
+            while (table_slots < 2 * (int64_t)missing.size() && table_slots < BATCH_TABLE_SLOTS) table_slots <<= 1;   // load <= 0.5: the kernel's filter keeps most hashes away from it
             uint2* table = bs->h_table;
             std::fill(table, table + table_slots, make_uint2(0u, 0u));
             const int32_t first_new = bs->term_slots_used;
@@ -1461,7 +1472,7 @@ int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t 
     std::lock_guard<std::mutex> g(bs->mu);
     const int dim = s->cfg.dim;
     const int bp = (batch + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
-    int rc = batch_prepare(s, bs, bp, 1);
+    int rc = batch_prepare(s, bs, bp, 1, s->batch_passes != 1);
     if (rc != ORR_OK) return rc;
     cudaStream_t st = bs->stream;
     const int64_t rows = s->rows_used, rows_pad = (rows + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;

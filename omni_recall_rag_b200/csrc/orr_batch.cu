@@ -506,8 +506,8 @@ __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         const float scale = (ss > 0.f && ss < 3e38f) ? w_cos * rsqrtf(ss) : 0.f;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(hi + row * dim);
-        __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(mid + row * dim);
+        __nv_bfloat162* h2 = hi ? reinterpret_cast<__nv_bfloat162*>(hi + row * dim) : nullptr;     // either plane may be skipped
+        __nv_bfloat162* m2 = mid ? reinterpret_cast<__nv_bfloat162*>(mid + row * dim) : nullptr;
         for (int c = lane; c < dim / 4; c += 32) {                          // second read of the row hits L1/L2
             const float4 v = x4[c];
             const float e[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb,
                 h[k] = __float2bfloat16_rn(ek);
                 m[k] = __float2bfloat16_rn(ek - __bfloat162float(h[k]));
             }
-            h2[2 * c] = __halves2bfloat162(h[0], h[1]); h2[2 * c + 1] = __halves2bfloat162(h[2], h[3]);
-            m2[2 * c] = __halves2bfloat162(m[0], m[1]); m2[2 * c + 1] = __halves2bfloat162(m[2], m[3]);
+            if (h2) { h2[2 * c] = __halves2bfloat162(h[0], h[1]); h2[2 * c + 1] = __halves2bfloat162(h[2], h[3]); }
+            if (m2) { m2[2 * c] = __halves2bfloat162(m[0], m[1]); m2[2 * c + 1] = __halves2bfloat162(m[2], m[3]); }
         }
     }
 }
@@ -638,7 +638,8 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     if ((rc = make_plane_map(&mqh, g.qhi, g.batch_padded, g.dim, BM)) != ORR_OK) return rc;
     if ((rc = make_plane_map(&mqm, g.qmid, g.batch_padded, g.dim, BM)) != ORR_OK) return rc;
     if ((rc = make_plane_map(&meh, g.ehi, g.rows, g.dim, BM)) != ORR_OK) return rc;
-    if ((rc = make_plane_map(&mem, g.emid, g.rows, g.dim, BM)) != ORR_OK) return rc;
+    // the bf16 screen (passes == 1) never touches the mid planes: their maps alias the hi planes
+    if ((rc = make_plane_map(&mem, g.passes == 1 ? g.ehi : g.emid, g.rows, g.dim, BM)) != ORR_OK) return rc;
     BatchArgs a{};
     const int64_t all_tiles = (g.rows + UN - 1) / UN;
     a.row_tile_stride = g.tile_stride < 1 ? 1 : g.tile_stride;

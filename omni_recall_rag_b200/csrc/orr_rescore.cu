@@ -786,20 +786,33 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
 
 // term bitmaps: bit r of bits[t] says row r holds batch term t.  A warp takes 32 consecutive rows (one
 // output word per term): the rows' 32-bit term tables are one contiguous block, streamed with 8
-// 16-byte loads in flight per lane; every stored hash is probed in an open-addressing table of the
-// batch's distinct terms (smem) and hits set their row's bit with atomicOr (hits are sparse).
+// 16-byte loads in flight per lane.  Every stored hash first tests one bit of a 2^18-bit filter of the
+// batch's new terms (smem, branch-free: multiply, shift, LDS, shift) — under 1-5 % of the stored hashes pass —
+// and only those probe the open-addressing table (smem) and set their row's bit (hits are sparse).
 constexpr int TERM_BITS_THREADS = 1024;
 constexpr int TERM_ACC = 64;                  // per-warp accumulator entries (direct-mapped by slot)
+constexpr int TERM_FILTER_LOG2 = 18;          // filter bits (32 KB of smem behind the probe table)
+constexpr int TERM_FILTER_WORDS = (1 << TERM_FILTER_LOG2) / 32;
 __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(const uint32_t* terms32, int slots, int64_t rows,
                                                                                const uint2* table, int table_mask,
                                                                                uint32_t* bits, int64_t slot_cap) {
     extern __shared__ uint2 tab[];
+    uint32_t* filt = reinterpret_cast<uint32_t*>(tab + table_mask + 1);
     // Zipf vocabularies: a handful of terms hit in most rows, i.e. up to 32 times per output word.  Each warp owns
     // its 32-row block's words, so it first ORs hits into a small shared accumulator ({slot + 1, bits}, claimed by
     // CAS) and flushes one atomic per (term, block); only accumulator conflicts go to global memory directly.
     __shared__ uint2 acc_all[TERM_BITS_THREADS / 32][TERM_ACC];
-    for (int i = threadIdx.x; i <= table_mask; i += blockDim.x) tab[i] = table[i];
+    for (int i = threadIdx.x; i < TERM_FILTER_WORDS; i += blockDim.x) filt[i] = 0u;
     for (int i = threadIdx.x; i < (TERM_BITS_THREADS / 32) * TERM_ACC; i += blockDim.x) (&acc_all[0][0])[i] = make_uint2(0u, 0u);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= table_mask; i += blockDim.x) {
+        const uint2 ent = table[i];
+        tab[i] = ent;
+        if (ent.x) {
+            const uint32_t f = (ent.x * 0x9E3779B1u) >> (32 - TERM_FILTER_LOG2);
+            atomicOr(filt + (f >> 5), 1u << (f & 31u));
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint32_t* acc = reinterpret_cast<uint32_t*>(acc_all[threadIdx.x >> 5]);
@@ -820,13 +833,20 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
+                const uint32_t hs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+                uint32_t pass = 0u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t f = (hs[c] * 0x9E3779B1u) >> (32 - TERM_FILTER_LOG2);
+                    pass |= ((filt[f >> 5] >> (f & 31u)) & 1u) << c;
+                }
+                if (pass == 0u) continue;
                 const int v = v0 + i * 32 + lane;
                 const uint32_t bit = 1u << (v >> vec_shift);
-                const uint32_t hs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t h = hs[c];
-                    if (!h) continue;
+                    if (!((pass >> c) & 1u) || !h) continue;
                     uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)table_mask;
                     for (;;) {
                         const uint2 ent = tab[pos];
@@ -899,8 +919,8 @@ int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows,
         orr_batch_clear_slots_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(bits), slot_cap, first_new, n_new, n_tiles);
         ORR_CUDA_OK(cudaGetLastError());
     }
-    const int smem = table_slots * 8;
-    ORR_SMEM_OPT_IN((orr_batch_term_bits_kernel), 128 * 1024);
+    const int smem = table_slots * 8 + TERM_FILTER_WORDS * 4;             // probe table + filter
+    ORR_SMEM_OPT_IN((orr_batch_term_bits_kernel), 160 * 1024);
     const int per_sm = smem <= 90 * 1024 ? 2 : 1;
     orr_batch_term_bits_kernel<<<sms * per_sm, TERM_BITS_THREADS, smem, st>>>(terms32, slots, rows, (const uint2*)table,
                                                                               table_slots - 1, bits, slot_cap);

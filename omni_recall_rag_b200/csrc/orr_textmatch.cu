@@ -15,15 +15,31 @@ namespace {
 constexpr int TM_THREADS = 256;
 constexpr int TM_WIN = 1024;                                  // text bytes staged per warp and window
 constexpr int TM_BUF = TM_WIN + ORR_TEXT_MAX_TERM_BYTES + 64; // window + overlap + alignment / look-ahead slack
+constexpr int TM_PRE = 3;                                     // 16-byte vectors per lane that hold a row's first window in flight
+static_assert(TM_PRE * 32 * 16 >= TM_BUF - 32, "the prefetch registers must cover a whole window");
 
-__global__ void __launch_bounds__(TM_THREADS) orr_text_bits_kernel(const OrrTextView tv, int64_t rows,
+struct TmWindow { const uint4* src; int head, want, n_vec; };
+
+__device__ __forceinline__ TmWindow tm_window(const uint8_t* text, uint64_t off, int len, int base, int overlap) {
+    // [base, base + TM_WIN + overlap) of the row's text, as 16-byte aligned vectors
+    TmWindow w;
+    w.want = max(0, min(len - base, TM_WIN + overlap));
+    const uint64_t g0 = off + (uint64_t)base;
+    w.head = (int)(g0 & 15u);
+    w.src = reinterpret_cast<const uint4*>(text + (g0 - w.head));
+    w.n_vec = w.want > 0 ? (w.head + w.want + 15) >> 4 : 0;
+    return w;
+}
+
+__global__ void __launch_bounds__(TM_THREADS, 4) orr_text_bits_kernel(const OrrTextView tv, int64_t rows,
                                                                    const OrrTextTerms* terms_g, const uint32_t* rows_list,
                                                                    int n_list, uint32_t* bits, int64_t row_words) {
     __shared__ OrrTextTerms tt;
     __shared__ __align__(16) uint8_t wbuf[TM_THREADS / 32][TM_BUF];
-    // per term: its first min(8, len) bytes as a little-endian word + mask, so one 64-bit compare per
-    // (position, term) decides almost every case; longer terms verify their tail byte by byte
-    __shared__ uint64_t t_pat[ORR_MAX_QUERY_TERMS], t_msk[ORR_MAX_QUERY_TERMS];
+    // per term: its first min(8, len) bytes as a little-endian word + mask ({pat lo, pat hi, mask lo, mask hi}, one
+    // 16-byte broadcast load), so one masked 64-bit compare per (position, term) decides almost every case;
+    // longer terms verify their tail byte by byte
+    __shared__ uint4 t_pm[ORR_MAX_QUERY_TERMS];
     __shared__ int t_len[ORR_MAX_QUERY_TERMS];
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(terms_g);
@@ -35,8 +51,8 @@ __global__ void __launch_bounds__(TM_THREADS) orr_text_bits_kernel(const OrrText
         const int t = threadIdx.x, o = tt.off[t], tl = tt.off[t + 1] - o;
         uint64_t pat = 0ull;
         for (int i = 0; i < min(tl, 8); ++i) pat |= (uint64_t)tt.bytes[o + i] << (8 * i);
-        t_pat[t] = pat;
-        t_msk[t] = tl >= 8 ? ~0ull : ((1ull << (8 * tl)) - 1ull);
+        const uint64_t msk = tl >= 8 ? ~0ull : ((1ull << (8 * tl)) - 1ull);
+        t_pm[t] = make_uint4((uint32_t)pat, (uint32_t)(pat >> 32), (uint32_t)msk, (uint32_t)(msk >> 32));
         t_len[t] = tl;
     }
     __syncthreads();
@@ -48,46 +64,86 @@ __global__ void __launch_bounds__(TM_THREADS) orr_text_bits_kernel(const OrrText
     const int64_t W = ((int64_t)gridDim.x * TM_THREADS) >> 5;
     const int64_t n_items = rows_list ? (int64_t)n_list : rows;
     const int64_t n_blocks = (n_items + 31) >> 5;
+
+    // matches every start position the staged window owns.  A lane takes 4 consecutive positions per step: the 11
+    // bytes they cover are 4 aligned smem words, re-aligned once (the sub-word shift is the same for the whole
+    // window) and funnel-shifted into the four 8-byte words; a term costs one broadcast load per step.
+    auto match_window = [&](const TmWindow& w, uint64_t found) -> uint64_t {
+        const uint8_t* tx = buf + w.head;
+        const int starts = min(w.want, TM_WIN);
+        const uint32_t sh = (uint32_t)(w.head & 3) * 8u;
+        for (int p4 = lane * 4; p4 < starts; p4 += 128) {
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(buf + ((w.head + p4) & ~3));
+            const uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3];
+            const uint32_t a0 = __funnelshift_r(x0, x1, sh), a1 = __funnelshift_r(x1, x2, sh), a2 = __funnelshift_r(x2, x3, sh);
+            uint32_t lo[4], hi[4];
+            lo[0] = a0; hi[0] = a1;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) { lo[j] = __funnelshift_r(a0, a1, 8u * j); hi[j] = __funnelshift_r(a1, a2, 8u * j); }
+            for (int t = 0; t < T; ++t) {
+                const uint4 pm = t_pm[t];
+                uint32_t hit = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hit |= ((((lo[j] ^ pm.x) & pm.z) | ((hi[j] ^ pm.y) & pm.w)) == 0u ? 1u : 0u) << j;
+                if (hit == 0u) continue;
+                const int tl = t_len[t];
+                if (tl == 0) continue;
+                for (int j = 0; j < 4; ++j) {
+                    const int p = p4 + j;
+                    if (!((hit >> j) & 1u) || p >= starts || p + tl > w.want) continue;   // bytes past `want` belong to no one
+                    if (tl > 8) {
+                        const int o = tt.off[t];
+                        int i = 8;
+                        while (i < tl && tx[p + i] == tt.bytes[o + i]) ++i;
+                        if (i < tl) continue;
+                    }
+                    found |= 1ull << t;
+                }
+            }
+        }
+        return found;
+    };
+
     for (int64_t blk = gw; blk < n_blocks; blk += W) {
         uint32_t acc_lo = 0u, acc_hi = 0u;                    // lane t: bits of the block's rows for term t / t+32
         const int n_here = (int)min((int64_t)32, n_items - (blk << 5));
+        // lane r holds row r's descriptor; the first window of row r + 1 is in flight (registers) while row r is matched
+        int64_t my_row = 0; unsigned long long my_off = 0ull; int my_len = 0;
+        if (lane < n_here) {
+            my_row = rows_list ? (int64_t)rows_list[(blk << 5) + lane] : (blk << 5) + lane;
+            my_off = tv.off[my_row];
+            my_len = (int)tv.len[my_row];
+        }
+        uint4 pre[TM_PRE];
+        auto fetch_first = [&](int r) {
+            const TmWindow w = tm_window(tv.text, __shfl_sync(0xffffffffu, my_off, r), __shfl_sync(0xffffffffu, my_len, r), 0, overlap);
+#pragma unroll
+            for (int i = 0; i < TM_PRE; ++i) {
+                const int v = lane + 32 * i;
+                pre[i] = v < w.n_vec ? __ldg(w.src + v) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        fetch_first(0);
         for (int r = 0; r < n_here; ++r) {
-            const int64_t row = rows_list ? (int64_t)rows_list[(blk << 5) + r] : (blk << 5) + r;
-            const uint64_t off = tv.off[row];
-            const int len = (int)tv.len[row];
-            uint64_t found = 0ull;                            // per lane: terms seen at this lane's positions
-            for (int base = 0; base < len; base += TM_WIN) {
-                // stage [base, base + TM_WIN + overlap) of the row's text, 16-byte aligned loads
-                const int want = min(len - base, TM_WIN + overlap);
-                const uint64_t g0 = off + (uint64_t)base;
-                const int head = (int)(g0 & 15u);
-                const uint4* src = reinterpret_cast<const uint4*>(tv.text + (g0 - head));
-                const int n_vec = (head + want + 15) >> 4;
+            const int64_t row = __shfl_sync(0xffffffffu, (unsigned long long)my_row, r);
+            const uint64_t off = __shfl_sync(0xffffffffu, my_off, r);
+            const int len = __shfl_sync(0xffffffffu, my_len, r);
+            TmWindow w = tm_window(tv.text, off, len, 0, overlap);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < TM_PRE; ++i) {
+                const int v = lane + 32 * i;
+                if (v < w.n_vec) reinterpret_cast<uint4*>(buf)[v] = pre[i];
+            }
+            __syncwarp();
+            if (r + 1 < n_here) fetch_first(r + 1);
+            uint64_t found = match_window(w, 0ull);           // per lane: terms seen at this lane's positions
+            for (int base = TM_WIN; base < len; base += TM_WIN) {
+                w = tm_window(tv.text, off, len, base, overlap);
                 __syncwarp();
-                for (int v = lane; v < n_vec; v += 32) reinterpret_cast<uint4*>(buf)[v] = __ldg(src + v);
+                for (int v = lane; v < w.n_vec; v += 32) reinterpret_cast<uint4*>(buf)[v] = __ldg(w.src + v);
                 __syncwarp();
-                const uint8_t* tx = buf + head;
-                const int starts = min(want, TM_WIN);         // start positions owned by this window
-                for (int p = lane; p < starts; p += 32) {
-                    // the 8 text bytes at p as one word: three aligned 32-bit smem loads + two funnel shifts
-                    const int at = head + p;
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(buf + (at & ~3));
-                    const uint32_t sh = (uint32_t)(at & 3) * 8u;
-                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-                    const uint64_t w = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | (uint64_t)__funnelshift_r(w0, w1, sh);
-                    for (int t = 0; t < T; ++t) {
-                        if (((w ^ t_pat[t]) & t_msk[t]) != 0ull) continue;
-                        const int tl = t_len[t];
-                        if (tl == 0 || p + tl > want) continue;                // bytes past `want` belong to no one
-                        if (tl > 8) {
-                            const int o = tt.off[t];
-                            int i = 8;
-                            while (i < tl && tx[p + i] == tt.bytes[o + i]) ++i;
-                            if (i < tl) continue;
-                        }
-                        found |= 1ull << t;
-                    }
-                }
+                found = match_window(w, found);
             }
             const uint32_t f_lo = __reduce_or_sync(0xffffffffu, (uint32_t)found);
             const uint32_t f_hi = __reduce_or_sync(0xffffffffu, (uint32_t)(found >> 32));
