@@ -42,6 +42,29 @@ struct SearchCtx {
 thread_local orr_timing g_timing{};
 thread_local int32_t g_batch_terms_built = 0;
 
+// 32-bit term hash (never 0) -> bitmap slot: flat open-addressing table, ~10 ns per query term on the host
+// (a node-based map cost 0.6 ms per 4096-term batch, all of it inside the timed step)
+struct FlatTermMap {
+    std::vector<uint32_t> keys; std::vector<int32_t> vals; uint32_t mask = 0;
+    void reset(size_t entries) {
+        size_t n = 1024;
+        while (n < 4 * entries) n <<= 1;
+        keys.assign(n, 0u); vals.assign(n, -1); mask = (uint32_t)(n - 1);
+    }
+    void clear() { std::fill(keys.begin(), keys.end(), 0u); }
+    int32_t get(uint32_t h) const {
+        for (uint32_t pos = (h * 0x9E3779B1u) & mask;; pos = (pos + 1) & mask) {
+            if (keys[pos] == h) return vals[pos];
+            if (keys[pos] == 0u) return -1;
+        }
+    }
+    void put(uint32_t h, int32_t v) {
+        uint32_t pos = (h * 0x9E3779B1u) & mask;
+        while (keys[pos] != 0u && keys[pos] != h) pos = (pos + 1) & mask;
+        keys[pos] = h; vals[pos] = v;
+    }
+};
+
 // state of the batched (tcgen05) path: split planes of the store + per-call scratch
 struct BatchState {
     std::mutex mu;                       // batched searches are serialised per store
@@ -62,7 +85,8 @@ struct BatchState {
     float* dense = nullptr; size_t dense_elems = 0;
     uint32_t* term_bits = nullptr; void* table = nullptr;
     // persistent per-term row bitmaps: 32-bit term hash -> slot in the tile-major term_bits[tile][slot][8 words]
-    std::unordered_map<uint32_t, int32_t> term_slot;
+    FlatTermMap term_slot;
+    std::vector<uint32_t> missing;                 // terms of the current batch that have no bitmap yet
     uint64_t term_version = ~0ull; int64_t term_row_words = 0;
     int32_t term_slots_used = 0, term_slots_cap = 0;
 };
@@ -1198,6 +1222,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         if (total_terms > BATCH_MAX_TERM_IDS) { orr_set_error("batch path: %lld query terms in one launch", (long long)total_terms); return ORR_E_INTERNAL; }
         // Term bitmaps persist across batches (keyed by the 32-bit term hash) until the store mutates:
         // a batch only builds the bitmaps of terms it is the first to ask for.
+        if (bs->term_slot.mask == 0) bs->term_slot.reset((size_t)ORR_BATCH_MAX_TERM_SLOTS + BATCH_MAX_TERM_IDS);
         if (bs->term_version != s->version || bs->term_row_words != row_words) {
             bs->term_slot.clear(); bs->term_slots_used = 0;
             bs->term_version = s->version; bs->term_row_words = row_words;
@@ -1208,9 +1233,12 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         std::fill(qterm, qterm + (size_t)bp * ORR_BATCH_TERMS, -1);
         std::fill(kww, kww + bp, 0.f);
         memset(hp, 0, sizeof(OrrBatchProbes) * (size_t)batch);
-        std::vector<uint32_t> distinct;
-        {
-            std::unordered_map<uint32_t, int32_t> seen;
+        std::vector<uint32_t>& missing = bs->missing;
+        int32_t first_new = bs->term_slots_used;
+        // one pass over the batch's terms: known terms resolve to their slot, unseen ones take the next slots in order
+        auto assign_slots = [&]() {
+            missing.clear();
+            first_new = bs->term_slots_used;
             for (int32_t b = 0; b < batch; ++b) {
                 const int32_t nt = n_terms[b];
                 hp[b].n_terms = nt;
@@ -1219,25 +1247,32 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
                     const uint64_t h = probe_hash[probe_offsets[b] + t] ? probe_hash[probe_offsets[b] + t] : 1ULL;
                     hp[b].h64[t] = h;
                     const uint32_t h32 = orr_hash_low(h);
-                    if (seen.emplace(h32, 0).second) distinct.push_back(h32);
+                    int32_t slot = bs->term_slot.get(h32);
+                    if (slot < 0) {
+                        slot = bs->term_slots_used++;
+                        bs->term_slot.put(h32, slot);
+                        missing.push_back(h32);
+                    }
+                    qterm[(size_t)b * ORR_BATCH_TERMS + t] = slot;
                 }
             }
-        }
-        std::vector<uint32_t> missing;
-        for (uint32_t h : distinct) if (!bs->term_slot.count(h)) missing.push_back(h);
-        if ((int64_t)bs->term_slots_used + (int64_t)missing.size() > bs->term_slots_cap) {
-            // out of slots: drop the cache; grow the pool if this batch alone does not fit
+        };
+        assign_slots();
+        if (bs->term_slots_used > bs->term_slots_cap) {
+            // out of slots: drop the cache (every term of this batch is unseen again); grow the pool if this batch
+            // alone does not fit
             bs->term_slot.clear(); bs->term_slots_used = 0;
-            missing = distinct;
-            if ((int64_t)distinct.size() > bs->term_slots_cap) {
+            assign_slots();
+            const size_t n_distinct = missing.size();
+            if ((int64_t)n_distinct > bs->term_slots_cap) {
                 size_t free_b = 0, total_b = 0;
                 cudaMemGetInfo(&free_b, &total_b);
                 // sized for the store's CAPACITY (32 B per slot and 256-row tile), so appended rows never outgrow it
                 const size_t slot_bytes = (size_t)((s->cfg.capacity_rows + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE) * 32;
                 const size_t have = (size_t)bs->term_slots_cap * slot_bytes;
                 size_t budget = std::min<size_t>((free_b + have) / 4, (size_t)12 << 30);
-                size_t want = std::max<size_t>(8 * distinct.size(), 16384);   // room for several batches before the pool recycles
-                if (want * slot_bytes > budget) want = std::max<size_t>(distinct.size(), budget / slot_bytes);
+                size_t want = std::max<size_t>(8 * n_distinct, 16384);   // room for several batches before the pool recycles
+                if (want * slot_bytes > budget) want = std::max<size_t>(n_distinct, budget / slot_bytes);
                 want = std::min<size_t>(want, ORR_BATCH_MAX_TERM_SLOTS);
                 cudaFree(bs->term_bits); bs->term_bits = nullptr; bs->term_slots_cap = 0;
                 ORR_CUDA_OK(cudaMalloc(&bs->term_bits, want * slot_bytes));
@@ -1249,12 +1284,11 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
             while (table_slots < 2 * (int64_t)missing.size() && table_slots < BATCH_TABLE_SLOTS) table_slots <<= 1;   // load <= 0.5: the kernel's filter keeps most hashes away from it
             uint2* table = bs->h_table;
             std::fill(table, table + table_slots, make_uint2(0u, 0u));
-            const int32_t first_new = bs->term_slots_used;
-            for (uint32_t h : missing) {
+            for (size_t i = 0; i < missing.size(); ++i) {
+                const uint32_t h = missing[i];
                 uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)(table_slots - 1);
                 while (table[pos].x != 0u) pos = (pos + 1) & (uint32_t)(table_slots - 1);
-                table[pos] = make_uint2(h, (uint32_t)bs->term_slots_used);
-                bs->term_slot[h] = bs->term_slots_used++;
+                table[pos] = make_uint2(h, (uint32_t)(first_new + (int32_t)i));
             }
             if (!bs->table) ORR_CUDA_OK(cudaMalloc(&bs->table, BATCH_TABLE_SLOTS * 8));
             ORR_CUDA_OK(cudaMemcpyAsync(bs->table, table, (size_t)table_slots * 8, cudaMemcpyHostToDevice, st));
@@ -1262,9 +1296,6 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
                                             bs->term_slots_cap, first_new, (int)missing.size(), st);
             if (rc != ORR_OK) return rc;
         }
-        for (int32_t b = 0; b < batch; ++b)
-            for (int32_t t = 0; t < n_terms[b]; ++t)
-                qterm[(size_t)b * ORR_BATCH_TERMS + t] = bs->term_slot[orr_hash_low(hp[b].h64[t])];
         ORR_CUDA_OK(cudaMemcpyAsync(bs->qterm, qterm, (size_t)bp * ORR_BATCH_TERMS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaMemcpyAsync(bs->kww, kww, (size_t)bp * sizeof(float), cudaMemcpyHostToDevice, st));
         ORR_CUDA_OK(cudaMemcpyAsync(bs->probes, hp, sizeof(OrrBatchProbes) * (size_t)batch, cudaMemcpyHostToDevice, st));

@@ -185,6 +185,41 @@ __device__ __forceinline__ void kw_add(KwPlanes& kp, const uint4& w) {
         kp.p[c][DEPTH - 1] ^= x;
     }
 }
+// Queries with more than 4 terms: all 16 term words at once through a carry-save adder tree (Harley-Seal
+// counter: 15 CSAs = 30 LOP3 per 32-row chunk for 16 one-bit inputs, against ~10 per term for the rippling
+// kw_add) — absent terms are zero words.
+__device__ __forceinline__ uint32_t u4c(const uint4& v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; }
+__device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
+    l = a ^ b ^ c;
+    h = (a & b) | ((a ^ b) & c);
+}
+__device__ __forceinline__ void kw_tree(KwPlanes& kp, const uint4 (&w0)[4], const uint4 (&w1)[12]) {
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+        uint32_t x[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = u4c(w0[i], c);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) x[4 + i] = u4c(w1[i], c);
+        uint32_t ones, twos, fours, eights, sixteens, tA, tB, fA, fB, eA, eB;
+        csa(tA, ones, x[0], x[1], x[2]);
+        csa(tB, ones, ones, x[3], x[4]);
+        csa(fA, twos, tA, tB, 0u);
+        csa(tA, ones, ones, x[5], x[6]);
+        csa(tB, ones, ones, x[7], x[8]);
+        csa(fB, twos, twos, tA, tB);
+        csa(eA, fours, fA, fB, 0u);
+        csa(tA, ones, ones, x[9], x[10]);
+        csa(tB, ones, ones, x[11], x[12]);
+        csa(fA, twos, twos, tA, tB);
+        csa(tA, ones, ones, x[13], x[14]);
+        csa(tB, ones, ones, x[15], 0u);
+        csa(fB, twos, twos, tA, tB);
+        csa(eB, fours, fours, fA, fB);
+        csa(sixteens, eights, eA, eB, 0u);
+        kp.p[c][0] = ones; kp.p[c][1] = twos; kp.p[c][2] = fours; kp.p[c][3] = eights; kp.p[c][4] = sixteens;
+    }
+}
 // `tile_half` = 2 * row tile + (0 | 1): the thread's 128-row half of the tile = 4 of the slot's 8 words
 __device__ __forceinline__ uint4 kw_load(const BatchArgs& a, uint32_t id, int64_t tile_half) {
     return id != NO_TERM ? __ldg(reinterpret_cast<const uint4*>(a.term_bits) + ((tile_half >> 1) * a.slot_cap + id) * 2 + (tile_half & 1))
@@ -217,7 +252,8 @@ __device__ __forceinline__ void epilogue_chunks(const BatchArgs& a, uint32_t tad
             s[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), qs, rr.z);
             s[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), qs, rr.w);
         }
-        if (HAS_KW) {
+        // adds kww * (terms matched) to every row of the chunk
+        auto add_keywords = [&]() {
 #pragma unroll
             for (int p = 0; p < 5; ++p) {
                 const uint32_t m = kp.p[cc][p];
@@ -227,12 +263,23 @@ __device__ __forceinline__ void epilogue_chunks(const BatchArgs& a, uint32_t tad
                     for (int j = 0; j < 32; ++j) if (m & (1u << j)) s[j] += add;
                 }
             }
-        }
+        };
+        if (HAS_KW && MODE != 0) add_keywords();
         if (MODE == 0) {
             float mx = s[0];
 #pragma unroll
             for (int j = 1; j < 32; ++j) mx = fmaxf(mx, s[j]);
-            if (__any_sync(0xffffffffu, mx > thr)) {                        // rare: ~1000 candidates per query and pass
+            // Main pass: only rows above the query's threshold matter, so the keyword side is applied to a chunk
+            // only if its best keyword-free score plus the most the chunk's planes can add (the weights of the
+            // non-empty planes bound the count; 1e-6 covers the rounding of the adds) could reach it.
+            float kw_room = 0.f;
+            if (HAS_KW) {
+                const int cnt = (kp.p[cc][0] ? 1 : 0) + (kp.p[cc][1] ? 2 : 0) + (kp.p[cc][2] ? 4 : 0) + (kp.p[cc][3] ? 8 : 0) +
+                                (kp.p[cc][4] ? 16 : 0);
+                kw_room = cnt ? fmaf(fabsf(kww), (float)cnt, 1.0e-6f) : 0.f;
+            }
+            if (__any_sync(0xffffffffu, mx + kw_room > thr)) {              // rare: ~1000 candidates per query and pass
+                if (HAS_KW) add_keywords();
                 uint32_t pass = 0u;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) pass |= (s[j] > thr) ? (1u << j) : 0u;
@@ -448,19 +495,24 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
             const int64_t row0 = (int64_t)row_tile * UN;
             KwPlanes kp;
             if (has_kw) {
-                kw_clear(kp);
-                if (kww != 0.f) {
-                    kw_add<3>(kp, wn[0]); kw_add<3>(kp, wn[1]); kw_add<3>(kp, wn[2]); kw_add<3>(kp, wn[3]);
-                    const uint2* idp = reinterpret_cast<const uint2*>(q_ids + qi * ORR_BATCH_MAX_TERMS);
+                const uint2* idp = reinterpret_cast<const uint2*>(q_ids + qi * ORR_BATCH_MAX_TERMS);
+                const uint2 id1 = idp[1];
+                if (!__any_sync(0xffffffffu, (id1.x & 0xFFFFu) != NO_TERM)) {
+                    // every query of the warp has <= 4 terms: their words were prefetched during the last unit
+                    kw_clear(kp);
+                    if (kww != 0.f) { kw_add<3>(kp, wn[0]); kw_add<3>(kp, wn[1]); kw_add<3>(kp, wn[2]); kw_add<3>(kp, wn[3]); }
+                } else {
+                    // up to 16 terms: the other 12 words in flight together, then one adder tree per chunk
                     const int64_t word0 = (int64_t)row_tile * 2 + (c_begin / HC);
-#pragma unroll 1
-                    for (int g = 1; g < ORR_BATCH_MAX_TERMS / 4; ++g) {   // queries with more than 4 terms
-                        const uint2 id4 = idp[g];
-                        if ((id4.x & 0xFFFFu) == NO_TERM) break;            // ids are packed front to back
-                        const uint4 w0 = kw_load(a, id4.x & 0xFFFFu, word0), w1 = kw_load(a, id4.x >> 16, word0);
-                        const uint4 w2 = kw_load(a, id4.y & 0xFFFFu, word0), w3 = kw_load(a, id4.y >> 16, word0);
-                        kw_add<5>(kp, w0); kw_add<5>(kp, w1); kw_add<5>(kp, w2); kw_add<5>(kp, w3);
-                    }
+                    const uint2 id2 = idp[2], id3 = idp[3];
+                    uint4 w[12];
+                    w[0] = kw_load(a, id1.x & 0xFFFFu, word0); w[1] = kw_load(a, id1.x >> 16, word0);
+                    w[2] = kw_load(a, id1.y & 0xFFFFu, word0); w[3] = kw_load(a, id1.y >> 16, word0);
+                    w[4] = kw_load(a, id2.x & 0xFFFFu, word0); w[5] = kw_load(a, id2.x >> 16, word0);
+                    w[6] = kw_load(a, id2.y & 0xFFFFu, word0); w[7] = kw_load(a, id2.y >> 16, word0);
+                    w[8] = kw_load(a, id3.x & 0xFFFFu, word0); w[9] = kw_load(a, id3.x >> 16, word0);
+                    w[10] = kw_load(a, id3.y & 0xFFFFu, word0); w[11] = kw_load(a, id3.y >> 16, word0);
+                    kw_tree(kp, wn, w);
                 }
                 if (u + 1 < my_units) prefetch_words(u + 1);
             }
