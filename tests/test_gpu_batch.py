@@ -94,6 +94,47 @@ def test_mixed_queries_zero_vectors_and_small_batches():
         assert sh.search_batch(Q[:0], [], NOW, 10) == []
 
 
+@pytest.mark.parametrize("passes", [0, 3])
+def test_term_counts_from_0_to_16_inside_one_warp(passes):
+    """Queries with 0..16 terms side by side (one warp of the epilogue holds 32 of them): the <= 4-term ripple
+    counter and the 16-input adder tree must agree with the oracle's match counts, frequent terms included
+    (rows matching several terms at once fill the higher count planes)."""
+    spec = synth.make_spec(256, gen_dim=256, terms_per_chunk=64)
+    n = 9_000
+    rows = synth.rows_host(spec, 0, n)
+    with _filled_shard(spec, n) as sh:
+        sh.set_option("batch_passes", passes)
+        qs = [synth.query_host(spec, qi, n, n_terms=(qi % 17), frequent_terms=(qi % 17) // 2) for qi in range(70)]
+        _check_batch(sh, rows, qs, 20, f"term counts 0..16 passes={passes}")
+        # all queries with exactly 16 frequent terms: rows match several terms at once
+        qs = [synth.query_host(spec, 100 + qi, n, n_terms=16, frequent_terms=16) for qi in range(33)]
+        _check_batch(sh, rows, qs, 20, f"16 frequent terms passes={passes}")
+
+
+def test_rows_matching_up_to_all_16_terms_fill_every_count_plane():
+    """Planted rows hold 0..16 of a query's 16 terms, so the per-row match count runs through every bit of the
+    5 count planes (1, 2, 4, 8, 16) — the carry chain of the adder tree against the oracle's plain count."""
+    dim, n = 128, 4096
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=64)
+    rows = synth.rows_host(spec, 0, n)
+    qs = [synth.query_host(spec, qi, n, n_terms=16, frequent_terms=4) for qi in range(40)]
+    tids = rows.term_ids.copy()
+    for i in range(0, n, 3):
+        q = qs[(i // 3) % len(qs)]
+        j = (i // 3) % 17
+        tids[i, :j] = q.term_ids[:j]
+    rows = synth.HostRows(rows.emb, rows.ticks, tids, rows.doc_first_row)
+    contents = synth.contents_of(tids)
+    with orr.RecallShard(dim, n) as sh:
+        for d in range(0, n, 64):
+            got_rows = sh.upsert_document_chunks(d // 64 + 1, rows.emb[d:d + 64], rows.ticks[d:d + 64],
+                                                 [orr.tokenize_content(c) for c in contents[d:d + 64]])
+            assert got_rows.tolist() == list(range(d, d + 64))
+        for passes in (0, 3):
+            sh.set_option("batch_passes", passes)
+            _check_batch(sh, rows, qs, 30, f"planted 0..16 matches passes={passes}")
+
+
 def test_batch_sees_mutations_and_rebuilds_its_term_bitmaps():
     """The batched path keeps bf16 planes and per-term row bitmaps beside the store; appends,
     replace-by-document and deletes must show up in the next batch."""
