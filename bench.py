@@ -222,7 +222,8 @@ def workload_config(args):
             "rows_total": total, "rows_per_gpu": args.rows_per_gpu, "dim": DIM, "top_k": TOP_K,
             "parallelism": (f"row-sharded x{args.gpus}, per-GPU exact top-{TOP_K}, "
                             + ("fused peer-memory all-gather + merge kernel over NVLink (orr_xchg_allgather_merge); NCCL only "
-                               "for set-up and the timing barrier" if args.exchange == "p2p" else
+                               "for set-up and the timing barrier" + ("" if args.no_pipeline else "; the exchange of query i runs on a "
+                               "side stream while the rank scans query i+1") if args.exchange == "p2p" else
                                "NCCL all_gather_into_tensor + merge kernel")) if args.gpus > 1 else "1 GPU",
             "l2": "inputs (12.3 GB/GPU) exceed L2 (126 MB); no flush needed",
             "value_units": "queries/s x (rows_total / 1M)"}
@@ -458,6 +459,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the per-GPU top-k lists meet (fused peer-memory kernel, or NCCL all-gather + merge)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="N>1: every query is a blocking collective step (no exchange/scan overlap between consecutive queries)")
     ap.add_argument("--batch-passes", type=int, default=0, choices=[0, 1, 3],
                     help="0 = auto (bf16 screen, bf16x3 cascade for unproven queries; the library default), 1, 3")
     args = ap.parse_args()
@@ -510,20 +513,47 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing: `value` ----
+    # N>1: a stream of queries with the exchange of query i on a side stream (ShardedRecall.search_device_pipelined),
+    # so a rank's next scan does not wait for the slowest peer; --no-pipeline keeps every query a blocking collective
+    # step.  Both forms are timed; `value` is the pipelined one unless --no-pipeline.
     flags_seen = 0
-    for i in range(warmup):
-        sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    status_log = []
-    with ClockSampler(local_rank) as clocks:
+    main_stream = torch.cuda.current_stream(dev)
+
+    def timed_loop(pipelined: bool):
+        for i in range(warmup):
+            if pipelined:
+                _, _, done = sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+            else:
+                sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
         barrier()
-        ev0.record()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        done = None
         for i in range(warmup, n_q):
-            _, st = sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
-        ev1.record()
+            if pipelined:
+                _, st, done = sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+            else:
+                _, st = sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+        if done is not None:
+            main_stream.wait_event(done)               # the last exchange (they complete in order) ends the region
+        e1.record()
         barrier()
-        dev_ms = ev0.elapsed_time(ev1)
+        ms = e0.elapsed_time(e1)
+        fl = int(st.cpu().numpy()[1])
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), fl
+
+    pipelined = world > 1 and sr.exchange == "p2p" and not args.no_pipeline
+    with ClockSampler(local_rank) as clocks:
+        dev_ms_sync, fl = timed_loop(False)
+        flags_seen |= fl
+        dev_ms = dev_ms_sync
+        if pipelined:
+            dev_ms, fl = timed_loop(True)
+            flags_seen |= fl
         # keep sampling under load for a moment longer so short runs still get samples
         t_end = time.time() + 0.6
         j = warmup
@@ -532,10 +562,6 @@ def main():
             j = warmup + (j + 1 - warmup) % steps
         torch.cuda.synchronize()
     clock_summary = clocks.summary()
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
 
     # ---- end-to-end timing through the host API: `e2e`, and the scan kernel's own duration ----
     for i in range(warmup):
@@ -563,6 +589,19 @@ def main():
     got, flags = sharded.hits_from_device(hd, sd)
     assert got.rows.tolist() == hits.rows.tolist() and got.scores.tolist() == hits.scores.tolist(), "device/host paths disagree"
     flags_seen |= flags
+    if pipelined:                                      # ... and so does the pipelined form, for a run of queries
+        outs = []
+        for i in range(n_q - 3, n_q):
+            hp_, sp_, done = sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+            outs.append((hp_, sp_, done))
+        for (hp_, sp_, done), i in zip(outs, range(n_q - 3, n_q)):
+            done.synchronize()
+            gp, fl = sharded.hits_from_device(hp_, sp_)
+            hd, sd = sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+            torch.cuda.synchronize()
+            gs, _ = sharded.hits_from_device(hd, sd)
+            assert gp.rows.tolist() == gs.rows.tolist() and gp.scores.tolist() == gs.scores.tolist(), "pipelined/blocking exchange disagree"
+            flags_seen |= fl
 
     # per-rank scan kernel time: the exchange makes every query wait for the slowest shard
     scan_avg_local = sum(scan_ms) / len(scan_ms)
@@ -595,6 +634,8 @@ def main():
         "gpu_launches": launches_per_step * steps,
         "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel"] + (exchange_kernel if world > 1 else []),
         "exchange": sr.exchange, "per_rank_scan_kernel_ms": per_rank_scan,
+        "pipelined_exchange": pipelined,
+        "value_blocking_exchange": steps / (dev_ms_sync / 1000.0) * scale,
         "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel<24,1>", "achieved": achieved, "peak": peak,
                      "peak_kind": f"{peak_kind} HBM copy GB/s (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6650 GB/s",
                      "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,

@@ -31,7 +31,10 @@ __device__ __forceinline__ TmWindow tm_window(const uint8_t* text, uint64_t off,
     return w;
 }
 
-__global__ void __launch_bounds__(TM_THREADS, 4) orr_text_bits_kernel(const OrrTextView tv, int64_t rows,
+// NT = the query's term count when it is 1..4 (patterns live in registers, the term loop is unrolled: the kernel
+// is ALU-bound, ncu: 78 % ALU pipe, LOP3 a third of the instructions), 0 = any count (patterns read from smem).
+template <int NT>
+__global__ void __launch_bounds__(TM_THREADS, NT >= 3 ? 3 : 4) orr_text_bits_kernel(const OrrTextView tv, int64_t rows,
                                                                    const OrrTextTerms* terms_g, const uint32_t* rows_list,
                                                                    int n_list, uint32_t* bits, int64_t row_words) {
     __shared__ OrrTextTerms tt;
@@ -58,7 +61,11 @@ __global__ void __launch_bounds__(TM_THREADS, 4) orr_text_bits_kernel(const OrrT
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* buf = wbuf[warp];
-    const int T = tt.n_terms;
+    const int T = NT > 0 ? NT : tt.n_terms;
+    uint4 pm_r[NT > 0 ? NT : 1];
+    int tl_r[NT > 0 ? NT : 1];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { pm_r[t] = t_pm[t]; tl_r[t] = t_len[t]; }
     const int overlap = max(tt.max_len - 1, 0);
     const int64_t gw = ((int64_t)blockIdx.x * TM_THREADS + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * TM_THREADS) >> 5;
@@ -80,13 +87,14 @@ __global__ void __launch_bounds__(TM_THREADS, 4) orr_text_bits_kernel(const OrrT
             lo[0] = a0; hi[0] = a1;
 #pragma unroll
             for (int j = 1; j < 4; ++j) { lo[j] = __funnelshift_r(a0, a1, 8u * j); hi[j] = __funnelshift_r(a1, a2, 8u * j); }
+#pragma unroll
             for (int t = 0; t < T; ++t) {
-                const uint4 pm = t_pm[t];
+                const uint4 pm = NT > 0 ? pm_r[NT > 0 ? t : 0] : t_pm[t];
                 uint32_t hit = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hit |= ((((lo[j] ^ pm.x) & pm.z) | ((hi[j] ^ pm.y) & pm.w)) == 0u ? 1u : 0u) << j;
                 if (hit == 0u) continue;
-                const int tl = t_len[t];
+                const int tl = NT > 0 ? tl_r[NT > 0 ? t : 0] : t_len[t];
                 if (tl == 0) continue;
                 for (int j = 0; j < 4; ++j) {
                     const int p = p4 + j;
@@ -178,7 +186,13 @@ int orr_launch_text_bits(const OrrTextView& tv, int64_t rows, const OrrTextTerms
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t blocks_needed = ((n_items + 31) / 32 + TM_THREADS / 32 - 1) / (TM_THREADS / 32);
     const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)sms * 8);
-    orr_text_bits_kernel<<<grid, TM_THREADS, 0, st>>>(tv, rows, terms_dev, rows_list, n_list, bits, row_words);
+    switch (n_terms) {
+        case 1: orr_text_bits_kernel<1><<<grid, TM_THREADS, 0, st>>>(tv, rows, terms_dev, rows_list, n_list, bits, row_words); break;
+        case 2: orr_text_bits_kernel<2><<<grid, TM_THREADS, 0, st>>>(tv, rows, terms_dev, rows_list, n_list, bits, row_words); break;
+        case 3: orr_text_bits_kernel<3><<<grid, TM_THREADS, 0, st>>>(tv, rows, terms_dev, rows_list, n_list, bits, row_words); break;
+        case 4: orr_text_bits_kernel<4><<<grid, TM_THREADS, 0, st>>>(tv, rows, terms_dev, rows_list, n_list, bits, row_words); break;
+        default: orr_text_bits_kernel<0><<<grid, TM_THREADS, 0, st>>>(tv, rows, terms_dev, rows_list, n_list, bits, row_words); break;
+    }
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }

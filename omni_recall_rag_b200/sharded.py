@@ -219,6 +219,52 @@ class ShardedRecall:
         return b["out_hits"], b["out_status"]
 
 
+    def search_device_pipelined(self, q_dev, terms: QueryTerms, now_ticks: int, top_k: int, depth: int = 3):
+        """Throughput form of search_device for a stream of queries: the exchange of query i runs on a side
+        stream, so this rank's scan of query i+1 starts as soon as its own local top-k of query i exists
+        instead of waiting for the slowest peer.  Every query is still a complete search (local exact top-k,
+        all-gather over peer memory, merge); only the waiting moves off the scan's stream.  Returns
+        (hits_dev, status_dev, done_event): the buffers are valid once `done_event` has completed and stay
+        untouched for the next `depth - 1` calls.  The exchange ring (ORR_XCHG_SLOTS = 4 sequence-tagged slots
+        per rank) bounds how far ranks may drift apart; kernels of one rank's exchanges run in order."""
+        import torch
+
+        if self.world == 1 or self._xchg is None:
+            h, st = self.search_device(q_dev, terms, now_ticks, top_k)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(q_dev.device))
+            return h, st, ev
+        k = max(1, int(top_k))
+        if k > self.max_top_k:
+            raise ValueError(f"top_k {k} > max_top_k {self.max_top_k} of the exchange buffers")
+        dev = q_dev.device
+        key = ("pipe", k, dev.index, depth)
+        if key not in self._dev_bufs:
+            self._dev_bufs[key] = dict(
+                side=torch.cuda.Stream(device=dev), idx=0,
+                slots=[dict(hits=torch.zeros(k * HIT_BYTES, dtype=torch.uint8, device=dev),
+                            status=torch.zeros(2, dtype=torch.int32, device=dev),
+                            out_hits=torch.zeros(k * HIT_BYTES, dtype=torch.uint8, device=dev),
+                            out_status=torch.zeros(2, dtype=torch.int32, device=dev),
+                            ready=torch.cuda.Event(), done=torch.cuda.Event(), used=False) for _ in range(max(2, depth))])
+        pipe = self._dev_bufs[key]
+        b = pipe["slots"][pipe["idx"] % len(pipe["slots"])]
+        pipe["idx"] += 1
+        main = torch.cuda.current_stream(dev)
+        if b["used"]:
+            main.wait_event(b["done"])                 # the slot's previous exchange has read hits/status
+        self.shard.search_device(q_dev.data_ptr(), terms, now_ticks, top_k, b["hits"].data_ptr(),
+                                 b["status"].data_ptr(), main.cuda_stream)
+        b["ready"].record(main)
+        side = pipe["side"]
+        side.wait_event(b["ready"])
+        N.check(N.lib().orr_xchg_allgather_merge(self._xchg, b["hits"].data_ptr(), b["status"].data_ptr(), top_k,
+                                                 b["out_hits"].data_ptr(), b["out_status"].data_ptr(), side.cuda_stream))
+        b["done"].record(side)
+        b["used"] = True
+        return b["out_hits"], b["out_status"], b["done"]
+
+
 def hits_from_device(hits_dev, status_dev) -> Tuple[Hits, int]:
     """D2H of a device hit list -> (Hits, flags)."""
     st = status_dev.cpu().numpy()

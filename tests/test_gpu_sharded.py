@@ -212,3 +212,25 @@ def test_single_process_cluster_matches_the_oracle():
         got = cl.search(q.q, q.terms, NOW, k)
         er, es, _ = oracle_search_synth(rows, q, NOW, k)
         assert_same_ranking(got.rows, got.scores, [to_global(r) for r in er], es, what="cluster after delete")
+
+
+def test_pipelined_device_search_equals_the_blocking_form_on_one_rank():
+    """search_device_pipelined with world == 1 is search_device plus a completion event (the N>1 form is checked
+    against the blocking exchange inside bench.py's multi-GPU run and tools/sharded_check.py)."""
+    import torch
+
+    dim, n, k = 256, 5_000, 10
+    spec = synth.make_spec(dim, gen_dim=dim)
+    with orr.RecallShard(dim, n) as sh:
+        sh.fill_synthetic(spec, 0, n)
+        sr = sharded.ShardedRecall(sh)
+        dev = torch.device("cuda", 0)
+        for qi in range(4):
+            q = synth.query_host(spec, qi, n, n_terms=4)
+            q_dev = torch.from_numpy(q.q).to(dev)
+            h, st, done = sr.search_device_pipelined(q_dev, q.terms, NOW, k)
+            done.synchronize()
+            a, fa = sharded.hits_from_device(h, st)
+            b = sh.search(q.q, q.terms, NOW, k)
+            assert fa == 0 and a.rows.tolist() == b.rows.tolist() and a.scores.tolist() == b.scores.tolist()
+        sr.close()
