@@ -64,6 +64,25 @@ BATCH_WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: anything a library prints to fd 1 meanwhile (NCCL's version banner
+    under NCCL_DEBUG=VERSION is a raw printf) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -172,14 +191,14 @@ def run_reference(args):
         wl = BATCH_WORKLOADS[args.workload]
         sample, steps = 200_000, max(1, args.steps if args.steps != 200 else 20)
         v, dt, n = oracle_batch_rate(wl, sample, steps, threads, 0.0)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": f"hybrid recall QPS, {wl['name']}", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wl["batch"] / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 products, f64 accumulation", "data": "synthetic", "config": batch_config(args, wl),
             "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
                              "sample": f"{n} queries x {sample} rows x {wl['dim']}, scaled linearly to {wl['rows']} rows; C port of "
                                        f"RecallSearchService.cs (dotnet absent)"},
-            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
     sample = args.cpu_sample_rows
     steps = max(1, args.steps)
@@ -212,7 +231,7 @@ def run_reference(args):
                                    f"scaled linearly to 1M rows; C port of RecallSearchService.cs (dotnet absent)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -345,7 +364,7 @@ def run_c1(args):
                                 "sample": "the whole workload (10000 rows, no sampling), >= 3 s per figure; 1 thread is the reference's own "
                                           "sequential execution of a request; C port of RecallSearchService.cs:20-119 + "
                                           "InMemoryIngestionStore.cs:57-65 (no dotnet in the image)"}
-    print(json.dumps(line))
+    emit(line)
     shard.close()
 
 
@@ -443,7 +462,7 @@ def run_batch(args):
         line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
                                 "sample": f"{n} queries x {sample} rows x {dim} (first rows of the same corpus) on {threads} threads "
                                           f"({dt:.1f} s), scaled linearly to {rows} rows; C port of RecallSearchService.cs:20-119"}
-    print(json.dumps(line))
+    emit(line)
     shard.close()
 
 
@@ -464,6 +483,7 @@ def main():
     ap.add_argument("--batch-passes", type=int, default=0, choices=[0, 1, 3],
                     help="0 = auto (bf16 screen, bf16x3 cascade for unproven queries; the library default), 1, 3")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -659,7 +679,7 @@ def main():
                       f"threads ({dt_all:.1f} s) and {n_one} queries on 1 thread ({dt_one:.1f} s), scaled linearly to 1M "
                       f"rows; C port of RecallSearchService.cs:20-119 (no dotnet in the image)"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     sr.close()
     shard.close()
     if world > 1:
