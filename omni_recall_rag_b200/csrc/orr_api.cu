@@ -1459,7 +1459,14 @@ int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
             std::vector<int32_t> n2((size_t)nb, 0), redo2;
             rc = batch_gemm_path(s, nb, q2.data(), nt2.data(), ph2.empty() ? nullptr : ph2.data(), off2.data(), now_ticks,
                                  top_k, out2.data(), n2.data(), 3, &redo2);
-            if (rc != ORR_OK) return rc;
+            if (rc == ORR_E_OOM) {
+                // no room for the second bf16 plane: the unproven queries take the per-query path below instead
+                cudaGetLastError();
+                redo2.clear();
+                for (int32_t i = 0; i < nb; ++i) redo2.push_back(i);
+            } else if (rc != ORR_OK) {
+                return rc;
+            }
             std::vector<int32_t> still;
             size_t r2 = 0;
             for (int32_t i = 0; i < nb; ++i) {

@@ -46,13 +46,14 @@ struct ExactArgs {
 };
 template <class A> __device__ __forceinline__ const uint32_t* kw_bits_of(const A&) { return nullptr; }
 __device__ __forceinline__ const uint32_t* kw_bits_of(const ExactArgs& a) { return a.kw_bits; }
-template <class A> __device__ __forceinline__ double kw_from_bits(const A&, int64_t, int) { return 0.0; }
-__device__ __forceinline__ double kw_from_bits(const ExactArgs& a, int64_t row, int lane) {
+template <class A> __device__ __forceinline__ int kw_terms_of(const A&) { return 0; }
+__device__ __forceinline__ int kw_terms_of(const ExactArgs& a) { return a.kw_terms; }
+template <class A> __device__ __forceinline__ int kw_count_from_bits(const A&, int64_t, int) { return 0; }
+__device__ __forceinline__ int kw_count_from_bits(const ExactArgs& a, int64_t row, int lane) {
     int cnt = 0;
     for (int t = lane; t < a.kw_terms; t += 32)
         cnt += (int)((__ldg(a.kw_bits + (int64_t)t * a.kw_row_words + (row >> 5)) >> (row & 31)) & 1u);
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    return __ddiv_rn((double)cnt, (double)a.kw_terms);               // :112
+    return __reduce_add_sync(0xffffffffu, cnt);
 }
 
 // Loads are issued in batches of EX_CHUNK float4 per lane BEFORE the dependent fp64 chains
@@ -86,13 +87,24 @@ __device__ __forceinline__ double exact_qnorm_q(const A& a, const float* q, int 
     return warp_sum_f64(nA);
 }
 
-// exact fused score of one row, computed by a full warp; all lanes return the same value.
+// The exact fused score of one row in two steps, so that callers holding many rows per warp can run the scalar
+// fp64 tail (2 sqrt, 4 divides, exp: ~200 instructions) once per LANE instead of once per warp:
+//   exact_row_partial — warp-collective: fp64 dot and ||b||^2 (lane-strided order + butterfly), keyword matches,
+//                       ticks; every lane returns the same values;
+//   exact_row_finish  — per thread: CosineSimilarity's tail, KeywordScore's ratio, RecencyScore, ScoreChunk.
+// exact_row_q = finish(partial): every path computes a row's score with the same operations on the same values.
+struct ExactPartial {
+    double  dot, nB;
+    int32_t matches;             // distinct query terms the row's content holds
+    int32_t kw_den;              // KeywordScore's denominator (-1 = no keyword side)
+    int64_t ticks;
+};
+
 // CHUNK = float4 loads per lane issued before the dependent fp64 chains; Q_SHARED = q lives in shared memory.
 template <class A, int CHUNK = EX_CHUNK, bool Q_SHARED = false, class P = OrrProbes>
-__device__ __forceinline__ double exact_row_q(const A& a, const float* q, const P& pr, int64_t row,
-                                              int lane, double nA, int64_t* ticks_out) {
-    const int64_t ticks = a.sh.ticks[row];
-    *ticks_out = ticks;
+__device__ __forceinline__ ExactPartial exact_row_partial(const A& a, const float* q, const P& pr, int64_t row, int lane) {
+    ExactPartial r;
+    r.ticks = a.sh.ticks[row];
     // term hashes are fetched up front so their latency overlaps the embedding loads
     uint64_t th[4] = {0, 0, 0, 0};
     const int n_probes = orr_probe_count(pr);
@@ -102,12 +114,11 @@ __device__ __forceinline__ double exact_row_q(const A& a, const float* q, const 
 #pragma unroll
         for (int w = 0; w < 4; ++w) if (w < spl) th[w] = __ldg(t64 + w * 32 + lane);
     }
-    double cosv = 0.0;
+    double dot = 0.0, nB = 0.0;
     if (a.q_dim == a.sh.dim && a.q_dim > 0) {                       // :71-72 length check
         const int nv4 = a.sh.dim >> 2;
         const float4* x4 = reinterpret_cast<const float4*>(a.sh.emb + row * (int64_t)a.sh.dim);
         const float4* q4 = reinterpret_cast<const float4*>(q);
-        double dot = 0.0, nB = 0.0;
         for (int base = 0; base < nv4; base += 32 * CHUNK) {
             float4 x[CHUNK];
 #pragma unroll
@@ -147,12 +158,12 @@ __device__ __forceinline__ double exact_row_q(const A& a, const float* q, const 
         }
         dot = warp_sum_f64(dot);
         nB = warp_sum_f64(nB);
-        if (!(nA <= 0.0) && !(nB <= 0.0))                             // :84-85 (NaN falls through)
-            cosv = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(nA), __dsqrt_rn(nB)));   // :87
     }
-    double kw = 0.0;
+    r.dot = dot; r.nB = nB;
+    r.matches = 0; r.kw_den = -1;
     if (kw_bits_of(a) != nullptr) {
-        kw = kw_from_bits(a, row, lane);
+        r.matches = kw_count_from_bits(a, row, lane);
+        r.kw_den = kw_terms_of(a);
     } else if (n_probes > 0) {                                      // :110-112
         uint32_t m0 = 0, m1 = 0;
         for (int p = 0; p < n_probes; ++p) {
@@ -165,10 +176,22 @@ __device__ __forceinline__ double exact_row_q(const A& a, const float* q, const 
         }
         m0 = __reduce_or_sync(FULL, m0);
         m1 = __reduce_or_sync(FULL, m1);
-        kw = __ddiv_rn((double)(__popc(m0) + __popc(m1)), (double)pr.n_terms);
+        r.matches = __popc(m0) + __popc(m1);
+        r.kw_den = pr.n_terms;
     }
+    return r;
+}
+
+template <class A>
+__device__ __forceinline__ double exact_row_finish(const A& a, double nA, const ExactPartial& r) {
+    double cosv = 0.0;
+    if (a.q_dim == a.sh.dim && a.q_dim > 0) {
+        if (!(nA <= 0.0) && !(r.nB <= 0.0))                           // :84-85 (NaN falls through)
+            cosv = __ddiv_rn(r.dot, __dmul_rn(__dsqrt_rn(nA), __dsqrt_rn(r.nB)));   // :87
+    }
+    const double kw = r.kw_den != -1 ? __ddiv_rn((double)r.matches, (double)r.kw_den) : 0.0;   // :112
     // RecencyScore: TimeSpan.TotalDays = ticks / 864e9; Math.Max(0, .); exp(-age/30)
-    double age = __ddiv_rn((double)(a.now_ticks - ticks), 864000000000.0);
+    double age = __ddiv_rn((double)(a.now_ticks - r.ticks), 864000000000.0);
     if (!(age > 0.0)) age = 0.0;
     const double rec = exp(__ddiv_rn(-age, a.w.recency_days));
     // ScoreChunk :66
@@ -176,6 +199,14 @@ __device__ __forceinline__ double exact_row_q(const A& a, const float* q, const 
                      __dmul_rn(rec, a.w.w_rec));
 }
 
+// exact fused score of one row, computed by a full warp; all lanes return the same value.
+template <class A, int CHUNK = EX_CHUNK, bool Q_SHARED = false, class P = OrrProbes>
+__device__ __forceinline__ double exact_row_q(const A& a, const float* q, const P& pr, int64_t row,
+                                              int lane, double nA, int64_t* ticks_out) {
+    const ExactPartial r = exact_row_partial<A, CHUNK, Q_SHARED, P>(a, q, pr, row, lane);
+    *ticks_out = r.ticks;
+    return exact_row_finish(a, nA, r);
+}
 __device__ __forceinline__ double exact_qnorm(const ExactArgs& a, int lane) { return exact_qnorm_q(a, a.q, lane); }
 __device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int lane, double nA, int64_t* ticks_out) {
     return exact_row_q(a, a.q, a.pr, row, lane, nA, ticks_out);
@@ -293,13 +324,23 @@ __global__ void __launch_bounds__(256) orr_exact_scores_kernel(const ExactArgs a
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const bool has_q = (a.q_dim == a.sh.dim && a.q_dim > 0);
     const double nA = has_q ? exact_qnorm(a, lane) : 0.0;
-    for (int64_t row = gw; row < a.sh.rows; row += W) {
-        int64_t ticks;
-        const double s = exact_row(a, row, lane, nA, &ticks);
-        if (lane == 0) {
-            scores[row] = s;
+    // a warp takes 32 consecutive rows: the warp-collective part row by row (lane j keeps row j's partial result),
+    // then the scalar fp64 tail once per lane and coalesced stores
+    const int64_t n_blocks = (a.sh.rows + 31) >> 5;
+    for (int64_t blk = gw; blk < n_blocks; blk += W) {
+        const int64_t row0 = blk << 5;
+        const int n_here = (int)min((int64_t)32, a.sh.rows - row0);
+        ExactPartial mine;
+        mine.dot = 0.0; mine.nB = 0.0; mine.matches = 0; mine.kw_den = -1; mine.ticks = 0;
+        for (int j = 0; j < n_here; ++j) {
+            const ExactPartial r = exact_row_partial(a, a.q, a.pr, row0 + j, lane);
+            if (lane == j) mine = r;
+        }
+        if (lane < n_here) {
+            const int64_t row = row0 + lane;
+            scores[row] = exact_row_finish(a, nA, mine);
             // first sort key: CreatedAtUtc, descending (flip the sign bit for unsigned order)
-            tick_keys[row] = (uint64_t)ticks ^ 0x8000000000000000ull;
+            tick_keys[row] = (uint64_t)mine.ticks ^ 0x8000000000000000ull;
             vals[row] = (uint32_t)row;
         }
     }
@@ -710,32 +751,82 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
     const uint32_t total = a.cand_count[b];
     const int c = (int)min(total, (uint32_t)a.cap);
     int flags = total > (uint32_t)a.cap ? 2 : 0;                             // candidate list overflowed
-    int np2 = 1;
-    while (np2 < c) np2 <<= 1;
     const uint2* src = a.cand + (int64_t)b * a.cap;
-    for (int i = tid; i < np2; i += BATCH_FIN_THREADS) {
-        uint64_t k = 0;
-        if (i < c) { const uint2 v = src[i]; k = ((uint64_t)fkey(__uint_as_float(v.y)) << 32) | (uint64_t)(~v.x); }
-        keys[i] = k;
+    // key = (monotone score key, ~row): unique per candidate, larger = better (ties: lower row first)
+    for (int i = tid; i < c; i += BATCH_FIN_THREADS) {
+        const uint2 v = src[i];
+        keys[i] = ((uint64_t)fkey(__uint_as_float(v.y)) << 32) | (uint64_t)(~v.x);
     }
-    __syncthreads();
-    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < np2; i += BATCH_FIN_THREADS) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const uint64_t x = keys[i], y = keys[p];
-                    const bool desc = ((i & k2) == 0);
-                    if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[p] = x; }
+    // The best M candidates by an MSB-first radix select over the 64-bit keys (8 passes of 256 bins, ~1k
+    // instructions per thread; the full bitonic sort it replaces cost ~7k and its order was never used: the
+    // survivors are re-ordered by their exact scores below).  kth = the M-th largest key; keys are unique, so
+    // exactly M candidates have key >= kth.
+    __shared__ uint32_t hist[BATCH_FIN_THREADS];
+    __shared__ unsigned long long s_prefix, s_below[BATCH_FIN_THREADS / 32];
+    __shared__ uint32_t s_rem, s_cnt;
+    const int M = a.n_surv;
+    const int ns = min(M, c);
+    unsigned long long kth = 0ull;
+    if (c > M) {
+        unsigned long long prefix = 0ull;
+        uint32_t rem = (uint32_t)M;
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            hist[tid] = 0u;
+            __syncthreads();
+            for (int i = tid; i < c; i += BATCH_FIN_THREADS) {
+                const unsigned long long k = keys[i];
+                if (pass == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(uint32_t)(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (warp == 0) {                                                 // lane l owns bins 8l .. 8l+7 (higher = better)
+                uint32_t h[8], sum = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; sum += h[j]; }
+                uint32_t suffix = sum;                                       // bins of this lane and every higher lane
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_down_sync(FULL, suffix, o);
+                    if (lane + o < 32) suffix += v;
+                }
+                const uint32_t above = suffix - sum;
+                if (above < rem && rem <= suffix) {                          // the rem-th best key falls into this lane's bins
+                    uint32_t r = rem - above;
+                    int d = 0;
+#pragma unroll
+                    for (int j = 7; j >= 0; --j) {
+                        if (h[j] >= r) { d = j; break; }
+                        r -= h[j];
+                    }
+                    s_prefix = prefix | ((unsigned long long)(8 * lane + d) << shift);
+                    s_rem = r;
                 }
             }
             __syncthreads();
+            prefix = s_prefix;
+            rem = s_rem;
         }
+        kth = prefix;
     }
-    const int M = a.n_surv;
-    const int ns = min(M, c);
+    if (tid == 0) s_cnt = 0u;
+    __syncthreads();
+    unsigned long long below = 0ull;                                         // best key that does not survive
+    for (int i = tid; i < c; i += BATCH_FIN_THREADS) {
+        const unsigned long long k = keys[i];
+        if (k >= kth) e[atomicAdd(&s_cnt, 1u)].row = (uint64_t)(~(uint32_t)k);
+        else below = max(below, k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below = max(below, __shfl_xor_sync(FULL, below, o));
+    if (lane == 0) s_below[warp] = below;
+    __syncthreads();
     float tau = a.thr[b];                                                    // no row outside the list beats it
-    if (c > M) tau = fmaxf(tau, fkey_inv((uint32_t)(keys[M] >> 32)));
+    if (c > M) {
+        unsigned long long bk = 0ull;
+#pragma unroll
+        for (int w = 0; w < BATCH_FIN_THREADS / 32; ++w) bk = max(bk, s_below[w]);
+        tau = fmaxf(tau, fkey_inv((uint32_t)(bk >> 32)));
+    }
     // exact re-score of the survivors
     const float* q = a.q + (int64_t)b * a.ex.sh.dim;
     const OrrBatchProbes& pr = a.probes ? a.probes[b] : g_no_probes;
@@ -743,11 +834,19 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
     const double nA = has_q ? exact_qnorm_q(a.ex, q, lane) : 0.0;
     if (has_q) for (int i = tid; i < a.ex.sh.dim; i += BATCH_FIN_THREADS) qs[i] = q[i];   // the query is re-read for every row
     __syncthreads();
-    for (int i = warp; i < ns; i += BATCH_FIN_THREADS / 32) {
-        const int64_t row = (int64_t)(~(uint32_t)keys[i]);
-        int64_t ticks;
-        const double s = exact_row_q<BatchExact, 6, true, OrrBatchProbes>(a.ex, qs, pr, row, lane, nA, &ticks);
-        if (lane == 0) { e[i].score = s; e[i].ticks = ticks; e[i].row = (uint64_t)row; }
+    // a warp takes survivors warp, warp + 8, ...; the warp-collective part (dot products, keyword matches) runs row
+    // by row, lane j keeps the partial result of the group's j-th row, and the scalar fp64 tail runs once per lane
+    for (int g = warp; g < ns; g += BATCH_FIN_THREADS) {
+        ExactPartial mine;
+        mine.dot = 0.0; mine.nB = 0.0; mine.matches = 0; mine.kw_den = -1; mine.ticks = 0;
+        for (int j = 0; j < 32; ++j) {
+            const int i = g + j * (BATCH_FIN_THREADS / 32);
+            if (i >= ns) break;                                              // warp-uniform
+            const ExactPartial r = exact_row_partial<BatchExact, 6, true, OrrBatchProbes>(a.ex, qs, pr, (int64_t)e[i].row, lane);
+            if (lane == j) mine = r;
+        }
+        const int i = g + lane * (BATCH_FIN_THREADS / 32);
+        if (i < ns) { e[i].score = exact_row_finish(a.ex, nA, mine); e[i].ticks = mine.ticks; }
     }
     int ep2 = 1;
     while (ep2 < ns) ep2 <<= 1;
