@@ -885,13 +885,20 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
 
 // term bitmaps: bit r of bits[t] says row r holds batch term t.  A warp takes 32 consecutive rows (one
 // output word per term): the rows' 32-bit term tables are one contiguous block, streamed with 8
-// 16-byte loads in flight per lane.  Every stored hash first tests one bit of a 2^18-bit filter of the
-// batch's new terms (smem, branch-free: multiply, shift, LDS, shift) — under 1-5 % of the stored hashes pass —
-// and only those probe the open-addressing table (smem) and set their row's bit (hits are sparse).
+// 16-byte loads in flight per lane.
+//   1. Every stored hash tests one bit of a 2^18-bit filter of the batch's new terms (smem, branch-free:
+//      multiply, shift, LDS, shift) — a few percent pass.
+//   2. The survivors of a 256-vector step are COMPACTED into a per-warp smem queue (per-lane pop-count, one warp
+//      scan, predicated stores: no divergent code) — with ~2 % passing, nearly every warp had one or two lanes in
+//      the probe loop and the other lanes idle (ncu: 141 instructions per warp and vector).
+//   3. The queue is drained with all lanes busy: probe the open-addressing table (smem), OR the row's bit into the
+//      warp's accumulator.  A step with more survivors than the queue holds (a very frequent new term) takes the
+//      per-lane path instead.
 constexpr int TERM_BITS_THREADS = 1024;
 constexpr int TERM_ACC = 64;                  // per-warp accumulator entries (direct-mapped by slot)
 constexpr int TERM_FILTER_LOG2 = 18;          // filter bits (32 KB of smem behind the probe table)
 constexpr int TERM_FILTER_WORDS = (1 << TERM_FILTER_LOG2) / 32;
+constexpr int TERM_QUEUE = 128;               // per-warp queue of {hash, row bit} that passed the filter
 __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(const uint32_t* terms32, int slots, int64_t rows,
                                                                                const uint2* table, int table_mask,
                                                                                uint32_t* bits, int64_t slot_cap) {
@@ -901,6 +908,7 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
     // its 32-row block's words, so it first ORs hits into a small shared accumulator ({slot + 1, bits}, claimed by
     // CAS) and flushes one atomic per (term, block); only accumulator conflicts go to global memory directly.
     __shared__ uint2 acc_all[TERM_BITS_THREADS / 32][TERM_ACC];
+    __shared__ uint2 queue_all[TERM_BITS_THREADS / 32][TERM_QUEUE];
     for (int i = threadIdx.x; i < TERM_FILTER_WORDS; i += blockDim.x) filt[i] = 0u;
     for (int i = threadIdx.x; i < (TERM_BITS_THREADS / 32) * TERM_ACC; i += blockDim.x) (&acc_all[0][0])[i] = make_uint2(0u, 0u);
     __syncthreads();
@@ -915,10 +923,29 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint32_t* acc = reinterpret_cast<uint32_t*>(acc_all[threadIdx.x >> 5]);
+    uint2* queue = queue_all[threadIdx.x >> 5];
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_blocks = (rows + 31) >> 5;
     const int vec_shift = 31 - __clz(slots >> 2);                            // uint4 per row = 8, 16 or 32
+
+    // probe the table for hash h; a hit ORs `bit` into the block's word of that term
+    auto probe = [&](uint32_t h, uint32_t bit, int64_t blk) {
+        uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)table_mask;
+        for (;;) {
+            const uint2 ent = tab[pos];
+            if (ent.x == 0u) break;
+            if (ent.x == h) {
+                uint32_t* e = acc + 2 * (ent.y & (TERM_ACC - 1));
+                const uint32_t cur = atomicCAS(e, 0u, ent.y + 1u);
+                if (cur == 0u || cur == ent.y + 1u) atomicOr(e + 1, bit);
+                else atomicOr(bits + (((blk >> 3) * slot_cap + ent.y) << 3) + (blk & 7), bit);
+                break;
+            }
+            pos = (pos + 1) & (uint32_t)table_mask;
+        }
+    };
+
     for (int64_t blk = gw; blk < n_blocks; blk += W) {
         const int rows_here = (int)min((int64_t)32, rows - (blk << 5));
         const int n_vec = rows_here << vec_shift;
@@ -930,35 +957,52 @@ __global__ void __launch_bounds__(TERM_BITS_THREADS) orr_batch_term_bits_kernel(
                 const int v = v0 + i * 32 + lane;
                 x[i] = v < n_vec ? __ldg(base + v) : make_uint4(0u, 0u, 0u, 0u);
             }
+            uint32_t pass = 0u;                                              // bit 4i + c: component c of x[i] passed the filter
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint32_t hs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
-                uint32_t pass = 0u;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t f = (hs[c] * 0x9E3779B1u) >> (32 - TERM_FILTER_LOG2);
-                    pass |= ((filt[f >> 5] >> (f & 31u)) & 1u) << c;
+                    pass |= ((hs[c] != 0u ? filt[f >> 5] >> (f & 31u) : 0u) & 1u) << (4 * i + c);
                 }
-                if (pass == 0u) continue;
-                const int v = v0 + i * 32 + lane;
-                const uint32_t bit = 1u << (v >> vec_shift);
+            }
+            // warp scan of the per-lane survivor counts
+            const uint32_t mine = (uint32_t)__popc(pass);
+            uint32_t incl = mine;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t h = hs[c];
-                    if (!((pass >> c) & 1u) || !h) continue;
-                    uint32_t pos = (h * 0x9E3779B1u) & (uint32_t)table_mask;
-                    for (;;) {
-                        const uint2 ent = tab[pos];
-                        if (ent.x == 0u) break;
-                        if (ent.x == h) {
-                            uint32_t* e = acc + 2 * (ent.y & (TERM_ACC - 1));
-                            const uint32_t cur = atomicCAS(e, 0u, ent.y + 1u);
-                            if (cur == 0u || cur == ent.y + 1u) atomicOr(e + 1, bit);
-                            else atomicOr(bits + (((blk >> 3) * slot_cap + ent.y) << 3) + (blk & 7), bit);
-                            break;
-                        }
-                        pos = (pos + 1) & (uint32_t)table_mask;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (total == 0u) continue;
+            if (total <= (uint32_t)TERM_QUEUE) {
+                uint32_t at = incl - mine;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t hs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+                    const uint32_t bit = 1u << ((v0 + i * 32 + lane) >> vec_shift);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if ((pass >> (4 * i + c)) & 1u) { queue[at] = make_uint2(hs[c], bit); ++at; }
                     }
+                }
+                __syncwarp();
+                for (uint32_t idx = lane; idx < total; idx += 32) {
+                    const uint2 qe = queue[idx];
+                    probe(qe.x, qe.y, blk);
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (((pass >> (4 * i)) & 15u) == 0u) continue;
+                    const uint32_t hs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+                    const uint32_t bit = 1u << ((v0 + i * 32 + lane) >> vec_shift);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if ((pass >> (4 * i + c)) & 1u) probe(hs[c], bit, blk);
                 }
             }
         }
@@ -1018,9 +1062,9 @@ int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows,
         orr_batch_clear_slots_kernel<<<sms * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(bits), slot_cap, first_new, n_new, n_tiles);
         ORR_CUDA_OK(cudaGetLastError());
     }
-    const int smem = table_slots * 8 + TERM_FILTER_WORDS * 4;             // probe table + filter
+    const int smem = table_slots * 8 + TERM_FILTER_WORDS * 4;             // probe table + filter (+ 48 KB static: accumulators, queues)
     ORR_SMEM_OPT_IN((orr_batch_term_bits_kernel), 160 * 1024);
-    const int per_sm = smem <= 90 * 1024 ? 2 : 1;
+    const int per_sm = smem <= 64 * 1024 ? 2 : 1;
     orr_batch_term_bits_kernel<<<sms * per_sm, TERM_BITS_THREADS, smem, st>>>(terms32, slots, rows, (const uint2*)table,
                                                                               table_slots - 1, bits, slot_cap);
     ORR_CUDA_OK(cudaGetLastError());
