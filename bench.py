@@ -574,10 +574,12 @@ def main():
         if pipelined:
             dev_ms, fl = timed_loop(True)
             flags_seen |= fl
-        # keep sampling under load for a moment longer so short runs still get samples
-        t_end = time.time() + 0.6
+        # keep sampling under load for ~0.6 s more so short runs still get samples.  The count comes from the
+        # all-reduced step time, so every rank issues the SAME number of searches: each one is a collective step
+        # (the exchange is sequence-numbered), a time-based loop would let the ranks drift apart.
+        extra = max(1, min(2000, int(600.0 / max(dev_ms / steps, 1.0e-3))))
         j = warmup
-        while time.time() < t_end:
+        for _ in range(extra):
             sr.search_device(q_dev[j], queries[j].terms, spec.now_ticks, TOP_K)
             j = warmup + (j + 1 - warmup) % steps
         torch.cuda.synchronize()
