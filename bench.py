@@ -51,10 +51,10 @@ N_TERMS = 4
 TERM_SLOTS = 64
 FALLBACK_HBM_GBS = 6650.0
 FALLBACK_BF16_TFLOPS = 1500.0
-# dram__bytes_read.sum + dram__bytes_write.sum of orr_scan_kernel<24,1> per launch at 1M x 3072, 4 terms,
-# from the ncu --set full capture summarised in profiles/r01_scan_kernel_first.md (12.5526 GB read + ~6.5 MB
+# dram__bytes_read.sum + dram__bytes_write.sum of orr_scan_kernel<24,1,0> per launch at 1M x 3072, 4 terms,
+# from the ncu --set full capture summarised in profiles/r01_final_kernels.md (12.5533 GB read + 3.6 MB
 # written); scales linearly with rows.
-NCU_SCAN_TRAFFIC_BYTES_PER_ROW = 12559.1
+NCU_SCAN_TRAFFIC_BYTES_PER_ROW = 12556.9
 BATCH_WORKLOADS = {
     "c3": dict(rows=5_000_000, dim=768, batch=1024, top_k=100, n_terms=4, frequent=0, dup_ppm=0,
                name="5M chunks x 768 fp32 (truncated embeddings), batch 1024 queries, 4 terms, top-100"),
@@ -665,7 +665,7 @@ def main():
                      "kernel_ms": scan_avg_ms, "finalize_kernel_ms": sum(fin_ms) / len(fin_ms),
                      "traffic": NCU_SCAN_TRAFFIC_BYTES_PER_ROW * n_local,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                       "(profiles/r01_scan_kernel_first.md), scaled by rows"},
+                                       "(profiles/r01_final_kernels.md), scaled by rows"},
         "clocks": clock_summary,
         "bound_check_escalations": escalated, "device_flags": flags_seen,
     }
