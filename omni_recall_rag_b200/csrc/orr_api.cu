@@ -1324,16 +1324,17 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
         bs->dense_elems = (size_t)bp * (size_t)n_s;
     }
     gm.dense = bs->dense; gm.dense_ld = n_s; gm.tile_stride = stride;
+    gm.dense_half = 1;                           // fp16 is plenty for a threshold estimate: half the stores and reads
     ORR_CUDA_OK(cudaEventRecord(bs->ev[0], st));
     rc = orr_batch_launch_gemm(gm, st);
     if (rc != ORR_OK) return rc;
     const int rstar = stride == 1 ? target : (int)std::max<int64_t>(1, (int64_t)target * n_s / rows_pad);
-    rc = orr_batch_launch_threshold(bs->dense, n_s, (int)n_s, rstar, bs->thr, batch, bp, st);
+    rc = orr_batch_launch_threshold(bs->dense, 1, n_s, (int)n_s, rstar, bs->thr, batch, bp, st);
     if (rc != ORR_OK) return rc;
 
     // ---- main pass: every row tile, candidates above the thresholds ----
     ORR_CUDA_OK(cudaMemsetAsync(bs->cand_count, 0, sizeof(uint32_t) * (size_t)bp, st));
-    gm.dense = nullptr; gm.dense_ld = 0; gm.tile_stride = 1;
+    gm.dense = nullptr; gm.dense_ld = 0; gm.dense_half = 0; gm.tile_stride = 1;
     ORR_CUDA_OK(cudaEventRecord(bs->ev[1], st));
     rc = orr_batch_launch_gemm(gm, st);
     if (rc != ORR_OK) return rc;

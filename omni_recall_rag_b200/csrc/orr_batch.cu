@@ -25,6 +25,7 @@
 //   E tile is re-read from L2, not HBM.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -91,6 +92,7 @@ struct BatchArgs {
     // dense output (sampling pass / debug): scores[b][dense_ld]
     float*    dense;
     int64_t   dense_ld;
+    int32_t   dense_half;        // dense holds __half (same buffer, ld in elements)
     // keyword side: per query up to ORR_BATCH_MAX_TERMS term bitmaps over rows
     // tile-major: term_bits[row tile][slot][8 words] — the 256 rows of one tile for every term slot are one
     // contiguous slot_cap x 32 B region, read once per tile and shared by all queries of the batch
@@ -301,9 +303,20 @@ __device__ __forceinline__ void epilogue_chunks(const BatchArgs& a, uint32_t tad
                 }
             }
         } else {
-            float4* dst = reinterpret_cast<float4*>(a.dense + (int64_t)b * a.dense_ld + (dense_col0 + c * 32));
+            if (a.dense_half) {                                             // sampling pass: 64 B per thread and chunk
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.dense) + (int64_t)b * a.dense_ld + (dense_col0 + c * 32));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+                for (int j = 0; j < 4; ++j) {
+                    const __half2 h0 = __floats2half2_rn(s[8 * j + 0], s[8 * j + 1]), h1 = __floats2half2_rn(s[8 * j + 2], s[8 * j + 3]);
+                    const __half2 h2 = __floats2half2_rn(s[8 * j + 4], s[8 * j + 5]), h3 = __floats2half2_rn(s[8 * j + 6], s[8 * j + 7]);
+                    dst[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                        *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+                }
+            } else {
+                float4* dst = reinterpret_cast<float4*>(a.dense + (int64_t)b * a.dense_ld + (dense_col0 + c * 32));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(s[4 * j], s[4 * j + 1], s[4 * j + 2], s[4 * j + 3]);
+            }
         }
     }
 }
@@ -707,6 +720,7 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     a.cand_cap = g.cand_cap;
     a.dense = g.dense;
     a.dense_ld = g.dense_ld;
+    a.dense_half = g.dense_half;
     a.term_bits = g.term_bits;
     a.slot_cap = g.slot_cap;
     a.q_term_ids = g.q_term_ids;

@@ -190,6 +190,7 @@ struct OrrBatchGemm {
     const float* thr;                        // [batch_padded] (main pass)
     void* cand; uint32_t* cand_count; int32_t cand_cap;
     float* dense; int64_t dense_ld;          // dense score output (sampling / debug) or NULL
+    int32_t dense_half;                      // 1: the dense scores are written as fp16 (the sampling pass: they only feed the threshold estimate)
     const uint32_t* term_bits; int64_t slot_cap; const int32_t* q_term_ids; const float* q_kw_w;   // tile-major bitmaps
     int64_t rows; int32_t dim; int32_t batch_padded; int32_t tile_stride; int32_t sms;
     int32_t passes;                          // 3 = split precision (default), 1 = bf16 screen
@@ -201,8 +202,8 @@ int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qsc
 int orr_batch_build_rowrec(const int64_t* ticks, float* rowrec, int64_t rows, int64_t rows_padded, int64_t now_ticks,
                            const OrrWeights& w, cudaStream_t st);
 int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st);
-int orr_batch_launch_threshold(const float* dense, int64_t ld, int n, int rstar, float* thr, int batch, int batch_padded,
-                               cudaStream_t st);
+int orr_batch_launch_threshold(const void* dense, int dense_half, int64_t ld, int n, int rstar, float* thr, int batch,
+                               int batch_padded, cudaStream_t st);
 int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrBatchProbes* probes, const OrrWeights& w,
                               int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
                               int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,

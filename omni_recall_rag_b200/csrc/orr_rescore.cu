@@ -19,6 +19,8 @@
 #include <cfloat>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cuda_fp16.h>
+
 #include "orr_internal.h"
 
 namespace {
@@ -687,15 +689,74 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
     return __uint_as_float(b);
 }
 
-// thr[b] = the rstar-th largest of dense[b][0..n): one CTA per query, MSB-first radix select
-__global__ void __launch_bounds__(256) orr_batch_threshold_kernel(const float* dense, int64_t ld, int n, int rstar,
+// thr[b] = the rstar-th largest of dense[b][0..n) (fp32, or fp16 from the sampling pass): one CTA per query.
+//   Small rstar (the sampling pass asks for the ~12th best of ~60 k scores): ONE pass over the scores in which every
+//   thread keeps its 4 largest keys in registers, then the rstar-th largest of those 1024.  That is the exact answer
+//   unless some thread's 4th-largest key exceeds it (it may then have dropped larger ones); the CTA checks and falls
+//   back to the general form.
+//   General form: MSB-first radix select, 4 passes over the scores with a shared 256-bin histogram.
+template <class T> __device__ __forceinline__ float thr_load(const T* x, int i);
+template <> __device__ __forceinline__ float thr_load<float>(const float* x, int i) { return x[i]; }
+template <> __device__ __forceinline__ float thr_load<__half>(const __half* x, int i) { return __half2float(x[i]); }
+
+constexpr int THR_KEEP = 4;                    // keys a thread keeps in the one-pass form
+constexpr int THR_FAST_RSTAR = 16;
+
+template <class T>
+__global__ void __launch_bounds__(256) orr_batch_threshold_kernel(const T* dense, int64_t ld, int n, int rstar,
                                                                   float* thr, int batch) {
     const int b = blockIdx.x, tid = threadIdx.x;
     if (b >= batch) { if (tid == 0) thr[b] = INFINITY; return; }   // padding queries never produce candidates
     if (n < rstar || rstar < 1) { if (tid == 0) thr[b] = -INFINITY; return; }
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rem;
-    const float* x = dense + (int64_t)b * ld;
+    __shared__ uint32_t s_keys[256 * THR_KEEP];
+    const T* x = dense + (int64_t)b * ld;
+    if (rstar <= THR_FAST_RSTAR) {
+        uint32_t t[THR_KEEP];                                        // descending; 0 = empty (fkey never returns 0)
+#pragma unroll
+        for (int j = 0; j < THR_KEEP; ++j) t[j] = 0u;
+        for (int i = tid; i < n; i += 256) {
+            uint32_t k = fkey(thr_load<T>(x, i));
+            if (k > t[THR_KEEP - 1]) {
+#pragma unroll
+                for (int j = 0; j < THR_KEEP; ++j) {                 // insertion: k ends up holding the evicted key
+                    const uint32_t hi = max(t[j], k), lo = min(t[j], k);
+                    t[j] = hi; k = lo;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < THR_KEEP; ++j) s_keys[j * 256 + tid] = t[j];
+        if (tid == 0) { s_prefix = 0; s_rem = (uint32_t)rstar; }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[tid] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t pmask = pass ? (0xffffffffu << (shift + 8)) : 0u;
+#pragma unroll
+            for (int j = 0; j < THR_KEEP; ++j) {
+                const uint32_t k = s_keys[j * 256 + tid];
+                if ((k & pmask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t rem = s_rem;
+                int d = 255;
+                for (; d > 0; --d) { if (hist[d] >= rem) break; rem -= hist[d]; }
+                s_prefix = prefix | ((uint32_t)d << shift);
+                s_rem = rem;
+            }
+            __syncthreads();
+        }
+        const uint32_t kth = s_prefix;
+        // a thread whose 4th key is above the answer may have dropped keys above it as well
+        if (!__syncthreads_or(t[THR_KEEP - 1] > kth)) {
+            if (tid == 0) thr[b] = fkey_inv(kth);
+            return;
+        }
+    }
     if (tid == 0) { s_prefix = 0; s_rem = (uint32_t)rstar; }
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
@@ -704,7 +765,7 @@ __global__ void __launch_bounds__(256) orr_batch_threshold_kernel(const float* d
         const uint32_t prefix = s_prefix;
         const uint32_t pmask = pass ? (0xffffffffu << (shift + 8)) : 0u;
         for (int i = tid; i < n; i += 256) {
-            const uint32_t k = fkey(x[i]);
+            const uint32_t k = fkey(thr_load<T>(x, i));
             if ((k & pmask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -1029,9 +1090,10 @@ __global__ void orr_batch_clear_slots_kernel(uint4* bits, int64_t slot_cap, int 
 
 }  // namespace
 
-int orr_batch_launch_threshold(const float* dense, int64_t ld, int n, int rstar, float* thr, int batch, int batch_padded,
-                               cudaStream_t st) {
-    orr_batch_threshold_kernel<<<batch_padded, 256, 0, st>>>(dense, ld, n, rstar, thr, batch);
+int orr_batch_launch_threshold(const void* dense, int dense_half, int64_t ld, int n, int rstar, float* thr, int batch,
+                               int batch_padded, cudaStream_t st) {
+    if (dense_half) orr_batch_threshold_kernel<__half><<<batch_padded, 256, 0, st>>>((const __half*)dense, ld, n, rstar, thr, batch);
+    else orr_batch_threshold_kernel<float><<<batch_padded, 256, 0, st>>>((const float*)dense, ld, n, rstar, thr, batch);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
