@@ -220,3 +220,37 @@ def test_sharded_search_world2_gloo_matches_single_shard():
         r, s, t = oracle_search_synth(rows, query, spec.now_ticks, top_k)
         for rank in range(world):
             assert got[rank][qi] == (r.tolist(), s.tolist(), t.tolist())
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU port on the host cores) needs no GPU; stdout must be ONE JSON line with
+    the contract's keys even when a library prints to fd 1 meanwhile (bench.py routes such output to stderr)."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--cpu-sample-rows", "1500"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["value"] > 0 and j["higher_is_better"] is True
+    assert j["metric"].startswith("hybrid recall QPS at 1M x 3072") and j["unit"].startswith("queries/s")
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and "sample" in j["cpu_baseline"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"] and j["n_gpus"] == 1 and j["steps"] == 2
+
+
+def test_bench_without_a_gpu_fails_loudly_instead_of_falling_back():
+    """The product arm has no CPU path: without CUDA bench.py exits non-zero and says so."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
