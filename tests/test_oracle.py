@@ -186,3 +186,48 @@ def test_nan_scores_sort_last():
     rows, scores, _ = oracle_c.search(emb=emb, dim=2, ticks=ticks, content_blob=blob, content_off=off, query="zzz",
                                       qvec=np.array([1, 0], dtype=np.float32), now_ticks=NOW, top_k=3)
     assert [int(r) for r in rows] == [0, 2, 1] and math.isnan(scores[2])
+
+
+# ---- the block-streamed form used at BASELINE sizes (oracle/orr_oracle_stream.c) ------------------------------
+def test_oracle_generator_equals_the_library_host_generator():
+    """oracle_synth_rows / oracle_synth_query (built from csrc/orr_synth.h inside the oracle library, so that the
+    reference arm never maps liborr.so) produce the rows and queries of liborr's own host generator bit for bit."""
+    from omni_recall_rag_b200 import synth
+    for dim, dup in ((768, 5000), (3072, 0), (100, 20000)):
+        spec = synth.make_spec(dim, gen_dim=max(dim, 256), dup_row_ppm=dup)
+        rows = synth.rows_host(spec, 12345, 300)
+        emb, ticks, tids = oracle_c.synth_rows(spec, 12345, 300, threads=3)
+        assert np.array_equal(emb, rows.emb) and np.array_equal(ticks, rows.ticks) and np.array_equal(tids, rows.term_ids)
+        blob, off = oracle_c.synth_contents(tids)
+        blob2, off2 = oracle_c.pack_contents(synth.contents_of(rows.term_ids))
+        assert np.array_equal(off, off2) and blob[: off[-1]].tobytes() == blob2[: off2[-1]].tobytes()
+        for qi in range(12):
+            for nt, fr in ((4, 0), (16, 8), (0, 0)):
+                q = synth.query_host(spec, qi, 100_000, n_terms=nt, frequent_terms=fr)
+                q2, t2, text2 = oracle_c.synth_query(spec, qi, 100_000, nt, fr)
+                assert np.array_equal(q2, q.q) and text2 == q.text
+        s2 = oracle_c.synth_spec(dim, gen_dim=max(dim, 256), dup_row_ppm=dup)
+        assert all(getattr(s2, f) == getattr(spec, f) for f, _ in oracle_c.SynthSpec._fields_)
+
+
+@pytest.mark.parametrize("block", [97, 1000, 4096, 100_000])
+def test_streamed_oracle_equals_the_oracle_on_the_whole_corpus(block):
+    """Block by block with a running top-k == one oracle_search over all rows, ties across block borders included
+    (planted duplicate rows share scores and, half of them, timestamps)."""
+    from omni_recall_rag_b200 import synth
+    from tests.util import oracle_search_synth
+    spec = synth.make_spec(256, gen_dim=256, dup_row_ppm=30000)
+    n, first = 6000, 1000
+    rows = synth.rows_host(spec, first, n)
+    qs = [synth.query_host(spec, qi, n, n_terms=nt, frequent_terms=fr) for qi, (nt, fr) in enumerate([(4, 0), (16, 8), (0, 0), (3, 3)])]
+    for k in (1, 10, 257):
+        res = oracle_c.search_streamed(spec, n, [q.text for q in qs], np.stack([q.q for q in qs]), NOW, k, first_row=first,
+                                       block_rows=block, threads=2)
+        noemb = oracle_c.search_streamed(spec, n, [q.text for q in qs], None, NOW, k, first_row=first, block_rows=block,
+                                         with_emb=False, threads=2)
+        for q, (r, s, t), (r0, s0, t0) in zip(qs, res, noemb):
+            er, es, et = oracle_search_synth(rows, q, NOW, k)
+            assert (r - first).tolist() == er.tolist() and s.tolist() == es.tolist() and t.tolist() == et.tolist()
+            q0 = synth.HostQuery(np.zeros(0, np.float32), q.term_ids, q.text, q.terms)
+            er, es, et = oracle_search_synth(rows, q0, NOW, k)
+            assert (r0 - first).tolist() == er.tolist() and s0.tolist() == es.tolist() and t0.tolist() == et.tolist()
