@@ -55,7 +55,7 @@ typedef struct orr_config {
     int32_t  abi_version;        /* ORR_ABI_VERSION                                           */
     int32_t  device;             /* CUDA ordinal of the GPU that owns this shard              */
     int32_t  dim;                /* embedding width D (fp32 per row); multiple of 4, <= 8192  */
-    int32_t  term_slots;         /* hashed-term slots per chunk: 32, 64 or 128                */
+    int32_t  term_slots;         /* hashed-term slots per chunk: 32, 64 or 128 (default 128)  */
     int64_t  capacity_rows;      /* rows of HBM reserved up front (row-major fp32[cap][D])    */
     uint64_t row_base;           /* global row id of local row 0 (row-sharded corpora)        */
     double   w_cos, w_kw, w_rec; /* RecallSearchService.cs:66                                 */
@@ -117,6 +117,22 @@ int  orr_store_upsert_document_chunks_text(orr_store* s, uint64_t doc_key, int32
         const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
         const uint64_t* term_hashes, const uint32_t* term_offsets,
         const char* text_lower_utf8, const uint64_t* text_offsets, uint64_t* out_rows);
+
+/* Text-level ingest — the form the C# shim uses: chunk i's Content is contents_utf8[content_offsets[i] ..
+ * content_offsets[i+1]) exactly as CosmosChunkRecord.Content holds it.  The library does what KeywordScore does to
+ * content (RecallSearchService.cs:110: ToLowerInvariant) plus the split into white-space tokens, hashes the distinct
+ * tokens into the chunk's term set, and keeps the LIVE VOCABULARY (every distinct token with the number of live chunks
+ * holding it; replace / delete release a document's words) that orr_search_query expands query terms over.  With option
+ * "keep_text" = 1 (set before the first row) the lower-cased Content is also kept in HBM for text mode; a chunk with more
+ * distinct tokens than cfg.term_slots is then still accepted (keyword matching goes through text mode while such a chunk
+ * is live), otherwise it is refused with ORR_E_UNSUPPORTED before anything is changed.  Other arguments as
+ * orr_store_upsert_document_chunks. */
+int  orr_store_upsert_document_texts(orr_store* s, uint64_t doc_key, int32_t n,
+        const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
+        const char* contents_utf8, const uint64_t* content_offsets, uint64_t* out_rows);
+
+/* Distinct tokens held by at least one live chunk (text-level ingest only). */
+int64_t orr_store_vocab_size(const orr_store* s);
 
 /* DeleteDocumentAsync (InMemoryIngestionStore.cs:50-55): tombstones the rows. */
 int  orr_store_delete_document(orr_store* s, uint64_t doc_key);
@@ -188,6 +204,18 @@ int  orr_search_text(orr_store* s, const float* q, int32_t q_dim,
         int64_t now_ticks, int32_t top_k, int32_t candidate_cap,
         orr_hit* out, int32_t* n_out);
 
+/* The whole keyword side in one call — what IRecallSearchService.SearchAsync(query, topK) needs between the embedding
+ * call and the citation build (RecallSearchService.cs:26-37): the query string is split, lower-cased, de-duplicated and
+ * stop-word filtered (:95-108, all-stop-words fallback included), every term is expanded into the live vocabulary words
+ * that contain it (a GPU scan of the vocabulary kept in HBM; the substring semantics of :110-111), and the probes go
+ * through orr_search.  keyword_mode: 0 = auto (text mode when a term expands past ORR_MAX_QUERY_PROBES, when there are
+ * more than ORR_MAX_QUERY_TERMS terms, or while an over-long chunk is live), 1 = hashed only, 2 = text mode only.
+ * A blank query returns ORR_E_INVALID ("Query is required.", :22-23).  The store must have been fed through
+ * orr_store_upsert_document_texts (or orr_store_fill_synthetic with option "synth_vocab"). */
+int  orr_search_query(orr_store* s, const char* query_utf8, int32_t query_len, const float* q, int32_t q_dim,
+        int64_t now_ticks, int32_t top_k, int32_t candidate_cap, int32_t keyword_mode,
+        orr_hit* out, int32_t* n_out);
+
 /* Same work with every buffer already resident in HBM on cfg.device and no host
  * synchronisation: q_dev fp32[q_dim], probes copied at enqueue time (host arrays),
  * out_dev orr_hit[max(1,top_k)], status_dev int32[2] = {n_out, flags}; flags bit0 set
@@ -216,6 +244,14 @@ int  orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim
  * keyword term; fp32) of every `tile_stride`-th 128-row tile, out[b*out_ld + i]. */
 int  orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
         int64_t now_ticks, int32_t tile_stride, float* out, int64_t out_ld);
+
+/* Diagnostic for the fused single-query path: the fp32 score K1 computes for every physical row (the values its
+ * selection and its discard bound tau are built from): out[row], row < orr_store_rows_used.  FLT_MAX marks a row the scan
+ * forces into the survivor list (magnitudes outside what fp32 ranks), -inf a tombstone.  tests use it to MEASURE the
+ * bound |fp32 scan score - exact score| <= eps the selection proof assumes. */
+int  orr_debug_scan_scores(orr_store* s, const float* q, int32_t q_dim,
+        int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+        int64_t now_ticks, float* out, int64_t out_cap);
 
 /* Merge per-shard hit lists (each already in reference order) into the global top-k
  * with the same tie chain; used after the NCCL all-gather of per-GPU candidates. */
@@ -310,6 +346,7 @@ int  orr_synth_rows_host(const orr_synth_spec* spec, uint64_t first_row, int64_t
 int  orr_synth_query_host(const orr_synth_spec* spec, uint64_t query_index, uint64_t corpus_rows,
         int32_t n_terms, int32_t frequent_terms, float* q /* dim */, uint32_t* term_ids /* n_terms */);
 int  orr_synth_term_text(uint32_t term_id, char* out9 /* 8 chars + NUL */);
+int64_t orr_synth_row_text(const orr_synth_spec* spec, uint64_t row, char* out, int64_t cap);   /* the row's Content; returns its length */
 int  orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t first_row, int64_t n);
 
 #ifdef __cplusplus

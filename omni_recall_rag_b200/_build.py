@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "liborr.so")
 
-SOURCES = ["orr_api.cu", "orr_scan.cu", "orr_rescore.cu", "orr_synth.cu", "orr_batch.cu", "orr_xchg.cu", "orr_cluster.cu", "orr_textmatch.cu", "orr_text.cpp"]
+SOURCES = ["orr_api.cu", "orr_scan.cu", "orr_rescore.cu", "orr_exact.cu", "orr_vocab.cu", "orr_synth.cu", "orr_batch.cu", "orr_xchg.cu", "orr_cluster.cu", "orr_textmatch.cu", "orr_text.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -63,6 +63,11 @@ _SIGNATURES = {
     "orr_store_upsert_document_chunks_text": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p,
                                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p,
                                                         C.c_void_p]),
+    "orr_store_upsert_document_texts": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_char_p, C.c_void_p, C.c_void_p]),
+    "orr_store_vocab_size": (C.c_int64, [C.c_void_p]),
+    "orr_search_query": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "orr_store_delete_document": (C.c_int, [C.c_void_p, C.c_uint64]),
     "orr_store_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "orr_store_save": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -84,6 +89,8 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "orr_debug_batch_scores": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                          C.c_void_p, C.c_int64]),
+    "orr_debug_scan_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_int64, C.c_void_p, C.c_int64]),
     "orr_merge_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                  C.POINTER(C.c_int32)]),
     "orr_merge_hits_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -116,6 +123,7 @@ _SIGNATURES = {
     "orr_synth_query_host": (C.c_int, [C.POINTER(OrrSynthSpec), C.c_uint64, C.c_uint64, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "orr_synth_term_text": (C.c_int, [C.c_uint32, C.c_char_p]),
+    "orr_synth_row_text": (C.c_int64, [C.POINTER(OrrSynthSpec), C.c_uint64, C.c_char_p, C.c_int64]),
     "orr_store_fill_synthetic": (C.c_int, [C.c_void_p, C.POINTER(OrrSynthSpec), C.c_uint64, C.c_int64]),
 }
 

@@ -76,7 +76,7 @@ struct BatchState {
     int64_t mid_rows = 0;                          // rows whose mid plane is built (allocated on the first bf16x3 pass)
     int bcap = 0, kcap = 0;
     float* q = nullptr; void* qhi = nullptr; void* qmid = nullptr;
-    float* qscale = nullptr; float* thr = nullptr; float* kww = nullptr; int32_t* qterm = nullptr;
+    float* qscale = nullptr; float* thr = nullptr; float* kww = nullptr; int32_t* qterm = nullptr; int32_t* qbad = nullptr;
     void* cand = nullptr; uint32_t* cand_count = nullptr; orr_hit* hits = nullptr; int32_t* status = nullptr;
     OrrBatchProbes* probes = nullptr;
     // pinned staging of the per-call host arrays (one batched search at a time per store)
@@ -126,6 +126,14 @@ struct orr_store {
     int64_t text_rows = 0;            // rows appended WITH text; text mode needs text_rows == rows_used
     double text_bytes_per_row = 1024.0;
     bool synth_text = false;          // option "synth_text": orr_store_fill_synthetic also writes the chunk text
+    // text-level ingest (orr_store_upsert_document_texts): live vocabulary + which words each document holds
+    OrrVocab* vocab = nullptr;
+    std::mutex vocab_mu;
+    std::unordered_map<uint64_t, std::vector<uint32_t>> doc_words;    // doc -> vocabulary ids, one per (chunk, distinct word)
+    std::unordered_map<uint64_t, int32_t> doc_overflow;               // doc -> chunks with more distinct tokens than term_slots
+    int64_t overflow_rows = 0;        // > 0: the hashed term table is incomplete, keyword matching goes through text mode
+    bool keep_text = false;           // option "keep_text": upsert_document_texts also keeps the lower-cased Content in HBM
+    bool synth_vocab = false;         // option "synth_vocab": fill_synthetic registers the 2^20 synthetic tokens
     std::unique_ptr<BatchState> batch;
     int batch_passes = 0;            // 0 = auto (bf16 screen, bf16x3 for what it cannot prove), 1 = screen only, 3 = bf16x3
     std::atomic<int> batch_hold{0};  // auto mode: batches still to run bf16x3 first after a screen that mostly failed
@@ -149,9 +157,7 @@ void free_ctx(SearchCtx* c) {
     else cudaDeviceSynchronize();
     cudaFree(c->sc.q); cudaFree(c->sc.cta_cands); cudaFree(c->sc.cta_floor); cudaFree(c->sc.surv_rows);
     cudaFree(c->sc.exact); cudaFree(c->sc.sel); cudaFree(c->sc.hits); cudaFree(c->sc.status);
-    cudaFree(c->sc.scores64); cudaFree(c->sc.cub_tmp);
-    cudaFree(c->sc.sort_keys[0]); cudaFree(c->sc.sort_keys[1]);
-    cudaFree(c->sc.sort_vals[0]); cudaFree(c->sc.sort_vals[1]);
+    cudaFree(c->sc.skey); cudaFree(c->sc.sel_state); cudaFree(c->sc.big);
     cudaFree(c->d_terms); cudaFree(c->d_kw_bits); cudaFreeHost(c->h_terms);
     cudaFreeHost(c->h_q); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_status); cudaFreeHost(c->h_rows);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -194,15 +200,20 @@ int make_ctx(orr_store* s, std::unique_ptr<SearchCtx>& out, bool own_stream) {
     return ORR_OK;
 }
 
-int ensure_exact_buffers(orr_store* s, SearchCtx* c) {
+int ensure_exact_buffers(orr_store* s, SearchCtx* c, int k) {
     const int64_t need = s->cfg.capacity_rows;
-    if (c->exact_rows_cap >= need) return ORR_OK;
-    ORR_CUDA_OK(cudaMalloc(&c->sc.scores64, sizeof(double) * (size_t)need));
-    for (int i = 0; i < 2; ++i) {
-        ORR_CUDA_OK(cudaMalloc(&c->sc.sort_keys[i], sizeof(uint64_t) * (size_t)need));
-        ORR_CUDA_OK(cudaMalloc(&c->sc.sort_vals[i], sizeof(uint32_t) * (size_t)need));
+    if (c->exact_rows_cap < need) {
+        ORR_CUDA_OK(cudaMalloc(&c->sc.skey, sizeof(uint64_t) * (size_t)need));
+        ORR_CUDA_OK(cudaMalloc(&c->sc.sel_state, orr_exact_state_bytes()));
+        c->exact_rows_cap = need;
     }
-    c->exact_rows_cap = need;
+    if (k > ORR_SORT_MAX && c->sc.big_cap < k) {              // the in-CTA sorter's capacity: larger k sorts in global memory
+        int64_t np2 = 1;
+        while (np2 < k) np2 <<= 1;
+        cudaFree(c->sc.big); c->sc.big = nullptr; c->sc.big_cap = 0;
+        ORR_CUDA_OK(cudaMalloc(&c->sc.big, sizeof(OrrExact) * (size_t)np2));
+        c->sc.big_cap = np2;
+    }
     return ORR_OK;
 }
 
@@ -291,7 +302,7 @@ void orr_config_default(orr_config* cfg) {
     cfg->abi_version = ORR_ABI_VERSION;
     cfg->device = 0;
     cfg->dim = 3072;
-    cfg->term_slots = 64;
+    cfg->term_slots = 128;                                 // the reference's default chunk is 120 words (appsettings.json:22)
     cfg->capacity_rows = 1 << 20;
     cfg->row_base = 0;
     cfg->w_cos = 0.7; cfg->w_kw = 0.2; cfg->w_rec = 0.1;   // RecallSearchService.cs:66
@@ -347,7 +358,7 @@ void orr_store_destroy(orr_store* s) {
         BatchState* b = s->batch.get();
         if (b->stream) cudaStreamSynchronize(b->stream);
         void* ptrs[] = {b->ehi, b->emid, b->rowaux, b->q, b->qhi, b->qmid, b->qscale, b->thr, b->kww, b->qterm,
-                        b->cand, b->cand_count, b->hits, b->status, b->probes, b->dense, b->term_bits, b->table};
+                        b->cand, b->cand_count, b->hits, b->status, b->probes, b->dense, b->term_bits, b->table, b->qbad};
         for (void* p : ptrs) cudaFree(p);
         cudaFreeHost(b->h_qterm); cudaFreeHost(b->h_kww); cudaFreeHost(b->h_probes); cudaFreeHost(b->h_table); cudaFreeHost(b->h_status);
         for (auto& e : b->ev) if (e) cudaEventDestroy(e);
@@ -355,6 +366,7 @@ void orr_store_destroy(orr_store* s) {
     }
     cudaFree(s->d_emb); cudaFree(s->d_ticks); cudaFree(s->d_terms32); cudaFree(s->d_terms64);
     cudaFree(s->d_text); cudaFree(s->d_text_off); cudaFree(s->d_text_len);
+    orr_vocab_free(s->vocab);
     delete s;
 }
 
@@ -368,6 +380,12 @@ int orr_store_set_option(orr_store* s, const char* name, double value) {
         return ORR_OK;
     }
     if (!strcmp(name, "synth_text")) { s->synth_text = value != 0.0; return ORR_OK; }
+    if (!strcmp(name, "synth_vocab")) { s->synth_vocab = value != 0.0; return ORR_OK; }
+    if (!strcmp(name, "keep_text")) {
+        if (s->rows_used != 0 && (value != 0.0) != s->keep_text) { orr_set_error("keep_text must be set before the first row arrives"); return ORR_E_INVALID; }
+        s->keep_text = value != 0.0;
+        return ORR_OK;
+    }
     if (!strcmp(name, "text_bytes_per_row")) {
         if (s->d_text) { orr_set_error("text_bytes_per_row must be set before the first chunk text arrives"); return ORR_E_INVALID; }
         if (!(value >= 16.0 && value <= 1048576.0)) { orr_set_error("text_bytes_per_row out of range"); return ORR_E_INVALID; }
@@ -390,6 +408,8 @@ static int ensure_text_arena(orr_store* s) {
     s->text_cap = cap_bytes;
     return ORR_OK;
 }
+
+static void release_doc_words(orr_store* s, uint64_t doc_key);
 
 static int tombstone_locked(orr_store* s, uint64_t doc_key) {
     auto it = s->docs.find(doc_key);
@@ -453,6 +473,7 @@ static int upsert_impl(orr_store* s, uint64_t doc_key, int32_t n, const float* e
     }
     int rc = tombstone_locked(s, doc_key);
     if (rc != ORR_OK) return rc;
+    release_doc_words(s, doc_key);
     if (text_offsets) {
         const uint64_t total = text_offsets[n] - text_offsets[0];
         std::vector<uint64_t> off((size_t)n);
@@ -514,11 +535,78 @@ int orr_store_upsert_document_chunks_text(orr_store* s, uint64_t doc_key, int32_
     return upsert_impl(s, doc_key, n, emb, has_emb, created_ticks, term_hashes, term_offsets, text_lower_utf8, text_offsets, out_rows);
 }
 
+// the document's words leave the vocabulary (their reference counts drop; a word nobody holds stops matching)
+static void release_doc_words(orr_store* s, uint64_t doc_key) {
+    std::lock_guard<std::mutex> g(s->vocab_mu);
+    auto it = s->doc_words.find(doc_key);
+    if (it != s->doc_words.end()) {
+        if (s->vocab) for (uint32_t id : it->second) orr_vocab_release(s->vocab, id);
+        s->doc_words.erase(it);
+    }
+    auto ov = s->doc_overflow.find(doc_key);
+    if (ov != s->doc_overflow.end()) { s->overflow_rows -= ov->second; s->doc_overflow.erase(ov); }
+}
+
 int orr_store_delete_document(orr_store* s, uint64_t doc_key) {
     if (!s) { orr_set_error("delete: NULL store"); return ORR_E_INVALID; }
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
-    return tombstone_locked(s, doc_key);
+    int rc = tombstone_locked(s, doc_key);
+    if (rc == ORR_OK) release_doc_words(s, doc_key);
+    return rc;
+}
+
+int64_t orr_store_vocab_size(const orr_store* s) { return (s && s->vocab) ? (int64_t)orr_vocab_live_words(s->vocab) : 0; }
+
+// ---- text-level ingest: Content strings in, the library tokenises / hashes / tracks the vocabulary --------------
+int orr_store_upsert_document_texts(orr_store* s, uint64_t doc_key, int32_t n, const float* emb, const uint8_t* has_emb,
+                                    const int64_t* created_ticks, const char* contents_utf8, const uint64_t* content_offsets,
+                                    uint64_t* out_rows) {
+    if (!s || n < 0 || (n > 0 && (!created_ticks || !contents_utf8 || !content_offsets))) { orr_set_error("upsert_texts: bad argument"); return ORR_E_INVALID; }
+    if (n == 0) return ORR_OK;
+    const int slots = s->cfg.term_slots;
+    std::vector<uint64_t> hashes;
+    std::vector<uint32_t> hoff((size_t)n + 1, 0u);
+    std::vector<std::vector<std::string>> toks((size_t)n);
+    std::string text;                              // lower-cased contents (text mode)
+    std::vector<uint64_t> toff((size_t)n + 1, 0ull);
+    int32_t overflow = 0;
+    try {
+        for (int32_t i = 0; i < n; ++i) {
+            if (content_offsets[i + 1] < content_offsets[i]) { orr_set_error("upsert_texts: bad content offsets at chunk %d", i); return ORR_E_INVALID; }
+            const char* c = contents_utf8 + content_offsets[i];
+            const int64_t cl = (int64_t)(content_offsets[i + 1] - content_offsets[i]);
+            toks[(size_t)i] = orr_distinct_lower_tokens(c, cl);
+            size_t keep = toks[(size_t)i].size();
+            if (keep > (size_t)slots) {
+                // the slot table cannot hold the chunk's term set: with the text kept in HBM the keyword side is evaluated
+                // there (text mode) for as long as such a row is live; without it the chunk cannot be represented
+                if (!s->keep_text) {
+                    orr_set_error("upsert_texts: chunk %d has %zu distinct tokens, the store has %d term slots (create the store with "
+                                  "more slots, or set option keep_text so that text mode carries it)", i, keep, slots);
+                    return ORR_E_UNSUPPORTED;
+                }
+                keep = (size_t)slots;
+                ++overflow;
+            }
+            for (size_t t = 0; t < keep; ++t) hashes.push_back(orr_hash_bytes(toks[(size_t)i][t].data(), (int64_t)toks[(size_t)i][t].size()));
+            hoff[(size_t)i + 1] = (uint32_t)hashes.size();
+            if (s->keep_text) { text += orr_lower_invariant(c, cl); toff[(size_t)i + 1] = text.size(); }
+        }
+    } catch (const std::exception& e) { orr_set_error("upsert_texts: %s", e.what()); return ORR_E_OOM; }
+    if (hashes.empty()) hashes.push_back(0ull);
+    if (text.empty()) text.push_back('\0');
+    int rc = upsert_impl(s, doc_key, n, emb, has_emb, created_ticks, hashes.data(), hoff.data(),
+                         s->keep_text ? text.data() : nullptr, s->keep_text ? toff.data() : nullptr, out_rows);
+    if (rc != ORR_OK) return rc;
+    // vocabulary: the document's previous words were released by upsert_impl's tombstoning; register the new ones
+    std::lock_guard<std::mutex> g(s->vocab_mu);
+    if (!s->vocab) s->vocab = orr_vocab_new(s->cfg.device);
+    std::vector<uint32_t>& ids = s->doc_words[doc_key];
+    for (int32_t i = 0; i < n; ++i)
+        for (const std::string& w : toks[(size_t)i]) ids.push_back(orr_vocab_add(s->vocab, w.data(), w.size(), 1u));
+    if (overflow) { s->doc_overflow[doc_key] += overflow; s->overflow_rows += overflow; }
+    return ORR_OK;
 }
 
 int orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t first_row, int64_t n) {
@@ -547,17 +635,50 @@ int orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t 
     s->rows_used += n;
     s->live_rows += n;
     s->version++;
+    if (s->synth_vocab && spec->terms_per_chunk > 0) {
+        // the synthetic corpus draws its tokens from "t%07d", id < 2^20: register them all once (orr_search_query expands
+        // query terms over the vocabulary, as it does for ingested text)
+        std::lock_guard<std::mutex> g(s->vocab_mu);
+        if (!s->vocab) s->vocab = orr_vocab_new(s->cfg.device);
+        if (orr_vocab_words(s->vocab) == 0) {
+            char w[16];
+            for (uint32_t id = 0; id < (1u << 20); ++id) {
+                snprintf(w, sizeof w, "t%07u", id);
+                orr_vocab_add(s->vocab, w, 8, 1u);
+            }
+        }
+    }
     return ORR_OK;
 }
 
 // ---- search --------------------------------------------------------------------------------
+// The exact path end to end: E1 (every row's score key), then rounds of digit passes + gather until the radix walk has
+// ended (two passes on ordinary scores).  Leaves {n_out, flags} and the hits in the context's pinned buffers.
+// `kw` carries text mode's row bitmaps (or NULLs).
 static int run_exact(orr_store* s, SearchCtx* c, const OrrShard& sh, const OrrProbes& pr, int64_t now_ticks,
-                     int q_dim, int top_k) {
-    int rc = ensure_exact_buffers(s, c);
+                     int q_dim, int top_k, cudaEvent_t after_scores = nullptr, const uint32_t* kw_bits = nullptr,
+                     int64_t kw_row_words = 0, int kw_terms = 0) {
+    const int k = (int)std::min<int64_t>(std::max(1, top_k), std::max<int64_t>(1, s->live_rows));
+    int rc = ensure_exact_buffers(s, c, k);
     if (rc != ORR_OK) return rc;
-    rc = orr_launch_exact_scores(sh, c->sc, pr, weights_of(s), now_ticks, q_dim, c->stream);
+    rc = ensure_hits(c, k);
     if (rc != ORR_OK) return rc;
-    return orr_exact_select(sh, c->sc, top_k, c->stream);
+    OrrScratch sc = c->sc;
+    sc.kw_bits = kw_bits; sc.kw_row_words = kw_row_words; sc.kw_terms = kw_terms;
+    rc = orr_launch_exact_scores(sh, sc, pr, weights_of(s), now_ticks, q_dim, c->stream);
+    if (rc != ORR_OK) return rc;
+    if (after_scores) ORR_CUDA_OK(cudaEventRecord(after_scores, c->stream));
+    for (int first = 1, n = 2;; first += n, n = 3) {
+        rc = orr_launch_exact_select(sh, sc, k, first, n, c->stream);
+        if (rc != ORR_OK) return rc;
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+        ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (c->h_status[1] & ORR_EXACT_INTERNAL) { orr_set_error("exact path: selection histogram inconsistent"); return ORR_E_INTERNAL; }
+        if (!(c->h_status[1] & ORR_EXACT_INCOMPLETE)) break;
+        if (first + n > ORR_EXACT_PASSES + 3) { orr_set_error("exact path: selection did not terminate"); return ORR_E_INTERNAL; }
+    }
+    return ORR_OK;
 }
 
 int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
@@ -609,9 +730,8 @@ int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, con
         if (rc != ORR_OK) return rc;
         g_timing.n_survivors = nl;
     } else if (eff_q_dim == 0 || k > ORR_FUSED_MAX_K) {
-        path = ORR_PATH_EXACT;
-        ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
-        rc = run_exact(s, c, sh, pr, now_ticks, eff_q_dim, (int)kk);
+        path = ORR_PATH_EXACT;                                          // scan_ms = the scoring kernel, finalize_ms = the selection
+        rc = run_exact(s, c, sh, pr, now_ticks, eff_q_dim, (int)kk, c->ev[1]);
         if (rc != ORR_OK) return rc;
     } else {
         path = ORR_PATH_FUSED;
@@ -624,8 +744,10 @@ int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, con
         g_timing.n_survivors = M;
     }
     ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-    ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
-    ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+    if (path != ORR_PATH_EXACT) {                                       // the exact path has already brought its results down
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+    }
     ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
     float scan_ms = 0.f, fin_ms = 0.f;
     cudaEventElapsedTime(&scan_ms, c->ev[0], c->ev[1]);
@@ -638,8 +760,6 @@ int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, con
         rc = run_exact(s, c, sh, pr, now_ticks, eff_q_dim, (int)kk);
         if (rc != ORR_OK) return rc;
         ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
         ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
         float extra = 0.f;
         cudaEventElapsedTime(&extra, c->ev[1], c->ev[2]);
@@ -703,7 +823,7 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
         ORR_CUDA_OK(cudaMemcpyAsync(c->sc.q, c->h_q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream));
     }
     const int64_t row_words = (s->rows_used + 31) / 32;
-    bool escalated = false;
+    bool escalated = false, exact = false;
     std::vector<uint32_t> sub_rows;
     if (candidate_cap > 0) {
         if (candidate_cap > ORR_SORT_MAX) { orr_set_error("candidate_cap %d > %d", candidate_cap, ORR_SORT_MAX); return ORR_E_UNSUPPORTED; }
@@ -770,19 +890,17 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
             if (c->h_status[1] & 1) { fused = false; escalated = true; }
         }
         if (!fused) {
-            rc = ensure_exact_buffers(s, c);
-            if (rc != ORR_OK) return rc;
-            sc = c->sc;                                      // buffers may just have been allocated
-            if (n_terms > 0) { sc.kw_bits = c->d_kw_bits; sc.kw_row_words = row_words; sc.kw_terms = n_terms; }
-            rc = orr_launch_exact_scores(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, c->stream);
-            if (rc != ORR_OK) return rc;
-            rc = orr_exact_select(sh, c->sc, (int)kk, c->stream);
+            exact = true;
+            rc = n_terms > 0 ? run_exact(s, c, sh, pr, now_ticks, eff_q_dim, (int)kk, nullptr, c->d_kw_bits, row_words, n_terms)
+                             : run_exact(s, c, sh, pr, now_ticks, eff_q_dim, (int)kk);
         }
     }
     if (rc != ORR_OK) return rc;
     ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-    ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
-    ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+    if (!exact) {                                            // the exact path has already brought its results down
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+    }
     ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
     float match_ms = 0.f, fin_ms = 0.f;
     cudaEventElapsedTime(&match_ms, c->ev[0], c->ev[1]);
@@ -797,6 +915,59 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
     g_timing.rows_scanned = (candidate_cap > 0) ? g_timing.n_survivors : s->rows_used;
     g_timing.wall_ms = (float)(now_ms() - t0);
     return ORR_OK;
+}
+
+// ---- query string in, hits out: KeywordScore's query side + vocabulary expansion + search, in one call ----------------
+// RecallSearchService.cs:95-108 (split, lower-case, distinct, stop words with the all-stop-words fallback) runs here, the
+// terms are expanded over the live vocabulary on the GPU (orr_vocab.cu: which words contain each term, :110-111), and the
+// scan is orr_search's.  keyword_mode 0 = auto (hashed probes; text mode when a term sits in more than 128 words, when
+// there are more than 64 terms, or while a chunk with more distinct tokens than term_slots is live), 1 = hashed only,
+// 2 = text only.
+int orr_search_query(orr_store* s, const char* query_utf8, int32_t query_len, const float* q, int32_t q_dim, int64_t now_ticks,
+                     int32_t top_k, int32_t candidate_cap, int32_t keyword_mode, orr_hit* out, int32_t* n_out) {
+    if (!s || !out || !n_out || query_len < 0 || (query_len > 0 && !query_utf8) || keyword_mode < 0 || keyword_mode > 2) {
+        orr_set_error("orr_search_query: bad argument");
+        return ORR_E_INVALID;
+    }
+    *n_out = 0;
+    std::vector<std::string> terms;
+    try {
+        std::vector<std::string> raw = orr_distinct_lower_tokens(query_utf8, query_len);          // :95-98
+        if (raw.empty()) { orr_set_error("Query is required."); return ORR_E_INVALID; }           // :22-23 (IsNullOrWhiteSpace)
+        for (const auto& t : raw) if (!orr_is_stop_word(t)) terms.push_back(t);                   // :103-105
+        if (terms.empty()) terms = raw;                                                           // :107-108
+    } catch (const std::exception& e) { orr_set_error("orr_search_query: %s", e.what()); return ORR_E_OOM; }
+    const int nt = (int)terms.size();
+    const bool has_text = s->d_text && s->text_rows == s->rows_used;
+    if (keyword_mode != 2 && nt <= ORR_MAX_QUERY_TERMS && s->overflow_rows == 0) {
+        uint64_t ph[ORR_MAX_QUERY_PROBES];
+        int32_t pt[ORR_MAX_QUERY_PROBES];
+        int32_t np = 0;
+        int rc = ORR_OK;
+        {
+            std::lock_guard<std::mutex> g(s->vocab_mu);
+            if (s->vocab) rc = orr_vocab_expand(s->vocab, terms, ph, pt, ORR_MAX_QUERY_PROBES, &np);
+            else if (s->live_rows > 0) {
+                orr_set_error("orr_search_query: the store has no vocabulary (rows must arrive through orr_store_upsert_document_texts)");
+                return ORR_E_INVALID;
+            }
+        }
+        if (rc != ORR_OK && rc != ORR_E_UNSUPPORTED) return rc;
+        if (rc == ORR_OK && np <= ORR_MAX_QUERY_PROBES)
+            return orr_search(s, q, q_dim, nt, np ? ph : nullptr, np ? pt : nullptr, np, now_ticks, top_k, candidate_cap, out, n_out);
+        if (keyword_mode == 1 || !has_text) {
+            if (rc == ORR_OK) orr_set_error("orr_search_query: the terms expand to %d vocabulary words (limit %d) and the store keeps no chunk text", np, ORR_MAX_QUERY_PROBES);
+            return ORR_E_UNSUPPORTED;
+        }
+    } else if (keyword_mode == 1 || !has_text) {
+        orr_set_error("orr_search_query: %d terms / %lld over-long chunks need text mode, and the store keeps no chunk text (option keep_text)",
+                      nt, (long long)s->overflow_rows);
+        return ORR_E_UNSUPPORTED;
+    }
+    std::string blob;
+    std::vector<uint32_t> off((size_t)nt + 1, 0u);
+    for (int t = 0; t < nt; ++t) { blob += terms[(size_t)t]; off[(size_t)t + 1] = (uint32_t)blob.size(); }
+    return orr_search_text(s, q, q_dim, nt, blob.data(), off.data(), now_ticks, top_k, candidate_cap, out, n_out);
 }
 
 // ---- snapshot / warm load ----------------------------------------------
@@ -875,6 +1046,28 @@ int orr_store_save(orr_store* s, const char* path) {
             orr_set_error("snapshot: short write");
             return ORR_E_INVALID;
         }
+        // trailer (absent in snapshots written before the vocabulary existed): "ORRVOC01", the vocabulary, the
+        // document -> word ids table and the per-document counts of over-long chunks
+        std::lock_guard<std::mutex> g(s->vocab_mu);
+        std::vector<uint8_t> vb;
+        if (s->vocab) orr_vocab_serialize(s->vocab, &vb);
+        std::vector<uint64_t> t2;
+        t2.push_back((uint64_t)vb.size());
+        t2.push_back((uint64_t)s->doc_words.size());
+        t2.push_back((uint64_t)s->doc_overflow.size());
+        if (fwrite("ORRVOC01", 1, 8, f) != 8 || fwrite(t2.data(), 8, t2.size(), f) != t2.size() ||
+            (!vb.empty() && fwrite(vb.data(), 1, vb.size(), f) != vb.size())) { orr_set_error("snapshot: short write"); return ORR_E_INVALID; }
+        for (auto& d : s->doc_words) {
+            const uint64_t hdr[2] = {d.first, (uint64_t)d.second.size()};
+            if (fwrite(hdr, 8, 2, f) != 2 || (!d.second.empty() && fwrite(d.second.data(), 4, d.second.size(), f) != d.second.size())) {
+                orr_set_error("snapshot: short write");
+                return ORR_E_INVALID;
+            }
+        }
+        for (auto& d : s->doc_overflow) {
+            const uint64_t rec[2] = {d.first, (uint64_t)d.second};
+            if (fwrite(rec, 8, 2, f) != 2) { orr_set_error("snapshot: short write"); return ORR_E_INVALID; }
+        }
         return ORR_OK;
     }();
     cudaFreeHost(bounce);
@@ -890,7 +1083,7 @@ int orr_store_load(orr_store* s, const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) { orr_set_error("orr_store_load: cannot open %s", path); return ORR_E_INVALID; }
     void* bounce = nullptr;
-    int rc = [&]() -> int {
+    auto body = [&]() -> int {
         SnapHeader h{};
         if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "ORRSNAP1", 8) != 0) { orr_set_error("orr_store_load: %s is not a snapshot", path); return ORR_E_INVALID; }
         if (h.abi_version != ORR_ABI_VERSION || h.dim != s->cfg.dim || h.term_slots != s->cfg.term_slots) {
@@ -919,22 +1112,97 @@ int orr_store_load(orr_store* s, const char* path) {
             if ((r = snap_read(f, s->d_text, (size_t)h.text_used, bounce)) != ORR_OK) return r;
             s->text_used = h.text_used; s->text_rows = h.rows_used;
         }
+        // the document table: sized from the header, so the header is checked against the file and the rows first
+        const long at = ftell(f);
+        fseek(f, 0, SEEK_END);
+        const long file_end = ftell(f);
+        fseek(f, at, SEEK_SET);
+        const uint64_t left = (at >= 0 && file_end >= at) ? (uint64_t)(file_end - at) : 0;
+        if (h.n_docs > left / 16 || h.n_runs > left / 16 || 16 * (h.n_docs + h.n_runs) > left || h.n_runs > (uint64_t)h.rows_used ||
+            h.live_rows < 0 || h.live_rows > h.rows_used) {
+            orr_set_error("orr_store_load: corrupt snapshot header (%llu documents, %llu runs, %lld live of %lld rows)",
+                          (unsigned long long)h.n_docs, (unsigned long long)h.n_runs, (long long)h.live_rows, (long long)h.rows_used);
+            return ORR_E_INVALID;
+        }
+        if (h.row_base != s->cfg.row_base) {
+            orr_set_error("orr_store_load: snapshot row_base %llu != store row_base %llu (row ids would not be preserved)",
+                          (unsigned long long)h.row_base, (unsigned long long)s->cfg.row_base);
+            return ORR_E_INVALID;
+        }
         std::vector<uint64_t> table((size_t)(2 * h.n_docs + 2 * h.n_runs));
         if (!table.empty() && fread(table.data(), sizeof(uint64_t), table.size(), f) != table.size()) { orr_set_error("snapshot: truncated file"); return ORR_E_INVALID; }
-        s->docs.clear();
+        std::unordered_map<uint64_t, std::vector<std::pair<int64_t, int64_t>>> docs;
         size_t i = 0;
+        uint64_t runs_seen = 0, rows_in_runs = 0;
         for (uint64_t d = 0; d < h.n_docs; ++d) {
             if (i + 2 > table.size()) { orr_set_error("snapshot: corrupt document table"); return ORR_E_INVALID; }
             const uint64_t key = table[i++], nr = table[i++];
-            if (i + 2 * nr > table.size()) { orr_set_error("snapshot: corrupt document table"); return ORR_E_INVALID; }
-            auto& runs = s->docs[key];
-            for (uint64_t k = 0; k < nr; ++k) { runs.push_back({(int64_t)table[i], (int64_t)table[i + 1]}); i += 2; }
+            if (nr > h.n_runs - runs_seen || i + 2 * nr > table.size()) { orr_set_error("snapshot: corrupt document table"); return ORR_E_INVALID; }
+            auto& runs = docs[key];
+            for (uint64_t k = 0; k < nr; ++k) {
+                const uint64_t first = table[i], count = table[i + 1];
+                i += 2;
+                if (first > (uint64_t)h.rows_used || count > (uint64_t)h.rows_used - first) { orr_set_error("snapshot: a document run lies outside the stored rows"); return ORR_E_INVALID; }
+                runs.push_back({(int64_t)first, (int64_t)count});
+                rows_in_runs += count;
+            }
+            runs_seen += nr;
         }
+        if (runs_seen != h.n_runs || rows_in_runs > (uint64_t)h.live_rows) { orr_set_error("snapshot: document table does not match the header"); return ORR_E_INVALID; }
+        // optional trailer: vocabulary, document -> words, over-long chunk counts
+        char vmagic[8];
+        std::unordered_map<uint64_t, std::vector<uint32_t>> doc_words;
+        std::unordered_map<uint64_t, int32_t> doc_overflow;
+        std::vector<uint8_t> vb;
+        bool have_vocab = false;
+        int64_t overflow_rows = 0;
+        if (fread(vmagic, 1, 8, f) == 8) {
+            if (memcmp(vmagic, "ORRVOC01", 8) != 0) { orr_set_error("snapshot: unknown trailer"); return ORR_E_INVALID; }
+            uint64_t t2[3];
+            const long at2 = ftell(f);
+            const uint64_t left2 = (at2 >= 0 && file_end >= at2) ? (uint64_t)(file_end - at2) : 0;
+            if (fread(t2, 8, 3, f) != 3 || t2[0] > left2 || t2[1] > left2 / 16 || t2[2] > left2 / 16) { orr_set_error("snapshot: corrupt vocabulary trailer"); return ORR_E_INVALID; }
+            vb.resize((size_t)t2[0]);
+            if (!vb.empty() && fread(vb.data(), 1, vb.size(), f) != vb.size()) { orr_set_error("snapshot: truncated file"); return ORR_E_INVALID; }
+            for (uint64_t d = 0; d < t2[1]; ++d) {
+                uint64_t hdr[2];
+                if (fread(hdr, 8, 2, f) != 2 || hdr[1] > left2 / 4) { orr_set_error("snapshot: corrupt document-words table"); return ORR_E_INVALID; }
+                std::vector<uint32_t>& ids = doc_words[hdr[0]];
+                ids.resize((size_t)hdr[1]);
+                if (!ids.empty() && fread(ids.data(), 4, ids.size(), f) != ids.size()) { orr_set_error("snapshot: truncated file"); return ORR_E_INVALID; }
+            }
+            for (uint64_t d = 0; d < t2[2]; ++d) {
+                uint64_t rec[2];
+                if (fread(rec, 8, 2, f) != 2 || rec[1] > (uint64_t)h.rows_used) { orr_set_error("snapshot: corrupt overflow table"); return ORR_E_INVALID; }
+                doc_overflow[rec[0]] = (int32_t)rec[1];
+                overflow_rows += (int64_t)rec[1];
+            }
+            have_vocab = true;
+        }
+        {
+            std::lock_guard<std::mutex> g(s->vocab_mu);
+            if (have_vocab && !vb.empty()) {
+                if (!s->vocab) s->vocab = orr_vocab_new(s->cfg.device);
+                if (orr_vocab_deserialize(s->vocab, vb.data(), vb.size()) != ORR_OK) { orr_set_error("snapshot: corrupt vocabulary"); return ORR_E_INVALID; }
+                const uint64_t nw = orr_vocab_words(s->vocab);
+                for (auto& d : doc_words) for (uint32_t id : d.second) if (id >= nw) { orr_vocab_clear(s->vocab); orr_set_error("snapshot: corrupt document-words table"); return ORR_E_INVALID; }
+            } else if (s->vocab) {
+                orr_vocab_clear(s->vocab);
+            }
+            s->doc_words.swap(doc_words);
+            s->doc_overflow.swap(doc_overflow);
+            s->overflow_rows = overflow_rows;
+        }
+        s->docs.swap(docs);
         s->rows_used = h.rows_used; s->live_rows = h.live_rows;
         s->h_ticks.clear();
         s->version++;
         return ORR_OK;
-    }();
+    };
+    int rc;
+    try { rc = body(); }                                       // a corrupt file must not throw across the C ABI
+    catch (const std::exception& e) { orr_set_error("orr_store_load: %s", e.what()); rc = ORR_E_INVALID; }
+    if (rc != ORR_OK) { s->text_used = 0; s->text_rows = 0; }  // the store stays empty
     if (bounce) cudaFreeHost(bounce);
     fclose(f);
     return rc;
@@ -1061,6 +1329,37 @@ int orr_store_compact(orr_store* s, uint64_t* old_rows_out, int64_t out_cap, int
     return ORR_OK;
 }
 
+// diagnostic: the fp32 score the fused scan computes for every row (what its selection and tau are built from)
+int orr_debug_scan_scores(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
+                          const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, float* out, int64_t out_cap) {
+    if (!s || !q || !out || q_dim != s->cfg.dim) { orr_set_error("orr_debug_scan_scores: bad argument"); return ORR_E_INVALID; }
+    OrrProbes pr;
+    int rc = build_probes(n_terms, probe_hash, probe_term, n_probes, &pr);
+    if (rc != ORR_OK) return rc;
+    std::shared_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (out_cap < s->rows_used) { orr_set_error("orr_debug_scan_scores: out holds %lld, store has %lld rows", (long long)out_cap, (long long)s->rows_used); return ORR_E_INVALID; }
+    if (s->rows_used == 0) return ORR_OK;
+    CtxLease lease(s);
+    rc = lease.acquire();
+    if (rc != ORR_OK) return rc;
+    SearchCtx* c = lease.c.get();
+    float* d_dense = nullptr;
+    ORR_CUDA_OK(cudaMalloc(&d_dense, sizeof(float) * (size_t)s->rows_used));
+    rc = [&]() -> int {
+        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.q, q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream));
+        OrrScratch sc = c->sc;
+        sc.scan_dense = d_dense;
+        int r = orr_launch_scan(shard_view(s), sc, pr, weights_of(s), now_ticks, 64, s->sms, c->stream);
+        if (r != ORR_OK) return r;
+        ORR_CUDA_OK(cudaMemcpyAsync(out, d_dense, sizeof(float) * (size_t)s->rows_used, cudaMemcpyDeviceToHost, c->stream));
+        ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
+        return ORR_OK;
+    }();
+    cudaFree(d_dense);
+    return rc;
+}
+
 int orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim, int32_t n_terms,
                       const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
                       int64_t now_ticks, int32_t top_k, orr_hit* out_dev, int32_t* status_dev,
@@ -1147,7 +1446,7 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k, 
     if (batch_padded > bs->bcap || k > bs->kcap) {
         void** ptrs[] = {(void**)&bs->q, &bs->qhi, &bs->qmid, (void**)&bs->qscale, (void**)&bs->thr, (void**)&bs->kww,
                          (void**)&bs->qterm, &bs->cand, (void**)&bs->cand_count, (void**)&bs->hits, (void**)&bs->status,
-                         (void**)&bs->probes};
+                         (void**)&bs->probes, (void**)&bs->qbad};
         for (void** p : ptrs) { cudaFree(*p); *p = nullptr; }
         cudaFreeHost(bs->h_qterm); cudaFreeHost(bs->h_kww); cudaFreeHost(bs->h_probes); cudaFreeHost(bs->h_status);
         bs->h_qterm = nullptr; bs->h_kww = nullptr; bs->h_probes = nullptr; bs->h_status = nullptr;
@@ -1158,6 +1457,7 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k, 
         ORR_CUDA_OK(cudaMalloc(&bs->qmid, B * dim * 2));
         ORR_CUDA_OK(cudaMalloc(&bs->qscale, B * sizeof(float)));
         ORR_CUDA_OK(cudaMalloc(&bs->thr, B * sizeof(float)));
+        ORR_CUDA_OK(cudaMalloc(&bs->qbad, B * sizeof(int32_t)));
         ORR_CUDA_OK(cudaMalloc(&bs->kww, B * sizeof(float)));
         ORR_CUDA_OK(cudaMalloc(&bs->qterm, B * ORR_BATCH_TERMS * sizeof(int32_t)));
         ORR_CUDA_OK(cudaMalloc(&bs->cand, B * BATCH_CAND_CAP * 8));
@@ -1207,7 +1507,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
 
     ORR_CUDA_OK(cudaMemcpyAsync(bs->q, q, sizeof(float) * (size_t)batch * dim, cudaMemcpyHostToDevice, st));
     ORR_CUDA_OK(cudaEventRecord(bs->ev[3], st));               // queries resident in HBM from here on
-    rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st);
+    rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, bs->qbad, batch, bp, dim, st);
     if (rc != ORR_OK) return rc;
     rc = orr_batch_build_rowrec(s->d_ticks, bs->rowaux, rows, rows_pad, now_ticks, w, st);
     if (rc != ORR_OK) return rc;
@@ -1343,7 +1643,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     // ---- per-query finalize: survivors, exact fp64 re-score, order, bound check ----
     const double eps = batch_eps(w, passes);
     rc = orr_batch_launch_finalize(sh, bs->q, dim, any_terms ? bs->probes : nullptr, w, now_ticks, bs->cand, bs->cand_count,
-                                   bs->thr, BATCH_CAND_CAP, M, top_k, k, eps, bs->hits, bs->status, batch, st);
+                                   bs->thr, BATCH_CAND_CAP, M, top_k, k, eps, bs->qbad, bs->hits, bs->status, batch, st);
     if (rc != ORR_OK) return rc;
     int32_t* st_host = bs->h_status;
     ORR_CUDA_OK(cudaEventRecord(bs->ev[4], st));
@@ -1518,7 +1818,7 @@ int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t 
     const int64_t s_tiles = (rows_pad / ORR_BATCH_TILE + tile_stride - 1) / tile_stride, n_s = s_tiles * ORR_BATCH_TILE;
     if (out_ld < n_s) { orr_set_error("orr_debug_batch_scores: out_ld %lld < %lld", (long long)out_ld, (long long)n_s); return ORR_E_INVALID; }
     ORR_CUDA_OK(cudaMemcpyAsync(bs->q, q, sizeof(float) * (size_t)batch * dim, cudaMemcpyHostToDevice, st));
-    if ((rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, batch, bp, dim, st)) != ORR_OK) return rc;
+    if ((rc = orr_batch_prep_queries(bs->q, bs->qhi, bs->qmid, bs->qscale, bs->qbad, batch, bp, dim, st)) != ORR_OK) return rc;
     if ((rc = orr_batch_build_rowrec(s->d_ticks, bs->rowaux, rows, rows_pad, now_ticks, weights_of(s), st)) != ORR_OK) return rc;
     if ((size_t)bp * (size_t)n_s > bs->dense_elems) {
         cudaFree(bs->dense); bs->dense = nullptr; bs->dense_elems = 0;

@@ -590,25 +590,33 @@ __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb,
 }
 
 // queries: planes (zero-padded to a multiple of 128 queries) and inv|q|
+// qbad[b] = 1: the query's squared norm is not representable in fp32 (under/overflow, NaN) although the query is not
+// all-zero — the screen cannot rank it (the reference accumulates the norm in fp64, RecallSearchService.cs:77-82); the
+// finalize kernel flags such queries and they re-run singly (-> exact path).
 __global__ void __launch_bounds__(128) orr_prep_queries_kernel(const float* q, __nv_bfloat16* qhi, __nv_bfloat16* qmid,
-                                                               float* qscale, int batch, int dim) {
+                                                               float* qscale, int32_t* qbad, int batch, int dim) {
     const int b = blockIdx.x;
-    __shared__ float red[4];
-    float ss = 0.f;
+    __shared__ float red[4], redm[4];
+    float ss = 0.f, mx = 0.f;
     for (int c = threadIdx.x; c < dim; c += blockDim.x) {
         const float v = b < batch ? q[(int64_t)b * dim + c] : 0.f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         qhi[(int64_t)b * dim + c] = h;
         qmid[(int64_t)b * dim + c] = __float2bfloat16_rn(v - __bfloat162float(h));
         ss = fmaf(v, v, ss);
+        mx = fmaxf(mx, fabsf(v));
+        if (v != v) mx = INFINITY;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; redm[threadIdx.x >> 5] = mx; }
     __syncthreads();
     if (threadIdx.x == 0) {
         const float t = red[0] + red[1] + red[2] + red[3];
-        qscale[b] = (t > 0.f && t < 3e38f) ? rsqrtf(t) : 0.f;
+        const float m = fmaxf(fmaxf(redm[0], redm[1]), fmaxf(redm[2], redm[3]));
+        const bool ok = t >= 1e-30f && t <= 1e30f;
+        qscale[b] = ok ? rsqrtf(t) : 0.f;
+        if (qbad) qbad[b] = (!ok && m != 0.f) ? 1 : 0;
     }
 }
 
@@ -667,9 +675,9 @@ int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first,
     return ORR_OK;
 }
 
-int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qscale, int batch, int batch_padded,
+int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qscale, int32_t* qbad, int batch, int batch_padded,
                            int dim, cudaStream_t st) {
-    orr_prep_queries_kernel<<<batch_padded, 128, 0, st>>>(q_dev, (__nv_bfloat16*)qhi, (__nv_bfloat16*)qmid, qscale, batch, dim);
+    orr_prep_queries_kernel<<<batch_padded, 128, 0, st>>>(q_dev, (__nv_bfloat16*)qhi, (__nv_bfloat16*)qmid, qscale, qbad, batch, dim);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }

@@ -92,13 +92,14 @@ struct OrrScratch {
     int32_t*  sel;            // [8]: {n_surv, tau_bits, ticket_scan, ticket_rescore, ...}
     orr_hit*  hits;           // [max k] results
     int32_t*  status;         // [2] {n_out, flags}
-    double*   scores64;       // [capacity] exact path: every row's score (lazily allocated)
-    void*     cub_tmp;        // exact path: cub temp storage (lazily allocated)
-    size_t    cub_tmp_bytes;
-    uint64_t* sort_keys[2];   // exact path: key double buffer
-    uint32_t* sort_vals[2];   // exact path: value double buffer
+    // exact path (orr_exact.cu), lazily allocated
+    uint64_t* skey;           // [capacity] order-preserving key of every row's exact score
+    void*     sel_state;      // digit-walk state (histograms, prefix points, counters)
+    OrrExact* big;            // top_k > ORR_SORT_MAX: the k selected rows (power-of-two capacity)
+    int64_t   big_cap;
     // text mode: per-term row bitmaps of the current query (NULL outside orr_search_text)
     const uint32_t* kw_bits; int64_t kw_row_words; int32_t kw_terms;
+    float*    scan_dense;     // diagnostic: every row's fp32 scan score (orr_debug_scan_scores), else NULL
 };
 
 struct OrrShard {              // device view of one shard
@@ -127,10 +128,16 @@ int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes
                        const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
                        int n_listed_max, bool check_bound, cudaStream_t st);
 
-// exact path: every row's fp64 score, then a stable two-key radix sort.
+// exact path (orr_exact.cu): every row's fp64 score as an order-preserving key, then an MSB-first radix select of the
+// top-k under (score desc / NaN last, ticks desc, row asc).  orr_launch_exact_select runs digit passes
+// [first_pass, first_pass + n_passes) and the gather; status[1] & ORR_EXACT_INCOMPLETE asks for the next passes.
+constexpr int32_t ORR_EXACT_INCOMPLETE = 8;
+constexpr int32_t ORR_EXACT_INTERNAL = 32;
+constexpr int ORR_EXACT_PASSES = 15;
+size_t orr_exact_state_bytes();
 int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
                             const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st);
-int orr_exact_select(const OrrShard& sh, OrrScratch& sc, int top_k, cudaStream_t st);
+int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k, int first_pass, int n_passes, cudaStream_t st);
 
 int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_lists, int stride, int top_k,
                      orr_hit* out_dev, int32_t* out_status_dev, cudaStream_t st);
@@ -197,7 +204,7 @@ struct OrrBatchGemm {
 };
 int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first, int64_t n, int dim, float w_cos,
                            cudaStream_t st);
-int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qscale, int batch, int batch_padded,
+int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qscale, int32_t* qbad, int batch, int batch_padded,
                            int dim, cudaStream_t st);
 int orr_batch_build_rowrec(const int64_t* ticks, float* rowrec, int64_t rows, int64_t rows_padded, int64_t now_ticks,
                            const OrrWeights& w, cudaStream_t st);
@@ -206,8 +213,8 @@ int orr_batch_launch_threshold(const void* dense, int dense_half, int64_t ld, in
                                int batch_padded, cudaStream_t st);
 int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrBatchProbes* probes, const OrrWeights& w,
                               int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
-                              int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
-                              cudaStream_t st);
+                              int n_surv, int top_k, int k_stride, double eps, const int32_t* qbad, orr_hit* hits, int32_t* status,
+                              int batch, cudaStream_t st);
 // bits is tile-major [row tile][slot_cap][8 words]; slots [first_new, first_new + n_new) are cleared first
 int orr_batch_launch_term_bits(const uint32_t* terms32, int slots, int64_t rows, const void* table, int table_slots,
                                uint32_t* bits, int64_t slot_cap, int first_new, int n_new, cudaStream_t st);
@@ -217,6 +224,23 @@ constexpr float ORR_BATCH_EPS = 2.0e-4f;     // bound on |bf16x3 GEMM score - ex
 
 // text
 uint64_t orr_hash_bytes(const char* s, int64_t n);
+std::vector<std::string> orr_distinct_lower_tokens(const char* s, int64_t n);   // white-space split, lower-case, distinct (A-2)
+bool orr_is_stop_word(const std::string& t);
+std::string orr_lower_invariant(const char* s, int64_t n);
+
+// live vocabulary + substring expansion of query terms (orr_vocab.cu); the caller serialises access
+struct OrrVocab;
+OrrVocab* orr_vocab_new(int device);
+void orr_vocab_free(OrrVocab* v);
+uint32_t orr_vocab_add(OrrVocab* v, const char* word, size_t len, uint32_t count);   // returns the word's id; count = chunks holding it
+void orr_vocab_release(OrrVocab* v, uint32_t id);
+void orr_vocab_clear(OrrVocab* v);
+uint64_t orr_vocab_live_words(const OrrVocab* v);
+uint64_t orr_vocab_words(const OrrVocab* v);
+void orr_vocab_serialize(const OrrVocab* v, std::vector<uint8_t>* out);
+int orr_vocab_deserialize(OrrVocab* v, const uint8_t* p, size_t len);
+int orr_vocab_expand(OrrVocab* v, const std::vector<std::string>& terms, uint64_t* probe_hash, int32_t* probe_term, int32_t cap,
+                     int32_t* n_probes);
 #if defined(__CUDACC__)
 __host__ __device__
 #endif

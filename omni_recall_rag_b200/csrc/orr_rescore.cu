@@ -17,211 +17,13 @@
 // the reference tie chain (score desc with NaN last, CreatedAtUtc desc, row asc — :34-35 plus
 // the stable-sort fallback), runs the selection bound check and emits hits.
 #include <cfloat>
-#include <cub/device/device_radix_sort.cuh>
-
 #include <cuda_fp16.h>
 
 #include "orr_internal.h"
 
+#include "orr_exact_row.cuh"
+
 namespace {
-
-constexpr uint32_t FULL = 0xffffffffu;
-
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
-struct ExactArgs {
-    OrrShard  sh;
-    const float* q;
-    int32_t   q_dim;             // 0 => no query embedding (cosine 0, :71)
-    OrrProbes pr;
-    OrrWeights w;
-    int64_t   now_ticks;
-    // text mode (orr_search_text): the keyword matches come from per-term row bitmaps produced by the
-    // substring kernel (orr_textmatch.cu) instead of the hashed term table
-    const uint32_t* kw_bits;     // [kw_terms][kw_row_words] or NULL
-    int64_t   kw_row_words;
-    int32_t   kw_terms;
-};
-template <class A> __device__ __forceinline__ const uint32_t* kw_bits_of(const A&) { return nullptr; }
-__device__ __forceinline__ const uint32_t* kw_bits_of(const ExactArgs& a) { return a.kw_bits; }
-template <class A> __device__ __forceinline__ int kw_terms_of(const A&) { return 0; }
-__device__ __forceinline__ int kw_terms_of(const ExactArgs& a) { return a.kw_terms; }
-template <class A> __device__ __forceinline__ int kw_count_from_bits(const A&, int64_t, int) { return 0; }
-__device__ __forceinline__ int kw_count_from_bits(const ExactArgs& a, int64_t row, int lane) {
-    int cnt = 0;
-    for (int t = lane; t < a.kw_terms; t += 32)
-        cnt += (int)((__ldg(a.kw_bits + (int64_t)t * a.kw_row_words + (row >> 5)) >> (row & 31)) & 1u);
-    return __reduce_add_sync(0xffffffffu, cnt);
-}
-
-// Loads are issued in batches of EX_CHUNK float4 per lane BEFORE the dependent fp64 chains
-// so a row costs ~2 memory round trips instead of one per 128 columns; the ORDER of the fp64
-// additions (lane-strided, increasing column, then the shuffle butterfly) is unchanged.
-constexpr int EX_CHUNK = 12;
-
-// fp64 ||q||^2 in the lane-strided order; all lanes return the same value
-template <class A>
-__device__ __forceinline__ double exact_qnorm_q(const A& a, const float* q, int lane) {
-    double nA = 0.0;
-    const int nv4 = a.sh.dim >> 2;
-    const float4* q4 = reinterpret_cast<const float4*>(q);
-    for (int base = 0; base < nv4; base += 32 * EX_CHUNK) {
-        float4 v[EX_CHUNK];
-#pragma unroll
-        for (int j = 0; j < EX_CHUNK; ++j) {
-            const int i = base + j * 32 + lane;
-            v[j] = (i < nv4) ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < EX_CHUNK; ++j) {
-            if (base + j * 32 + lane < nv4) {
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].x, v[j].x));
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].y, v[j].y));
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].z, v[j].z));
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].w, v[j].w));
-            }
-        }
-    }
-    return warp_sum_f64(nA);
-}
-
-// The exact fused score of one row in two steps, so that callers holding many rows per warp can run the scalar
-// fp64 tail (2 sqrt, 4 divides, exp: ~200 instructions) once per LANE instead of once per warp:
-//   exact_row_partial — warp-collective: fp64 dot and ||b||^2 (lane-strided order + butterfly), keyword matches,
-//                       ticks; every lane returns the same values;
-//   exact_row_finish  — per thread: CosineSimilarity's tail, KeywordScore's ratio, RecencyScore, ScoreChunk.
-// exact_row_q = finish(partial): every path computes a row's score with the same operations on the same values.
-struct ExactPartial {
-    double  dot, nB;
-    int32_t matches;             // distinct query terms the row's content holds
-    int32_t kw_den;              // KeywordScore's denominator (-1 = no keyword side)
-    int64_t ticks;
-};
-
-// CHUNK = float4 loads per lane issued before the dependent fp64 chains; Q_SHARED = q lives in shared memory.
-template <class A, int CHUNK = EX_CHUNK, bool Q_SHARED = false, class P = OrrProbes>
-__device__ __forceinline__ ExactPartial exact_row_partial(const A& a, const float* q, const P& pr, int64_t row, int lane) {
-    ExactPartial r;
-    r.ticks = a.sh.ticks[row];
-    // term hashes are fetched up front so their latency overlaps the embedding loads
-    uint64_t th[4] = {0, 0, 0, 0};
-    const int n_probes = orr_probe_count(pr);
-    if (n_probes > 0) {
-        const int spl = a.sh.slots >> 5;
-        const uint64_t* t64 = a.sh.terms64 + row * (int64_t)a.sh.slots;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) if (w < spl) th[w] = __ldg(t64 + w * 32 + lane);
-    }
-    double dot = 0.0, nB = 0.0;
-    if (a.q_dim == a.sh.dim && a.q_dim > 0) {                       // :71-72 length check
-        const int nv4 = a.sh.dim >> 2;
-        const float4* x4 = reinterpret_cast<const float4*>(a.sh.emb + row * (int64_t)a.sh.dim);
-        const float4* q4 = reinterpret_cast<const float4*>(q);
-        for (int base = 0; base < nv4; base += 32 * CHUNK) {
-            float4 x[CHUNK];
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const int i = base + j * 32 + lane;
-                x[j] = (i < nv4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (Q_SHARED) {
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
-                    const int i = base + j * 32 + lane;
-                    if (i < nv4) {
-                        const float4 v = q4[i];
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
-                    }
-                }
-            } else {
-                float4 v[CHUNK];
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
-                    const int i = base + j * 32 + lane;
-                    v[j] = (i < nv4) ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
-                    if (base + j * 32 + lane < nv4) {
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
-                    }
-                }
-            }
-        }
-        dot = warp_sum_f64(dot);
-        nB = warp_sum_f64(nB);
-    }
-    r.dot = dot; r.nB = nB;
-    r.matches = 0; r.kw_den = -1;
-    if (kw_bits_of(a) != nullptr) {
-        r.matches = kw_count_from_bits(a, row, lane);
-        r.kw_den = kw_terms_of(a);
-    } else if (n_probes > 0) {                                      // :110-112
-        uint32_t m0 = 0, m1 = 0;
-        for (int p = 0; p < n_probes; ++p) {
-            const uint64_t h = pr.h64[p];
-            const bool hit = (th[0] == h) | (th[1] == h) | (th[2] == h) | (th[3] == h);
-            if (hit) {
-                const uint32_t t = orr_probe_term(pr, p);
-                if (t < 32) m0 |= 1u << t; else m1 |= 1u << (t - 32);
-            }
-        }
-        m0 = __reduce_or_sync(FULL, m0);
-        m1 = __reduce_or_sync(FULL, m1);
-        r.matches = __popc(m0) + __popc(m1);
-        r.kw_den = pr.n_terms;
-    }
-    return r;
-}
-
-template <class A>
-__device__ __forceinline__ double exact_row_finish(const A& a, double nA, const ExactPartial& r) {
-    double cosv = 0.0;
-    if (a.q_dim == a.sh.dim && a.q_dim > 0) {
-        if (!(nA <= 0.0) && !(r.nB <= 0.0))                           // :84-85 (NaN falls through)
-            cosv = __ddiv_rn(r.dot, __dmul_rn(__dsqrt_rn(nA), __dsqrt_rn(r.nB)));   // :87
-    }
-    const double kw = r.kw_den != -1 ? __ddiv_rn((double)r.matches, (double)r.kw_den) : 0.0;   // :112
-    // RecencyScore: TimeSpan.TotalDays = ticks / 864e9; Math.Max(0, .); exp(-age/30)
-    double age = __ddiv_rn((double)(a.now_ticks - r.ticks), 864000000000.0);
-    if (!(age > 0.0)) age = 0.0;
-    const double rec = exp(__ddiv_rn(-age, a.w.recency_days));
-    // ScoreChunk :66
-    return __dadd_rn(__dadd_rn(__dmul_rn(cosv, a.w.w_cos), __dmul_rn(kw, a.w.w_kw)),
-                     __dmul_rn(rec, a.w.w_rec));
-}
-
-// exact fused score of one row, computed by a full warp; all lanes return the same value.
-template <class A, int CHUNK = EX_CHUNK, bool Q_SHARED = false, class P = OrrProbes>
-__device__ __forceinline__ double exact_row_q(const A& a, const float* q, const P& pr, int64_t row,
-                                              int lane, double nA, int64_t* ticks_out) {
-    const ExactPartial r = exact_row_partial<A, CHUNK, Q_SHARED, P>(a, q, pr, row, lane);
-    *ticks_out = r.ticks;
-    return exact_row_finish(a, nA, r);
-}
-__device__ __forceinline__ double exact_qnorm(const ExactArgs& a, int lane) { return exact_qnorm_q(a, a.q, lane); }
-__device__ __forceinline__ double exact_row(const ExactArgs& a, int64_t row, int lane, double nA, int64_t* ticks_out) {
-    return exact_row_q(a, a.q, a.pr, row, lane, nA, ticks_out);
-}
-
-// reference ordering: true if x ranks strictly before y
-__device__ __forceinline__ bool ranks_before(const OrrExact& x, const OrrExact& y) {
-    const bool xn = (x.score != x.score), yn = (y.score != y.score);
-    if (xn != yn) return yn;                                          // NaN last (:34)
-    if (!xn && x.score != y.score) return x.score > y.score;
-    if (x.ticks != y.ticks) return x.ticks > y.ticks;                 // :35
-    return x.row < y.row;                                             // stable fallback (A-6)
-}
 
 struct RescoreArgs {
     ExactArgs ex;
@@ -308,72 +110,6 @@ __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
         *a.ticket = 0;                                                // re-arm
         __threadfence();
     }
-}
-
-// ---- exact path: every row's score -------------------------------------------------------
-// key for a descending radix sort: larger = ranks earlier; dead rows 0, NaN 1
-__device__ __forceinline__ uint64_t score_key(double s, bool dead) {
-    if (dead) return 0ull;
-    if (s != s) return 1ull;
-    const uint64_t b = (uint64_t)__double_as_longlong(s);
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-
-__global__ void __launch_bounds__(256) orr_exact_scores_kernel(const ExactArgs a, double* scores,
-                                                               uint64_t* tick_keys, uint32_t* vals) {
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const bool has_q = (a.q_dim == a.sh.dim && a.q_dim > 0);
-    const double nA = has_q ? exact_qnorm(a, lane) : 0.0;
-    // a warp takes 32 consecutive rows: the warp-collective part row by row (lane j keeps row j's partial result),
-    // then the scalar fp64 tail once per lane and coalesced stores
-    const int64_t n_blocks = (a.sh.rows + 31) >> 5;
-    for (int64_t blk = gw; blk < n_blocks; blk += W) {
-        const int64_t row0 = blk << 5;
-        const int n_here = (int)min((int64_t)32, a.sh.rows - row0);
-        ExactPartial mine;
-        mine.dot = 0.0; mine.nB = 0.0; mine.matches = 0; mine.kw_den = -1; mine.ticks = 0;
-        for (int j = 0; j < n_here; ++j) {
-            const ExactPartial r = exact_row_partial(a, a.q, a.pr, row0 + j, lane);
-            if (lane == j) mine = r;
-        }
-        if (lane < n_here) {
-            const int64_t row = row0 + lane;
-            scores[row] = exact_row_finish(a, nA, mine);
-            // first sort key: CreatedAtUtc, descending (flip the sign bit for unsigned order)
-            tick_keys[row] = (uint64_t)mine.ticks ^ 0x8000000000000000ull;
-            vals[row] = (uint32_t)row;
-        }
-    }
-}
-
-__global__ void orr_gather_score_keys(const double* scores, const int64_t* ticks, const uint32_t* vals,
-                                      uint64_t* keys, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const uint32_t r = vals[i];
-        keys[i] = score_key(scores[r], ticks[r] == ORR_DEAD_TICKS);
-    }
-}
-
-__global__ void orr_emit_sorted(const uint64_t* keys, const uint32_t* vals, const double* scores,
-                                const int64_t* ticks, uint64_t row_base, int64_t n, int top_k,
-                                orr_hit* hits, int32_t* status) {
-    const int k = max(1, top_k);
-    __shared__ int s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < k && i < n; i += blockDim.x) {
-        if (keys[i] != 0ull) {                                        // dead rows sort to the end
-            const uint32_t r = vals[i];
-            orr_hit h; h.row = row_base + r; h.score = scores[r]; h.created_ticks = ticks[r];
-            hits[i] = h;
-            atomicAdd(&s_n, 1);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { status[0] = s_n; status[1] = 0; }
 }
 
 // ---- merge of all-gathered per-GPU hit lists (multi-GPU) -----------------------------------
@@ -547,12 +283,6 @@ __global__ void __launch_bounds__(256) orr_xchg_merge_kernel(const OrrXchgArgs a
 
 }  // namespace
 
-static void fill_exact_args(ExactArgs& e, const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
-                            const OrrWeights& w, int64_t now_ticks, int q_dim) {
-    e.sh = sh; e.q = sc.q; e.q_dim = q_dim; e.pr = pr; e.w = w; e.now_ticks = now_ticks;
-    e.kw_bits = sc.kw_bits; e.kw_row_words = sc.kw_row_words; e.kw_terms = sc.kw_terms;
-}
-
 int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
                        const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
                        int n_listed_max, bool check_bound, cudaStream_t st) {
@@ -576,52 +306,6 @@ int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes
     while (np2 < n_listed_max) np2 <<= 1;
     const int grid = (n_listed_max + 3) / 4;
     orr_rescore_kernel<<<grid, 128, np2 * sizeof(OrrExact), st>>>(a);
-    ORR_CUDA_OK(cudaGetLastError());
-    return ORR_OK;
-}
-
-int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
-                            const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st) {
-    if (sh.rows == 0) return ORR_OK;
-    ExactArgs e;
-    fill_exact_args(e, sh, sc, pr, w, now_ticks, q_dim);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    orr_exact_scores_kernel<<<sms * 8, 256, 0, st>>>(e, sc.scores64, sc.sort_keys[0], sc.sort_vals[0]);
-    ORR_CUDA_OK(cudaGetLastError());
-    return ORR_OK;
-}
-
-// two stable LSD passes: by CreatedAtUtc desc (initial order = row asc), then by score desc
-int orr_exact_select(const OrrShard& sh, OrrScratch& sc, int top_k, cudaStream_t st) {
-    const int64_t n = sh.rows;
-    if (n == 0) {
-        ORR_CUDA_OK(cudaMemsetAsync(sc.status, 0, 2 * sizeof(int32_t), st));
-        return ORR_OK;
-    }
-    if (n > 0x7fffffff) { orr_set_error("exact path: shard too large"); return ORR_E_UNSUPPORTED; }
-    size_t need = 0;
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, need, sc.sort_keys[0], sc.sort_keys[1],
-                                              sc.sort_vals[0], sc.sort_vals[1], (int)n, 0, 64, st);
-    if (need > sc.cub_tmp_bytes) {
-        if (sc.cub_tmp) cudaFree(sc.cub_tmp);
-        sc.cub_tmp = nullptr; sc.cub_tmp_bytes = 0;
-        ORR_CUDA_OK(cudaMalloc(&sc.cub_tmp, need));
-        sc.cub_tmp_bytes = need;
-    }
-    size_t bytes = sc.cub_tmp_bytes;
-    ORR_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(sc.cub_tmp, bytes, sc.sort_keys[0], sc.sort_keys[1],
-                                                          sc.sort_vals[0], sc.sort_vals[1], (int)n, 0, 64, st));
-    const int threads = 256;
-    orr_gather_score_keys<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
-        sc.scores64, sh.ticks, sc.sort_vals[1], sc.sort_keys[0], n);
-    ORR_CUDA_OK(cudaGetLastError());
-    bytes = sc.cub_tmp_bytes;
-    ORR_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(sc.cub_tmp, bytes, sc.sort_keys[0], sc.sort_keys[1],
-                                                          sc.sort_vals[1], sc.sort_vals[0], (int)n, 0, 64, st));
-    orr_emit_sorted<<<1, 256, 0, st>>>(sc.sort_keys[1], sc.sort_vals[0], sc.scores64, sh.ticks, sh.row_base, n,
-                                       top_k, sc.hits, sc.status);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
@@ -797,6 +481,7 @@ struct BatchFinArgs {
     const float* thr;                 // [B]
     int32_t cap, n_surv, top_k, k_stride;
     double eps;
+    const int32_t* qbad;              // [B] 1 = the screen could not rank this query (norm outside fp32): always unproven
     orr_hit* hits;                    // [B][k_stride]
     int32_t* status;                  // [B][2]
 };
@@ -812,6 +497,7 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
     const uint32_t total = a.cand_count[b];
     const int c = (int)min(total, (uint32_t)a.cap);
     int flags = total > (uint32_t)a.cap ? 2 : 0;                             // candidate list overflowed
+    if (a.qbad != nullptr && a.qbad[b]) flags |= 1;
     const uint2* src = a.cand + (int64_t)b * a.cap;
     // key = (monotone score key, ~row): unique per candidate, larger = better (ties: lower row first)
     for (int i = tid; i < c; i += BATCH_FIN_THREADS) {
@@ -1100,15 +786,15 @@ int orr_batch_launch_threshold(const void* dense, int dense_half, int64_t ld, in
 
 int orr_batch_launch_finalize(const OrrShard& sh, const float* q, int q_dim, const OrrBatchProbes* probes, const OrrWeights& w,
                               int64_t now_ticks, const void* cand, const uint32_t* cand_count, const float* thr, int cap,
-                              int n_surv, int top_k, int k_stride, double eps, orr_hit* hits, int32_t* status, int batch,
-                              cudaStream_t st) {
+                              int n_surv, int top_k, int k_stride, double eps, const int32_t* qbad, orr_hit* hits, int32_t* status,
+                              int batch, cudaStream_t st) {
     if (n_surv > ORR_BATCH_MAX_SURV || (cap & (cap - 1)) != 0) { orr_set_error("batch finalize: bad sizes"); return ORR_E_INTERNAL; }
     const int smem = cap * 8 + ORR_BATCH_MAX_SURV * (int)sizeof(OrrExact) + sh.dim * (int)sizeof(float);
     ORR_SMEM_OPT_IN((orr_batch_finalize_kernel), 8192 * 8 + ORR_BATCH_MAX_SURV * 24 + 8192 * 4);
     BatchFinArgs a;
     a.ex.sh = sh; a.ex.q_dim = q_dim; a.ex.w = w; a.ex.now_ticks = now_ticks;
     a.q = q; a.probes = probes; a.cand = (const uint2*)cand; a.cand_count = cand_count; a.thr = thr;
-    a.cap = cap; a.n_surv = n_surv; a.top_k = top_k; a.k_stride = k_stride; a.eps = eps; a.hits = hits; a.status = status;
+    a.cap = cap; a.n_surv = n_surv; a.top_k = top_k; a.k_stride = k_stride; a.eps = eps; a.qbad = qbad; a.hits = hits; a.status = status;
     orr_batch_finalize_kernel<<<batch, BATCH_FIN_THREADS, smem, st>>>(a);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;

@@ -149,6 +149,7 @@ struct ScanArgs {
     const uint32_t* bm_bits;     // [n_bm][bm_row_words] or NULL
     int64_t   bm_row_words;
     int32_t   n_bm;
+    float*    dense;             // diagnostic (orr_debug_scan_scores): every row's fp32 scan score, or NULL
 };
 
 // ---- the per-row fp32 epilogue ---------------------------------------------------------
@@ -217,21 +218,30 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
     __syncthreads();
 
     float4 qr[NV > 0 ? NV : 1];
-    float qn = 0.f;
+    float qn = 0.f, qmax = 0.f;
     if (NV > 0) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             qr[j] = reinterpret_cast<const float4*>(sq)[j * 32 + lane];
             qn += qr[j].x * qr[j].x + qr[j].y * qr[j].y + qr[j].z * qr[j].z + qr[j].w * qr[j].w;
+            qmax = fmaxf(qmax, fmaxf(fmaxf(fabsf(qr[j].x), fabsf(qr[j].y)), fmaxf(fabsf(qr[j].z), fabsf(qr[j].w))));
         }
     } else {
         for (int i = lane; i < nv4; i += 32) {
             float4 v = reinterpret_cast<const float4*>(sq)[i];
             qn += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            qmax = fmaxf(qmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
     }
     qn = warp_sum(qn);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(FULL, qmax, o));
     const float inv_qn = (qn > 0.f) ? rsqrtf(qn) : 0.f;            // :84 normA <= 0 -> 0
+    // The selection proof assumes |fp32 score - exact| <= eps, which needs ||q||^2 representable in fp32: a query whose
+    // squared norm under/overflows (|q_i| ~ 1e-20 or 1e+19; the reference accumulates it in fp64 and returns a real
+    // cosine) or holds NaN makes every fp32 cosine meaningless.  An all-zero query is fine (cosine 0 everywhere, :84).
+    // Such a query reports tau = +inf: K3's bound check fails and the caller escalates to the exact path.
+    const bool q_unscreenable = !(qmax == 0.f) && !(qn >= 1e-30f && qn <= 1e30f);
 
     // ---- per-warp pipeline over interleaved tiles ----
     const int64_t rows = a.sh.rows;
@@ -292,6 +302,7 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
                 const int64_t ticks = __shfl_sync(FULL, ptk, r);
                 const int bm = a.n_bm ? __popc(__ballot_sync(FULL, (pbw >> ((uint32_t)(pr0 + r) & 31u)) & 1u)) : 0;
                 const float s = fuse_row(a, dot, nb, inv_qn, ticks, pth[r], spl, bm);
+                if (a.dense != nullptr && lane == 0) a.dense[pr0 + r] = s;
                 if (s > wmin) {                                          // warp-uniform
                     if (lane == wmin_lane) { es = s; er = (uint32_t)(pr0 + r); }
                     const uint32_t k = order_key(es);
@@ -508,6 +519,7 @@ __global__ void __launch_bounds__(ORR_SCAN_WARPS * 32, 1) orr_scan_kernel(const 
     if (tid == 0) {
         float t = (total_real > (uint32_t)M) ? key_to_float(T) : -INFINITY;
         for (int w = 0; w < a.warps; ++w) t = fmaxf(t, s_wtau[w]);
+        if (q_unscreenable) t = INFINITY;
         const uint32_t n_eq = (total_real > (uint32_t)M) ? min(s_cnt_eq, need_eq) : 0u;
         a.sel[0] = (int32_t)(n_gt + n_eq);
         a.sel[1] = __float_as_int(t);
@@ -592,6 +604,7 @@ int orr_launch_scan(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& p
     a.sel = sc.sel;
     a.surv_rows = sc.surv_rows;
     a.bm_bits = nullptr; a.bm_row_words = 0; a.n_bm = 0;
+    a.dense = sc.scan_dense;
     if (sc.kw_bits) {
         if (sc.kw_terms < 1 || sc.kw_terms > 32 || pr.n_probes > 0) { orr_set_error("scan: bitmap terms must be 1..32 and exclusive of probes"); return ORR_E_INTERNAL; }
         a.bm_bits = sc.kw_bits; a.bm_row_words = sc.kw_row_words; a.n_bm = sc.kw_terms;

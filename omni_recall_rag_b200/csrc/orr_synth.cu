@@ -187,6 +187,26 @@ int orr_synth_query_host(const orr_synth_spec* spec, uint64_t qi, uint64_t corpu
     return ORR_OK;
 }
 
+// Content of synthetic row `row`: its tokens joined by single spaces (what the reference's chunker would have stored,
+// SlidingWindowTextChunker.cs:29); returns the byte length (9 * terms_per_chunk - 1), or a negative code.
+int64_t orr_synth_row_text(const orr_synth_spec* spec, uint64_t row, char* out, int64_t cap) {
+    if (!synth_spec_ok(spec) || !out) return ORR_E_INVALID;
+    const int tpc = spec->terms_per_chunk;
+    const int64_t len = tpc > 0 ? 9 * (int64_t)tpc - 1 : 0;
+    if (cap < len) { orr_set_error("orr_synth_row_text: buffer too small"); return ORR_E_INVALID; }
+    uint32_t ids[128];
+    orr_synth_chunk_terms(spec->seed, orr_synth_content_row(spec->seed, row, spec->dup_row_ppm), tpc, ids);
+    int64_t o = 0;
+    for (int s = 0; s < tpc; ++s) {
+        if (s) out[o++] = ' ';
+        uint32_t v = ids[s];
+        out[o] = 't';
+        for (int d = 7; d >= 1; --d) { out[o + d] = (char)('0' + v % 10u); v /= 10u; }
+        o += 8;
+    }
+    return len;
+}
+
 int orr_synth_term_text(uint32_t term_id, char* out9) {
     if (!out9 || term_id >= (1u << ORR_SYNTH_VOCAB_LOG2)) return ORR_E_INVALID;
     snprintf(out9, 9, "t%07u", term_id);

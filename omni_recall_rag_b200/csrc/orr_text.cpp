@@ -120,6 +120,24 @@ bool is_stop_word(const std::string& t) {
 
 }  // namespace
 
+// ---- shared with the text-level entry points of orr_api.cu --------------------------------------------------
+std::vector<std::string> orr_distinct_lower_tokens(const char* s, int64_t n) { return distinct_lower_tokens(s, n); }
+bool orr_is_stop_word(const std::string& t) { return is_stop_word(t); }
+// ToLowerInvariant over a whole string (white space kept): what text mode stores per chunk (:110)
+std::string orr_lower_invariant(const char* s, int64_t n) {
+    std::string out;
+    out.reserve((size_t)(n > 0 ? n : 0));
+    Utf8Cursor it{(const unsigned char*)s, (const unsigned char*)s + (n > 0 ? n : 0)};
+    while (!it.done()) {
+        const unsigned char* at = it.p;
+        int nb = 0;
+        const uint32_t c = it.next(&nb);
+        if (nb == 1 && *at >= 0x80) { out.push_back((char)*at); continue; }   // malformed byte
+        put_utf8(out, fold(c));
+    }
+    return out;
+}
+
 void orr_set_error(const char* fmt, ...) {
     char buf[512];
     va_list ap;

@@ -202,6 +202,33 @@ class RecallShard:
                                                              p(flat), p(off), p(out_rows)))
         return out_rows[:n]
 
+    def upsert_document_texts(self, doc_key: int, emb: Optional[np.ndarray], ticks: np.ndarray, contents: Sequence[str],
+                              has_emb: Optional[np.ndarray] = None) -> np.ndarray:
+        """orr_store_upsert_document_texts: Content strings as the reference holds them; the library lower-cases,
+        tokenises, hashes and maintains the live vocabulary (and keeps the text in HBM with option keep_text)."""
+        ticks = np.ascontiguousarray(ticks, dtype=np.int64)
+        n = int(ticks.shape[0])
+        if len(contents) != n:
+            raise ValueError(f"{len(contents)} contents for {n} chunks")
+        if emb is not None:
+            emb = np.ascontiguousarray(emb, dtype=np.float32)
+            if emb.shape != (n, self.dim):
+                raise ValueError(f"emb must be ({n}, {self.dim}), got {emb.shape}")
+        if has_emb is not None:
+            has_emb = np.ascontiguousarray(has_emb, dtype=np.uint8)
+        enc = [(c or "").encode("utf-8") for c in contents]
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        coff[1:] = np.cumsum([len(b) for b in enc])
+        blob = b"".join(enc) or b"\0"
+        out_rows = np.zeros(max(n, 1), dtype=np.uint64)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        N.check(N.lib().orr_store_upsert_document_texts(self._h, doc_key, n, p(emb), p(has_emb), p(ticks), blob, p(coff), p(out_rows)))
+        return out_rows[:n]
+
+    @property
+    def vocab_size(self) -> int:
+        return int(N.lib().orr_store_vocab_size(self._h))
+
     def delete_document(self, doc_key: int) -> None:
         N.check(N.lib().orr_store_delete_document(self._h, doc_key))
 
@@ -252,6 +279,22 @@ class RecallShard:
             ph.ctypes.data_as(C.c_void_p) if ph.size else None,
             None if pt is None else pt.ctypes.data_as(C.c_void_p), int(ph.size),
             int(now_ticks), int(top_k), int(candidate_cap), C.cast(out, C.c_void_p), C.byref(n)))
+        return _hits_from(out, n.value)
+
+    def search_query(self, query: str, q: Optional[np.ndarray], now_ticks: int, top_k: int, candidate_cap: int = 0,
+                     keyword_mode: int = 0) -> Hits:
+        """orr_search_query: the query STRING in; tokenising, stop words, vocabulary expansion (GPU) and the search
+        happen behind the C ABI.  keyword_mode 0 = auto, 1 = hashed probes only, 2 = text mode only."""
+        if q is None:
+            q = np.zeros(0, dtype=np.float32)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        k = max(1, int(top_k))
+        out = (N.OrrHit * k)()
+        n = C.c_int32(0)
+        b = query.encode("utf-8")
+        N.check(N.lib().orr_search_query(self._h, b, len(b), q.ctypes.data_as(C.c_void_p) if q.size else None, int(q.size),
+                                         int(now_ticks), int(top_k), int(candidate_cap), int(keyword_mode),
+                                         C.cast(out, C.c_void_p), C.byref(n)))
         return _hits_from(out, n.value)
 
     def search_text(self, q: Optional[np.ndarray], terms_lower: Sequence[str], now_ticks: int, top_k: int,
@@ -305,6 +348,18 @@ class RecallShard:
                                          p(bt.probe_term) if bt else None, p(bt.probe_offsets) if bt else None,
                                          int(now_ticks), int(top_k), p(raw), p(n_out)))
         return BatchHits(raw[:B], n_out[:B])
+
+    def debug_scan_scores(self, q: np.ndarray, terms: QueryTerms, now_ticks: int) -> np.ndarray:
+        """The fp32 score the fused scan computes for every physical row (orr_debug_scan_scores)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        out = np.zeros(max(self.rows_used, 1), dtype=np.float32)
+        ph = np.ascontiguousarray(terms.probe_hash, dtype=np.uint64)
+        pt = None if terms.probe_term is None else np.ascontiguousarray(terms.probe_term, dtype=np.int32)
+        N.check(N.lib().orr_debug_scan_scores(
+            self._h, q.ctypes.data_as(C.c_void_p), int(q.size), int(terms.n_terms),
+            ph.ctypes.data_as(C.c_void_p) if ph.size else None, None if pt is None else pt.ctypes.data_as(C.c_void_p),
+            int(ph.size), int(now_ticks), out.ctypes.data_as(C.c_void_p), out.shape[0]))
+        return out[: self.rows_used]
 
     def debug_batch_scores(self, q: np.ndarray, now_ticks: int, tile_stride: int = 1) -> np.ndarray:
         """Raw fused GEMM scores (w_cos*cos + w_rec*rec) of every stride-th 256-row tile: [B, n]."""
