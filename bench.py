@@ -3,30 +3,34 @@
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
 
-A "step" is one hybrid query (0.7 cosine + 0.2 keyword + 0.1 recency, 4 query terms, top-10)
-over the whole HBM-resident corpus.  At N=1 the corpus is BASELINE.json configs[1]
-(1M chunks x 3072 fp32, ~12.3 GB).  For N>1 the corpus is row-sharded, 1M rows per GPU (weak
-scaling; --rows-per-gpu 5000000 gives configs[3], 40M rows on 8 GPUs): every rank scans its
-shard, computes its exact local top-10, and the lists are all-gathered over NCCL and merged.
+A "step" is one hybrid query (0.7 cosine + 0.2 keyword + 0.1 recency, 4 query terms, top-10) over the whole
+HBM-resident corpus.
 
-    value  = (total rows / 1M) x queries / second, device-timed (CUDA events, max over ranks),
-             query already in HBM: "1M x 3072 scans per second".  At N=1 this is plain QPS.
-    e2e    = the same through the public host API (ShardedRecall.search -> orr_search): the
-             query is copied from pinned host memory and the hits are read back every step.
-    roofline = algorithmic bytes of the scan kernel / its CUDA-event duration vs the
-             measured HBM copy bandwidth (MEASURED_PEAKS.json).
-    cpu_baseline = the C oracle (a port of the reference's C# scorer; the C# cannot run
-             here) timed on this box's host cores on a bounded sample of the same corpus.
+  N = 1   the corpus is BASELINE.json configs[1]: 1M chunks x 3072 fp32 (~12.3 GB).  The line also carries, under
+          "configs", every other BASELINE config measured in the same process — c1 (configs[0], 10k x 3072, the reference's
+          own CPU-runnable case), c3 (configs[2], 5M x 768, batch 1024, top-100: tcgen05 path), c5 (configs[4],
+          keyword-heavy batch 256, top-50), c2_noemb (the reference's DEFAULT configuration: no embeddings, keyword +
+          recency only, on the 1M corpus) — each with value / e2e / roofline / cpu_baseline, and "e2e_service": the
+          query STRING in, citations out, through GpuRecallSearchService (tokenise, vocabulary expansion on the GPU
+          over a 1M-word vocabulary, orr_search, citation build).  --headline-only skips them.
+  N > 1   row-sharded, 5M rows per GPU by default (N = 8 is configs[3]: 40M x 3072, 61 GB per GPU; weak scaling): every
+          rank scans its shard, computes its exact local top-10, and the lists meet in a fused peer-memory all-gather +
+          merge kernel over NVLink.  "rows_1m_per_gpu" repeats the measurement with 1M rows per GPU.
 
---workload c3 | c5 (N=1 only) benches the batched path instead — BASELINE.json configs[2] and
-configs[4]: 5M x 768, batch 1024 top-100 (4 terms) / batch 256 top-50 (16 terms, tie-heavy) — a
-"step" is one orr_search_batch call; roofline.bound is "tensor" (useful 2*N*D*B flops of the main
-tcgen05 pass against the measured bf16 throughput).  The default line stays the headline metric.
+    value  = (total rows / 1M) x queries / second, device-timed (CUDA events, max over ranks), query already in
+             HBM: "1M x 3072 scans per second".  At N=1 this is plain QPS.
+    e2e    = the same through the public host API (ShardedRecall.search -> orr_search): the query is copied from
+             pinned host memory and the hits are read back every step.
+    roofline = algorithmic bytes of the scan kernel / its CUDA-event duration vs the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json).
+    cpu_baseline = the C oracle (a port of the reference's C# scorer; the C# cannot run here) timed on this box's host
+             cores on a bounded sample of the same corpus.
 
---workload c1 (N=1) is BASELINE.json configs[0], the reference's own CPU-runnable case, in full: 10k x 3072,
-single query, top-10, with the reference's 300-most-recent pre-selection (InMemoryIngestionStore.cs:57-65,
-candidate_cap=300 — the line's value) and over all rows (cap=0, under "all_rows"); the CPU port runs the
-whole workload (no sampling) on 1 thread (the reference's own execution) and on all threads.
+--impl reference: the oracle port alone on all host threads.  It generates its corpus with the oracle library's own
+generator (never loads liborr.so) and every step scans the WHOLE sample it reports — 1M x 3072 rows when the host has
+the memory — so ms_per_step is a measurement, not an extrapolation.
+
+--workload c1 | c3 | c5 (N=1) prints that config alone as the line (profiling runs).
 """
 from __future__ import annotations
 
@@ -51,10 +55,11 @@ N_TERMS = 4
 TERM_SLOTS = 64
 FALLBACK_HBM_GBS = 6650.0
 FALLBACK_BF16_TFLOPS = 1500.0
-# dram__bytes_read.sum + dram__bytes_write.sum of orr_scan_kernel<24,1,0> per launch at 1M x 3072, 4 terms,
-# from the ncu --set full capture summarised in profiles/r01_final_kernels.md (12.5533 GB read + 3.6 MB
-# written); scales linearly with rows.
+# dram__bytes_read.sum + dram__bytes_write.sum of orr_scan_kernel<24,1,0> per launch and row at 1M x 3072, 4 terms: a
+# CONSTANT taken from the ncu --set full capture summarised in the file below (not measured in this run); it scales
+# linearly with rows.
 NCU_SCAN_TRAFFIC_BYTES_PER_ROW = 12556.9
+NCU_SCAN_TRAFFIC_SOURCE = "profiles/r01_final_kernels.md"
 BATCH_WORKLOADS = {
     "c3": dict(rows=5_000_000, dim=768, batch=1024, top_k=100, n_terms=4, frequent=0, dup_ppm=0,
                name="5M chunks x 768 fp32 (truncated embeddings), batch 1024 queries, 4 terms, top-100"),
@@ -62,6 +67,7 @@ BATCH_WORKLOADS = {
                name="keyword-heavy: 5M chunks x 768, 16-term queries (8 from the 1000 most frequent tokens), "
                     "planted duplicate rows, batch 256, top-50"),
 }
+PORT_NOTE = "C port of RecallSearchService.cs:20-119 (no dotnet in the image)"
 
 
 _REAL_STDOUT = None
@@ -83,6 +89,10 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+def note(msg: str) -> None:
+    print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -99,6 +109,10 @@ def measured_tensor_peak():
             return float(j["bf16_tflops"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured"
     except Exception:
         return FALLBACK_BF16_TFLOPS, FALLBACK_BF16_TFLOPS, "fallback"
+
+
+def hbm_peak_kind(kind: str) -> str:
+    return f"{kind} HBM copy GB/s (MEASURED_PEAKS.json)" if kind == "measured" else "fallback 6650 GB/s"
 
 
 class ClockSampler:
@@ -149,36 +163,62 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline_run(sample_rows: int, n_queries: int, threads: int, corpus_rows: int, min_seconds: float = 0.0):
-    """Times the oracle port on `sample_rows` rows of the same synthetic corpus; returns
-    1M x 3072 scans per second (linear in rows: the scorer is a per-row loop)."""
-    import numpy as np  # noqa: F401
-    from omni_recall_rag_b200 import synth
-    from oracle import oracle_c
+def p99(xs):
+    return sorted(xs)[min(len(xs) - 1, int(0.99 * len(xs)))]
 
-    spec = synth.make_spec(DIM)
-    rows = synth.rows_host(spec, 0, sample_rows)
-    blob, off = oracle_c.pack_contents(synth.contents_of(rows.term_ids))
-    queries = [synth.query_host(spec, qi, corpus_rows, n_terms=N_TERMS) for qi in range(n_queries)]
-    oracle_c.search(emb=rows.emb, dim=DIM, ticks=rows.ticks, content_blob=blob, content_off=off,
-                    query=queries[0].text, qvec=queries[0].q, now_ticks=spec.now_ticks, top_k=TOP_K, threads=threads)
+
+# ================================================================================================================
+# CPU side: the oracle port timed on the host cores.  Nothing here touches liborr.so: the corpus comes from the oracle
+# library's own generator (oracle/orr_oracle_stream.c, built from the header the device fill kernel uses).
+# ================================================================================================================
+class OracleCorpus:
+    """`rows` synthetic rows materialised on the host for the oracle: embeddings (optional), ticks, Content blob."""
+
+    def __init__(self, spec, rows: int, *, want_emb: bool = True):
+        from oracle import oracle_c
+        self.oc = oracle_c
+        self.spec, self.rows, self.dim = spec, rows, spec.dim
+        self.emb, self.ticks, tids = oracle_c.synth_rows(spec, 0, rows, want_emb=want_emb)
+        self.blob, self.off = oracle_c.synth_contents(tids)
+
+    def search(self, text: str, qvec, top_k: int, threads: int, candidate_cap: int = 0):
+        import numpy as np
+        return self.oc.search(emb=self.emb, dim=self.dim, ticks=self.ticks, content_blob=self.blob, content_off=self.off,
+                              query=text, qvec=np.zeros(0, np.float32) if qvec is None else qvec, now_ticks=self.spec.now_ticks,
+                              top_k=top_k, candidate_cap=candidate_cap, threads=threads)
+
+
+def timed_queries(fn, queries, min_seconds: float, min_queries: int):
+    """Runs fn(query) round-robin until both bounds are met; -> (queries/s, seconds, n)."""
+    fn(queries[0])
     t0 = time.perf_counter()
     done = 0
-    while True:                       # bounded by time: keep going until ~min_seconds of CPU work
-        q = queries[done % n_queries]
-        oracle_c.search(emb=rows.emb, dim=DIM, ticks=rows.ticks, content_blob=blob, content_off=off,
-                        query=q.text, qvec=q.q, now_ticks=spec.now_ticks, top_k=TOP_K, threads=threads)
+    while True:
+        fn(queries[done % len(queries)])
         done += 1
         dt = time.perf_counter() - t0
-        if dt >= min_seconds and done >= n_queries:
-            break
-    return (done / dt) * (sample_rows / 1.0e6), dt, done
+        if dt >= min_seconds and done >= min_queries:
+            return done / dt, dt, done
+
+
+def host_sample_rows(want_rows: int, bytes_per_row: int) -> int:
+    """The largest sample <= want_rows whose host copy fits comfortably in the box's free memory."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    rows = want_rows
+    while rows > 50_000 and rows * bytes_per_row > 0.6 * avail:
+        rows //= 2
+    return rows
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  The C# cannot be
-    built here (no dotnet), so this is the oracle port on all host threads; each step is one
-    query over a bounded sample of the corpus, scaled linearly to 1M rows."""
+    """--impl reference: the reference's own CPU implementation of the path.  The C# cannot be built here (no dotnet),
+    so this is the oracle port on all host threads.  Every step is one query over the whole sample the line reports
+    (1M x 3072 rows = the full configs[1] corpus when host memory allows); value is in the metric's unit, rows scanned
+    per second / 1M, so no step time is ever scaled."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -187,116 +227,100 @@ def run_reference(args):
     threads = oracle_c.max_threads()
     if args.workload == "c1":
         raise SystemExit("--impl reference --workload c1: the c1 line times the CPU port itself (cpu_baseline); use --workload c1")
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     if args.workload != "c2":
         wl = BATCH_WORKLOADS[args.workload]
-        sample, steps = 200_000, max(1, args.steps if args.steps != 200 else 20)
-        v, dt, n = oracle_batch_rate(wl, sample, steps, threads, 0.0)
+        sample = host_sample_rows(args.cpu_sample_rows or 500_000, 4 * wl["dim"] + 600)
+        spec = oracle_c.synth_spec(wl["dim"], dup_row_ppm=wl["dup_ppm"])
+        corpus = OracleCorpus(spec, sample)
+        qs = [oracle_c.synth_query(spec, qi, wl["rows"], wl["n_terms"], wl["frequent"]) for qi in range(steps + warmup)]
+        for q, _, text in qs[:warmup]:
+            corpus.search(text, q, wl["top_k"], threads)
+        t0 = time.perf_counter()
+        for q, _, text in qs[warmup:]:
+            corpus.search(text, q, wl["top_k"], threads)
+        dt = time.perf_counter() - t0
+        v = steps / dt * (sample / float(wl["rows"]))
         emit({
             "impl": "reference", "metric": f"hybrid recall QPS, {wl['name']}", "value": v, "unit": "queries/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wl["batch"] / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 products, f64 accumulation", "data": "synthetic", "config": batch_config(args, wl),
+            "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 products, f64 accumulation", "data": "synthetic",
+            "config": batch_config(args, wl), "reference_sample_rows": sample,
             "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} queries x {sample} rows x {wl['dim']}, scaled linearly to {wl['rows']} rows; C port of "
-                                       f"RecallSearchService.cs (dotnet absent)"},
+                             "sample": f"{steps} steps, each ONE query over {sample} of the {wl['rows']} rows x {wl['dim']} (ms_per_step is "
+                                       f"that step, unscaled; value = steps/s x {sample}/{wl['rows']}: the scorer is a per-row loop); {PORT_NOTE}"},
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
-    sample = args.cpu_sample_rows
-    steps = max(1, args.steps)
-    from omni_recall_rag_b200 import synth
-
-    spec = synth.make_spec(DIM)
-    rows = synth.rows_host(spec, 0, sample)
-    blob, off = oracle_c.pack_contents(synth.contents_of(rows.term_ids))
-    total_rows = args.rows_per_gpu * args.gpus
-    qs = [synth.query_host(spec, qi, total_rows, n_terms=N_TERMS) for qi in range(steps + args.warmup)]
-
-    def one(q):
-        oracle_c.search(emb=rows.emb, dim=DIM, ticks=rows.ticks, content_blob=blob, content_off=off, query=q.text,
-                        qvec=q.q, now_ticks=spec.now_ticks, top_k=TOP_K, threads=threads)
-
-    for q in qs[: args.warmup]:
-        one(q)
+    rows_per_gpu = args.rows_per_gpu or (1_000_000 if args.gpus == 1 else 5_000_000)
+    total_rows = rows_per_gpu * args.gpus
+    sample = host_sample_rows(args.cpu_sample_rows or 1_000_000, 4 * DIM + 600)
+    sample = min(sample, total_rows)
+    spec = oracle_c.synth_spec(DIM)
+    t_gen = time.perf_counter()
+    corpus = OracleCorpus(spec, sample)
+    note(f"reference arm: {sample} x {DIM} rows generated on {threads} host threads in {time.perf_counter() - t_gen:.1f} s")
+    qs = [oracle_c.synth_query(spec, qi, total_rows, N_TERMS) for qi in range(steps + warmup)]
+    for q, _, text in qs[:warmup]:
+        corpus.search(text, q, TOP_K, threads)
     t0 = time.perf_counter()
-    for q in qs[args.warmup:]:
-        one(q)
+    for q, _, text in qs[warmup:]:
+        corpus.search(text, q, TOP_K, threads)
     dt = time.perf_counter() - t0
     value = (steps / dt) * (sample / 1.0e6)
+    cfg = workload_config(args, rows_per_gpu)        # identical to the GPU arm's config; the sample is reported beside it
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / steps * (1.0e6 / sample), "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 products, f64 accumulation", "data": "synthetic",
-        "config": workload_config(args),
+        "config": cfg, "reference_sample_rows": sample,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} queries x {sample} rows x {DIM} (first rows of the same synthetic corpus), "
-                                   f"scaled linearly to 1M rows; C port of RecallSearchService.cs (dotnet absent)"},
+                         "sample": f"{steps} steps, each ONE query over {sample} x {DIM} rows of the same synthetic corpus"
+                                   + (" (the whole configs[1] corpus)" if sample == 1_000_000 and total_rows == 1_000_000 else
+                                      f" (of {total_rows}; the scorer is a per-row loop)")
+                                   + f"; ms_per_step is that step, unscaled; value = steps/s x rows/1M; {PORT_NOTE}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
-def workload_config(args):
-    total = args.rows_per_gpu * args.gpus
-    return {"workload": f"{total} chunks x {DIM} fp32 row-major in HBM ({args.rows_per_gpu} rows/GPU), single query, "
+def workload_config(args, rows_per_gpu: int):
+    total = rows_per_gpu * args.gpus
+    return {"workload": f"{total} chunks x {DIM} fp32 row-major in HBM ({rows_per_gpu} rows/GPU), single query, "
                         f"hybrid 0.7/0.2/0.1, {N_TERMS} query terms, {TERM_SLOTS} hashed terms/chunk, top-{TOP_K}",
-            "rows_total": total, "rows_per_gpu": args.rows_per_gpu, "dim": DIM, "top_k": TOP_K,
+            "rows_total": total, "rows_per_gpu": rows_per_gpu, "dim": DIM, "top_k": TOP_K,
             "parallelism": (f"row-sharded x{args.gpus}, per-GPU exact top-{TOP_K}, "
                             + ("fused peer-memory all-gather + merge kernel over NVLink (orr_xchg_allgather_merge); NCCL only "
                                "for set-up and the timing barrier" + ("" if args.no_pipeline else "; the exchange of query i runs on a "
                                "side stream while the rank scans query i+1") if args.exchange == "p2p" else
                                "NCCL all_gather_into_tensor + merge kernel")) if args.gpus > 1 else "1 GPU",
-            "l2": "inputs (12.3 GB/GPU) exceed L2 (126 MB); no flush needed",
+            "l2": f"inputs ({rows_per_gpu * 4 * DIM / 1e9:.1f} GB/GPU) exceed L2 (126 MB); no flush needed",
             "value_units": "queries/s x (rows_total / 1M)"}
-
-
-def oracle_batch_rate(wl, sample_rows: int, n_queries: int, threads: int, min_seconds: float):
-    """The oracle port on the first `sample_rows` rows of the batch workload's corpus: queries/s scaled
-    linearly to the workload's row count (the scorer is a per-row loop, one query at a time)."""
-    from omni_recall_rag_b200 import synth
-    from oracle import oracle_c
-
-    spec = synth.make_spec(wl["dim"], dup_row_ppm=wl["dup_ppm"])
-    rows = synth.rows_host(spec, 0, sample_rows)
-    blob, off = oracle_c.pack_contents(synth.contents_of(rows.term_ids))
-    qs = [synth.query_host(spec, qi, wl["rows"], n_terms=wl["n_terms"], frequent_terms=wl["frequent"]) for qi in range(n_queries)]
-
-    def one(q):
-        oracle_c.search(emb=rows.emb, dim=wl["dim"], ticks=rows.ticks, content_blob=blob, content_off=off, query=q.text,
-                        qvec=q.q, now_ticks=spec.now_ticks, top_k=wl["top_k"], threads=threads)
-
-    one(qs[0])
-    t0 = time.perf_counter()
-    done = 0
-    while True:
-        one(qs[done % n_queries])
-        done += 1
-        dt = time.perf_counter() - t0
-        if dt >= min_seconds and done >= n_queries:
-            break
-    return (done / dt) * (sample_rows / float(wl["rows"])), dt, done
 
 
 def batch_config(args, wl):
     return {"workload": wl["name"], "rows_total": wl["rows"], "rows_per_gpu": wl["rows"], "dim": wl["dim"], "batch": wl["batch"],
             "top_k": wl["top_k"], "n_terms": wl["n_terms"], "parallelism": "1 GPU",
             "split_precision_passes": args.batch_passes,
-            "l2": "bf16 planes (15.4 GB) exceed L2 (126 MB); every step is a fresh batch of queries; no flush needed"}
+            "l2": "bf16 planes (7.7 GB) exceed L2 (126 MB); every step is a fresh batch of queries; no flush needed"}
 
 
-def run_c1(args):
-    """--workload c1: 10k x 3072, single query, top-10 — candidate_cap=300 (the reference's behaviour) and all rows."""
-    import numpy as np
+# ================================================================================================================
+# GPU side
+# ================================================================================================================
+def need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: liborr has no CPU path (use --impl reference for the CPU baseline)")
+
+
+def measure_c1(steps: int, warmup: int, cpu_seconds: float):
+    """configs[0]: 10k x 3072, single query, top-10 — candidate_cap=300 (the reference's behaviour) and all rows."""
     import torch
 
     import omni_recall_rag_b200 as orr
-    from omni_recall_rag_b200 import _native as N  # noqa: F401
     from omni_recall_rag_b200 import synth
 
-    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
-        raise SystemExit("--workload c1 is a single-GPU bench")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: liborr has no CPU path")
     rows_n = 10_000
-    steps, warmup = max(1, args.steps), max(3, args.warmup)
     spec = synth.make_spec(DIM)
     shard = orr.RecallShard(DIM, rows_n, device=0, term_slots=TERM_SLOTS)
     shard.fill_synthetic(spec, 0, rows_n)
@@ -317,8 +341,7 @@ def run_c1(args):
                 dev_ms.append(tm["total_device_ms"]); wall.append(tm["wall_ms"])
             e2e_s = time.perf_counter() - t0
             res[cap] = dict(qps_device=steps / (sum(dev_ms) / 1000.0), qps_e2e=steps / e2e_s, device_ms=sum(dev_ms) / steps,
-                            call_ms_median=statistics.median(wall), call_ms_p99=sorted(wall)[min(len(wall) - 1, int(0.99 * len(wall)))],
-                            path=tm["path"])
+                            call_ms_median=statistics.median(wall), call_ms_p99=p99(wall), path=tm["path"])
     peak, peak_kind = measured_peak()
     bytes_all = rows_n * (4 * DIM + 8 + 4 * TERM_SLOTS)
     line = {
@@ -335,41 +358,32 @@ def run_c1(args):
                      "call_ms": {"median": res[0]["call_ms_median"], "p99": res[0]["call_ms_p99"]}},
         "gpu_launches": 2 * steps * 2,
         "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel (all rows, cap=0)", "achieved": bytes_all / (res[0]["device_ms"] / 1000.0) / 1.0e9,
-                     "peak": peak, "unit": "GB/s", "frac": bytes_all / (res[0]["device_ms"] / 1000.0) / 1.0e9 / peak, "traffic": None,
+                     "peak": peak, "peak_kind": hbm_peak_kind(peak_kind), "unit": "GB/s",
+                     "frac": bytes_all / (res[0]["device_ms"] / 1000.0) / 1.0e9 / peak, "kernel_ms": res[0]["device_ms"], "traffic": None,
                      "note": "a 125 MB pass is launch/latency-bound (and L2-resident), not a bandwidth measurement; the headline roofline is the c2 line"},
         "clocks": clocks.summary(),
     }
-    if not args.no_cpu_baseline:
+    shard.close()
+    if cpu_seconds > 0:
         from oracle import oracle_c
         threads = oracle_c.max_threads()
-        rows = synth.rows_host(spec, 0, rows_n)
-        blob, off = oracle_c.pack_contents(synth.contents_of(rows.term_ids))
+        corpus = OracleCorpus(oracle_c.copy_spec(spec), rows_n)
         cpu = {}
+        qs = [(q.q, q.text) for q in queries]
         for cap in (300, 0):
             for th in (1, threads):
-                nq = 0
-                t0 = time.perf_counter()
-                while True:
-                    q = queries[nq % n_q]
-                    oracle_c.search(emb=rows.emb, dim=DIM, ticks=rows.ticks, content_blob=blob, content_off=off, query=q.text, qvec=q.q,
-                                    now_ticks=spec.now_ticks, top_k=TOP_K, candidate_cap=cap, threads=th)
-                    nq += 1
-                    dt = time.perf_counter() - t0
-                    if dt >= 3.0 and nq >= 8:
-                        break
-                cpu[(cap, th)] = nq / dt
+                cpu[(cap, th)], _, _ = timed_queries(lambda qt: corpus.search(qt[1], qt[0], TOP_K, th, candidate_cap=cap), qs, cpu_seconds, 8)
         line["cpu_baseline"] = {"value": cpu[(300, 1)], "unit": "queries/s", "cores": 1, "kind": "port",
                                 "value_all_threads": cpu[(300, threads)], "threads": threads,
                                 "all_rows_1_thread": cpu[(0, 1)], "all_rows_all_threads": cpu[(0, threads)],
-                                "sample": "the whole workload (10000 rows, no sampling), >= 3 s per figure; 1 thread is the reference's own "
+                                "sample": f"the whole workload (10000 rows, no sampling), >= {cpu_seconds:.1f} s per figure; 1 thread is the reference's own "
                                           "sequential execution of a request; C port of RecallSearchService.cs:20-119 + "
                                           "InMemoryIngestionStore.cs:57-65 (no dotnet in the image)"}
-    emit(line)
-    shard.close()
+    return line
 
 
-def run_batch(args):
-    """--workload c3 | c5: the tcgen05 batched path through orr_search_batch (N=1)."""
+def measure_batch(args, name: str, steps: int, warmup: int, cpu_seconds: float):
+    """configs[2] / configs[4]: the tcgen05 batched path through orr_search_batch (N=1)."""
     import numpy as np
     import torch
 
@@ -377,14 +391,8 @@ def run_batch(args):
     from omni_recall_rag_b200 import _native as N
     from omni_recall_rag_b200 import synth
 
-    wl = BATCH_WORKLOADS[args.workload]
+    wl = BATCH_WORKLOADS[name]
     main_passes = 3 if args.batch_passes == 3 else 1
-    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
-        raise SystemExit("--workload c3/c5 is a single-GPU bench (the batched path shards like the single-query path; not benched)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: liborr has no CPU path")
-    steps = max(1, args.steps if args.steps != 200 else 20)
-    warmup = max(3, args.warmup if args.warmup != 20 else 3)
     rows, dim, B, k = wl["rows"], wl["dim"], wl["batch"], wl["top_k"]
     spec = synth.make_spec(dim, dup_row_ppm=wl["dup_ppm"])
     shard = orr.RecallShard(dim, rows, device=0, term_slots=TERM_SLOTS)
@@ -454,16 +462,127 @@ def run_batch(args):
         "clocks": clocks.summary(),
         "queries_rerun_singly": redo, "steps_with_bf16x3_cascade": cascaded,
     }
-    if not args.no_cpu_baseline:
+    shard.close()
+    if cpu_seconds > 0:
         from oracle import oracle_c
         threads = oracle_c.max_threads()
         sample = 200_000
-        v, dt, n = oracle_batch_rate(wl, sample, 8, threads, 10.0)
-        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+        ospec = oracle_c.synth_spec(dim, dup_row_ppm=wl["dup_ppm"])
+        corpus = OracleCorpus(ospec, sample)
+        qs = [oracle_c.synth_query(ospec, qi, rows, wl["n_terms"], wl["frequent"]) for qi in range(8)]
+        rate, dt, n = timed_queries(lambda q: corpus.search(q[2], q[0], k, threads), qs, cpu_seconds, 4)
+        line["cpu_baseline"] = {"value": rate * sample / float(rows), "unit": "queries/s", "cores": threads, "kind": "port",
                                 "sample": f"{n} queries x {sample} rows x {dim} (first rows of the same corpus) on {threads} threads "
-                                          f"({dt:.1f} s), scaled linearly to {rows} rows; C port of RecallSearchService.cs:20-119"}
-    emit(line)
-    shard.close()
+                                          f"({dt:.1f} s), scaled linearly to {rows} rows (the scorer is a per-row loop); {PORT_NOTE}"}
+    return line
+
+
+def measure_noemb(shard, spec, n_local: int, steps: int, warmup: int, cpu_seconds: float):
+    """The reference's DEFAULT configuration (appsettings.json:30-32, NoOpEmbeddingClient.cs:5-8): no query embedding,
+    every cosine is 0 (RecallSearchService.cs:71-72), ranking = keyword + recency.  Same 1M-row corpus, 4 terms, top-10:
+    the exact path (orr_noemb_scores_kernel reads terms64 + ticks only, then the radix select under the tie chain)."""
+    import torch
+
+    from omni_recall_rag_b200 import _native as N
+    from omni_recall_rag_b200 import synth
+
+    n_q = steps + warmup
+    queries = [synth.query_host(spec, 1000 + qi, n_local, n_terms=N_TERMS) for qi in range(n_q)]
+    for i in range(warmup):
+        shard.search(None, queries[i].terms, spec.now_ticks, TOP_K)
+    torch.cuda.synchronize()
+    score_ms, sel_ms, wall = [], [], []
+    t0 = time.perf_counter()
+    for i in range(warmup, n_q):
+        shard.search(None, queries[i].terms, spec.now_ticks, TOP_K)
+        tm = shard.last_timing()
+        assert tm["path"] == N.PATH_EXACT, tm
+        score_ms.append(tm["scan_ms"]); sel_ms.append(tm["finalize_ms"]); wall.append(tm["wall_ms"])
+    e2e_s = time.perf_counter() - t0
+    peak, peak_kind = measured_peak()
+    scale = n_local / 1.0e6
+    bytes_per_launch = n_local * (8 * TERM_SLOTS + 8)
+    k_ms = sum(score_ms) / steps
+    dev_ms = k_ms + sum(sel_ms) / steps
+    achieved = bytes_per_launch / (k_ms / 1000.0) / 1.0e9
+    entry = {
+        "metric": "keyword + recency-only recall QPS at 1M x 3072 (no embeddings: the reference's default configuration), top-10",
+        "value": 1000.0 / dev_ms * scale, "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms,
+        "dtype": "f64 exact scores (order-preserving u64 keys) + radix select under (score, ticks, row)",
+        "config": {"workload": f"{n_local} chunks x {DIM} fp32 in HBM, query WITHOUT an embedding (cosine 0, RecallSearchService.cs:71-72), "
+                               f"{N_TERMS} query terms over {TERM_SLOTS} hashed terms/chunk, recency, top-{TOP_K}; exact path",
+                   "rows_total": n_local, "top_k": TOP_K},
+        "e2e": {"value": steps / e2e_s * scale, "unit": UNIT, "h2d_bytes_per_step": 12 * N_TERMS, "d2h_bytes_per_step": 24 * TOP_K + 8,
+                "ms_per_step": 1000.0 * e2e_s / steps, "call_ms": {"median": statistics.median(wall), "p99": p99(wall)}},
+        "roofline": {"bound": "hbm", "kernel": "orr_noemb_scores_kernel<2>", "achieved": achieved, "peak": peak,
+                     "peak_kind": hbm_peak_kind(peak_kind), "unit": "GB/s", "frac": achieved / peak, "bytes_per_launch": bytes_per_launch,
+                     "bytes_per_row": "8 B x 64 term hashes + 8 B ticks = 520 B (embeddings are not read)", "kernel_ms": k_ms,
+                     "select_ms": sum(sel_ms) / steps, "traffic": None,
+                     "note": "kernel_ms spans the 48 KB state clear + the scoring kernel (CUDA events); select_ms = digit passes + gather + "
+                             "D2H + host sync of the exact path"},
+        "gpu_launches": 4 * steps,
+        "kernels_per_step": ["orr_noemb_scores_kernel<2>", "orr_sel_pass_kernel x2", "orr_sel_gather_kernel"],
+    }
+    if cpu_seconds > 0:
+        from oracle import oracle_c
+        threads = oracle_c.max_threads()
+        sample = min(n_local, 250_000)
+        corpus = OracleCorpus(oracle_c.copy_spec(spec), sample, want_emb=False)
+        qs = [q.text for q in queries[:8]]
+        rate, dt, n = timed_queries(lambda t: corpus.search(t, None, TOP_K, threads), qs, cpu_seconds, 4)
+        rate1, dt1, n1 = timed_queries(lambda t: corpus.search(t, None, TOP_K, 1), qs, min(cpu_seconds, 2.0), 2)
+        entry["cpu_baseline"] = {"value": rate * sample / 1.0e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "value_1_thread": rate1 * sample / 1.0e6,
+                                 "sample": f"{n} queries x {sample} rows (Content of ~575 B/chunk, no embeddings) on {threads} threads ({dt:.1f} s), "
+                                           f"{n1} on 1 thread; scaled linearly to 1M rows; {PORT_NOTE}"}
+    return entry
+
+
+def measure_service(store, spec, n_local: int, steps: int, warmup: int):
+    """Query STRING in, citations out: GpuRecallSearchService.search = embedding client (stub: the vector is known),
+    orr_search_query (tokenise, stop words, vocabulary expansion on the GPU over the 2^20-word vocabulary, fused scan,
+    exact re-score) and the citation build (document lookup, snippet, Math.Round(score, 4))."""
+    import numpy as np
+
+    from omni_recall_rag_b200 import _native as N
+    from omni_recall_rag_b200 import recall as R
+    from omni_recall_rag_b200 import synth
+
+    n_q = steps + warmup
+    queries = [synth.query_host(spec, 2000 + qi, n_local, n_terms=N_TERMS) for qi in range(n_q)]
+    table = {q.text: q.q for q in queries}
+
+    class KnownVectors:
+        def embed(self, text):
+            return R.EmbeddingResult(table[text], "Success", "synthetic")
+
+    svc = R.GpuRecallSearchService(store, KnownVectors(), candidate_cap=0, clock=lambda: spec.now_ticks)
+    for i in range(warmup):
+        svc.search(queries[i].text, TOP_K)
+    wall, dev = [], []
+    t0 = time.perf_counter()
+    for i in range(warmup, n_q):
+        tq = time.perf_counter()
+        resp = svc.search(queries[i].text, TOP_K)
+        wall.append((time.perf_counter() - tq) * 1000.0)
+        tm = store.shard.last_timing()
+        assert tm["path"] == N.PATH_FUSED and len(resp.citations) == TOP_K, tm
+        dev.append(tm["total_device_ms"])
+    e2e_s = time.perf_counter() - t0
+    # the same query through the pre-hashed entry point returns the same rows
+    q = queries[-1]
+    direct = store.shard.search(q.q, q.terms, spec.now_ticks, TOP_K)
+    assert [c.score for c in resp.citations] == [R.math_round4(float(s)) for s in direct.scores], "service and orr_search disagree"
+    scale = n_local / 1.0e6
+    return {
+        "value": steps / e2e_s * scale, "unit": UNIT, "ms_per_step": 1000.0 * e2e_s / steps,
+        "call_ms": {"median": statistics.median(wall), "p99": p99(wall)}, "device_ms_per_step": sum(dev) / steps,
+        "vocabulary_words": store.vocabulary_size,
+        "h2d_bytes_per_step": 4 * DIM + 36 + 4232 + 12 * N_TERMS, "d2h_bytes_per_step": 24 * TOP_K + 8 + 4 + 8 * N_TERMS,
+        "what": "GpuRecallSearchService.search(query string, 10): embedding stub -> orr_search_query (A-2 tokenising, GPU substring "
+                "expansion of the 4 terms over the live vocabulary kept in HBM, fused scan + exact re-score) -> 10 RecallCitationDto "
+                "(chunk records rebuilt from the generator, 180-char snippet, Math.Round(score, 4)); Python host standing in for the C# shim",
+    }
 
 
 def main():
@@ -472,9 +591,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows-per-gpu", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
+    ap.add_argument("--rows-per-gpu", type=int, default=0, help="default: 1M at N=1 (configs[1]), 5M at N>1 (N=8: configs[3])")
+    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the corpus the CPU port scans per query (default: 1M for "
+                    "--impl reference, memory permitting; 100k for the inline cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="N=1: only the c2 headline (no configs / e2e_service sub-results)")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the per-GPU top-k lists meet (fused peer-memory kernel, or NCCL all-gather + merge)")
@@ -487,25 +608,31 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    need_gpu()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu_s = 0.0 if args.no_cpu_baseline else 1.0
     if args.workload == "c1":
-        run_c1(args)
+        if args.gpus != 1 or world != 1:
+            raise SystemExit("--workload c1 is a single-GPU bench")
+        emit(measure_c1(max(1, args.steps), max(3, args.warmup), 3.0 * cpu_s))
         return
     if args.workload != "c2":
-        run_batch(args)
+        if args.gpus != 1 or world != 1:
+            raise SystemExit("--workload c3/c5 is a single-GPU bench")
+        emit(measure_batch(args, args.workload, max(1, args.steps if args.steps != 200 else 20),
+                           max(3, args.warmup if args.warmup != 20 else 3), 10.0 * cpu_s))
         return
 
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
     import omni_recall_rag_b200 as orr
     from omni_recall_rag_b200 import sharded, synth
+    from omni_recall_rag_b200 import store as S
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: liborr has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -514,176 +641,224 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    n_local = args.rows_per_gpu
-    total_rows = n_local * world
-    row_base = rank * n_local
     spec = synth.make_spec(DIM)
-    shard = orr.RecallShard(DIM, n_local, device=local_rank, term_slots=TERM_SLOTS, row_base=row_base)
-    shard.fill_synthetic(spec, row_base, n_local)
-    sr = sharded.ShardedRecall(shard, exchange=args.exchange)
-
     n_q = steps + warmup
-    queries = [synth.query_host(spec, qi, total_rows, n_terms=N_TERMS) for qi in range(n_q)]
-    q_dev = [torch.from_numpy(q.q).to(dev) for q in queries]
-    q_pinned = [torch.from_numpy(q.q).pin_memory() for q in queries]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: `value` ----
-    # N>1: a stream of queries with the exchange of query i on a side stream (ShardedRecall.search_device_pipelined),
-    # so a rank's next scan does not wait for the slowest peer; --no-pipeline keeps every query a blocking collective
-    # step.  Both forms are timed; `value` is the pipelined one unless --no-pipeline.
-    flags_seen = 0
-    main_stream = torch.cuda.current_stream(dev)
+    def measure_sharded(n_local: int, with_service: bool):
+        """One corpus of n_local rows per GPU: device-timed stream of queries (`value`), the host-API loop (`e2e`) and the
+        scan kernel's own duration (roofline).  Returns (line fields, shard, store-or-None, ShardedRecall)."""
+        total_rows = n_local * world
+        row_base = rank * n_local
+        store = None
+        if with_service:          # N=1: the shard lives inside the reference-shaped store so the service leg reuses the corpus
+            store = S.GpuIngestionStore(DIM, n_local, device=local_rank, term_slots=TERM_SLOTS, keep_text=False)
+            store.fill_synthetic(spec, n_local)
+            shard = store.shard
+        else:
+            shard = orr.RecallShard(DIM, n_local, device=local_rank, term_slots=TERM_SLOTS, row_base=row_base)
+            shard.fill_synthetic(spec, row_base, n_local)
+        sr = sharded.ShardedRecall(shard, exchange=args.exchange)
+        queries = [synth.query_host(spec, qi, total_rows, n_terms=N_TERMS) for qi in range(n_q)]
+        q_dev = [torch.from_numpy(q.q).to(dev) for q in queries]
+        q_pinned = [torch.from_numpy(q.q).pin_memory() for q in queries]
+        flags_seen = 0
+        main_stream = torch.cuda.current_stream(dev)
 
-    def timed_loop(pipelined: bool):
+        # ---- device-resident timing: `value` ----
+        # N>1: a stream of queries with the exchange of query i on a side stream (ShardedRecall.search_device_pipelined),
+        # so a rank's next scan does not wait for the slowest peer; --no-pipeline keeps every query a blocking collective
+        # step.  Both forms are timed; `value` is the pipelined one unless --no-pipeline.
+        def timed_loop(pipelined: bool):
+            for i in range(warmup):
+                if pipelined:
+                    sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+                else:
+                    sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            done = None
+            for i in range(warmup, n_q):
+                if pipelined:
+                    _, st, done = sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+                else:
+                    _, st = sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+            if done is not None:
+                main_stream.wait_event(done)               # the last exchange (they complete in order) ends the region
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            fl = int(st.cpu().numpy()[1])
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()), fl
+
+        pipelined = world > 1 and sr.exchange == "p2p" and not args.no_pipeline
+        with ClockSampler(local_rank) as clocks:
+            dev_ms_sync, fl = timed_loop(False)
+            flags_seen |= fl
+            dev_ms = dev_ms_sync
+            if pipelined:
+                dev_ms, fl = timed_loop(True)
+                flags_seen |= fl
+            # keep sampling under load for ~0.6 s more so short runs still get samples.  The count comes from the
+            # all-reduced step time, so every rank issues the SAME number of searches: each one is a collective step
+            # (the exchange is sequence-numbered), a time-based loop would let the ranks drift apart.
+            extra = max(1, min(2000, int(600.0 / max(dev_ms / steps, 1.0e-3))))
+            j = warmup
+            for _ in range(extra):
+                sr.search_device(q_dev[j], queries[j].terms, spec.now_ticks, TOP_K)
+                j = warmup + (j + 1 - warmup) % steps
+            torch.cuda.synchronize()
+        clock_summary = clocks.summary()
+
+        # ---- end-to-end timing through the host API: `e2e`, and the scan kernel's own duration ----
         for i in range(warmup):
-            if pipelined:
-                _, _, done = sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
-            else:
-                sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+            sr.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        done = None
+        scan_ms, fin_ms, wall_ms, escalated = [], [], [], 0
+        t0 = time.perf_counter()
         for i in range(warmup, n_q):
-            if pipelined:
-                _, st, done = sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
-            else:
-                _, st = sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
-        if done is not None:
-            main_stream.wait_event(done)               # the last exchange (they complete in order) ends the region
-        e1.record()
+            tq = time.perf_counter()
+            hits = sr.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K)
+            tm = sr.last_timing()
+            scan_ms.append(tm["scan_ms"]); fin_ms.append(tm["finalize_ms"])
+            wall_ms.append(tm["wall_ms"] if world == 1 else (time.perf_counter() - tq) * 1000.0)
+            escalated += 1 if (tm["path"] & 0x100) else 0
         barrier()
-        ms = e0.elapsed_time(e1)
-        fl = int(st.cpu().numpy()[1])
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), fl
+        e2e_s = float(t.item())
 
-    pipelined = world > 1 and sr.exchange == "p2p" and not args.no_pipeline
-    with ClockSampler(local_rank) as clocks:
-        dev_ms_sync, fl = timed_loop(False)
-        flags_seen |= fl
-        dev_ms = dev_ms_sync
-        if pipelined:
-            dev_ms, fl = timed_loop(True)
-            flags_seen |= fl
-        # keep sampling under load for ~0.6 s more so short runs still get samples.  The count comes from the
-        # all-reduced step time, so every rank issues the SAME number of searches: each one is a collective step
-        # (the exchange is sequence-numbered), a time-based loop would let the ranks drift apart.
-        extra = max(1, min(2000, int(600.0 / max(dev_ms / steps, 1.0e-3))))
-        j = warmup
-        for _ in range(extra):
-            sr.search_device(q_dev[j], queries[j].terms, spec.now_ticks, TOP_K)
-            j = warmup + (j + 1 - warmup) % steps
+        # sanity: the device-resident path and the host path return the same hits
+        hd, sd = sr.search_device(q_dev[n_q - 1], queries[n_q - 1].terms, spec.now_ticks, TOP_K)
         torch.cuda.synchronize()
-    clock_summary = clocks.summary()
+        got, flags = sharded.hits_from_device(hd, sd)
+        assert got.rows.tolist() == hits.rows.tolist() and got.scores.tolist() == hits.scores.tolist(), "device/host paths disagree"
+        flags_seen |= flags
+        if pipelined:                                      # ... and so does the pipelined form, for a run of queries
+            outs = []
+            for i in range(n_q - 3, n_q):
+                outs.append(sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K))
+            for (hp_, sp_, done), i in zip(outs, range(n_q - 3, n_q)):
+                done.synchronize()
+                gp, fl = sharded.hits_from_device(hp_, sp_)
+                hd, sd = sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
+                torch.cuda.synchronize()
+                gs, _ = sharded.hits_from_device(hd, sd)
+                assert gp.rows.tolist() == gs.rows.tolist() and gp.scores.tolist() == gs.scores.tolist(), "pipelined/blocking exchange disagree"
+                flags_seen |= fl
 
-    # ---- end-to-end timing through the host API: `e2e`, and the scan kernel's own duration ----
-    for i in range(warmup):
-        sr.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K)
-    barrier()
-    scan_ms, fin_ms, wall_ms, escalated = [], [], [], 0
-    t0 = time.perf_counter()
-    for i in range(warmup, n_q):
-        tq = time.perf_counter()
-        hits = sr.search(q_pinned[i].numpy(), queries[i].terms, spec.now_ticks, TOP_K)
-        tm = sr.last_timing()
-        scan_ms.append(tm["scan_ms"]); fin_ms.append(tm["finalize_ms"])
-        wall_ms.append(tm["wall_ms"] if world == 1 else (time.perf_counter() - tq) * 1000.0)
-        escalated += 1 if (tm["path"] & 0x100) else 0
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+        # per-rank scan kernel time: the exchange makes every query wait for the slowest shard
+        scan_avg_local = sum(scan_ms) / len(scan_ms)
+        per_rank_scan = [scan_avg_local]
+        if world > 1:
+            tl = torch.tensor([scan_avg_local], dtype=torch.float64, device=dev)
+            tg = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(tg, tl)
+            per_rank_scan = [round(float(x), 4) for x in tg.cpu().tolist()]
 
-    # sanity: the device-resident path and the host path return the same hits
-    hd, sd = sr.search_device(q_dev[n_q - 1], queries[n_q - 1].terms, spec.now_ticks, TOP_K)
-    torch.cuda.synchronize()
-    got, flags = sharded.hits_from_device(hd, sd)
-    assert got.rows.tolist() == hits.rows.tolist() and got.scores.tolist() == hits.scores.tolist(), "device/host paths disagree"
-    flags_seen |= flags
-    if pipelined:                                      # ... and so does the pipelined form, for a run of queries
-        outs = []
-        for i in range(n_q - 3, n_q):
-            hp_, sp_, done = sr.search_device_pipelined(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
-            outs.append((hp_, sp_, done))
-        for (hp_, sp_, done), i in zip(outs, range(n_q - 3, n_q)):
-            done.synchronize()
-            gp, fl = sharded.hits_from_device(hp_, sp_)
-            hd, sd = sr.search_device(q_dev[i], queries[i].terms, spec.now_ticks, TOP_K)
-            torch.cuda.synchronize()
-            gs, _ = sharded.hits_from_device(hd, sd)
-            assert gp.rows.tolist() == gs.rows.tolist() and gp.scores.tolist() == gs.scores.tolist(), "pipelined/blocking exchange disagree"
-            flags_seen |= fl
+        scale = total_rows / 1.0e6
+        peak, peak_kind = measured_peak()
+        bytes_per_launch = n_local * (4 * DIM + 8 + 4 * TERM_SLOTS)
+        scan_avg_ms = sum(scan_ms) / len(scan_ms)
+        achieved = bytes_per_launch / (scan_avg_ms / 1000.0) / 1.0e9
+        launches_per_step = 2 + (1 if world > 1 else 0)
+        exchange_kernel = ["orr_xchg_merge_kernel"] if sr.exchange == "p2p" else ["orr_merge_kernel"]
+        fields = {
+            "value": steps / (dev_ms / 1000.0) * scale, "ms_per_step": dev_ms / steps,
+            "config": workload_config(args, n_local),
+            "corpus_qps": steps / (dev_ms / 1000.0),
+            "e2e": {"value": steps / e2e_s * scale, "unit": UNIT, "h2d_bytes_per_step": 4 * DIM + 12 * N_TERMS,
+                    "d2h_bytes_per_step": 24 * TOP_K + 8, "ms_per_step": 1000.0 * e2e_s / steps,
+                    "call_ms": {"what": "orr_search wall clock" if world == 1 else "ShardedRecall.search wall clock",
+                                "median": statistics.median(wall_ms), "p99": p99(wall_ms)}},
+            "gpu_launches": launches_per_step * steps,
+            "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel"] + (exchange_kernel if world > 1 else []),
+            "exchange": sr.exchange, "per_rank_scan_kernel_ms": per_rank_scan,
+            "pipelined_exchange": pipelined,
+            "value_blocking_exchange": steps / (dev_ms_sync / 1000.0) * scale,
+            "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel<24,1>", "achieved": achieved, "peak": peak,
+                         "peak_kind": hbm_peak_kind(peak_kind),
+                         "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
+                         "bytes_per_launch": bytes_per_launch, "bytes_per_launch_emb_only": n_local * 4 * DIM,
+                         "kernel_ms": scan_avg_ms, "finalize_kernel_ms": sum(fin_ms) / len(fin_ms),
+                         "traffic": NCU_SCAN_TRAFFIC_BYTES_PER_ROW * n_local,
+                         "traffic_source": f"CONSTANT, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per launch from the "
+                                           f"ncu --set full capture summarised in {NCU_SCAN_TRAFFIC_SOURCE} (12556.9 B/row), scaled by rows"},
+            "clocks": clock_summary,
+            "bound_check_escalations": escalated, "device_flags": flags_seen,
+        }
+        return fields, shard, store, sr
 
-    # per-rank scan kernel time: the exchange makes every query wait for the slowest shard
-    scan_avg_local = sum(scan_ms) / len(scan_ms)
-    per_rank_scan = [scan_avg_local]
-    if world > 1:
-        tl = torch.tensor([scan_avg_local], dtype=torch.float64, device=dev)
-        tg = torch.empty(world, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(tg, tl)
-        per_rank_scan = [round(float(x), 4) for x in tg.cpu().tolist()]
+    n_local = args.rows_per_gpu or (1_000_000 if world == 1 else 5_000_000)
+    with_service = world == 1 and not args.headline_only
+    fields, shard, store, sr = measure_sharded(n_local, with_service)
+    line = {"metric": METRIC, "value": fields.pop("value"), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": fields.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 scan select + f64 exact re-score", "data": "synthetic"}
+    line.update(fields)
 
-    scale = total_rows / 1.0e6
-    value = steps / (dev_ms / 1000.0) * scale
-    e2e_value = steps / e2e_s * scale
-    peak, peak_kind = measured_peak()
-    bytes_per_launch = n_local * (4 * DIM + 8 + 4 * TERM_SLOTS)
-    scan_avg_ms = sum(scan_ms) / len(scan_ms)
-    achieved = bytes_per_launch / (scan_avg_ms / 1000.0) / 1.0e9
-    launches_per_step = 2 + (1 if world > 1 else 0)
-    exchange_kernel = ["orr_xchg_merge_kernel"] if sr.exchange == "p2p" else ["orr_merge_kernel"]
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 scan select + f64 exact re-score", "data": "synthetic",
-        "config": workload_config(args),
-        "corpus_qps": steps / (dev_ms / 1000.0),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * DIM + 12 * N_TERMS,
-                "d2h_bytes_per_step": 24 * TOP_K + 8, "ms_per_step": 1000.0 * e2e_s / steps,
-                "call_ms": {"what": "orr_search wall clock" if world == 1 else "ShardedRecall.search wall clock", "median": statistics.median(wall_ms), "p99": sorted(wall_ms)[min(len(wall_ms) - 1, int(0.99 * len(wall_ms)))]}},
-        "gpu_launches": launches_per_step * steps,
-        "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel"] + (exchange_kernel if world > 1 else []),
-        "exchange": sr.exchange, "per_rank_scan_kernel_ms": per_rank_scan,
-        "pipelined_exchange": pipelined,
-        "value_blocking_exchange": steps / (dev_ms_sync / 1000.0) * scale,
-        "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel<24,1>", "achieved": achieved, "peak": peak,
-                     "peak_kind": f"{peak_kind} HBM copy GB/s (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6650 GB/s",
-                     "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
-                     "bytes_per_launch": bytes_per_launch, "bytes_per_launch_emb_only": n_local * 4 * DIM,
-                     "kernel_ms": scan_avg_ms, "finalize_kernel_ms": sum(fin_ms) / len(fin_ms),
-                     "traffic": NCU_SCAN_TRAFFIC_BYTES_PER_ROW * n_local,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                       "(profiles/r01_final_kernels.md), scaled by rows"},
-        "clocks": clock_summary,
-        "bound_check_escalations": escalated, "device_flags": flags_seen,
-    }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle_c
         threads = oracle_c.max_threads()
-        v_all, dt_all, n_all = cpu_baseline_run(args.cpu_sample_rows, 8, threads, total_rows, min_seconds=10.0)
-        v_one, dt_one, n_one = cpu_baseline_run(args.cpu_sample_rows, 3, 1, total_rows, min_seconds=8.0)
+        sample = args.cpu_sample_rows or 100_000
+        corpus = OracleCorpus(oracle_c.copy_spec(spec), sample)
+        qs = [oracle_c.synth_query(corpus.spec, qi, n_local, N_TERMS) for qi in range(8)]
+        v_all, dt_all, n_all = timed_queries(lambda q: corpus.search(q[2], q[0], TOP_K, threads), qs, 6.0, 8)
+        v_one, dt_one, n_one = timed_queries(lambda q: corpus.search(q[2], q[0], TOP_K, 1), qs, 4.0, 2)
         line["cpu_baseline"] = {
-            "value": v_all, "unit": UNIT, "cores": threads, "kind": "port",
-            "value_1_thread": v_one,
-            "sample": f"{n_all} queries x {args.cpu_sample_rows} rows x {DIM} (first rows of the same corpus) on {threads} "
+            "value": v_all * sample / 1.0e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "value_1_thread": v_one * sample / 1.0e6,
+            "sample": f"{n_all} queries x {sample} rows x {DIM} (first rows of the same corpus) on {threads} "
                       f"threads ({dt_all:.1f} s) and {n_one} queries on 1 thread ({dt_one:.1f} s), scaled linearly to 1M "
-                      f"rows; C port of RecallSearchService.cs:20-119 (no dotnet in the image)"}
+                      f"rows (the reference arm, --impl reference, scans the full 1M rows per step); {PORT_NOTE}"}
+        del corpus
+
+    if world == 1 and not args.headline_only:
+        # ---- every other BASELINE config, in this process ----
+        sub_steps, sub_warm = min(steps, 50), max(3, min(warmup, 10))
+        t_sub = time.perf_counter()
+        configs = {}
+        configs["c2_noemb"] = measure_noemb(shard, spec, n_local, sub_steps, sub_warm, 3.0 * cpu_s)
+        line["e2e_service"] = measure_service(store, spec, n_local, sub_steps, sub_warm)
+        line["e2e_service"]["vs_e2e_ms"] = line["e2e_service"]["ms_per_step"] / line["e2e"]["ms_per_step"]
+        sr.close()
+        store.close()
+        sr = shard = store = None
+        configs["c1"] = measure_c1(max(sub_steps, 100), sub_warm, 1.5 * cpu_s)
+        b_steps, b_warm = min(steps, 20), max(3, min(warmup, 5))
+        for name in ("c3", "c5"):
+            configs[name] = measure_batch(args, name, b_steps, b_warm, 4.0 * cpu_s)
+        line["configs"] = configs
+        line["configs_seconds"] = round(time.perf_counter() - t_sub, 1)
+
+    if world > 1 and not args.headline_only and n_local != 1_000_000:
+        # the same measurement at 1M rows per GPU (round 1's scaling series), as a sub-line
+        sr.close()
+        shard.close()
+        sr = shard = None
+        f1, shard, _, sr = measure_sharded(1_000_000, False)
+        line["rows_1m_per_gpu"] = {k: f1[k] for k in ("value", "ms_per_step", "corpus_qps", "e2e", "value_blocking_exchange",
+                                                      "per_rank_scan_kernel_ms", "roofline", "config")}
+
     if rank == 0:
         emit(line)
-    sr.close()
-    shard.close()
+    if sr is not None:
+        sr.close()
+    if store is not None:
+        store.close()
+    elif shard is not None:
+        shard.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -216,6 +216,12 @@ int  orr_search_query(orr_store* s, const char* query_utf8, int32_t query_len, c
         int64_t now_ticks, int32_t top_k, int32_t candidate_cap, int32_t keyword_mode,
         orr_hit* out, int32_t* n_out);
 
+/* The keyword side orr_search_query derives from a query string, without searching: *n_terms = |terms| after the A-2
+ * filtering, and the vocabulary expansion as (hash, term) probes.  *n_probes may exceed cap (nothing beyond cap is
+ * written): such a query runs in text mode. */
+int  orr_expand_query(orr_store* s, const char* query_utf8, int32_t query_len,
+        uint64_t* probe_hash, int32_t* probe_term, int32_t cap, int32_t* n_terms, int32_t* n_probes);
+
 /* Same work with every buffer already resident in HBM on cfg.device and no host
  * synchronisation: q_dev fp32[q_dim], probes copied at enqueue time (host arrays),
  * out_dev orr_hit[max(1,top_k)], status_dev int32[2] = {n_out, flags}; flags bit0 set
@@ -292,6 +298,12 @@ int  orr_xchg_open_peer(orr_xchg* x, int32_t peer_rank, const void* handle);
 int  orr_xchg_attach_peer(orr_xchg* x, int32_t peer_rank, orr_xchg* peer);
 int  orr_xchg_allgather_merge(orr_xchg* x, const orr_hit* hits_dev, const int32_t* status_dev, int32_t top_k,
         orr_hit* out_dev, int32_t* out_status_dev, void* cuda_stream);
+/* Recovery after ORR_STATUS_XCHG_TIMEOUT: the ranks drain their streams, agree out of band on a number above every
+ * orr_xchg_sequence() in use, each calls orr_xchg_resync with it, and a barrier precedes the next exchange.
+ * orr_xchg_set_timeout_ms bounds how long the exchange kernel waits for a missing peer (default 5000). */
+uint32_t orr_xchg_sequence(orr_xchg* x);
+int  orr_xchg_resync(orr_xchg* x, uint32_t next_seq_base);
+int  orr_xchg_set_timeout_ms(orr_xchg* x, double ms);
 
 /* ---- one host process, N GPUs (the .NET deployment of the row-sharded layout) ----------------------
  * An orr_cluster owns one orr_store per device (global row id = shard << 40 | local row), their exchange
@@ -299,8 +311,9 @@ int  orr_xchg_allgather_merge(orr_xchg* x, const orr_hit* hits_dev, const int32_
  * thread and without NCCL, for every device: query -> HBM, orr_search_device, orr_xchg_allgather_merge; then
  * reads the merged hits from device 0.  A document lives on one shard (the one that already holds it, else the
  * emptiest), so replace / delete touch one GPU.  Queries without an embedding, of another width, or with
- * top_k > max_top_k run shard by shard through orr_search and are merged on the host.  One search or
- * mutation at a time per cluster (a query saturates every GPU's HBM anyway). */
+ * top_k > max_top_k run through orr_search on every shard AT ONCE (one host thread per GPU) and are merged on the host.
+ * One search or mutation at a time per cluster (a query saturates every GPU's HBM anyway).  If a device fails to
+ * launch its part of a query, the cluster drains the others and re-synchronises its exchange buffers before returning. */
 typedef struct orr_cluster orr_cluster;
 struct orr_synth_spec;
 int  orr_cluster_create(const orr_config* cfg /* per shard; device and row_base are overwritten */,
@@ -317,6 +330,12 @@ int  orr_cluster_delete_document(orr_cluster* c, uint64_t doc_key);
 int  orr_cluster_fill_synthetic(orr_cluster* c, const struct orr_synth_spec* spec, uint64_t first_row, int64_t n_per_shard);
 int  orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim,
         int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
+        int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
+
+/* Batched queries over the cluster: orr_search_batch on every shard (one host thread per GPU), then a k-way merge of each
+ * query's per-shard lists under the reference tie chain.  Arguments as orr_search_batch. */
+int  orr_cluster_search_batch(orr_cluster* c, int32_t batch, const float* q, int32_t q_dim,
+        const int32_t* n_terms, const uint64_t* probe_hash, const int32_t* probe_term, const uint32_t* probe_offsets,
         int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
 
 const char* orr_last_error(void);

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "orr_store_vocab_size": (C.c_int64, [C.c_void_p]),
     "orr_search_query": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    "orr_expand_query": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32)]),
     "orr_store_delete_document": (C.c_int, [C.c_void_p, C.c_uint64]),
     "orr_store_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "orr_store_save": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -104,6 +106,9 @@ _SIGNATURES = {
     "orr_xchg_attach_peer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "orr_xchg_allgather_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
+    "orr_xchg_sequence": (C.c_uint32, [C.c_void_p]),
+    "orr_xchg_resync": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "orr_xchg_set_timeout_ms": (C.c_int, [C.c_void_p, C.c_double]),
     "orr_cluster_create": (C.c_int, [C.POINTER(OrrConfig), C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "orr_cluster_destroy": (None, [C.c_void_p]),
     "orr_cluster_size": (C.c_int32, [C.c_void_p]),
@@ -115,6 +120,8 @@ _SIGNATURES = {
     "orr_cluster_fill_synthetic": (C.c_int, [C.c_void_p, C.POINTER(OrrSynthSpec), C.c_uint64, C.c_int64]),
     "orr_cluster_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                      C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    "orr_cluster_search_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "orr_last_error": (C.c_char_p, []),
     "orr_last_timing": (C.c_int, [C.POINTER(OrrTiming)]),
     "orr_synth_spec_default": (None, [C.POINTER(OrrSynthSpec), C.c_int32]),

@@ -37,6 +37,9 @@ struct SearchCtx {
     // text mode scratch
     OrrTextTerms* d_terms = nullptr; OrrTextTerms* h_terms = nullptr;   // device / pinned
     uint32_t* d_kw_bits = nullptr; size_t kw_bits_words = 0;
+    // orr_search_device leases: the scratch is busy until `done` (recorded on the caller's stream) has completed
+    cudaEvent_t done = nullptr;
+    bool busy = false;
 };
 
 thread_local orr_timing g_timing{};
@@ -111,10 +114,14 @@ struct orr_store {
     std::shared_mutex mu;                                                           // searches shared, mutators exclusive
     std::mutex pool_mu;
     std::vector<std::unique_ptr<SearchCtx>> pool;
+    // orr_search_device: one scratch context per IN-FLIGHT call (several host threads may enqueue on different streams);
+    // a context is reused once the event recorded behind its kernels has completed.  Mutators that move rows
+    // (compact, load) wait for every in-flight device search first.
     std::mutex dev_mu;
-    std::unique_ptr<SearchCtx> dev_ctx;                                             // orr_search_device scratch
-    bool dev_timing_valid = false;
+    std::vector<std::unique_ptr<SearchCtx>> dev_pool;
+    SearchCtx* dev_last = nullptr;                                                  // the call orr_search_device_timing reports
     int64_t dev_rows = 0;
+    std::once_flag batch_once;
     std::mutex cap_mu;
     uint64_t cap_version = ~0ull;
     int32_t cap_value = -1;
@@ -161,6 +168,7 @@ void free_ctx(SearchCtx* c) {
     cudaFree(c->d_terms); cudaFree(c->d_kw_bits); cudaFreeHost(c->h_terms);
     cudaFreeHost(c->h_q); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_status); cudaFreeHost(c->h_rows);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->done) cudaEventDestroy(c->done);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -352,7 +360,7 @@ void orr_store_destroy(orr_store* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     for (auto& c : s->pool) free_ctx(c.get());
-    if (s->dev_ctx) free_ctx(s->dev_ctx.get());
+    for (auto& c : s->dev_pool) free_ctx(c.get());
     if (s->mut_stream) cudaStreamDestroy(s->mut_stream);
     if (s->batch) {
         BatchState* b = s->batch.get();
@@ -410,6 +418,7 @@ static int ensure_text_arena(orr_store* s) {
 }
 
 static void release_doc_words(orr_store* s, uint64_t doc_key);
+static int wait_device_searches(orr_store* s);
 
 static int tombstone_locked(orr_store* s, uint64_t doc_key) {
     auto it = s->docs.find(doc_key);
@@ -954,7 +963,7 @@ int orr_search_query(orr_store* s, const char* query_utf8, int32_t query_len, co
         }
         if (rc != ORR_OK && rc != ORR_E_UNSUPPORTED) return rc;
         if (rc == ORR_OK && np <= ORR_MAX_QUERY_PROBES)
-            return orr_search(s, q, q_dim, nt, np ? ph : nullptr, np ? pt : nullptr, np, now_ticks, top_k, candidate_cap, out, n_out);
+            return orr_search(s, q, q_dim, nt, ph, pt, np, now_ticks, top_k, candidate_cap, out, n_out);   // np may be 0: no live word holds any term
         if (keyword_mode == 1 || !has_text) {
             if (rc == ORR_OK) orr_set_error("orr_search_query: the terms expand to %d vocabulary words (limit %d) and the store keeps no chunk text", np, ORR_MAX_QUERY_PROBES);
             return ORR_E_UNSUPPORTED;
@@ -968,6 +977,27 @@ int orr_search_query(orr_store* s, const char* query_utf8, int32_t query_len, co
     std::vector<uint32_t> off((size_t)nt + 1, 0u);
     for (int t = 0; t < nt; ++t) { blob += terms[(size_t)t]; off[(size_t)t + 1] = (uint32_t)blob.size(); }
     return orr_search_text(s, q, q_dim, nt, blob.data(), off.data(), now_ticks, top_k, candidate_cap, out, n_out);
+}
+
+// The keyword side of a query as orr_search would receive it (inspection / tests): |terms| after A-2 filtering and the
+// (hash, term) probes of the vocabulary expansion.  *n_probes may exceed cap (nothing beyond cap is written).
+int orr_expand_query(orr_store* s, const char* query_utf8, int32_t query_len, uint64_t* probe_hash, int32_t* probe_term,
+                     int32_t cap, int32_t* n_terms, int32_t* n_probes) {
+    if (!s || !n_terms || !n_probes || query_len < 0 || (query_len > 0 && !query_utf8) || cap < 0 || (cap > 0 && (!probe_hash || !probe_term))) {
+        orr_set_error("orr_expand_query: bad argument");
+        return ORR_E_INVALID;
+    }
+    *n_terms = 0; *n_probes = 0;
+    std::vector<std::string> terms;
+    try {
+        std::vector<std::string> raw = orr_distinct_lower_tokens(query_utf8, query_len);
+        for (const auto& t : raw) if (!orr_is_stop_word(t)) terms.push_back(t);
+        if (terms.empty()) terms = raw;
+    } catch (const std::exception& e) { orr_set_error("orr_expand_query: %s", e.what()); return ORR_E_OOM; }
+    *n_terms = (int32_t)terms.size();
+    std::lock_guard<std::mutex> g(s->vocab_mu);
+    if (!s->vocab || terms.empty()) return ORR_OK;
+    return orr_vocab_expand(s->vocab, terms, probe_hash, probe_term, cap, n_probes);
 }
 
 // ---- snapshot / warm load ----------------------------------------------
@@ -1080,6 +1110,7 @@ int orr_store_load(orr_store* s, const char* path) {
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     if (s->rows_used != 0) { orr_set_error("orr_store_load: the store is not empty"); return ORR_E_INVALID; }
+    { const int wrc = wait_device_searches(s); if (wrc != ORR_OK) return wrc; }
     FILE* f = fopen(path, "rb");
     if (!f) { orr_set_error("orr_store_load: cannot open %s", path); return ORR_E_INVALID; }
     void* bounce = nullptr;
@@ -1255,6 +1286,7 @@ int orr_store_compact(orr_store* s, uint64_t* old_rows_out, int64_t out_cap, int
     if (!s || !n_live_out) { orr_set_error("orr_store_compact: NULL argument"); return ORR_E_INVALID; }
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    { const int wrc = wait_device_searches(s); if (wrc != ORR_OK) return wrc; }   // rows are about to move under any in-flight scan
     if ((int64_t)s->h_ticks.size() < s->rows_used) {
         const size_t have = s->h_ticks.size();
         s->h_ticks.resize((size_t)s->rows_used);
@@ -1376,23 +1408,55 @@ int orr_search_device(orr_store* s, const float* q_dev, int32_t q_dim, int32_t n
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (s->live_rows == 0) { ORR_CUDA_OK(cudaMemsetAsync(status_dev, 0, 2 * sizeof(int32_t), st)); return ORR_OK; }
     std::lock_guard<std::mutex> g(s->dev_mu);
-    if (!s->dev_ctx) { rc = make_ctx(s, s->dev_ctx, false); if (rc != ORR_OK) return rc; }
-    OrrScratch sc = s->dev_ctx->sc;
+    // lease a scratch context nobody's kernels are using: two calls on two streams must not share tickets / candidate buffers
+    SearchCtx* c = nullptr;
+    for (auto& cand : s->dev_pool) {
+        if (cand->busy && cudaEventQuery(cand->done) == cudaSuccess) cand->busy = false;
+        if (!cand->busy) { c = cand.get(); break; }
+    }
+    cudaGetLastError();                                              // cudaErrorNotReady from the queries above is not an error
+    if (!c) {
+        if (s->dev_pool.size() >= 64) {                              // 64 searches in flight: wait for the oldest instead of growing
+            c = s->dev_pool.front().get();
+            ORR_CUDA_OK(cudaEventSynchronize(c->done));
+            c->busy = false;
+        } else {
+            std::unique_ptr<SearchCtx> fresh;
+            rc = make_ctx(s, fresh, false);
+            if (rc != ORR_OK) return rc;
+            ORR_CUDA_OK(cudaEventCreateWithFlags(&fresh->done, cudaEventDisableTiming));
+            c = fresh.get();
+            s->dev_pool.push_back(std::move(fresh));
+        }
+    }
+    OrrScratch sc = c->sc;
     sc.q = const_cast<float*>(q_dev);
     sc.hits = out_dev;
     sc.status = status_dev;
     const OrrShard sh = shard_view(s);
     const int M = survivors_for(k);
-    SearchCtx* c = s->dev_ctx.get();
     ORR_CUDA_OK(cudaEventRecord(c->ev[0], st));
     rc = orr_launch_scan(sh, sc, pr, weights_of(s), now_ticks, M, s->sms, st);
-    if (rc != ORR_OK) return rc;
-    ORR_CUDA_OK(cudaEventRecord(c->ev[1], st));
-    rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, q_dim, k, M, true, st);
-    if (rc != ORR_OK) return rc;
+    if (rc == ORR_OK) {
+        cudaEventRecord(c->ev[1], st);
+        rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, q_dim, k, M, true, st);
+    }
+    // whatever was enqueued keeps the context busy until it has run, also on a failed launch
+    c->busy = true;
     ORR_CUDA_OK(cudaEventRecord(c->ev[2], st));
-    s->dev_timing_valid = true;
+    ORR_CUDA_OK(cudaEventRecord(c->done, st));
+    if (rc != ORR_OK) return rc;
+    s->dev_last = c;
     s->dev_rows = s->rows_used;
+    return ORR_OK;
+}
+
+// compact / load move rows: no orr_search_device kernel may still be reading them (the shared lock of the enqueue is long
+// gone by the time the kernels run).  Called with the exclusive lock held, so no new device search can be enqueued.
+int wait_device_searches(orr_store* s) {
+    std::lock_guard<std::mutex> g(s->dev_mu);
+    for (auto& c : s->dev_pool)
+        if (c->busy) { ORR_CUDA_OK(cudaEventSynchronize(c->done)); c->busy = false; }
     return ORR_OK;
 }
 
@@ -1400,9 +1464,9 @@ int orr_search_device_timing(orr_store* s, orr_timing* out) {
     if (!s || !out) { orr_set_error("orr_search_device_timing: NULL argument"); return ORR_E_INVALID; }
     std::lock_guard<std::mutex> g(s->dev_mu);
     memset(out, 0, sizeof *out);
-    if (!s->dev_ctx || !s->dev_timing_valid) { orr_set_error("orr_search_device_timing: no orr_search_device call yet"); return ORR_E_INVALID; }
+    if (!s->dev_last) { orr_set_error("orr_search_device_timing: no orr_search_device call yet"); return ORR_E_INVALID; }
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
-    SearchCtx* c = s->dev_ctx.get();
+    SearchCtx* c = s->dev_last;
     ORR_CUDA_OK(cudaEventSynchronize(c->ev[2]));
     ORR_CUDA_OK(cudaEventElapsedTime(&out->scan_ms, c->ev[0], c->ev[1]));
     ORR_CUDA_OK(cudaEventElapsedTime(&out->finalize_ms, c->ev[1], c->ev[2]));
@@ -1491,7 +1555,7 @@ static double batch_eps(const OrrWeights& w, int passes) {
 static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const int32_t* n_terms,
                            const uint64_t* probe_hash, const uint32_t* probe_offsets, int64_t now_ticks, int32_t top_k,
                            orr_hit* out, int32_t* n_out, int passes, std::vector<int32_t>* redo) {
-    if (!s->batch) s->batch.reset(new BatchState());
+    std::call_once(s->batch_once, [&] { s->batch.reset(new BatchState()); });    // searches hold the lock SHARED: create once
     BatchState* bs = s->batch.get();
     std::lock_guard<std::mutex> g(bs->mu);
     const int dim = s->cfg.dim, k = std::max(1, top_k);
@@ -1806,7 +1870,7 @@ int orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t 
     if (!s || !q || !out || batch < 1 || batch > ORR_BATCH_MAX_QUERIES || q_dim != s->cfg.dim || tile_stride < 1) { orr_set_error("orr_debug_batch_scores: bad argument"); return ORR_E_INVALID; }
     std::shared_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
-    if (!s->batch) s->batch.reset(new BatchState());
+    std::call_once(s->batch_once, [&] { s->batch.reset(new BatchState()); });
     BatchState* bs = s->batch.get();
     std::lock_guard<std::mutex> g(bs->mu);
     const int dim = s->cfg.dim;
@@ -1843,9 +1907,6 @@ int orr_merge_hits(const orr_hit* lists, const int32_t* list_len, int32_t n_list
                    int32_t top_k, orr_hit* out, int32_t* n_out) {
     if (!lists || !list_len || !out || !n_out || n_lists < 0 || list_stride < 0) { orr_set_error("orr_merge_hits: bad argument"); return ORR_E_INVALID; }
     const int k = std::max(1, top_k);
-    std::vector<orr_hit> all;
-    for (int32_t l = 0; l < n_lists; ++l)
-        for (int32_t i = 0; i < list_len[l] && i < list_stride; ++i) all.push_back(lists[(int64_t)l * list_stride + i]);
     auto before = [](const orr_hit& x, const orr_hit& y) {
         const bool xn = std::isnan(x.score), yn = std::isnan(y.score);
         if (xn != yn) return yn;
@@ -1853,9 +1914,18 @@ int orr_merge_hits(const orr_hit* lists, const int32_t* list_len, int32_t n_list
         if (x.created_ticks != y.created_ticks) return x.created_ticks > y.created_ticks;
         return x.row < y.row;
     };
-    std::sort(all.begin(), all.end(), before);
-    const int got = std::min<int>(k, (int)all.size());
-    for (int i = 0; i < got; ++i) out[i] = all[(size_t)i];
+    // every list is already in reference order: a k-way pick of the best head, k times
+    std::vector<int32_t> head((size_t)n_lists, 0);
+    int got = 0;
+    while (got < k) {
+        int best = -1;
+        for (int32_t l = 0; l < n_lists; ++l) {
+            if (head[(size_t)l] >= list_len[l] || head[(size_t)l] >= list_stride) continue;
+            if (best < 0 || before(lists[(int64_t)l * list_stride + head[(size_t)l]], lists[(int64_t)best * list_stride + head[(size_t)best]])) best = l;
+        }
+        if (best < 0) break;
+        out[got++] = lists[(int64_t)best * list_stride + head[(size_t)best]++];
+    }
     *n_out = got;
     return ORR_OK;
 }

@@ -8,6 +8,7 @@
 // Built on the public C ABI only (orr_store_*, orr_search_device, orr_xchg_*).
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 #include "orr_internal.h"
 
@@ -147,6 +148,34 @@ int orr_cluster_fill_synthetic(orr_cluster* c, const orr_synth_spec* spec, uint6
     return ORR_OK;
 }
 
+// after a partial launch (device d failed after devices < d had already pushed their lists): let the launched exchange
+// kernels run into their time-out, then give every exchange buffer a common sequence base again
+static void cluster_recover(orr_cluster* c) {
+    uint32_t top = 0;
+    for (int d = 0; d < c->n; ++d) {
+        cudaSetDevice(c->devices[d]);
+        cudaStreamSynchronize(c->stream[d]);
+        top = std::max(top, orr_xchg_sequence(c->xchg[d]));
+    }
+    cudaGetLastError();
+    for (int d = 0; d < c->n; ++d) orr_xchg_resync(c->xchg[d], (top + ORR_XCHG_SLOTS) & 0x7fffffffu);
+}
+
+// runs fn(d) for every shard on its own host thread (the shards' searches are independent and each saturates its GPU)
+template <class F>
+static int for_each_shard_parallel(orr_cluster* c, F fn) {
+    std::vector<int> rcs((size_t)c->n, ORR_OK);
+    std::vector<std::string> errs((size_t)c->n);
+    std::vector<std::thread> th;
+    for (int d = 1; d < c->n; ++d)
+        th.emplace_back([&, d] { rcs[(size_t)d] = fn(d); if (rcs[(size_t)d] != ORR_OK) errs[(size_t)d] = orr_last_error(); });
+    rcs[0] = fn(0);
+    for (auto& t : th) t.join();
+    for (int d = 0; d < c->n; ++d)
+        if (rcs[(size_t)d] != ORR_OK) { if (d > 0) orr_set_error("shard %d: %s", d, errs[(size_t)d].c_str()); return rcs[(size_t)d]; }
+    return ORR_OK;
+}
+
 int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
                        const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
     if (!c || !out || !n_out || q_dim < 0 || (q_dim > 0 && !q)) { orr_set_error("orr_cluster_search: bad argument"); return ORR_E_INVALID; }
@@ -156,20 +185,32 @@ int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_
     bool fused = q_dim == c->dim && k <= c->max_k;
     if (fused) {
         memcpy(c->h_q, q, sizeof(float) * (size_t)q_dim);
-        for (int d = 0; d < c->n; ++d) {
-            ORR_CUDA_OK(cudaSetDevice(c->devices[d]));
-            ORR_CUDA_OK(cudaMemcpyAsync(c->d_q[d], c->h_q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream[d]));
-            int rc = orr_search_device(c->store[d], c->d_q[d], q_dim, n_terms, probe_hash, probe_term, n_probes, now_ticks, top_k,
-                                       c->d_hits[d], c->d_status[d], c->stream[d]);
-            if (rc != ORR_OK) return rc;
-            rc = orr_xchg_allgather_merge(c->xchg[d], c->d_hits[d], c->d_status[d], top_k, c->d_out[d], c->d_out_status[d], c->stream[d]);
-            if (rc != ORR_OK) return rc;
+        int rc = ORR_OK;
+        for (int d = 0; d < c->n && rc == ORR_OK; ++d) {
+            rc = [&]() -> int {
+                ORR_CUDA_OK(cudaSetDevice(c->devices[d]));
+                ORR_CUDA_OK(cudaMemcpyAsync(c->d_q[d], c->h_q, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream[d]));
+                int r = orr_search_device(c->store[d], c->d_q[d], q_dim, n_terms, probe_hash, probe_term, n_probes, now_ticks, top_k,
+                                          c->d_hits[d], c->d_status[d], c->stream[d]);
+                if (r != ORR_OK) return r;
+                return orr_xchg_allgather_merge(c->xchg[d], c->d_hits[d], c->d_status[d], top_k, c->d_out[d], c->d_out_status[d], c->stream[d]);
+            }();
+        }
+        if (rc != ORR_OK) {
+            const std::string msg = orr_last_error();
+            cluster_recover(c);                                    // the devices that did launch are waiting for the one that did not
+            orr_set_error("%s", msg.c_str());
+            return rc;
         }
         ORR_CUDA_OK(cudaSetDevice(c->devices[0]));
         ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->d_out_status[0], sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream[0]));
         ORR_CUDA_OK(cudaMemcpyAsync(c->h_out, c->d_out[0], sizeof(orr_hit) * (size_t)k, cudaMemcpyDeviceToHost, c->stream[0]));
         ORR_CUDA_OK(cudaStreamSynchronize(c->stream[0]));
-        if (c->h_status[1] & ORR_STATUS_XCHG_TIMEOUT) { orr_set_error("orr_cluster_search: a shard never published its list"); return ORR_E_CUDA; }
+        if (c->h_status[1] & ORR_STATUS_XCHG_TIMEOUT) {
+            cluster_recover(c);
+            orr_set_error("orr_cluster_search: a shard never published its list");
+            return ORR_E_CUDA;
+        }
         if (c->h_status[1] == 0) {
             const int got = std::min(c->h_status[0], k);
             memcpy(out, c->h_out, sizeof(orr_hit) * (size_t)got);
@@ -179,15 +220,49 @@ int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_
         // a shard could not prove its fp32 selection: fall through to the per-shard host path (which escalates)
         for (int d = 0; d < c->n; ++d) { ORR_CUDA_OK(cudaSetDevice(c->devices[d])); ORR_CUDA_OK(cudaStreamSynchronize(c->stream[d])); }
     }
-    // no query embedding, a query of another width, k beyond the fused path: per-shard orr_search + host merge
+    // no query embedding (the reference's default configuration), a query of another width, k beyond the fused path:
+    // every shard runs orr_search (-> exact path) on its own host thread, the lists are merged on the host
     std::vector<orr_hit> lists((size_t)c->n * k);
     std::vector<int32_t> lens((size_t)c->n, 0);
-    for (int d = 0; d < c->n; ++d) {
-        const int rc = orr_search(c->store[d], q, q_dim, n_terms, probe_hash, probe_term, n_probes, now_ticks, top_k, 0,
-                                  lists.data() + (size_t)d * k, &lens[(size_t)d]);
-        if (rc != ORR_OK) return rc;
-    }
+    const int rc = for_each_shard_parallel(c, [&](int d) {
+        return orr_search(c->store[d], q, q_dim, n_terms, probe_hash, probe_term, n_probes, now_ticks, top_k, 0,
+                          lists.data() + (size_t)d * k, &lens[(size_t)d]);
+    });
+    if (rc != ORR_OK) return rc;
     return orr_merge_hits(lists.data(), lens.data(), c->n, k, top_k, out, n_out);
+}
+
+// Batched queries over the shards: every shard runs orr_search_batch (tcgen05 contraction + exact re-rank, with its own
+// cascade / re-run handling) on its own host thread — the hits come down once per shard, in parallel over the GPUs' own
+// PCIe links — and each query's N sorted lists are merged by a k-way pick under the reference tie chain, the queries
+// split over the same threads.
+int orr_cluster_search_batch(orr_cluster* c, int32_t batch, const float* q, int32_t q_dim, const int32_t* n_terms,
+                             const uint64_t* probe_hash, const int32_t* probe_term, const uint32_t* probe_offsets,
+                             int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
+    if (!c || batch < 0 || !out || !n_out || (batch > 0 && q_dim > 0 && !q)) { orr_set_error("orr_cluster_search_batch: bad argument"); return ORR_E_INVALID; }
+    if (batch == 0) return ORR_OK;
+    const int k = std::max(1, top_k);
+    std::lock_guard<std::mutex> g(c->mu);
+    std::vector<orr_hit> lists((size_t)c->n * (size_t)batch * k);
+    std::vector<int32_t> lens((size_t)c->n * (size_t)batch, 0);
+    int rc = for_each_shard_parallel(c, [&](int d) {
+        return orr_search_batch(c->store[d], batch, q, q_dim, n_terms, probe_hash, probe_term, probe_offsets, now_ticks, top_k,
+                                lists.data() + (size_t)d * batch * k, lens.data() + (size_t)d * batch);
+    });
+    if (rc != ORR_OK) return rc;
+    return for_each_shard_parallel(c, [&](int d) {
+        std::vector<orr_hit> mine((size_t)c->n * k);
+        std::vector<int32_t> ml((size_t)c->n);
+        for (int32_t b = d; b < batch; b += c->n) {
+            for (int l = 0; l < c->n; ++l) {
+                ml[(size_t)l] = lens[(size_t)l * batch + b];
+                memcpy(mine.data() + (size_t)l * k, lists.data() + ((size_t)l * batch + b) * k, sizeof(orr_hit) * (size_t)k);
+            }
+            const int r = orr_merge_hits(mine.data(), ml.data(), c->n, k, top_k, out + (size_t)b * k, n_out + b);
+            if (r != ORR_OK) return r;
+        }
+        return (int)ORR_OK;
+    });
 }
 
 }  // extern "C"

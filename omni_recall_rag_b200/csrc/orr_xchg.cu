@@ -98,6 +98,33 @@ int orr_xchg_attach_peer(orr_xchg* x, int32_t peer_rank, orr_xchg* peer) {
     return ORR_OK;
 }
 
+// After a time-out (a rank issued fewer searches than its peers, or died) the ranks' sequence numbers are out of step and
+// every later exchange would time out too.  Resynchronisation is an agreement made OUT OF BAND: every rank drains its
+// stream, the ranks agree on a number larger than any sequence number in use (e.g. an all-reduce MAX of
+// orr_xchg_sequence() plus ORR_XCHG_SLOTS), every rank calls orr_xchg_resync with it, and a barrier follows before the
+// next exchange.  Stale words in the slots carry older tags and can never match.
+int orr_xchg_resync(orr_xchg* x, uint32_t next_seq_base) {
+    if (!x) { orr_set_error("orr_xchg_resync: NULL argument"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> g(x->mu);
+    x->seq = next_seq_base;
+    return ORR_OK;
+}
+
+uint32_t orr_xchg_sequence(orr_xchg* x) {
+    if (!x) return 0;
+    std::lock_guard<std::mutex> g(x->mu);
+    return x->seq;
+}
+
+// How long the exchange kernel spins for a missing peer before it gives up and flags ORR_STATUS_XCHG_TIMEOUT
+// (default 5 s; the GPU is occupied by one CTA meanwhile).
+int orr_xchg_set_timeout_ms(orr_xchg* x, double ms) {
+    if (!x || !(ms > 0.0) || ms > 600000.0) { orr_set_error("orr_xchg_set_timeout_ms: bad argument"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> g(x->mu);
+    x->timeout_s = ms / 1000.0;
+    return ORR_OK;
+}
+
 int orr_xchg_allgather_merge(orr_xchg* x, const orr_hit* hits_dev, const int32_t* status_dev, int32_t top_k,
                              orr_hit* out_dev, int32_t* out_status_dev, void* cuda_stream) {
     if (!x || !hits_dev || !status_dev || !out_dev || !out_status_dev) { orr_set_error("orr_xchg_allgather_merge: NULL argument"); return ORR_E_INVALID; }

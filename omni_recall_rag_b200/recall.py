@@ -13,7 +13,7 @@ from typing import List, Optional, Protocol, Sequence
 
 import numpy as np
 
-from .shard import QueryTerms, hash_term
+from .shard import QueryTerms, hash_term  # noqa: F401
 from .store import GpuIngestionStore, _distinct_lower_tokens, _WS  # noqa: F401
 from . import _native as N
 
@@ -103,39 +103,33 @@ class GpuRecallSearchService:
         raw = _distinct_lower_tokens(query)
         return [t for t in raw if t not in STOP_WORDS] or raw
 
+    _MODES = {"auto": 0, "hashed": 1, "text": 2}
+
     def query_terms(self, query: str) -> QueryTerms:
-        """KeywordScore's query side (:95-108) + substring expansion over the live vocabulary
-        (:111): term t matches a chunk iff some word of the chunk contains t."""
-        raw = _distinct_lower_tokens(query)
-        terms = [t for t in raw if t not in STOP_WORDS] or raw
-        hashes, owner = [], []
-        for i, t in enumerate(terms):
-            words = self.store.vocabulary_words_containing(t)
-            for w in words:
-                hashes.append(hash_term(w))
-                owner.append(i)
-        if len(terms) > N.ORR_MAX_QUERY_TERMS or len(hashes) > N.ORR_MAX_QUERY_PROBES:
+        """The hashed keyword side the library derives from `query` (orr_expand_query): KeywordScore's query side
+        (:95-108) + substring expansion over the live vocabulary (:111).  search() does not need it (orr_search_query
+        does both in one call); it is here for inspection and tests."""
+        qt, n_probes = self.store.shard.expand_query(query)
+        if qt.n_terms > N.ORR_MAX_QUERY_TERMS or n_probes > N.ORR_MAX_QUERY_PROBES:
             raise UnsupportedQueryError(
-                f"{len(terms)} terms / {len(hashes)} vocabulary probes exceed the kernel limits "
+                f"{qt.n_terms} terms / {n_probes} vocabulary probes exceed the kernel limits "
                 f"({N.ORR_MAX_QUERY_TERMS} / {N.ORR_MAX_QUERY_PROBES})")
-        return QueryTerms(len(terms), np.array(hashes, dtype=np.uint64), np.array(owner, dtype=np.int32))
+        return qt
 
     def search(self, query: str, top_k: int) -> RecallSearchResponseDto:  # SearchAsync :20-57
         if query is None or all(ord(ch) in _WS for ch in query):
             raise ValueError("Query is required.")  # ArgumentException (:22-23)
         query_embedding = self.embedding_client.embed(query)  # :25
         qvec = np.asarray(query_embedding.vector, dtype=np.float32)
-        hits = None
-        if self.keyword_mode != "text":
-            try:
-                hits = self.store.shard.search(qvec, self.query_terms(query), self._clock(), top_k,
-                                               candidate_cap=self.candidate_cap)  # :26-37 on the GPU
-            except UnsupportedQueryError:
-                if self.keyword_mode == "hashed" or not self.store.keep_text:
-                    raise
-        if hits is None:     # a term is a substring of too many words (or text mode was asked for)
-            hits = self.store.shard.search_text(qvec, self.filtered_terms(query), self._clock(), top_k,
-                                                candidate_cap=self.candidate_cap)
+        try:
+            # :26-37 behind the C ABI: tokenise + stop words (:95-108), vocabulary expansion on the GPU (:110-111),
+            # fused scan, exact re-score, ordering
+            hits = self.store.shard.search_query(query, qvec, self._clock(), top_k, candidate_cap=self.candidate_cap,
+                                                 keyword_mode=self._MODES[self.keyword_mode])
+        except N.OrrError as e:
+            if e.code == N.ORR_E_UNSUPPORTED:
+                raise UnsupportedQueryError(str(e)) from e
+            raise
         scored = [(self.store.chunk_of_row(int(r)), float(s)) for r, s in zip(hits.rows, hits.scores)]
         documents = self.store.get_documents_by_ids(list({c.document_id for c, _ in scored}))  # :39
         citations = []

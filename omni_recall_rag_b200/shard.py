@@ -297,6 +297,17 @@ class RecallShard:
                                          C.cast(out, C.c_void_p), C.byref(n)))
         return _hits_from(out, n.value)
 
+    def expand_query(self, query: str, cap: int = N.ORR_MAX_QUERY_PROBES):
+        """orr_expand_query -> (QueryTerms, n_probes): the probes are truncated to `cap`; n_probes is the full count."""
+        b = query.encode("utf-8")
+        ph = np.zeros(max(cap, 1), dtype=np.uint64)
+        pt = np.zeros(max(cap, 1), dtype=np.int32)
+        nt, npb = C.c_int32(0), C.c_int32(0)
+        N.check(N.lib().orr_expand_query(self._h, b, len(b), ph.ctypes.data_as(C.c_void_p), pt.ctypes.data_as(C.c_void_p), cap,
+                                         C.byref(nt), C.byref(npb)))
+        m = min(cap, npb.value)
+        return QueryTerms(nt.value, ph[:m].copy(), pt[:m].copy()), npb.value
+
     def search_text(self, q: Optional[np.ndarray], terms_lower: Sequence[str], now_ticks: int, top_k: int,
                     candidate_cap: int = 0) -> Hits:
         """orr_search_text: the keyword predicate evaluated as an ordinal substring search of each (lower-cased,

@@ -101,6 +101,25 @@ class ShardedRecall:
                 N.check(L.orr_xchg_open_peer(x, r, C.cast(h, C.c_void_p)))
         self.dist.barrier(group=self.group)            # every rank has every peer mapped before the first push
 
+    def resync(self) -> None:
+        """Recovery after an exchange time-out (a peer issued a different number of searches): a collective.  Every
+        rank drains its device, the ranks agree on a sequence number above any in use, and a barrier precedes the next
+        exchange (orr_xchg_resync)."""
+        if self._xchg is None:
+            return
+        import torch
+
+        torch.cuda.synchronize()
+        dev = torch.device("cuda", self.shard.device)
+        t = torch.tensor([int(N.lib().orr_xchg_sequence(self._xchg))], dtype=torch.int64, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        N.check(N.lib().orr_xchg_resync(self._xchg, (int(t.item()) + 16) & 0x7fffffff))
+        self.dist.barrier(group=self.group)
+
+    def set_exchange_timeout_ms(self, ms: float) -> None:
+        if self._xchg is not None:
+            N.check(N.lib().orr_xchg_set_timeout_ms(self._xchg, float(ms)))
+
     def last_timing(self) -> dict:
         """Kernel durations (CUDA events) of this rank's part of the last search()."""
         return dict(getattr(self, "_last_timing", {}))

@@ -39,9 +39,10 @@ class CosmosChunkRecord:  # Data/Models/CosmosIngestionRecords.cs:19-30
 
 
 class GpuIngestionStore:
-    """IIngestionStore over one RecallShard.  Document records, chunk text and ids stay on
-    the host (they are only needed for the <= top_k citations); embeddings, timestamps and
-    hashed term sets are mirrored into HBM on every upsert."""
+    """IIngestionStore over one RecallShard.  Document records, chunk text and ids stay on the host (they are only
+    needed for the <= top_k citations); embeddings, timestamps, hashed term sets, the live vocabulary and (keep_text)
+    the lower-cased Content are mirrored into HBM on every upsert, behind ONE C-ABI call per document
+    (orr_store_upsert_document_texts: the library tokenises and hashes)."""
 
     def __init__(self, dim: int, capacity_rows: int = 1 << 16, *, device: int = 0, term_slots: int = 128,
                  keep_text: bool = True, text_bytes_per_row: int = 2048):
@@ -50,12 +51,13 @@ class GpuIngestionStore:
         self.keep_text = keep_text          # lower-cased Content mirrored into HBM (text mode, orr_search_text)
         if keep_text:
             self.shard.set_option("text_bytes_per_row", text_bytes_per_row)
+            self.shard.set_option("keep_text", 1)
         self._lock = threading.RLock()
         self._documents: Dict[str, CosmosDocumentRecord] = {}
         self._chunks_by_document: Dict[str, List[CosmosChunkRecord]] = {}
         self._rows_by_document: Dict[str, np.ndarray] = {}
         self._chunk_by_row: Dict[int, CosmosChunkRecord] = {}
-        self._vocab: Dict[str, int] = {}          # lower-cased token -> live chunks containing it
+        self._synth = None                  # (spec, first_row, n): rows filled by fill_synthetic have no host records
 
     def close(self) -> None:
         self.shard.close()
@@ -75,8 +77,6 @@ class GpuIngestionStore:
         emb = np.zeros((n, self.dim), dtype=np.float32)
         has = np.zeros(n, dtype=np.uint8)
         ticks = np.zeros(n, dtype=np.int64)
-        hashes = []
-        tokens_per_chunk = []
         for i, c in enumerate(ordered):
             e = c.embedding
             # an Embedding that is null/empty/of another width scores cosine 0 against any
@@ -85,22 +85,13 @@ class GpuIngestionStore:
                 emb[i] = np.asarray(e, dtype=np.float32)
                 has[i] = 1
             ticks[i] = c.created_at_utc
-            toks = _distinct_lower_tokens(c.content)
-            if len(toks) > self.shard.term_slots:
-                raise ValueError(f"chunk {c.id!r} has {len(toks)} distinct tokens; the store was created "
-                                 f"with term_slots={self.shard.term_slots}")
-            tokens_per_chunk.append(toks)
-            hashes.append(np.array([hash_term(t) for t in toks], dtype=np.uint64))
         with self._lock:
+            rows = self.shard.upsert_document_texts(_doc_key(document_id), emb, ticks, [c.content or "" for c in ordered], has)
             self._forget_rows(document_id)
-            texts = [_lower_invariant(c.content or "") for c in ordered] if self.keep_text else None
-            rows = self.shard.upsert_document_chunks(_doc_key(document_id), emb, ticks, hashes, has, texts)
             self._chunks_by_document[document_id] = ordered
             self._rows_by_document[document_id] = rows
-            for r, c, toks in zip(rows, ordered, tokens_per_chunk):
+            for r, c in zip(rows, ordered):
                 self._chunk_by_row[int(r)] = c
-                for t in toks:
-                    self._vocab[t] = self._vocab.get(t, 0) + 1
 
     def get_document(self, document_id: str) -> Optional[CosmosDocumentRecord]:  # :27-31
         return self._documents.get(document_id)
@@ -147,53 +138,87 @@ class GpuIngestionStore:
             return before - len(old_rows)
 
     def save(self, directory: str) -> None:
-        """HBM image (orr_store_save) + the host-side records, so a restart does not re-ingest."""
+        """HBM image + vocabulary (orr_store_save) and the host-side records as JSON, so a restart does not re-ingest."""
+        import json
         import os
-        import pickle
 
         os.makedirs(directory, exist_ok=True)
         with self._lock:
             self.shard.save(os.path.join(directory, "shard.orrsnap"))
-            with open(os.path.join(directory, "host.pkl"), "wb") as f:
-                pickle.dump({"documents": self._documents, "chunks": self._chunks_by_document,
-                             "rows": self._rows_by_document, "vocab": self._vocab}, f)
+            host = {
+                "documents": [vars(d) for d in self._documents.values()],
+                "chunks": {d: [dict(vars(c), embedding=None) for c in cs] for d, cs in self._chunks_by_document.items()},
+                "rows": {d: [int(r) for r in rows] for d, rows in self._rows_by_document.items()},
+            }
+            with open(os.path.join(directory, "host.json"), "w", encoding="utf-8") as f:
+                json.dump(host, f)
 
     def load(self, directory: str) -> None:
+        """Plain data only (JSON): nothing in a snapshot directory is executed.  Embeddings live in the HBM image;
+        the host records come back without them (they are never read on the host)."""
+        import json
         import os
-        import pickle
 
         with self._lock:
             self.shard.load(os.path.join(directory, "shard.orrsnap"))
-            with open(os.path.join(directory, "host.pkl"), "rb") as f:
-                h = pickle.load(f)
-            self._documents, self._chunks_by_document = h["documents"], h["chunks"]
-            self._rows_by_document, self._vocab = h["rows"], h["vocab"]
+            with open(os.path.join(directory, "host.json"), encoding="utf-8") as f:
+                h = json.load(f)
+            self._documents = {d["id"]: CosmosDocumentRecord(**d) for d in h["documents"]}
+            self._chunks_by_document = {d: [CosmosChunkRecord(**c) for c in cs] for d, cs in h["chunks"].items()}
+            self._rows_by_document = {d: np.array(rows, dtype=np.uint64) for d, rows in h["rows"].items()}
             self._chunk_by_row = {int(r): c for d, rows in self._rows_by_document.items()
                                   for r, c in zip(rows, self._chunks_by_document[d])}
 
+    # -- synthetic corpora (bench / tests): rows generated on the device, records derived on demand ---------------
+    def fill_synthetic(self, spec, n: int, first_row: int = 0) -> None:
+        """The bench corpus behind the service API: rows come from orr_store_fill_synthetic (with the chunk text if the
+        store keeps text), the 2^20 synthetic tokens are registered as the vocabulary, and a hit's CosmosChunkRecord is
+        rebuilt from the generator when a citation needs it (document = the run of rows sharing one timestamp)."""
+        with self._lock:
+            if self.shard.rows_used != 0:
+                raise ValueError("fill_synthetic needs an empty store")
+            self.shard.set_option("synth_vocab", 1)
+            if self.keep_text:
+                self.shard.set_option("synth_text", 1)
+            self.shard.fill_synthetic(spec, first_row, n)
+            self._synth = (spec, first_row, n)
+
+    def _synthetic_chunk(self, row: int) -> CosmosChunkRecord:
+        import ctypes as C
+
+        from . import _native as N
+        from . import synth
+
+        spec, first_row, _ = self._synth
+        g = first_row + (row - self.shard.row_base)
+        r = synth.rows_host(spec, g, 1, want_emb=False)
+        buf = C.create_string_buffer(9 * max(spec.terms_per_chunk, 1))
+        ln = N.lib().orr_synth_row_text(C.byref(spec), g, buf, len(buf))
+        doc_first = int(r.doc_first_row[0])
+        return CosmosChunkRecord(id=f"synth-{doc_first}:{g - doc_first:04d}", document_id=f"synth-{doc_first}",
+                                 chunk_index=g - doc_first, content=buf.raw[:ln].decode("ascii"), embedding=None,
+                                 created_at_utc=int(r.ticks[0]))
+
     # -- used by GpuRecallSearchService -------------------------------------------------------
     def chunk_of_row(self, row: int) -> CosmosChunkRecord:
-        return self._chunk_by_row[int(row)]
+        c = self._chunk_by_row.get(int(row))
+        if c is None and self._synth is not None:
+            return self._synthetic_chunk(int(row))
+        if c is None:
+            raise KeyError(row)
+        return c
 
-    def vocabulary_words_containing(self, term: str) -> List[str]:
-        """Words of the live corpus that contain `term` as an ordinal substring — the host
-        half of `contentLower.Contains(term)` (RecallSearchService.cs:111)."""
-        with self._lock:
-            return [w for w in self._vocab if term in w]
+    @property
+    def vocabulary_size(self) -> int:
+        """Distinct tokens held by live chunks (kept in HBM; query terms are expanded over it on the GPU)."""
+        return self.shard.vocab_size
 
     def _forget_rows(self, document_id: str) -> None:
         rows = self._rows_by_document.pop(document_id, None)
         if rows is None:
             return
         for r in rows:
-            c = self._chunk_by_row.pop(int(r), None)
-            if c is not None:
-                for t in _distinct_lower_tokens(c.content):
-                    left = self._vocab.get(t, 0) - 1
-                    if left <= 0:
-                        self._vocab.pop(t, None)
-                    else:
-                        self._vocab[t] = left
+            self._chunk_by_row.pop(int(r), None)
 
 
 def _doc_key(document_id: str) -> int:
