@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _native as N
-from .shard import Hits, QueryTerms, _hits_from
+from .shard import BatchHits, BatchTerms, Hits, QueryTerms, _HIT_DTYPE, _hits_from
 
 ROW_SHIFT = 40  # global row id = shard << 40 | local row
 
@@ -94,3 +94,20 @@ class RecallCluster:
             ph.ctypes.data_as(C.c_void_p) if ph.size else None, None if pt is None else pt.ctypes.data_as(C.c_void_p),
             int(ph.size), int(now_ticks), int(top_k), C.cast(out, C.c_void_p), C.byref(n)))
         return _hits_from(out, n.value)
+
+    def search_batch(self, q: np.ndarray, terms, now_ticks: int, top_k: int) -> BatchHits:
+        """orr_cluster_search_batch: orr_search_batch on every shard (one host thread per GPU) + per-query k-way merge."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B, qd = int(q.shape[0]), int(q.shape[1]) if q.ndim == 2 else 0
+        k = max(1, int(top_k))
+        raw = np.zeros((max(B, 1), k), dtype=_HIT_DTYPE)
+        n_out = np.zeros(max(B, 1), dtype=np.int32)
+        bt = None
+        if terms is not None:
+            bt = terms if isinstance(terms, BatchTerms) else BatchTerms.pack(terms)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        N.check(N.lib().orr_cluster_search_batch(self._h, B, p(q) if q.size else None, qd,
+                                                 p(bt.n_terms) if bt else None, p(bt.probe_hash) if bt else None,
+                                                 p(bt.probe_term) if bt else None, p(bt.probe_offsets) if bt else None,
+                                                 int(now_ticks), int(top_k), p(raw), p(n_out)))
+        return BatchHits(raw[:B], n_out[:B])

@@ -148,6 +148,8 @@ int orr_cluster_fill_synthetic(orr_cluster* c, const orr_synth_spec* spec, uint6
     return ORR_OK;
 }
 
+}  // extern "C"
+
 // after a partial launch (device d failed after devices < d had already pushed their lists): let the launched exchange
 // kernels run into their time-out, then give every exchange buffer a common sequence base again
 static void cluster_recover(orr_cluster* c) {
@@ -175,6 +177,8 @@ static int for_each_shard_parallel(orr_cluster* c, F fn) {
         if (rcs[(size_t)d] != ORR_OK) { if (d > 0) orr_set_error("shard %d: %s", d, errs[(size_t)d].c_str()); return rcs[(size_t)d]; }
     return ORR_OK;
 }
+
+extern "C" {
 
 int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
                        const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {

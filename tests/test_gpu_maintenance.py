@@ -187,3 +187,95 @@ def test_searches_run_against_concurrent_mutations():
         assert got == _oracle_citations(st, "azure vector", qv, 10, 0)
     finally:
         st.close()
+
+
+def test_device_searches_on_distinct_streams_batches_and_mutators_stress():
+    """ADVICE r1 / VERDICT r1 item 8: several host threads call orr_search_device on their OWN streams (each call leases
+    its own scratch: tickets, candidate buffers), another runs orr_search_batch, another mutates (replace, delete,
+    compact: rows move, so compact first waits for every in-flight device search).  The queried rows are a synthetic
+    block at the front of the store that the mutators never touch (compaction keeps leading live rows in place); the
+    mutated documents carry zero embeddings and 10-year-old timestamps, so they cannot enter a top-10.  EVERY result must
+    equal the oracle's.  ORR_STRESS_SMALL=1 shrinks it for compute-sanitizer --tool racecheck (tools/racecheck.sh)."""
+    import os
+
+    import torch
+
+    from omni_recall_rag_b200 import sharded
+    from tests.util import assert_same_ranking, oracle_search_synth
+
+    small = bool(os.environ.get("ORR_STRESS_SMALL"))
+    dim, n_syn, iters, k = (128, 1500, 4, 10) if small else (256, 20_000, 40, 10)
+    spec = synth.make_spec(dim, gen_dim=dim, dup_row_ppm=10000)
+    rows = synth.rows_host(spec, 0, n_syn)
+    n_q = 6 if small else 24
+    qs = [synth.query_host(spec, qi, n_syn, n_terms=4) for qi in range(n_q)]
+    expected = [oracle_search_synth(rows, q, NOW, k) for q in qs]
+    sh = orr.RecallShard(dim, n_syn + 4096)
+    errors, stop = [], threading.Event()
+    try:
+        sh.fill_synthetic(spec, 0, n_syn)
+        old = NOW - 3650 * DAY
+
+        def check(got_rows, got_scores, qi, what):
+            er, es, _ = expected[qi]
+            assert_same_ranking(got_rows, got_scores, er, es, what=what)
+
+        def device_searcher(tid):
+            try:
+                dev = torch.device("cuda", 0)
+                stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(stream):
+                    q_dev = [torch.from_numpy(q.q).to(dev) for q in qs]
+                    hits = [torch.zeros(k * 24, dtype=torch.uint8, device=dev) for _ in range(3)]
+                    status = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(3)]
+                stream.synchronize()
+                it = 0
+                while not stop.is_set() and it < iters:
+                    ids = [(tid + 3 * it + j) % n_q for j in range(3)]        # three searches in flight on this stream
+                    for j, qi in enumerate(ids):
+                        sh.search_device(q_dev[qi].data_ptr(), qs[qi].terms, NOW, k, hits[j].data_ptr(), status[j].data_ptr(),
+                                         stream.cuda_stream)
+                    stream.synchronize()
+                    for j, qi in enumerate(ids):
+                        got, flags = sharded.hits_from_device(hits[j], status[j])
+                        assert flags == 0, flags
+                        check(got.rows, got.scores, qi, f"device thread {tid} it {it} q {qi}")
+                    it += 1
+            except Exception as e:                                     # noqa: BLE001
+                errors.append(e)
+
+        def batch_searcher():
+            try:
+                Q = np.stack([q.q for q in qs])
+                it = 0
+                while not stop.is_set() and it < max(2, iters // 4):
+                    got = sh.search_batch(Q, [q.terms for q in qs], NOW, k)
+                    for qi in range(n_q):
+                        check(got[qi].rows, got[qi].scores, qi, f"batch it {it} q {qi}")
+                    h = sh.search(qs[it % n_q].q, qs[it % n_q].terms, NOW, k)
+                    check(h.rows, h.scores, it % n_q, f"host search it {it}")
+                    it += 1
+            except Exception as e:                                     # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=device_searcher, args=(i,)) for i in range(2 if small else 4)]
+        threads.append(threading.Thread(target=batch_searcher))
+        for t in threads:
+            t.start()
+        try:
+            rng = np.random.default_rng(5)
+            for i in range(12 if small else 120):
+                d = 1000 + int(rng.integers(0, 40))
+                if i % 4 == 3:
+                    sh.delete_document(d)
+                else:
+                    sh.upsert_document_chunks(d, None, np.full(8, old, dtype=np.int64))
+                if i % 10 == 9:
+                    sh.compact()
+        finally:
+            for t in threads:
+                t.join(timeout=300)
+            stop.set()
+        assert not errors, errors[:2]
+    finally:
+        sh.close()
