@@ -366,6 +366,7 @@ int  orr_synth_query_host(const orr_synth_spec* spec, uint64_t query_index, uint
         int32_t n_terms, int32_t frequent_terms, float* q /* dim */, uint32_t* term_ids /* n_terms */);
 int  orr_synth_term_text(uint32_t term_id, char* out9 /* 8 chars + NUL */);
 int64_t orr_synth_row_text(const orr_synth_spec* spec, uint64_t row, char* out, int64_t cap);   /* the row's Content; returns its length */
+int  orr_synth_row_info(const orr_synth_spec* spec, uint64_t row, int64_t* ticks, uint64_t* doc_first_row);
 int  orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t first_row, int64_t n);
 
 #ifdef __cplusplus

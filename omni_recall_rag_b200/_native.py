@@ -130,6 +130,7 @@ _SIGNATURES = {
     "orr_synth_query_host": (C.c_int, [C.POINTER(OrrSynthSpec), C.c_uint64, C.c_uint64, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "orr_synth_term_text": (C.c_int, [C.c_uint32, C.c_char_p]),
+    "orr_synth_row_info": (C.c_int, [C.POINTER(OrrSynthSpec), C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]),
     "orr_synth_row_text": (C.c_int64, [C.POINTER(OrrSynthSpec), C.c_uint64, C.c_char_p, C.c_int64]),
     "orr_store_fill_synthetic": (C.c_int, [C.c_void_p, C.POINTER(OrrSynthSpec), C.c_uint64, C.c_int64]),
 }

@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
 #include <cstdlib>
 
 #include "orr_internal.h"
@@ -136,10 +137,17 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// arrives (once) on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+// arrives (once) on the barrier at this offset in every CTA of `mask` when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mask(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// the same box lands at the same smem offset of every CTA in `mask`; the bytes are counted on the barrier at `bar`'s offset
+// in the LEADER of each destination's pair (`bar` is this CTA's own barrier address with the pair bit, bit 24, cleared)
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu), "h"(mask) : "memory");
 }
 
 // ---- TMEM loads split into issue and wait so the load of chunk c+1 overlaps the math of chunk c ----
@@ -339,14 +347,20 @@ template <int PASSES> struct GemmCfg {
 static_assert(GemmCfg<3>::SMEM <= 232448 && GemmCfg<1>::SMEM <= 232448, "batched GEMM kernel exceeds 227 KB of shared memory");
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-template <int PASSES, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BATCH_THREADS, 1)
+// CL = CTAs per cluster: 2 = one pair; 4 = two pairs that work on two different row tiles in lockstep while the QUERY
+// k-blocks — the operand that is the same for every row tile — are TMA-MULTICAST to both pairs: each of the 4 CTAs loads
+// one 64-query quarter of the k-block and multicasts it to the two CTAs that need it, so a query k-block crosses the
+// L2 -> SM fabric once per 4 SMs instead of once per 2.  Both batched configs sit at the L2 fabric's throughput cap with
+// pairs alone (ncu: 9.1 TB/s L2->SM at the power-capped clock; half of it query tiles re-read for every row tile).
+template <int PASSES, int MODE, int CL>
+__global__ void __launch_bounds__(BATCH_THREADS, 1)
 orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qmid,
                       const __grid_constant__ CUtensorMap map_ehi, const __grid_constant__ CUtensorMap map_emid,
                       const BatchArgs a) {
     using C = GemmCfg<PASSES>;
+    constexpr int PP = CL / 2;                                              // pairs per cluster
     extern __shared__ uint8_t smem_raw[];
-    // the dynamic smem base is only 16-B aligned by contract; both CTAs compute the same offset
+    // the dynamic smem base is only 16-B aligned by contract; every CTA computes the same offset
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_mem = smem;                                              // NSTAGE x STAGE, 1024-B aligned
     float* rec = reinterpret_cast<float*>(smem + C::REC_OFF);               // [2][UN]
@@ -355,20 +369,25 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
     float* q_kww = q_thr + MAX_QBLOCKS * BM;
     uint16_t* q_ids = reinterpret_cast<uint16_t*>(smem + C::ID_OFF);        // [MAX_QBLOCKS][BM][16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
-    uint64_t* full_bar = bars;                          // [NSTAGE]  leader's copy is the live one
-    uint64_t* empty_bar = bars + C::NSTAGE;             // [NSTAGE]  per CTA (multicast commit)
-    uint64_t* tfull_bar = bars + 2 * C::NSTAGE;         // [2]       per CTA (multicast commit)
-    uint64_t* tempty_bar = bars + 2 * C::NSTAGE + 2;    // [2]       leader's copy: 16 epilogue warps of the pair
+    uint64_t* full_bar = bars;                          // [NSTAGE]  the pair leader's copy is the live one
+    uint64_t* empty_bar = bars + C::NSTAGE;             // [NSTAGE]  per CTA: one arrival per pair of the cluster (multicast commit)
+    uint64_t* tfull_bar = bars + 2 * C::NSTAGE;         // [2]       per CTA (multicast commit of its own pair)
+    uint64_t* tempty_bar = bars + 2 * C::NSTAGE + 2;    // [2]       pair leader's copy: 16 epilogue warps of the pair
     uint64_t* aux_full = bars + 2 * C::NSTAGE + 4;      // [2]       per CTA
     uint64_t* aux_empty = bars + 2 * C::NSTAGE + 6;     // [2]       per CTA: 8 local epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
+    const uint32_t half = rank & 1u;                    // which 128 queries / 128 rows of the pair's unit this CTA stages
+    const uint32_t pair = rank >> 1;                    // pair within the cluster
+    const uint32_t pair_leader = rank & ~1u;
+    const bool leader = half == 0;
+    const uint16_t pair_mask = (uint16_t)(3u << pair_leader);
+    const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), PP); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tfull_bar[b]), 1);
             mbar_init(smem_u32(&tempty_bar[b]), 16);
@@ -384,7 +403,7 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
     }
     // this CTA's queries (128 per query block): per-query constants and term slots, staged once
     for (int i = threadIdx.x; i < a.n_qblocks * BM; i += BATCH_THREADS) {
-        const int b = (i / BM) * 256 + (int)rank * BM + (i % BM);
+        const int b = (i / BM) * 256 + (int)half * BM + (i % BM);
         q_qs[i] = a.qscale[b];
         q_thr[i] = MODE == 0 ? a.thr[b] : 0.f;
         q_kww[i] = a.q_kw_w ? a.q_kw_w[b] : 0.f;
@@ -395,49 +414,65 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();                                   // barriers of BOTH CTAs initialised, TMEM allocated, queries staged
+    cluster_sync_all();                                   // barriers of EVERY CTA initialised, TMEM allocated, queries staged
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    const int n_clusters = (int)gridDim.x >> 1, cid = (int)blockIdx.x >> 1;
+    // Work split: cluster g takes tile groups g, g + n_clusters, ...; group j = row tiles j*PP .. j*PP + PP - 1, one per pair.
+    // Every CTA of a cluster runs the SAME number of units (the stage ring is shared by the multicast); a pair whose tile
+    // does not exist (odd tile count) runs the unit on the group's first tile and discards it.
+    const int n_clusters = (int)gridDim.x / CL, cid = (int)blockIdx.x / CL;
+    const int n_groups = (a.n_row_tiles + PP - 1) / PP;
     const int units_per_tile = a.n_qblocks;
-    const int my_tiles = (a.n_row_tiles > cid) ? (a.n_row_tiles - 1 - cid) / n_clusters + 1 : 0;
-    const int my_units = my_tiles * units_per_tile;
+    const int my_groups = (n_groups > cid) ? (n_groups - 1 - cid) / n_clusters + 1 : 0;
+    const int my_units = my_groups * units_per_tile;
+    auto tile_of = [&](int u, bool* valid) {
+        const int first = (cid + (u / units_per_tile) * n_clusters) * PP;
+        const int t = first + (int)pair;
+        *valid = t < a.n_row_tiles;
+        return *valid ? t : first;
+    };
 
     if (warp == 0) {
         // ===================== TMA producer (one per CTA) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int u = 0; u < my_units; ++u) {
-                const int t = cid + (u / units_per_tile) * n_clusters;
+                bool valid;
+                const int t = tile_of(u, &valid);
                 const int row_tile = t * a.row_tile_stride;
                 const int qb = u % units_per_tile;
                 const int buf = u & 1;
                 mbar_wait(smem_u32(&aux_empty[buf]), ((uint32_t)(u >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(smem_u32(&aux_full[buf]), UN * 4);
                 bulk_g2s(smem_u32(rec + buf * UN), a.rowrec + (int64_t)row_tile * UN, UN * 4, smem_u32(&aux_full[buf]));
-                const int qrow = qb * 256 + (int)rank * BM, erow = row_tile * UN + (int)rank * BM;
+                const int qrow = qb * 256 + (int)half * BM, erow = row_tile * UN + (int)half * BM;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);     // free in every CTA this one writes to
                     const uint32_t fb_local = smem_u32(&full_bar[stage]);
-                    const uint32_t fb = mapa_shared(fb_local, 0);
+                    const uint32_t fb = mapa_shared(fb_local, pair_leader);
                     const uint32_t base = smem_u32(stage_mem + stage * C::STAGE);
-                    if (leader) mbar_expect_tx(fb_local, 2 * C::STAGE);     // both halves land on this barrier
-                    if (PASSES == 3) {
+                    if (leader) mbar_expect_tx(fb_local, 2 * C::STAGE);     // both halves of the pair land on this barrier
+                    constexpr int E0 = PASSES == 3 ? 2 : 1;                 // first row plane of a stage
+                    if (CL == 2) {
                         tma_load_2d_pair(base + 0 * PLANE_BYTES, &map_qhi, kb * BK, qrow, fb);
-                        tma_load_2d_pair(base + 1 * PLANE_BYTES, &map_qmid, kb * BK, qrow, fb);
-                        tma_load_2d_pair(base + 2 * PLANE_BYTES, &map_ehi, kb * BK, erow, fb);
-                        tma_load_2d_pair(base + 3 * PLANE_BYTES, &map_emid, kb * BK, erow, fb);
+                        if (PASSES == 3) tma_load_2d_pair(base + 1 * PLANE_BYTES, &map_qmid, kb * BK, qrow, fb);
                     } else {
-                        tma_load_2d_pair(base + 0 * PLANE_BYTES, &map_qhi, kb * BK, qrow, fb);
-                        tma_load_2d_pair(base + 1 * PLANE_BYTES, &map_ehi, kb * BK, erow, fb);
+                        // this CTA's quarter (64 queries) of its half, to the same-half CTA of both pairs
+                        const uint16_t qmask = (uint16_t)(0x5u << half);
+                        const uint32_t qoff = pair * (uint32_t)(PLANE_BYTES / 2);
+                        tma_load_2d_pair_mc(base + 0 * PLANE_BYTES + qoff, &map_qhi, kb * BK, qrow + (int)pair * (BM / 2), fb_local, qmask);
+                        if (PASSES == 3)
+                            tma_load_2d_pair_mc(base + 1 * PLANE_BYTES + qoff, &map_qmid, kb * BK, qrow + (int)pair * (BM / 2), fb_local, qmask);
                     }
+                    tma_load_2d_pair(base + E0 * PLANE_BYTES, &map_ehi, kb * BK, erow, fb);
+                    if (PASSES == 3) tma_load_2d_pair(base + 3 * PLANE_BYTES, &map_emid, kb * BK, erow, fb);
                     if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA only) =====================
+        // ===================== MMA issuer (the leader CTA of each pair) =====================
         if (leader) {
             int stage = 0; uint32_t phase = 0;
             for (int u = 0; u < my_units; ++u) {
@@ -468,8 +503,8 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                                 umma_bf16_pair(tmem_d, qhi + adv, ehi + adv, IDESC2, (kb | k) ? 1u : 0u);
                             }
                         }
-                        umma_commit_pair(smem_u32(&empty_bar[stage]));       // frees the stage in both CTAs
-                        if (kb == a.k_blocks - 1) umma_commit_pair(smem_u32(&tfull_bar[buf]));
+                        umma_commit_mask(smem_u32(&empty_bar[stage]), all_mask);       // this pair is done with the stage, in every CTA
+                        if (kb == a.k_blocks - 1) umma_commit_mask(smem_u32(&tfull_bar[buf]), pair_mask);
                     }
                     __syncwarp();
                     if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
@@ -483,13 +518,14 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
         const int quarter = warp & 3;
         const int c_begin = ((warp - 2) >> 2) * HC;
         const int qloc = quarter * 32 + lane;                               // query within the CTA's 128
-        const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
-        const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+        const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), pair_leader);
+        const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), pair_leader);
         const bool has_kw = a.q_term_ids != nullptr;
         // the first 4 term words of the NEXT unit are loaded while this unit's scores are processed
         uint4 wn[4];
         auto prefetch_words = [&](int u) {
-            const int row_tile = (cid + (u / units_per_tile) * n_clusters) * a.row_tile_stride;
+            bool valid;
+            const int row_tile = tile_of(u, &valid) * a.row_tile_stride;
             const int qi = (u % units_per_tile) * BM + qloc;
             const int64_t word0 = (int64_t)row_tile * 2 + (c_begin / HC);
             const uint2 id4 = *reinterpret_cast<const uint2*>(q_ids + qi * ORR_BATCH_MAX_TERMS);
@@ -498,12 +534,13 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
         };
         if (has_kw && my_units > 0) prefetch_words(0);
         for (int u = 0; u < my_units; ++u) {
-            const int t = cid + (u / units_per_tile) * n_clusters;
+            bool valid;
+            const int t = tile_of(u, &valid);
             const int row_tile = t * a.row_tile_stride;
             const int qb = u % units_per_tile;
             const int buf = u & 1;
             const int qi = qb * BM + qloc;
-            const int b = qb * 256 + (int)rank * BM + qloc;                 // this thread's query
+            const int b = qb * 256 + (int)half * BM + qloc;                 // this thread's query
             const float qs = q_qs[qi], thr = q_thr[qi], kww = q_kww[qi];
             const int64_t row0 = (int64_t)row_tile * UN;
             KwPlanes kp;
@@ -533,8 +570,10 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
             mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)(u >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * UN);
-            if (has_kw) epilogue_chunks<MODE, true>(a, taddr, rec + buf * UN, b, row0, (int64_t)t * UN, c_begin, qs, thr, kww, kp);
-            else epilogue_chunks<MODE, false>(a, taddr, rec + buf * UN, b, row0, (int64_t)t * UN, c_begin, qs, thr, 0.f, kp);
+            if (valid) {                                                    // warp-uniform; a filler unit's scores are discarded
+                if (has_kw) epilogue_chunks<MODE, true>(a, taddr, rec + buf * UN, b, row0, (int64_t)t * UN, c_begin, qs, thr, kww, kp);
+                else epilogue_chunks<MODE, false>(a, taddr, rec + buf * UN, b, row0, (int64_t)t * UN, c_begin, qs, thr, 0.f, kp);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
@@ -543,7 +582,7 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
             }
         }
     }
-    // no CTA may leave while its peer can still signal its barriers or read its smem
+    // no CTA may leave while a peer can still signal its barriers or write its smem
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();
     if (warp == 1) {
@@ -691,13 +730,72 @@ int orr_batch_build_rowrec(const int64_t* ticks, float* rowrec, int64_t rows, in
     return ORR_OK;
 }
 
+template <int PASSES, int MODE, int CL>
+static int launch_gemm_cl(const CUtensorMap& mqh, const CUtensorMap& mqm, const CUtensorMap& meh, const CUtensorMap& mem,
+                          const BatchArgs& a, int grid, cudaStream_t st) {
+    ORR_SMEM_OPT_IN((orr_batch_gemm_kernel<PASSES, MODE, CL>), GemmCfg<PASSES>::SMEM);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(BATCH_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = GemmCfg<PASSES>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ORR_CUDA_OK(cudaLaunchKernelEx(&cfg, orr_batch_gemm_kernel<PASSES, MODE, CL>, mqh, mqm, meh, mem, a));
+    return ORR_OK;
+}
+
+// how many clusters of CL CTAs of this kernel the device can hold at once (GPC boundaries can strand SMs)
+template <int PASSES, int MODE, int CL>
+static int max_clusters(int sms) {
+    cudaFuncSetAttribute(orr_batch_gemm_kernel<PASSES, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<PASSES>::SMEM);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(sms / CL * CL), 1, 1);
+    cfg.blockDim = dim3(BATCH_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = GemmCfg<PASSES>::SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, orr_batch_gemm_kernel<PASSES, MODE, CL>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// Cluster shape of the batched GEMM: 4 (query k-blocks multicast to two pairs) when the device can keep (nearly) as many
+// SMs busy with clusters of 4 as with pairs, else 2.  ORR_BATCH_CLUSTER=2|4 overrides (experiments).
+struct ClusterPlan { int cl; int n_clusters; };
+template <int PASSES, int MODE>
+static ClusterPlan plan_clusters(int sms) {
+    static int choice[64] = {};                                              // per device ordinal: 0 = undecided
+    static int clusters[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!choice[dev]) {
+        const int c2 = max_clusters<PASSES, MODE, 2>(sms), c4 = max_clusters<PASSES, MODE, 4>(sms);
+        clusters[dev][0] = c2 > 0 ? std::min(c2, sms / 2) : sms / 2;
+        clusters[dev][1] = std::min(c4, sms / 4);
+        int pick = (4 * clusters[dev][1] >= 2 * clusters[dev][0] - 4) ? 4 : 2;   // tolerate up to 4 stranded SMs for the halved query traffic
+        if (const char* e = getenv("ORR_BATCH_CLUSTER")) { const int v = atoi(e); if (v == 2 || (v == 4 && clusters[dev][1] > 0)) pick = v; }
+        if (getenv("ORR_BATCH_TRACE")) fprintf(stderr, "[orr batch] device %d: %d pairs / %d clusters of 4 fit; cluster size %d\n", dev, c2, c4, pick);
+        choice[dev] = pick;
+    }
+    return choice[dev] == 4 ? ClusterPlan{4, clusters[dev][1]} : ClusterPlan{2, clusters[dev][0]};
+}
 template <int PASSES, int MODE>
 static int launch_gemm_t(const CUtensorMap& mqh, const CUtensorMap& mqm, const CUtensorMap& meh, const CUtensorMap& mem,
-                         const BatchArgs& a, int grid, cudaStream_t st) {
-    ORR_SMEM_OPT_IN((orr_batch_gemm_kernel<PASSES, MODE>), GemmCfg<PASSES>::SMEM);
-    orr_batch_gemm_kernel<PASSES, MODE><<<grid, BATCH_THREADS, GemmCfg<PASSES>::SMEM, st>>>(mqh, mqm, meh, mem, a);
-    ORR_CUDA_OK(cudaGetLastError());
-    return ORR_OK;
+                         const BatchArgs& a, const ClusterPlan& plan, cudaStream_t st) {
+    if (plan.cl == 4) {
+        const int n = std::min(plan.n_clusters, (a.n_row_tiles + 1) / 2);
+        return launch_gemm_cl<PASSES, MODE, 4>(mqh, mqm, meh, mem, a, 4 * std::max(1, n), st);
+    }
+    const int pairs = std::min(plan.n_clusters, a.n_row_tiles);
+    return launch_gemm_cl<PASSES, MODE, 2>(mqh, mqm, meh, mem, a, 2 * std::max(1, pairs), st);
 }
 
 int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
@@ -706,10 +804,14 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
         orr_set_error("batch path: padded batch %d not a multiple of 256 in [256, %d]", g.batch_padded, ORR_BATCH_MAX_QUERIES);
         return ORR_E_INTERNAL;
     }
+    const bool dense = g.dense != nullptr;
+    const ClusterPlan plan = g.passes == 1 ? (dense ? plan_clusters<1, 1>(g.sms) : plan_clusters<1, 0>(g.sms))
+                                           : (dense ? plan_clusters<3, 1>(g.sms) : plan_clusters<3, 0>(g.sms));
+    const int q_box = plan.cl == 4 ? BM / 2 : BM;           // clusters of 4: every CTA loads (and multicasts) a 64-query quarter
     CUtensorMap mqh, mqm, meh, mem;
     int rc;
-    if ((rc = make_plane_map(&mqh, g.qhi, g.batch_padded, g.dim, BM)) != ORR_OK) return rc;
-    if ((rc = make_plane_map(&mqm, g.qmid, g.batch_padded, g.dim, BM)) != ORR_OK) return rc;
+    if ((rc = make_plane_map(&mqh, g.qhi, g.batch_padded, g.dim, q_box)) != ORR_OK) return rc;
+    if ((rc = make_plane_map(&mqm, g.qmid, g.batch_padded, g.dim, q_box)) != ORR_OK) return rc;
     if ((rc = make_plane_map(&meh, g.ehi, g.rows, g.dim, BM)) != ORR_OK) return rc;
     // the bf16 screen (passes == 1) never touches the mid planes: their maps alias the hi planes
     if ((rc = make_plane_map(&mem, g.passes == 1 ? g.ehi : g.emid, g.rows, g.dim, BM)) != ORR_OK) return rc;
@@ -733,11 +835,10 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     a.slot_cap = g.slot_cap;
     a.q_term_ids = g.q_term_ids;
     a.q_kw_w = g.q_kw_w;
-    const int pairs = std::min<int64_t>(g.sms / 2, a.n_row_tiles);
-    if (pairs < 1) return ORR_OK;
-    if (g.dense)
-        return g.passes == 1 ? launch_gemm_t<1, 1>(mqh, mqm, meh, mem, a, 2 * pairs, st)
-                             : launch_gemm_t<3, 1>(mqh, mqm, meh, mem, a, 2 * pairs, st);
-    return g.passes == 1 ? launch_gemm_t<1, 0>(mqh, mqm, meh, mem, a, 2 * pairs, st)
-                         : launch_gemm_t<3, 0>(mqh, mqm, meh, mem, a, 2 * pairs, st);
+    if (a.n_row_tiles < 1) return ORR_OK;
+    if (dense)
+        return g.passes == 1 ? launch_gemm_t<1, 1>(mqh, mqm, meh, mem, a, plan, st)
+                             : launch_gemm_t<3, 1>(mqh, mqm, meh, mem, a, plan, st);
+    return g.passes == 1 ? launch_gemm_t<1, 0>(mqh, mqm, meh, mem, a, plan, st)
+                         : launch_gemm_t<3, 0>(mqh, mqm, meh, mem, a, plan, st);
 }

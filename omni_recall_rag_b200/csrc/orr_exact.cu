@@ -114,11 +114,15 @@ __global__ void __launch_bounds__(256) orr_exact_scores_kernel(const ExactArgs a
 }
 
 // ---- E1 without a query embedding: keyword + recency only --------------------------------------------------------
-// A warp takes 32 consecutive rows = one contiguous 32 * slots * 8 B block of the 64-bit term table, streamed with 8
-// coalesced 16-byte loads in flight per lane; every stored hash is compared with the query's probes (kernel-parameter
-// constant memory), the per-row term masks are OR-reduced across the lanes that hold the row (REDUX), lane j keeps
-// row j's match count and runs the scalar fp64 tail (exact_row_finish: the same operations as every other path).
-// SPL = slots / 32: 16-byte vectors per row = 16 * SPL.
+// A warp takes 32 consecutive rows = one contiguous 32 * slots * 4 B block of the 32-BIT term table (the scan's table:
+// half the bytes of the 64-bit one), streamed with 8 coalesced 16-byte loads in flight per lane.  Every stored low word
+// is compared with the probes' low words (kernel-parameter constant memory); a 32-bit hit is CONFIRMED against the
+// 64-bit table (one scattered 8-byte load; rare — a query term sits in a few percent of the rows at most) so the match
+// counts are exact, never a hash collision.  The per-row term masks are OR-reduced across the lanes that hold the row
+// (one REDUX per 16-byte load, member masks split the warp when a load spans two rows), lane j keeps row j's count and
+// runs the scalar fp64 tail (exact_row_finish: the same operations as every other path).
+// Algorithmic bytes per row: 4 * slots (terms32) + 8 (ticks); embeddings are never read.
+// SPL = slots / 32: 16-byte vectors per row VR = 8 * SPL (8, 16, 32).  WIDE = more than 32 query terms (two mask words).
 struct NoembArgs {
     OrrShard sh; OrrProbes pr; OrrWeights w; int64_t now_ticks;
 };
@@ -127,8 +131,8 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-template <int SPL>
-__global__ void __launch_bounds__(512) orr_noemb_scores_kernel(const NoembArgs a, uint64_t* skey, uint32_t* hist0) {
+template <int SPL, bool WIDE>
+__global__ void __launch_bounds__(512, 2) orr_noemb_scores_kernel(const NoembArgs a, uint64_t* skey, uint32_t* hist0) {
     __shared__ uint32_t s_hist[SEL_BINS];
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
@@ -136,18 +140,19 @@ __global__ void __launch_bounds__(512) orr_noemb_scores_kernel(const NoembArgs a
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_blocks = (a.sh.rows + 31) >> 5;
-    constexpr int VR = 16 * SPL;                       // vectors per row
-    constexpr int STEPS = (32 * VR) / 256;             // 8-load steps per 32-row block
+    constexpr int VR = 8 * SPL;                        // 16-byte vectors per row
+    constexpr int RPL = 32 / VR;                       // rows one warp-wide load spans (4, 2, 1)
+    constexpr int STEPS = (32 * VR) / 256;             // 8-load steps per 32-row block (1, 2, 4)
     const int n_probes = a.pr.n_probes;
-    const bool wide = a.pr.n_terms > 32;
-    // the fields exact_row_finish reads
+    // REDUX member mask: the lanes that hold the same row as this one within a load
+    const uint32_t seg_mask = RPL == 1 ? FULL : (RPL == 2 ? (lane < 16 ? 0x0000ffffu : 0xffff0000u) : (0xffu << (lane & 24)));
     ExactLite ex;
     ex.sh = a.sh; ex.q_dim = 0; ex.w = a.w; ex.now_ticks = a.now_ticks;
     for (int64_t blk = gw; blk < n_blocks; blk += W) {
         const int64_t row0 = blk << 5;
         const int n_here = (int)min((int64_t)32, a.sh.rows - row0);
         const int n_vec = n_here * VR;
-        const uint4* base = reinterpret_cast<const uint4*>(a.sh.terms64 + row0 * (int64_t)a.sh.slots);
+        const uint4* base = reinterpret_cast<const uint4*>(a.sh.terms32 + row0 * (int64_t)a.sh.slots);
         const int64_t my_ticks = lane < n_here ? __ldg(a.sh.ticks + row0 + lane) : ORR_DEAD_TICKS;
         int my_matches = 0;
         if (n_probes > 0) {
@@ -161,45 +166,40 @@ __global__ void __launch_bounds__(512) orr_noemb_scores_kernel(const NoembArgs a
                     const int v = v0 + i * 32 + lane;
                     x[i] = v < n_vec ? ldg_stream_u4(base + v) : make_uint4(0u, 0u, 0u, 0u);
                 }
-                uint32_t m0[8], m1[8];
+                uint32_t m0[8], m1[WIDE ? 8 : 1];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { m0[i] = 0u; m1[i] = 0u; }
+                for (int i = 0; i < 8; ++i) { m0[i] = 0u; if (WIDE) m1[i] = 0u; }
                 for (int p = 0; p < n_probes; ++p) {
-                    const uint64_t h = a.pr.h64[p];
-                    const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
+                    const uint32_t hl = a.pr.h32[p];
                     const uint32_t t = a.pr.term[p];
                     const uint32_t b0 = t < 32 ? (1u << t) : 0u, b1 = t < 32 ? 0u : (1u << (t - 32));
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const bool hit = ((x[i].x == hl) & (x[i].y == hh)) | ((x[i].z == hl) & (x[i].w == hh));
+                        bool hit = (x[i].x == hl) | (x[i].y == hl) | (x[i].z == hl) | (x[i].w == hl);
+                        if (hit) {                                           // rare: confirm with the full 64-bit hashes of the 4 slots
+                            const int v = v0 + i * 32 + lane;
+                            const uint64_t* full = a.sh.terms64 + row0 * (int64_t)a.sh.slots + (int64_t)v * 4;
+                            const uint64_t h = a.pr.h64[p];
+                            hit = ((x[i].x == hl) && __ldg(full + 0) == h) || ((x[i].y == hl) && __ldg(full + 1) == h) ||
+                                  ((x[i].z == hl) && __ldg(full + 2) == h) || ((x[i].w == hl) && __ldg(full + 3) == h);
+                        }
                         m0[i] |= hit ? b0 : 0u;
-                        m1[i] |= hit ? b1 : 0u;
+                        if (WIDE) m1[i] |= hit ? b1 : 0u;
                     }
                 }
                 // reduce across the lanes that hold one row, hand the count to the row's lane
-                if (SPL == 2) {                                              // load i == one row
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        uint32_t r0 = __reduce_or_sync(FULL, m0[i]);
-                        int c = __popc(r0);
-                        if (wide) c += __popc(__reduce_or_sync(FULL, m1[i]));
-                        if (lane == st * 8 + i) my_matches = c;
-                    }
-                } else if (SPL == 1) {                                       // load i == two rows (half-warps)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool lo = lane < 16;
-                        int c0 = __popc(__reduce_or_sync(FULL, lo ? m0[i] : 0u)), c1 = __popc(__reduce_or_sync(FULL, lo ? 0u : m0[i]));
-                        if (wide) { c0 += __popc(__reduce_or_sync(FULL, lo ? m1[i] : 0u)); c1 += __popc(__reduce_or_sync(FULL, lo ? 0u : m1[i])); }
-                        if (lane == st * 16 + 2 * i) my_matches = c0;
-                        if (lane == st * 16 + 2 * i + 1) my_matches = c1;
-                    }
-                } else {                                                     // SPL == 4: loads 2j, 2j+1 == one row
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        int c = __popc(__reduce_or_sync(FULL, m0[2 * j] | m0[2 * j + 1]));
-                        if (wide) c += __popc(__reduce_or_sync(FULL, m1[2 * j] | m1[2 * j + 1]));
-                        if (lane == st * 4 + j) my_matches = c;
+                for (int i = 0; i < 8; ++i) {
+                    int c = __popc(__reduce_or_sync(seg_mask, m0[i]));
+                    if (WIDE) c += __popc(__reduce_or_sync(seg_mask, m1[i]));
+                    // load i of step st holds rows (st * 8 + i) * RPL + segment; the segment's count is in all its lanes
+                    const int first_row = (st * 8 + i) * RPL;
+                    if (RPL == 1) { if (lane == first_row) my_matches = c; }
+                    else {
+                        // every lane of segment g has row first_row + g's count: hand it to lane (first_row + g)
+                        const int want = lane - first_row;                   // which segment this lane's row is, if in range
+                        const int got = __shfl_sync(FULL, c, (want >= 0 && want < RPL) ? want * VR : 0);
+                        if (want >= 0 && want < RPL) my_matches = got;
                     }
                 }
             }
@@ -444,10 +444,17 @@ int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrP
     if (q_dim == 0 && sc.kw_bits == nullptr) {
         NoembArgs a;
         a.sh = sh; a.pr = pr; a.w = w; a.now_ticks = now_ticks;
-        const int grid = sms * 3;
-        if (sh.slots == 32) orr_noemb_scores_kernel<1><<<grid, 512, 0, st>>>(a, sc.skey, state->hist[0]);
-        else if (sh.slots == 64) orr_noemb_scores_kernel<2><<<grid, 512, 0, st>>>(a, sc.skey, state->hist[0]);
-        else orr_noemb_scores_kernel<4><<<grid, 512, 0, st>>>(a, sc.skey, state->hist[0]);
+        const int grid = sms * 2;
+        const bool wide = pr.n_terms > 32;
+#define ORR_NOEMB_LAUNCH(SPL)                                                                                         \
+        do {                                                                                                              \
+            if (wide) orr_noemb_scores_kernel<SPL, true><<<grid, 512, 0, st>>>(a, sc.skey, state->hist[0]);             \
+            else orr_noemb_scores_kernel<SPL, false><<<grid, 512, 0, st>>>(a, sc.skey, state->hist[0]);                  \
+        } while (0)
+        if (sh.slots == 32) ORR_NOEMB_LAUNCH(1);
+        else if (sh.slots == 64) ORR_NOEMB_LAUNCH(2);
+        else ORR_NOEMB_LAUNCH(4);
+#undef ORR_NOEMB_LAUNCH
     } else {
         ExactArgs e;
         fill_exact_args(e, sh, sc, pr, w, now_ticks, q_dim);

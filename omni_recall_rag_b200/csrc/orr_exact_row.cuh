@@ -52,14 +52,16 @@ __device__ __forceinline__ int kw_count_from_bits(const ExactArgs& a, int64_t ro
 }
 
 // Loads are issued in batches of EX_CHUNK float4 per lane BEFORE the dependent fp64 chains
-// so a row costs ~2 memory round trips instead of one per 128 columns; the ORDER of the fp64
-// additions (lane-strided, increasing column, then the shuffle butterfly) is unchanged.
+// so a row costs ~2 memory round trips instead of one per 128 columns.  ORDER of the fp64 additions (the one departure
+// from the reference's sequential loop, a few 1e-16 relative): every lane keeps one chain per float4 component over its
+// lane-strided columns in increasing order, the four chains are combined as (c0 + c1) + (c2 + c3), then the shuffle
+// butterfly.  Every path (K3, batched finalize, exact path, ||q||^2) uses this one definition.
 constexpr int EX_CHUNK = 12;
 
 // fp64 ||q||^2 in the lane-strided order; all lanes return the same value
 template <class A>
 __device__ __forceinline__ double exact_qnorm_q(const A& a, const float* q, int lane) {
-    double nA = 0.0;
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;              // one chain per float4 component, as in exact_row_partial
     const int nv4 = a.sh.dim >> 2;
     const float4* q4 = reinterpret_cast<const float4*>(q);
     for (int base = 0; base < nv4; base += 32 * EX_CHUNK) {
@@ -72,14 +74,14 @@ __device__ __forceinline__ double exact_qnorm_q(const A& a, const float* q, int 
 #pragma unroll
         for (int j = 0; j < EX_CHUNK; ++j) {
             if (base + j * 32 + lane < nv4) {
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].x, v[j].x));
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].y, v[j].y));
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].z, v[j].z));
-                nA = __dadd_rn(nA, (double)__fmul_rn(v[j].w, v[j].w));
+                n0 = __dadd_rn(n0, (double)__fmul_rn(v[j].x, v[j].x));
+                n1 = __dadd_rn(n1, (double)__fmul_rn(v[j].y, v[j].y));
+                n2 = __dadd_rn(n2, (double)__fmul_rn(v[j].z, v[j].z));
+                n3 = __dadd_rn(n3, (double)__fmul_rn(v[j].w, v[j].w));
             }
         }
     }
-    return warp_sum_f64(nA);
+    return warp_sum_f64(__dadd_rn(__dadd_rn(n0, n1), __dadd_rn(n2, n3)));
 }
 
 // The exact fused score of one row in two steps, so that callers holding many rows per warp can run the scalar
@@ -111,6 +113,9 @@ __device__ __forceinline__ ExactPartial exact_row_partial(const A& a, const floa
     }
     double dot = 0.0, nB = 0.0;
     if (a.q_dim == a.sh.dim && a.q_dim > 0) {                       // :71-72 length check
+        // 4 + 4 independent fp64 chains per lane (one per float4 component): the per-lane work is a latency chain of
+        // dependent DADDs, and two chains left the fp64 pipe idle most of the time
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
         const int nv4 = a.sh.dim >> 2;
         const float4* x4 = reinterpret_cast<const float4*>(a.sh.emb + row * (int64_t)a.sh.dim);
         const float4* q4 = reinterpret_cast<const float4*>(q);
@@ -127,10 +132,10 @@ __device__ __forceinline__ ExactPartial exact_row_partial(const A& a, const floa
                     const int i = base + j * 32 + lane;
                     if (i < nv4) {
                         const float4 v = q4[i];
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v.w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
+                        d0 = __dadd_rn(d0, (double)__fmul_rn(v.x, x[j].x)); b0 = __dadd_rn(b0, (double)__fmul_rn(x[j].x, x[j].x));
+                        d1 = __dadd_rn(d1, (double)__fmul_rn(v.y, x[j].y)); b1 = __dadd_rn(b1, (double)__fmul_rn(x[j].y, x[j].y));
+                        d2 = __dadd_rn(d2, (double)__fmul_rn(v.z, x[j].z)); b2 = __dadd_rn(b2, (double)__fmul_rn(x[j].z, x[j].z));
+                        d3 = __dadd_rn(d3, (double)__fmul_rn(v.w, x[j].w)); b3 = __dadd_rn(b3, (double)__fmul_rn(x[j].w, x[j].w));
                     }
                 }
             } else {
@@ -143,16 +148,16 @@ __device__ __forceinline__ ExactPartial exact_row_partial(const A& a, const floa
 #pragma unroll
                 for (int j = 0; j < CHUNK; ++j) {
                     if (base + j * 32 + lane < nv4) {
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].x, x[j].x)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].x, x[j].x));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].y, x[j].y)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].y, x[j].y));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].z, x[j].z)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].z, x[j].z));
-                        dot = __dadd_rn(dot, (double)__fmul_rn(v[j].w, x[j].w)); nB = __dadd_rn(nB, (double)__fmul_rn(x[j].w, x[j].w));
+                        d0 = __dadd_rn(d0, (double)__fmul_rn(v[j].x, x[j].x)); b0 = __dadd_rn(b0, (double)__fmul_rn(x[j].x, x[j].x));
+                        d1 = __dadd_rn(d1, (double)__fmul_rn(v[j].y, x[j].y)); b1 = __dadd_rn(b1, (double)__fmul_rn(x[j].y, x[j].y));
+                        d2 = __dadd_rn(d2, (double)__fmul_rn(v[j].z, x[j].z)); b2 = __dadd_rn(b2, (double)__fmul_rn(x[j].z, x[j].z));
+                        d3 = __dadd_rn(d3, (double)__fmul_rn(v[j].w, x[j].w)); b3 = __dadd_rn(b3, (double)__fmul_rn(x[j].w, x[j].w));
                     }
                 }
             }
         }
-        dot = warp_sum_f64(dot);
-        nB = warp_sum_f64(nB);
+        dot = warp_sum_f64(__dadd_rn(__dadd_rn(d0, d1), __dadd_rn(d2, d3)));
+        nB = warp_sum_f64(__dadd_rn(__dadd_rn(b0, b1), __dadd_rn(b2, b3)));
     }
     r.dot = dot; r.nB = nB;
     r.matches = 0; r.kw_den = -1;

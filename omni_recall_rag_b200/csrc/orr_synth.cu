@@ -207,6 +207,14 @@ int64_t orr_synth_row_text(const orr_synth_spec* spec, uint64_t row, char* out, 
     return len;
 }
 
+// CreatedAtUtc ticks and the first row of the document (run of rows sharing one timestamp) of synthetic row `row`
+int orr_synth_row_info(const orr_synth_spec* spec, uint64_t row, int64_t* ticks, uint64_t* doc_first_row) {
+    if (!synth_spec_ok(spec)) return ORR_E_INVALID;
+    if (ticks) *ticks = orr_synth_row_ticks(spec->seed, row, spec->now_ticks, spec->dup_row_ppm);
+    if (doc_first_row) *doc_first_row = orr_synth_doc_first_row(spec->seed, row);
+    return ORR_OK;
+}
+
 int orr_synth_term_text(uint32_t term_id, char* out9) {
     if (!out9 || term_id >= (1u << ORR_SYNTH_VOCAB_LOG2)) return ORR_E_INVALID;
     snprintf(out9, 9, "t%07u", term_id);

@@ -187,17 +187,19 @@ class GpuIngestionStore:
         import ctypes as C
 
         from . import _native as N
-        from . import synth
 
         spec, first_row, _ = self._synth
+        L = N.lib()
         g = first_row + (row - self.shard.row_base)
-        r = synth.rows_host(spec, g, 1, want_emb=False)
-        buf = C.create_string_buffer(9 * max(spec.terms_per_chunk, 1))
-        ln = N.lib().orr_synth_row_text(C.byref(spec), g, buf, len(buf))
-        doc_first = int(r.doc_first_row[0])
-        return CosmosChunkRecord(id=f"synth-{doc_first}:{g - doc_first:04d}", document_id=f"synth-{doc_first}",
-                                 chunk_index=g - doc_first, content=buf.raw[:ln].decode("ascii"), embedding=None,
-                                 created_at_utc=int(r.ticks[0]))
+        if getattr(self, "_synth_buf", None) is None:
+            self._synth_buf = C.create_string_buffer(9 * max(spec.terms_per_chunk, 1))
+            self._synth_spec_ref = C.byref(spec)
+        ticks, first = C.c_int64(0), C.c_uint64(0)
+        L.orr_synth_row_info(self._synth_spec_ref, g, C.byref(ticks), C.byref(first))
+        ln = L.orr_synth_row_text(self._synth_spec_ref, g, self._synth_buf, len(self._synth_buf))
+        doc_first = first.value
+        return CosmosChunkRecord(f"synth-{doc_first}:{g - doc_first:04d}", f"synth-{doc_first}", g - doc_first,
+                                 self._synth_buf.raw[:ln].decode("ascii"), None, ticks.value)
 
     # -- used by GpuRecallSearchService -------------------------------------------------------
     def chunk_of_row(self, row: int) -> CosmosChunkRecord:
