@@ -1,6 +1,7 @@
 // GpuIngestionStore.cs — IIngestionStore (Services/IIngestionStore.cs:5-17) whose chunk rows live
 // in HBM.  Behaviour follows InMemoryIngestionStore.cs line by line; the only additions are the
-// two native calls in UpsertChunksAsync / DeleteDocumentAsync.  Source only (no .NET SDK here);
+// two native calls in UpsertChunksAsync / DeleteDocumentAsync (orr_store_upsert_document_texts takes the
+// Content strings as they are: tokenising, hashing and the vocabulary are the library's business).  Source only (no .NET SDK here);
 // omni_recall_rag_b200/store.py is the tested mirror of this class.
 using System.Collections.Concurrent;
 using System.Text;
@@ -14,7 +15,6 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
     private readonly ConcurrentDictionary<string, List<CosmosChunkRecord>> _chunksByDocument = new();
     private readonly ConcurrentDictionary<ulong, CosmosChunkRecord> _chunkByRow = new();
     private readonly ConcurrentDictionary<string, ulong[]> _rowsByDocument = new();
-    private readonly ConcurrentDictionary<string, int> _vocabulary = new(StringComparer.Ordinal);
     private readonly object _mutate = new();
     internal nint Handle { get; }
     internal int Dim { get; }
@@ -30,6 +30,13 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
         cfg.CapacityRows = configuration.GetValue("Gpu:CapacityRows", 1L << 20);
         OrrNative.Check(OrrNative.orr_store_create(in cfg, out var h));
         Handle = h;
+        // keep the lower-cased Content in HBM: terms inside many vocabulary words ("ai", one letter) and chunks with more
+        // distinct tokens than Gpu:TermSlots are then matched in text mode instead of being refused
+        if (configuration.GetValue("Gpu:KeepText", true))
+        {
+            OrrNative.Check(OrrNative.orr_store_set_option(h, "text_bytes_per_row", configuration.GetValue("Gpu:TextBytesPerRow", 2048.0)));
+            OrrNative.Check(OrrNative.orr_store_set_option(h, "keep_text", 1));
+        }
     }
 
     public Task<CosmosDocumentRecord> UpsertDocumentAsync(CosmosDocumentRecord document, CancellationToken ct = default)
@@ -47,9 +54,11 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
         var emb = new float[(long)n * Dim];
         var has = new byte[n];
         var ticks = new long[n];
-        var offsets = new uint[n + 1];
-        var hashes = new List<ulong>();
-        var tokens = new List<string[]>(n);
+        // Content goes down as it is: the library lower-cases (RecallSearchService.cs:110), splits into white-space
+        // tokens, hashes the distinct ones into the chunk's term set, registers them in the live vocabulary and (option
+        // keep_text) keeps the lower-cased text in HBM for text mode
+        var contentOffsets = new ulong[n + 1];
+        using var text = new MemoryStream();
         for (var i = 0; i < n; i++)
         {
             var c = ordered[i];
@@ -59,40 +68,21 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
                 has[i] = 1;
             }
             ticks[i] = c.CreatedAtUtc.Ticks;
-            var toks = DistinctLowerTokens(c.Content);
-            if (toks.Length > TermSlots)
-                throw new InvalidOperationException($"chunk {c.Id} has {toks.Length} distinct tokens; Gpu:TermSlots={TermSlots}");
-            tokens.Add(toks);
-            foreach (var t in toks) hashes.Add(HashTerm(t));
-            offsets[i + 1] = (uint)hashes.Count;
+            text.Write(Encoding.UTF8.GetBytes(c.Content ?? string.Empty));
+            contentOffsets[i + 1] = (ulong)text.Length;
         }
         var rows = new ulong[n];
-        var flat = hashes.Count > 0 ? hashes.ToArray() : new ulong[1];
-        // text mode: content.ToLowerInvariant() (RecallSearchService.cs:110) as UTF-8, kept in HBM so that
-        // orr_search_text can evaluate Contains(term) literally when a term expands past the probe limit
-        var textOffsets = new ulong[n + 1];
-        using var text = new MemoryStream();
-        for (var i = 0; i < n; i++)
-        {
-            text.Write(Encoding.UTF8.GetBytes((ordered[i].Content ?? string.Empty).ToLowerInvariant()));
-            textOffsets[i + 1] = (ulong)text.Length;
-        }
         var textBytes = text.Length > 0 ? text.ToArray() : new byte[1];
         lock (_mutate)
         {
+            fixed (float* pe = emb) fixed (byte* ph = has) fixed (long* pt = ticks) fixed (ulong* pr = rows)
+            fixed (byte* ptx = textBytes) fixed (ulong* pto = contentOffsets)
+                OrrNative.Check(OrrNative.orr_store_upsert_document_texts(
+                    Handle, HashTerm("doc:" + documentId), n, pe, ph, pt, ptx, pto, pr));
             ForgetRows(documentId);
-            fixed (float* pe = emb) fixed (byte* ph = has) fixed (long* pt = ticks)
-            fixed (ulong* pf = flat) fixed (uint* po = offsets) fixed (ulong* pr = rows)
-            fixed (byte* ptx = textBytes) fixed (ulong* pto = textOffsets)
-                OrrNative.Check(OrrNative.orr_store_upsert_document_chunks_text(
-                    Handle, HashTerm("doc:" + documentId), n, pe, ph, pt, pf, po, ptx, pto, pr));
             _chunksByDocument[documentId] = ordered;
             _rowsByDocument[documentId] = rows;
-            for (var i = 0; i < n; i++)
-            {
-                _chunkByRow[rows[i]] = ordered[i];
-                foreach (var t in tokens[i]) _vocabulary.AddOrUpdate(t, 1, (_, v) => v + 1);
-            }
+            for (var i = 0; i < n; i++) _chunkByRow[rows[i]] = ordered[i];
         }
         return Task.CompletedTask;
     }
@@ -162,14 +152,8 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
     public void SaveShard(string path) { lock (_mutate) OrrNative.Check(OrrNative.orr_store_save(Handle, path)); }
     public void LoadShard(string path) { lock (_mutate) OrrNative.Check(OrrNative.orr_store_load(Handle, path)); }
 
-    /// words of the live corpus that contain `term` — the host half of Contains (RecallSearchService.cs:111)
-    internal IEnumerable<string> VocabularyWordsContaining(string term)
-        => _vocabulary.Keys.Where(w => w.Contains(term, StringComparison.Ordinal));
-
-    internal static string[] DistinctLowerTokens(string content)
-        => (content ?? string.Empty)
-            .Split((char[]?)null, StringSplitOptions.RemoveEmptyEntries | StringSplitOptions.TrimEntries)
-            .Select(t => t.ToLowerInvariant()).Distinct().ToArray();
+    /// distinct tokens held by live chunks; the vocabulary lives in HBM and query terms are expanded over it on the GPU
+    public long VocabularySize => OrrNative.orr_store_vocab_size(Handle);
 
     internal static unsafe ulong HashTerm(string lower)
     {
@@ -180,10 +164,7 @@ public sealed class GpuIngestionStore : IIngestionStore, IDisposable
     private void ForgetRows(string documentId)
     {
         if (!_rowsByDocument.TryRemove(documentId, out var rows)) return;
-        foreach (var r in rows)
-            if (_chunkByRow.TryRemove(r, out var c))
-                foreach (var t in DistinctLowerTokens(c.Content))
-                    if (_vocabulary.AddOrUpdate(t, 0, (_, v) => v - 1) <= 0) _vocabulary.TryRemove(t, out _);
+        foreach (var r in rows) _chunkByRow.TryRemove(r, out _);   // the library released the document's words itself
     }
 
     public void Dispose() => OrrNative.orr_store_destroy(Handle);

@@ -34,6 +34,15 @@ internal static partial class OrrNative
     [LibraryImport(Lib)] internal static unsafe partial int orr_store_upsert_document_chunks_text(
         nint store, ulong docKey, int n, float* emb, byte* hasEmb, long* createdTicks,
         ulong* termHashes, uint* termOffsets, byte* textLowerUtf8, ulong* textOffsets, ulong* outRows);
+    // text-level ingest: Content strings in; the library lower-cases, tokenises, hashes and keeps the live vocabulary
+    [LibraryImport(Lib)] internal static unsafe partial int orr_store_upsert_document_texts(
+        nint store, ulong docKey, int n, float* emb, byte* hasEmb, long* createdTicks,
+        byte* contentsUtf8, ulong* contentOffsets, ulong* outRows);
+    [LibraryImport(Lib)] internal static partial long orr_store_vocab_size(nint store);
+    // the query STRING in: tokenising, stop words, vocabulary expansion on the GPU and the search in one call
+    [LibraryImport(Lib)] internal static unsafe partial int orr_search_query(
+        nint store, byte* queryUtf8, int queryLen, float* q, int qDim, long nowTicks, int topK, int candidateCap,
+        int keywordMode, OrrHit* hits, out int nOut);
     [LibraryImport(Lib)] internal static partial int orr_store_delete_document(nint store, ulong docKey);
     [LibraryImport(Lib)] internal static unsafe partial int orr_store_compact(nint store, ulong* oldRowsOut, long outCap, out long nLive);
     [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] internal static partial int orr_store_save(nint store, string path);

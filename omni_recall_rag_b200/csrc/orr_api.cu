@@ -40,6 +40,12 @@ struct SearchCtx {
     // orr_search_device leases: the scratch is busy until `done` (recorded on the caller's stream) has completed
     cudaEvent_t done = nullptr;
     bool busy = false;
+    // host-API contexts: the kernels write hits and status STRAIGHT into the pinned host buffers (sc.hits == h_hits,
+    // sc.status == h_status; pinned memory is device-accessible under UVA), so a call has no D2H copies at all
+    bool zero_copy = false;
+    // subset path: the capped row list last uploaded to sc.surv_rows
+    uint32_t* d_cap_rows = nullptr;            // [ORR_SORT_MAX], its own buffer: the fused path overwrites sc.surv_rows
+    uint64_t cap_version = ~0ull; int32_t cap_value = -1; int32_t cap_n = 0;
 };
 
 thread_local orr_timing g_timing{};
@@ -163,9 +169,10 @@ void free_ctx(SearchCtx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     else cudaDeviceSynchronize();
     cudaFree(c->sc.q); cudaFree(c->sc.cta_cands); cudaFree(c->sc.cta_floor); cudaFree(c->sc.surv_rows);
-    cudaFree(c->sc.exact); cudaFree(c->sc.sel); cudaFree(c->sc.hits); cudaFree(c->sc.status);
+    cudaFree(c->sc.exact); cudaFree(c->sc.sel);
+    if (!c->zero_copy) { cudaFree(c->sc.hits); cudaFree(c->sc.status); }
     cudaFree(c->sc.skey); cudaFree(c->sc.sel_state); cudaFree(c->sc.big);
-    cudaFree(c->d_terms); cudaFree(c->d_kw_bits); cudaFreeHost(c->h_terms);
+    cudaFree(c->d_terms); cudaFree(c->d_kw_bits); cudaFreeHost(c->h_terms); cudaFree(c->d_cap_rows);
     cudaFreeHost(c->h_q); cudaFreeHost(c->h_hits); cudaFreeHost(c->h_status); cudaFreeHost(c->h_rows);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->done) cudaEventDestroy(c->done);
@@ -175,18 +182,44 @@ void free_ctx(SearchCtx* c) {
 int ensure_hits(SearchCtx* c, int k) {
     if (k <= c->hits_cap) return ORR_OK;
     int cap = std::max(k, 256);
-    cudaFree(c->sc.hits); c->sc.hits = nullptr;
+    if (!c->zero_copy) cudaFree(c->sc.hits);
+    c->sc.hits = nullptr;
     cudaFreeHost(c->h_hits); c->h_hits = nullptr;
     c->hits_cap = 0;
-    ORR_CUDA_OK(cudaMalloc(&c->sc.hits, sizeof(orr_hit) * (size_t)cap));
     ORR_CUDA_OK(cudaMallocHost(&c->h_hits, sizeof(orr_hit) * (size_t)cap));
+    if (c->zero_copy) c->sc.hits = c->h_hits;
+    else ORR_CUDA_OK(cudaMalloc(&c->sc.hits, sizeof(orr_hit) * (size_t)cap));
     c->hits_cap = cap;
+    return ORR_OK;
+}
+
+// the reference's candidate pre-selection as a device-resident row list: re-uploaded only when the store (or the cap) changed
+int capped_rows(orr_store* s, int32_t cap, std::vector<uint32_t>* out);
+int ensure_cap_rows(orr_store* s, SearchCtx* c, int32_t cap, uint64_t version) {
+    if (c->cap_version == version && c->cap_value == cap && c->d_cap_rows) return ORR_OK;
+    if (!c->d_cap_rows) ORR_CUDA_OK(cudaMalloc(&c->d_cap_rows, sizeof(uint32_t) * ORR_SORT_MAX));
+    std::vector<uint32_t> rows;
+    int rc = capped_rows(s, cap, &rows);
+    if (rc != ORR_OK) return rc;
+    ORR_CUDA_OK(cudaStreamSynchronize(c->stream));               // h_rows may still feed an earlier upload
+    memcpy(c->h_rows, rows.data(), sizeof(uint32_t) * rows.size());
+    ORR_CUDA_OK(cudaMemcpyAsync(c->d_cap_rows, c->h_rows, sizeof(uint32_t) * rows.size(), cudaMemcpyHostToDevice, c->stream));
+    c->cap_version = version; c->cap_value = cap; c->cap_n = (int32_t)rows.size();
+    return ORR_OK;
+}
+
+// results -> host: nothing to do for a zero-copy context (the kernels wrote them there), else two D2H copies
+int fetch_results(SearchCtx* c, int k) {
+    if (c->zero_copy) return ORR_OK;
+    ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+    ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
     return ORR_OK;
 }
 
 int make_ctx(orr_store* s, std::unique_ptr<SearchCtx>& out, bool own_stream) {
     std::unique_ptr<SearchCtx> c(new SearchCtx());
     const int dim = s->cfg.dim;
+    c->zero_copy = own_stream;                     // host-API contexts; orr_search_device writes to the caller's device buffers
     int rc = [&]() -> int {
         if (own_stream) ORR_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) ORR_CUDA_OK(cudaEventCreate(&e));
@@ -197,9 +230,10 @@ int make_ctx(orr_store* s, std::unique_ptr<SearchCtx>& out, bool own_stream) {
         ORR_CUDA_OK(cudaMalloc(&c->sc.exact, sizeof(OrrExact) * ORR_SORT_MAX));
         ORR_CUDA_OK(cudaMalloc(&c->sc.sel, sizeof(int32_t) * 8));
         ORR_CUDA_OK(cudaMemset(c->sc.sel, 0, sizeof(int32_t) * 8));
-        ORR_CUDA_OK(cudaMalloc(&c->sc.status, sizeof(int32_t) * 2));
         ORR_CUDA_OK(cudaMallocHost(&c->h_q, sizeof(float) * (size_t)dim));
         ORR_CUDA_OK(cudaMallocHost(&c->h_status, sizeof(int32_t) * 2));
+        if (c->zero_copy) c->sc.status = c->h_status;
+        else ORR_CUDA_OK(cudaMalloc(&c->sc.status, sizeof(int32_t) * 2));
         ORR_CUDA_OK(cudaMallocHost(&c->h_rows, sizeof(uint32_t) * ORR_SORT_MAX));
         return ensure_hits(c.get(), 256);
     }();
@@ -674,18 +708,26 @@ static int run_exact(orr_store* s, SearchCtx* c, const OrrShard& sh, const OrrPr
     if (rc != ORR_OK) return rc;
     OrrScratch sc = c->sc;
     sc.kw_bits = kw_bits; sc.kw_row_words = kw_row_words; sc.kw_terms = kw_terms;
-    rc = orr_launch_exact_scores(sh, sc, pr, weights_of(s), now_ticks, q_dim, c->stream);
-    if (rc != ORR_OK) return rc;
-    if (after_scores) ORR_CUDA_OK(cudaEventRecord(after_scores, c->stream));
-    for (int first = 1, n = 2;; first += n, n = 3) {
-        rc = orr_launch_exact_select(sh, sc, k, first, n, c->stream);
+    const OrrWeights w = weights_of(s);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // attempt 0 may score on the 32-bit term table (a screen the gather verifies); attempt 1 = the 64-bit kernel
+        const bool force_general = attempt == 1;
+        const bool screened = orr_exact_keys_are_screened(sc, pr, q_dim, force_general);
+        rc = orr_launch_exact_scores(sh, sc, pr, w, now_ticks, q_dim, c->stream, force_general);
         if (rc != ORR_OK) return rc;
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
-        ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
-        if (c->h_status[1] & ORR_EXACT_INTERNAL) { orr_set_error("exact path: selection histogram inconsistent"); return ORR_E_INTERNAL; }
-        if (!(c->h_status[1] & ORR_EXACT_INCOMPLETE)) break;
-        if (first + n > ORR_EXACT_PASSES + 3) { orr_set_error("exact path: selection did not terminate"); return ORR_E_INTERNAL; }
+        if (after_scores && attempt == 0) ORR_CUDA_OK(cudaEventRecord(after_scores, c->stream));
+        for (int first = 1, n = 2;; first += n, n = 3) {
+            rc = orr_launch_exact_select(sh, sc, k, first, n, c->stream, screened ? &pr : nullptr, screened ? &w : nullptr, now_ticks);
+            if (rc != ORR_OK) return rc;
+            rc = fetch_results(c, k);
+            if (rc != ORR_OK) return rc;
+            ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
+            if (c->h_status[1] & ORR_EXACT_INTERNAL) { orr_set_error("exact path: selection histogram inconsistent"); return ORR_E_INTERNAL; }
+            if (!(c->h_status[1] & ORR_EXACT_INCOMPLETE)) break;
+            if (first + n > ORR_EXACT_PASSES + 3) { orr_set_error("exact path: selection did not terminate"); return ORR_E_INTERNAL; }
+        }
+        if (!(c->h_status[1] & ORR_EXACT_UNPROVEN)) break;
+        if (attempt == 1) { orr_set_error("exact path: unproven selection from exact keys"); return ORR_E_INTERNAL; }
     }
     return ORR_OK;
 }
@@ -726,16 +768,14 @@ int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, con
     if (candidate_cap > 0) {
         path = ORR_PATH_SUBSET;
         if (candidate_cap > ORR_SORT_MAX) { orr_set_error("candidate_cap %d > %d", candidate_cap, ORR_SORT_MAX); return ORR_E_UNSUPPORTED; }
-        std::vector<uint32_t> rows;
-        rc = capped_rows(s, candidate_cap, &rows);
+        // the capped row list only changes when the store does: it stays in this context's device buffer between queries
+        rc = ensure_cap_rows(s, c, candidate_cap, s->version);
         if (rc != ORR_OK) return rc;
-        const int32_t nl = (int32_t)rows.size();
-        memcpy(c->h_rows, rows.data(), sizeof(uint32_t) * rows.size());
-        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.surv_rows, c->h_rows, sizeof(uint32_t) * rows.size(), cudaMemcpyHostToDevice, c->stream));
-        c->h_status[0] = nl;
-        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.sel, c->h_status, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        const int32_t nl = c->cap_n;
+        OrrScratch sc = c->sc;
+        sc.surv_rows = c->d_cap_rows;
         ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
-        rc = orr_launch_rescore(sh, c->sc, pr, weights_of(s), now_ticks, eff_q_dim, (int)kk, nl, false, c->stream);
+        rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, (int)kk, nl, false, c->stream, nl);
         if (rc != ORR_OK) return rc;
         g_timing.n_survivors = nl;
     } else if (eff_q_dim == 0 || k > ORR_FUSED_MAX_K) {
@@ -754,8 +794,8 @@ int orr_search(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms, con
     }
     ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
     if (path != ORR_PATH_EXACT) {                                       // the exact path has already brought its results down
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+        rc = fetch_results(c, (int)kk);
+        if (rc != ORR_OK) return rc;
     }
     ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
     float scan_ms = 0.f, fin_ms = 0.f;
@@ -833,13 +873,12 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
     }
     const int64_t row_words = (s->rows_used + 31) / 32;
     bool escalated = false, exact = false;
-    std::vector<uint32_t> sub_rows;
+    int32_t n_sub = 0;
     if (candidate_cap > 0) {
         if (candidate_cap > ORR_SORT_MAX) { orr_set_error("candidate_cap %d > %d", candidate_cap, ORR_SORT_MAX); return ORR_E_UNSUPPORTED; }
-        rc = capped_rows(s, candidate_cap, &sub_rows);
+        rc = ensure_cap_rows(s, c, candidate_cap, s->version);
         if (rc != ORR_OK) return rc;
-        memcpy(c->h_rows, sub_rows.data(), sizeof(uint32_t) * sub_rows.size());
-        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.surv_rows, c->h_rows, sizeof(uint32_t) * sub_rows.size(), cudaMemcpyHostToDevice, c->stream));
+        n_sub = c->cap_n;
     }
     ORR_CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
     OrrScratch sc = c->sc;
@@ -865,7 +904,7 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
         OrrTextView tv{s->d_text, s->d_text_off, s->d_text_len};
         if (candidate_cap > 0) {
             ORR_CUDA_OK(cudaMemsetAsync(c->d_kw_bits, 0, need * sizeof(uint32_t), c->stream));
-            rc = orr_launch_text_bits(tv, s->rows_used, c->d_terms, n_terms, max_len, c->sc.surv_rows, (int)sub_rows.size(),
+            rc = orr_launch_text_bits(tv, s->rows_used, c->d_terms, n_terms, max_len, c->d_cap_rows, n_sub,
                                       c->d_kw_bits, row_words, c->stream);
         } else {
             rc = orr_launch_text_bits(tv, s->rows_used, c->d_terms, n_terms, max_len, nullptr, 0, c->d_kw_bits, row_words, c->stream);
@@ -878,10 +917,9 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
     pr.n_terms = n_terms;                                   // the denominator; matches come from the bitmaps
     ORR_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
     if (candidate_cap > 0) {
-        const int32_t nl = (int32_t)sub_rows.size();
-        c->h_status[0] = nl;
-        ORR_CUDA_OK(cudaMemcpyAsync(c->sc.sel, c->h_status, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, (int)kk, nl, false, c->stream);
+        const int32_t nl = n_sub;
+        sc.surv_rows = c->d_cap_rows;
+        rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, (int)kk, nl, false, c->stream, nl);
         g_timing.n_survivors = nl;
     } else {
         // every row is a candidate: the fused scan selects with the bitmaps as its keyword side (<= 32 terms),
@@ -893,7 +931,7 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
             if (rc != ORR_OK) return rc;
             rc = orr_launch_rescore(sh, sc, pr, weights_of(s), now_ticks, eff_q_dim, k, M, true, c->stream);
             if (rc != ORR_OK) return rc;
-            ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
+            if (!c->zero_copy) ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
             ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
             g_timing.n_survivors = M;
             if (c->h_status[1] & 1) { fused = false; escalated = true; }
@@ -907,8 +945,8 @@ int orr_search_text(orr_store* s, const float* q, int32_t q_dim, int32_t n_terms
     if (rc != ORR_OK) return rc;
     ORR_CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
     if (!exact) {                                            // the exact path has already brought its results down
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_status, c->sc.status, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
-        ORR_CUDA_OK(cudaMemcpyAsync(c->h_hits, c->sc.hits, sizeof(orr_hit) * (size_t)kk, cudaMemcpyDeviceToHost, c->stream));
+        rc = fetch_results(c, (int)kk);
+        if (rc != ORR_OK) return rc;
     }
     ORR_CUDA_OK(cudaStreamSynchronize(c->stream));
     float match_ms = 0.f, fin_ms = 0.f;

@@ -20,6 +20,7 @@
 //       timestamps) walk on into the ticks and row digits.  top_k > 4096 gathers exactly k rows and orders them with
 //       a global-memory bitonic sort.
 #include <algorithm>
+#include <cstring>
 
 #include "orr_exact_row.cuh"
 
@@ -50,6 +51,8 @@ struct SelState {
     SelPoint pt[SEL_NPASS + 1];
     uint32_t n_gathered;
     int32_t  ticket;
+    uint32_t n_verified;       // screened keys only: gathered rows whose EXACT key is still at or above the walk's lower edge
+    uint32_t pad;
 };
 
 // order-preserving key of an exact score: larger key = ranks earlier; dead rows 0, NaN 1 (NaN sorts last, :34;
@@ -116,11 +119,16 @@ __global__ void __launch_bounds__(256) orr_exact_scores_kernel(const ExactArgs a
 // ---- E1 without a query embedding: keyword + recency only --------------------------------------------------------
 // A warp takes 32 consecutive rows = one contiguous 32 * slots * 4 B block of the 32-BIT term table (the scan's table:
 // half the bytes of the 64-bit one), streamed with 8 coalesced 16-byte loads in flight per lane.  Every stored low word
-// is compared with the probes' low words (kernel-parameter constant memory); a 32-bit hit is CONFIRMED against the
-// 64-bit table (one scattered 8-byte load; rare — a query term sits in a few percent of the rows at most) so the match
-// counts are exact, never a hash collision.  The per-row term masks are OR-reduced across the lanes that hold the row
-// (one REDUX per 16-byte load, member masks split the warp when a load spans two rows), lane j keeps row j's count and
-// runs the scalar fp64 tail (exact_row_finish: the same operations as every other path).
+// is compared with the probes' low words (kernel-parameter constant memory).  The per-row term masks are OR-reduced
+// across the lanes that hold the row (one REDUX per 16-byte load, member masks split the warp when a load spans two
+// rows), lane j keeps row j's count and runs the scalar fp64 tail (exact_row_finish: the same operations as every
+// other path).
+// SCREEN, NOT RESULT: a 32-bit word can collide with a probe, which can only RAISE a row's match count, so this key is an
+// upper bound of the row's exact key.  The selection walk runs on these keys; the gather kernel recounts every candidate's
+// matches on the 64-bit table (exact score, <= the screen's) and proves that k candidates still rank at or above the
+// walk's lower edge — no row outside the candidate set can then belong to the top-k.  If a collision breaks the proof the
+// caller re-runs with the 64-bit scoring kernel.  (Confirming hits inline was tried first: with Zipf terms most rows hold
+// some query term, and a latency-serialised 64-bit load per hit made the kernel 3x slower than the table scan.)
 // Algorithmic bytes per row: 4 * slots (terms32) + 8 (ticks); embeddings are never read.
 // SPL = slots / 32: 16-byte vectors per row VR = 8 * SPL (8, 16, 32).  WIDE = more than 32 query terms (two mask words).
 struct NoembArgs {
@@ -175,14 +183,7 @@ __global__ void __launch_bounds__(512, 2) orr_noemb_scores_kernel(const NoembArg
                     const uint32_t b0 = t < 32 ? (1u << t) : 0u, b1 = t < 32 ? 0u : (1u << (t - 32));
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        bool hit = (x[i].x == hl) | (x[i].y == hl) | (x[i].z == hl) | (x[i].w == hl);
-                        if (hit) {                                           // rare: confirm with the full 64-bit hashes of the 4 slots
-                            const int v = v0 + i * 32 + lane;
-                            const uint64_t* full = a.sh.terms64 + row0 * (int64_t)a.sh.slots + (int64_t)v * 4;
-                            const uint64_t h = a.pr.h64[p];
-                            hit = ((x[i].x == hl) && __ldg(full + 0) == h) || ((x[i].y == hl) && __ldg(full + 1) == h) ||
-                                  ((x[i].z == hl) && __ldg(full + 2) == h) || ((x[i].w == hl) && __ldg(full + 3) == h);
-                        }
+                        const bool hit = (x[i].x == hl) | (x[i].y == hl) | (x[i].z == hl) | (x[i].w == hl);
                         m0[i] |= hit ? b0 : 0u;
                         if (WIDE) m1[i] |= hit ? b1 : 0u;
                     }
@@ -316,10 +317,14 @@ __global__ void __launch_bounds__(256) orr_sel_pass_kernel(SelState* st, int pas
 
 constexpr int32_t SEL_FLAG_INCOMPLETE = 8;      // the walk has not ended: the host launches more digit passes
 constexpr int32_t SEL_FLAG_INTERNAL = 32;       // histogram inconsistent with k (bug)
+constexpr int32_t SEL_FLAG_UNPROVEN = 64;       // a 32-bit hash collision inside the candidate set: re-run with the 64-bit scoring kernel
 
 struct GatherArgs {
     SelState* st; int32_t last_pass; uint32_t k;
     const uint64_t* skey; const int64_t* ticks; int64_t rows; uint64_t row_base;
+    // keys that are a 32-bit-hash SCREEN (no-embedding path): every gathered row's matches are recounted on the 64-bit
+    // table and its exact score replaces the screen's
+    int32_t verify; const uint64_t* terms64; int32_t slots; OrrProbes pr; OrrWeights w; int64_t now_ticks;
     OrrExact* big; uint32_t big_cap;            // top_k > SEL_CAP: the k selected rows go here (padded to a power of two)
     OrrExact* small;                            // otherwise: <= SEL_CAP candidates, ordered by the last CTA
     orr_hit* hits; int32_t* status;
@@ -356,8 +361,32 @@ __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a)
         }
         if (!take) continue;
         if (!have_tk) tk = a.ticks[row];
+        double score = key_score(w0);
+        if (a.verify && tk != ORR_DEAD_TICKS) {
+            // exact recount on the full hashes: one thread per candidate, 16-byte loads over the row's slots
+            uint32_t m0 = 0u, m1 = 0u;
+            const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(a.terms64 + row * (int64_t)a.slots);
+            for (int v = 0; v < a.slots / 2; ++v) {
+                const ulonglong2 h2 = __ldg(t2 + v);
+                for (int p = 0; p < a.pr.n_probes; ++p) {
+                    const uint64_t h = a.pr.h64[p];
+                    if (h2.x == h || h2.y == h) { const uint32_t t = a.pr.term[p]; if (t < 32) m0 |= 1u << t; else m1 |= 1u << (t - 32); }
+                }
+            }
+            ExactLite ex = {};
+            ex.q_dim = 0; ex.w = a.w; ex.now_ticks = a.now_ticks;
+            ExactPartial pt;
+            pt.dot = 0.0; pt.nB = 0.0; pt.ticks = tk; pt.matches = __popc(m0) + __popc(m1);
+            pt.kw_den = a.pr.n_probes > 0 ? a.pr.n_terms : -1;
+            score = exact_row_finish(ex, 0.0, pt);
+            // does the row still rank at or above the walk's lower edge with its exact score?
+            const uint64_t e0 = score_key(score, false);
+            bool ge = e0 > cur.p0;
+            if (!ge && e0 == cur.p0) { const uint64_t w1 = ticks_key(tk); ge = w1 > cur.p1 || (w1 == cur.p1 && ~(uint32_t)row >= cur.p2); }
+            if (ge) atomicAdd(&st->n_verified, 1u);
+        }
         const uint32_t slot = atomicAdd(&st->n_gathered, 1u);
-        if (slot < cap) { OrrExact r; r.score = key_score(w0); r.ticks = tk; r.row = (uint64_t)row; out[slot] = r; }
+        if (slot < cap) { OrrExact r; r.score = score; r.ticks = tk; r.row = (uint64_t)row; out[slot] = r; }
     }
     // ---- the last CTA to finish orders the candidates (or pads the big list for the global sort) ----
     __shared__ int s_last;
@@ -368,6 +397,8 @@ __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a)
     if (!s_last) return;
     __threadfence();
     const uint32_t m = min(*((volatile uint32_t*)&st->n_gathered), cap);
+    // screened keys: the candidate set is complete iff k of its rows still rank at or above the lower edge after the recount
+    const int32_t unproven = (a.verify && *((volatile uint32_t*)&st->n_verified) < min(a.k, (uint32_t)m)) ? SEL_FLAG_UNPROVEN : 0;
     if (big) {
         uint32_t np2 = 1u;
         while (np2 < m) np2 <<= 1;
@@ -375,7 +406,7 @@ __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a)
             OrrExact v; v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull;
             out[i] = v;
         }
-        if (tid == 0) { a.status[0] = (int32_t)m; a.status[1] = 0; }
+        if (tid == 0) { a.status[0] = (int32_t)m; a.status[1] = unproven; }
         return;
     }
     OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
@@ -407,7 +438,7 @@ __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a)
         orr_hit h; h.row = a.row_base + e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
         a.hits[i] = h;
     }
-    if (tid == 0) { a.status[0] = n_out; a.status[1] = 0; }
+    if (tid == 0) { a.status[0] = n_out; a.status[1] = unproven; }
 }
 
 // ---- top_k > SEL_CAP: global-memory bitonic sort of the k selected rows, then the hits ---------------------------------
@@ -433,15 +464,20 @@ __global__ void orr_big_emit(const OrrExact* e, const int32_t* status, uint32_t 
 
 size_t orr_exact_state_bytes() { return sizeof(SelState); }
 
+// true: the keys orr_launch_exact_scores writes for this query are the 32-bit screen (the gather must verify)
+bool orr_exact_keys_are_screened(const OrrScratch& sc, const OrrProbes& pr, int q_dim, bool force_general) {
+    return !force_general && q_dim == 0 && sc.kw_bits == nullptr && pr.n_probes > 0;
+}
+
 int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
-                            const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st) {
+                            const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st, bool force_general) {
     if (sh.rows == 0) return ORR_OK;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     SelState* state = reinterpret_cast<SelState*>(sc.sel_state);
     ORR_CUDA_OK(cudaMemsetAsync(state, 0, sizeof(SelState), st));
-    if (q_dim == 0 && sc.kw_bits == nullptr) {
+    if (q_dim == 0 && sc.kw_bits == nullptr && !force_general) {
         NoembArgs a;
         a.sh = sh; a.pr = pr; a.w = w; a.now_ticks = now_ticks;
         const int grid = sms * 2;
@@ -466,7 +502,8 @@ int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrP
 
 // Digit passes [first_pass, first_pass + n_passes) (pass 0 was counted by E1), then the gather.  status[1] carries
 // ORR_EXACT_INCOMPLETE when the walk needs more passes: the caller reads it back and calls again with the next passes.
-int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k, int first_pass, int n_passes, cudaStream_t st) {
+int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k, int first_pass, int n_passes, cudaStream_t st,
+                            const OrrProbes* verify_pr, const OrrWeights* verify_w, int64_t now_ticks) {
     const int64_t n = sh.rows;
     if (n == 0) { ORR_CUDA_OK(cudaMemsetAsync(sc.status, 0, 2 * sizeof(int32_t), st)); return ORR_OK; }
     if (n > 0x7fffffff) { orr_set_error("exact path: shard too large"); return ORR_E_UNSUPPORTED; }
@@ -485,6 +522,9 @@ int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k,
     GatherArgs g;
     g.st = state; g.last_pass = last; g.k = k; g.skey = sc.skey; g.ticks = sh.ticks; g.rows = n; g.row_base = sh.row_base;
     g.big = nullptr; g.big_cap = 0; g.small = sc.exact; g.hits = sc.hits; g.status = sc.status;
+    g.verify = verify_pr != nullptr ? 1 : 0;
+    g.terms64 = sh.terms64; g.slots = sh.slots; g.now_ticks = now_ticks;
+    if (verify_pr) { g.pr = *verify_pr; g.w = *verify_w; } else { memset(&g.pr, 0, sizeof g.pr); memset(&g.w, 0, sizeof g.w); }
     const bool big = k > (uint32_t)SEL_CAP;
     if (big) {
         if (!sc.big || sc.big_cap < k) { orr_set_error("exact path: big-k buffer missing"); return ORR_E_INTERNAL; }

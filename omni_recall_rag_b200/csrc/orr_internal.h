@@ -126,18 +126,21 @@ int orr_launch_scan(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& p
 // reference tie chain, runs the selection bound check and emits the top-k hits.
 int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
                        const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
-                       int n_listed_max, bool check_bound, cudaStream_t st);
+                       int n_listed_max, bool check_bound, cudaStream_t st, int n_listed_host = -1);
 
 // exact path (orr_exact.cu): every row's fp64 score as an order-preserving key, then an MSB-first radix select of the
 // top-k under (score desc / NaN last, ticks desc, row asc).  orr_launch_exact_select runs digit passes
 // [first_pass, first_pass + n_passes) and the gather; status[1] & ORR_EXACT_INCOMPLETE asks for the next passes.
 constexpr int32_t ORR_EXACT_INCOMPLETE = 8;
 constexpr int32_t ORR_EXACT_INTERNAL = 32;
+constexpr int32_t ORR_EXACT_UNPROVEN = 64;      // the 32-bit screen's candidate set could not be proven complete: use the 64-bit kernel
 constexpr int ORR_EXACT_PASSES = 15;
 size_t orr_exact_state_bytes();
+bool orr_exact_keys_are_screened(const OrrScratch& sc, const OrrProbes& pr, int q_dim, bool force_general);
 int orr_launch_exact_scores(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
-                            const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st);
-int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k, int first_pass, int n_passes, cudaStream_t st);
+                            const OrrWeights& w, int64_t now_ticks, int q_dim, cudaStream_t st, bool force_general = false);
+int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k, int first_pass, int n_passes, cudaStream_t st,
+                            const OrrProbes* verify_pr = nullptr, const OrrWeights* verify_w = nullptr, int64_t now_ticks = 0);
 
 int orr_launch_merge(const orr_hit* lists_dev, const int32_t* status_dev, int n_lists, int stride, int top_k,
                      orr_hit* out_dev, int32_t* out_status_dev, cudaStream_t st);

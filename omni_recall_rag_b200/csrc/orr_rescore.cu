@@ -28,9 +28,10 @@ namespace {
 struct RescoreArgs {
     ExactArgs ex;
     const uint32_t* rows;        // listed local rows
-    const int32_t*  n_listed;    // device count (sel[0])
+    const int32_t*  n_listed;    // device count (sel[0]), or NULL: n_listed_value
     const int32_t*  tau_bits;    // device float bits (sel[1])
     int32_t   n_listed_max;
+    int32_t   n_listed_value;    // the count when the host knows it (subset path): saves a 4-byte H2D copy per query
     int32_t   top_k;
     int32_t   check_bound;
     double    eps;
@@ -43,7 +44,7 @@ struct RescoreArgs {
 __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n = min(*a.n_listed, a.n_listed_max);
+    const int n = min(a.n_listed ? *a.n_listed : a.n_listed_value, a.n_listed_max);
     const int idx = blockIdx.x * 4 + warp;
     if (idx < n) {
         const double nA = (a.ex.q_dim == a.ex.sh.dim && a.ex.q_dim > 0) ? exact_qnorm(a.ex, lane) : 0.0;
@@ -62,37 +63,48 @@ __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
     __threadfence();
 
     OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    const volatile OrrExact* src = a.exact;
-    for (int i = tid; i < np2; i += blockDim.x) {
-        OrrExact v;
-        if (i < n) { v.score = src[i].score; v.ticks = src[i].ticks; v.row = src[i].row; }
-        else { v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull; }  // pads rank last
-        e[i] = v;
-    }
-    __syncthreads();
-    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < np2; i += blockDim.x) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const OrrExact x = e[i], y = e[p];
-                    const bool up = ((i & k2) == 0);                  // ascending rank in this run
-                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
     const int k = max(1, a.top_k);                                    // Math.Max(1, topK) :36
     const int n_out = min(k, n);
-    for (int i = tid; i < n_out; i += blockDim.x) {
-        orr_hit h;
-        h.row = a.ex.sh.row_base + e[i].row;
-        h.score = e[i].score;
-        h.created_ticks = e[i].ticks;
-        a.hits[i] = h;
+    const volatile OrrExact* src = a.exact;
+    __shared__ double s_kth;
+    if (tid == 0) s_kth = __longlong_as_double(0x7ff8000000000000LL);
+    if (n <= ORR_RANK_MAX) {
+        for (int i = tid; i < n; i += blockDim.x) { OrrExact v; v.score = src[i].score; v.ticks = src[i].ticks; v.row = src[i].row; e[i] = v; }
+        __syncthreads();
+        rank_emit(e, n, n_out, k, a.ex.sh.row_base, a.hits, &s_kth);
+        __syncthreads();
+    } else {
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        for (int i = tid; i < np2; i += blockDim.x) {
+            OrrExact v;
+            if (i < n) { v.score = src[i].score; v.ticks = src[i].ticks; v.row = src[i].row; }
+            else { v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull; }  // pads rank last
+            e[i] = v;
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < np2; i += blockDim.x) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const OrrExact x = e[i], y = e[p];
+                        const bool up = ((i & k2) == 0);                  // ascending rank in this run
+                        if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < n_out; i += blockDim.x) {
+            orr_hit h;
+            h.row = a.ex.sh.row_base + e[i].row;
+            h.score = e[i].score;
+            h.created_ticks = e[i].ticks;
+            a.hits[i] = h;
+        }
+        if (tid == 0 && n >= k) s_kth = e[k - 1].score;
+        __syncthreads();
     }
     if (tid == 0) {
         int flags = 0;
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
             // safe iff the k-th exact score clears tau by more than eps.
             const float tau = __int_as_float(*a.tau_bits);
             if (tau != -INFINITY) {
-                const double sk = (n >= k) ? e[k - 1].score : __longlong_as_double(0x7ff8000000000000LL);
+                const double sk = s_kth;                                  // NaN when fewer than k rows were listed
                 if (!(sk - a.eps > (double)tau)) flags |= 1;
             }
         }
@@ -121,42 +133,45 @@ __device__ __forceinline__ void merge_lists_cta(const orr_hit* lists, const int3
                                                 OrrExact* e) {
     const int tid = threadIdx.x;
     const int total = n_lists * stride;
-    int np2 = 1;
-    while (np2 < total) np2 <<= 1;
     __shared__ int s_n, s_flags;
     if (tid == 0) { s_n = 0; s_flags = extra_flags; }
     __syncthreads();
-    for (int i = tid; i < np2; i += blockDim.x) {
-        OrrExact v; v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull;
-        if (i < total) {
-            const int l = i / stride, j = i - l * stride;
-            if (j < status[2 * l]) {
-                const orr_hit h = lists[i];
-                v.score = h.score; v.ticks = h.created_ticks; v.row = h.row;
-                atomicAdd(&s_n, 1);
-            }
+    for (int i = tid; i < total; i += blockDim.x) {                  // the valid hits, compacted (their order does not matter)
+        const int l = i / stride, j = i - l * stride;
+        if (j < status[2 * l]) {
+            const orr_hit h = lists[i];
+            OrrExact v; v.score = h.score; v.ticks = h.created_ticks; v.row = h.row;
+            e[atomicAdd(&s_n, 1)] = v;
         }
-        e[i] = v;
     }
     if (tid < n_lists) atomicOr(&s_flags, status[2 * tid + 1]);
     __syncthreads();
-    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < np2; i += blockDim.x) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const OrrExact x = e[i], y = e[p];
-                    const bool up = ((i & k2) == 0);
-                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+    const int n = s_n;
+    const int n_out = min(max(1, top_k), n);
+    if (n <= ORR_RANK_MAX) {
+        rank_emit(e, n, n_out, max(1, top_k), 0ull, out, nullptr);
+    } else {
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        for (int i = n + tid; i < np2; i += blockDim.x) { OrrExact v; v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull; e[i] = v; }
+        __syncthreads();
+        for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < np2; i += blockDim.x) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const OrrExact x = e[i], y = e[p];
+                        const bool up = ((i & k2) == 0);
+                        if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
-    }
-    const int n_out = min(max(1, top_k), s_n);
-    for (int i = tid; i < n_out; i += blockDim.x) {
-        orr_hit h; h.row = e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
-        out[i] = h;
+        for (int i = tid; i < n_out; i += blockDim.x) {
+            orr_hit h; h.row = e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
+            out[i] = h;
+        }
     }
     if (tid == 0) { out_status[0] = n_out; out_status[1] = s_flags; }
 }
@@ -285,14 +300,15 @@ __global__ void __launch_bounds__(256) orr_xchg_merge_kernel(const OrrXchgArgs a
 
 int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
                        const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
-                       int n_listed_max, bool check_bound, cudaStream_t st) {
+                       int n_listed_max, bool check_bound, cudaStream_t st, int n_listed_host) {
     ORR_SMEM_OPT_IN((orr_rescore_kernel), ORR_SORT_MAX * (int)sizeof(OrrExact));
     if (n_listed_max < 1) n_listed_max = 1;
     if (n_listed_max > ORR_SORT_MAX) { orr_set_error("rescore: %d rows exceed the sorter", n_listed_max); return ORR_E_INTERNAL; }
     RescoreArgs a;
     fill_exact_args(a.ex, sh, sc, pr, w, now_ticks, q_dim);
     a.rows = sc.surv_rows;
-    a.n_listed = sc.sel + 0;
+    a.n_listed = n_listed_host >= 0 ? nullptr : sc.sel + 0;
+    a.n_listed_value = n_listed_host;
     a.tau_bits = sc.sel + 1;
     a.n_listed_max = n_listed_max;
     a.top_k = top_k;
@@ -595,34 +611,18 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
         const int i = g + lane * (BATCH_FIN_THREADS / 32);
         if (i < ns) { e[i].score = exact_row_finish(a.ex, nA, mine); e[i].ticks = mine.ticks; }
     }
-    int ep2 = 1;
-    while (ep2 < ns) ep2 <<= 1;
-    for (int i = ns + tid; i < ep2; i += BATCH_FIN_THREADS) {
-        e[i].score = __longlong_as_double(0x7ff8000000000000LL); e[i].ticks = INT64_MIN; e[i].row = ~0ull;
-    }
     __syncthreads();
-    for (int k2 = 2; k2 <= ep2; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < ep2; i += BATCH_FIN_THREADS) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const OrrExact x = e[i], y = e[p];
-                    const bool up = ((i & k2) == 0);
-                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    // order the survivors by counting, not sorting (ns <= ORR_BATCH_MAX_SURV <= ORR_RANK_MAX)
+    __shared__ double s_kth;
+    if (tid == 0) s_kth = __longlong_as_double(0x7ff8000000000000LL);
+    __syncthreads();
     const int k = max(1, a.top_k);
     const int n_out = min(k, ns);
-    for (int i = tid; i < n_out; i += BATCH_FIN_THREADS) {
-        orr_hit h; h.row = a.ex.sh.row_base + e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
-        a.hits[(int64_t)b * a.k_stride + i] = h;
-    }
+    rank_emit(e, ns, n_out, k, a.ex.sh.row_base, a.hits + (int64_t)b * a.k_stride, &s_kth);
+    __syncthreads();
     if (tid == 0) {
         if (tau != -INFINITY) {
-            const double sk = (ns >= k) ? e[k - 1].score : __longlong_as_double(0x7ff8000000000000LL);
+            const double sk = s_kth;                                         // NaN when fewer than k survivors
             if (!(sk - a.eps > (double)tau)) flags |= 1;                     // selection not provably safe
         }
         a.status[2 * b] = n_out;

@@ -151,3 +151,32 @@ def test_queries_whose_norm_leaves_fp32_are_ranked_by_the_exact_path(scale):
         for b, q in enumerate(qs):
             er, es, _ = oracle_search_synth(rows, q, NOW, 10)
             assert_same_ranking(hits[b].rows, hits[b].scores, er, es, what=f"batch scale {scale} b={b}")
+
+
+def test_a_32_bit_hash_collision_cannot_change_the_result():
+    """The no-embedding kernel screens on the 32-bit term table; a stored hash that agrees with a probe in its low word but
+    not in its high word is a false match there.  The gather recounts the candidates on the 64-bit table and, when the
+    collision leaves fewer than k proven candidates, the query re-runs on the 64-bit kernel: the result is the oracle's."""
+    n, dim, k = 4_000, 8, 13
+    rng = np.random.default_rng(11)
+    word = "needle"
+    h = orr.hash_term(word)
+    fake = np.uint64(h ^ (1 << 40))                                   # same low 32 bits, different token
+    ticks = (NOW - DAY * (1 + rng.integers(0, 300, size=n))).astype(np.int64)
+    true_rows = rng.choice(np.arange(100, n), size=12, replace=False)
+    contents = ["filler"] * n
+    hashes = [np.array([orr.hash_term("filler")], dtype=np.uint64) for _ in range(n)]
+    for r in true_rows:
+        contents[r] = "filler needle"
+        hashes[r] = np.array([orr.hash_term("filler"), h], dtype=np.uint64)
+    ticks[7] = NOW                                                    # the colliding row is the newest: first on the screen
+    hashes[7] = np.array([orr.hash_term("filler"), fake], dtype=np.uint64)
+    with orr.RecallShard(dim, n, term_slots=32) as sh:
+        sh.upsert_document_chunks(1, None, ticks, hashes)
+        terms = orr.QueryTerms(1, np.array([h], dtype=np.uint64), None)
+        for kk in (k, 12, 5, 40):
+            got = sh.search(None, terms, NOW, kk)
+            assert sh.last_timing()["path"] == N.PATH_EXACT
+            er, es, _ = _oracle(None, dim, ticks, contents, word, None, kk)
+            assert_same_ranking(got.rows, got.scores, er, es, what=f"collision k={kk}")
+        assert 7 not in sh.search(None, terms, NOW, 12).rows.tolist()

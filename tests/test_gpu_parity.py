@@ -342,3 +342,28 @@ def test_error_codes_and_limits():
         with pytest.raises(N.OrrError):
             sh.search_text(q, ["x" * 300], NOW, 3)                   # term longer than the substring kernel takes
         assert sh.count == 3 and len(sh.search(q, orr.QueryTerms.none(), NOW, 3)) == 3   # the store survived all of it
+
+
+def test_shim_call_sequence_replayed_from_plain_c(tmp_path, golden):
+    """tests/shim/shim_driver.c dlopen()s liborr.so and makes the calls dotnet/GpuIngestionStore.cs and
+    dotnet/GpuRecallSearchService.cs make, in their order, on the reference's own fixture
+    (RecallSearchServiceTests.cs:51-117); its output must equal the golden cases derived from that fixture."""
+    import json
+    import subprocess
+
+    from tests.test_host import _build_shim_driver
+
+    exe = _build_shim_driver(tmp_path)
+    out = subprocess.run([exe, "--replay", N.library_path()], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = {j["case"]: j for j in map(json.loads, out.stdout.strip().splitlines())}
+    assert lines["upsert"]["rows"] == [0, 1, 2] and lines["upsert"]["count"] == 3
+    by_query = {c["query"]: c for c in golden["cases"] if len(c["chunks"]) == 3}
+    for case in ("vector+keyword", "keyword-only", "stop-words"):
+        got = lines[case]
+        exp = by_query[got["query"]]["derived_hits"]
+        assert [h["row"] for h in got["hits"]] == [h["row"] for h in exp], case
+        for g, e in zip(got["hits"], exp):
+            assert same_score(g["score"], e["score"]), (case, g, e)
+    assert lines["blank"]["rc"] == N.ORR_E_INVALID
+    assert lines["empty-store"]["hits"] == []

@@ -254,3 +254,57 @@ def test_bench_without_a_gpu_fails_loudly_instead_of_falling_back():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def _build_shim_driver(tmp_path):
+    import subprocess
+
+    exe = str(tmp_path / "shim_driver")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "shim", "shim_driver.c"), "-ldl", "-o", exe])
+    return exe
+
+
+def test_csharp_struct_declarations_match_the_c_layout(tmp_path):
+    """SURVEY 8 f3 without a .NET SDK: the structs DECLARED in dotnet/OrrNative.cs ([StructLayout(Sequential)], parsed from
+    the C# source) must lay out exactly as the C compiler lays out orr_config / orr_hit (tests/shim/shim_driver.c
+    --layout, compiled against include/orr.h) and as the ctypes binding declares them."""
+    import ctypes as C
+    import json
+    import re
+    import subprocess
+
+    c_layout = json.loads(subprocess.check_output([_build_shim_driver(tmp_path), "--layout"]))
+    src = open(os.path.join(ROOT, "dotnet", "OrrNative.cs"), encoding="utf-8").read()
+    size_of = {"int": 4, "uint": 4, "long": 8, "ulong": 8, "double": 8, "float": 4, "byte": 1}
+
+    def cs_fields(struct):
+        body = re.search(r"\[StructLayout\(LayoutKind\.Sequential\)\]\s*internal struct " + struct + r"\s*\{(.*?)\}", src, re.S).group(1)
+        fields = []
+        for typ, names in re.findall(r"public\s+(\w+)\s+([^;]+);", body):
+            fields += [(n.strip(), size_of[typ]) for n in names.split(",")]
+        return fields
+
+    def sequential(fields):                       # .NET sequential layout = C natural alignment (Pack = 0)
+        off, out, align = 0, [], 1
+        for name, sz in fields:
+            off = (off + sz - 1) // sz * sz
+            out.append(off)
+            off += sz
+            align = max(align, sz)
+        return out, (off + align - 1) // align * align
+
+    snake = lambda s: re.sub(r"(?<!^)(?=[A-Z])", "_", s).lower()
+    for cs_name, c_name, ctype in (("OrrConfig", "orr_config", N.OrrConfig), ("OrrHit", "orr_hit", N.OrrHit)):
+        fields = cs_fields(cs_name)
+        offs, size = sequential(fields)
+        assert size == c_layout[f"sizeof.{c_name}"] == C.sizeof(ctype), cs_name
+        assert len(fields) == len(ctype._fields_)
+        for (name, _), off, (py_name, _) in zip(fields, offs, ctype._fields_):
+            assert snake(name) == py_name, (name, py_name)                       # same field order on all three sides
+            assert off == c_layout[f"{c_name}.{py_name}"] == getattr(ctype, py_name).offset, (cs_name, name)
+    assert C.sizeof(N.OrrTiming) == c_layout["sizeof.orr_timing"]
+    assert c_layout["ORR_ABI_VERSION"] == N.ORR_ABI_VERSION
+    # every entry point the C# binding imports exists in the header and in the library
+    imported = set(re.findall(r"partial\s+\w+\s+(orr_\w+)\s*\(", src))
+    assert imported and imported <= set(N.declared_symbols()), imported - set(N.declared_symbols())
