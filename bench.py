@@ -391,7 +391,9 @@ def measure_batch(args, name: str, steps: int, warmup: int, cpu_seconds: float):
     from omni_recall_rag_b200 import _native as N
     from omni_recall_rag_b200 import synth
 
-    wl = BATCH_WORKLOADS[name]
+    wl = dict(BATCH_WORKLOADS[name])
+    if os.environ.get("ORR_BENCH_TERMS"):          # tuning experiments only: how much of a pass is the keyword side
+        wl["n_terms"] = int(os.environ["ORR_BENCH_TERMS"]); wl["frequent"] = min(wl["frequent"], wl["n_terms"])
     main_passes = 3 if args.batch_passes == 3 else 1
     rows, dim, B, k = wl["rows"], wl["dim"], wl["batch"], wl["top_k"]
     spec = synth.make_spec(dim, dup_row_ppm=wl["dup_ppm"])

@@ -1524,7 +1524,7 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k, 
     }
     if (!bs->ehi) {
         const size_t cap_pad = (cap + ORR_BATCH_TILE - 1) / ORR_BATCH_TILE * ORR_BATCH_TILE;
-        ORR_CUDA_OK(cudaMalloc(&bs->ehi, cap * dim * 2));
+        ORR_CUDA_OK(cudaMalloc(&bs->ehi, (size_t)orr_batch_plane_elems((int64_t)cap, dim) * 2));
         ORR_CUDA_OK(cudaMalloc(&bs->rowaux, cap_pad * sizeof(float)));
         bs->planes_rows = 0;
     }
@@ -1537,7 +1537,7 @@ static int batch_prepare(orr_store* s, BatchState* bs, int batch_padded, int k, 
     // the mid plane (the other half of the split) costs as much HBM as the hi plane and is only read by bf16x3
     // passes: it is allocated and built the first time one runs (auto mode: the first cascade)
     if (need_mid) {
-        if (!bs->emid) { ORR_CUDA_OK(cudaMalloc(&bs->emid, cap * dim * 2)); bs->mid_rows = 0; }
+        if (!bs->emid) { ORR_CUDA_OK(cudaMalloc(&bs->emid, (size_t)orr_batch_plane_elems((int64_t)cap, dim) * 2)); bs->mid_rows = 0; }
         if (bs->mid_rows < s->rows_used) {
             int rc = orr_batch_build_planes(s->d_emb, nullptr, bs->emid, bs->mid_rows, s->rows_used - bs->mid_rows, dim,
                                             (float)s->cfg.w_cos, bs->stream);

@@ -446,7 +446,9 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                 mbar_wait(smem_u32(&aux_empty[buf]), ((uint32_t)(u >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(smem_u32(&aux_full[buf]), UN * 4);
                 bulk_g2s(smem_u32(rec + buf * UN), a.rowrec + (int64_t)row_tile * UN, UN * 4, smem_u32(&aux_full[buf]));
-                const int qrow = qb * 256 + (int)half * BM, erow = row_tile * UN + (int)half * BM;
+                const int qrow = qb * 256 + (int)half * BM;
+                // this CTA's 128 rows of the unit are ONE 128-row tile of the k-block-major row planes
+                const int64_t etile = ((int64_t)row_tile * (UN / BM) + (int64_t)half) * a.k_blocks;
                 for (int kb = 0; kb < a.k_blocks; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);     // free in every CTA this one writes to
                     const uint32_t fb_local = smem_u32(&full_bar[stage]);
@@ -465,8 +467,9 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                         if (PASSES == 3)
                             tma_load_2d_pair_mc(base + 1 * PLANE_BYTES + qoff, &map_qmid, kb * BK, qrow + (int)pair * (BM / 2), fb_local, qmask);
                     }
-                    tma_load_2d_pair(base + E0 * PLANE_BYTES, &map_ehi, kb * BK, erow, fb);
-                    if (PASSES == 3) tma_load_2d_pair(base + 3 * PLANE_BYTES, &map_emid, kb * BK, erow, fb);
+                    const int ecoord = (int)((etile + kb) * BM);            // row of the [tiles * kblocks * 128][64] view
+                    tma_load_2d_pair(base + E0 * PLANE_BYTES, &map_ehi, 0, ecoord, fb);
+                    if (PASSES == 3) tma_load_2d_pair(base + 3 * PLANE_BYTES, &map_emid, 0, ecoord, fb);
                     if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -594,26 +597,35 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
 // Rows are stored pre-scaled so the accumulator already is w_cos * cos * |q| and the epilogue needs one FFMA
 // per score.  Rows whose squared norm is 0, non-finite or overflows fp32 get all-zero planes (screen cosine 0,
 // as CosineSimilarity returns for a zero norm, RecallSearchService.cs:84-85).
+// LAYOUT of a row plane: k-block-major tiles.  The GEMM's TMA box is 128 rows x 64 columns (one 128-byte swizzle row per
+// corpus row); in a row-major plane that box is 128 separate 128-byte pieces 2*dim bytes apart, and the 12 k-blocks of a
+// unit revisit every DRAM page 12 times, ~0.6 us apart: the main pass of the single-query-block config reached only
+// 4.5 TB/s of HBM.  Here element (row r, column c) lives at
+//     ((r / 128) * (dim / 64) + c / 64) * 128 * 64  +  (r % 128) * 64  +  c % 64
+// so every box is ONE contiguous 16 KB piece and a CTA's 12 k-blocks of a unit are 192 KB of sequential HBM.  The TMA
+// tensor map sees a [rows_padded * dim / 64][64] matrix.  Rows of the last tile beyond `first + n` are zero-filled.
 __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb, __nv_bfloat16* hi, __nv_bfloat16* mid,
-                                                               int64_t first, int64_t n, int dim, float w_cos) {
+                                                               int64_t first, int64_t n, int64_t n_fill, int dim, float w_cos) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = gw; i < n; i += W) {
+    const int kblocks = dim / BK;
+    for (int64_t i = gw; i < n_fill; i += W) {
         const int64_t row = first + i;
+        const bool real = i < n;                                            // else: padding row of the last tile
         const float4* x4 = reinterpret_cast<const float4*>(emb + row * dim);
         float ss = 0.f;
-        for (int c = lane; c < dim / 4; c += 32) {
-            const float4 v = x4[c];
-            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-        }
+        if (real)
+            for (int c = lane; c < dim / 4; c += 32) {
+                const float4 v = x4[c];
+                ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+            }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float scale = (ss > 0.f && ss < 3e38f) ? w_cos * rsqrtf(ss) : 0.f;
-        __nv_bfloat162* h2 = hi ? reinterpret_cast<__nv_bfloat162*>(hi + row * dim) : nullptr;     // either plane may be skipped
-        __nv_bfloat162* m2 = mid ? reinterpret_cast<__nv_bfloat162*>(mid + row * dim) : nullptr;
+        const float scale = (real && ss > 0.f && ss < 3e38f) ? w_cos * rsqrtf(ss) : 0.f;
+        const int64_t tile_base = (row / BM) * (int64_t)kblocks * BM * BK + (row % BM) * BK;
         for (int c = lane; c < dim / 4; c += 32) {                          // second read of the row hits L1/L2
-            const float4 v = x4[c];
+            const float4 v = scale != 0.f ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float e[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
             __nv_bfloat16 h[4], m[4];
 #pragma unroll
@@ -622,13 +634,20 @@ __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb,
                 h[k] = __float2bfloat16_rn(ek);
                 m[k] = __float2bfloat16_rn(ek - __bfloat162float(h[k]));
             }
-            if (h2) { h2[2 * c] = __halves2bfloat162(h[0], h[1]); h2[2 * c + 1] = __halves2bfloat162(h[2], h[3]); }
-            if (m2) { m2[2 * c] = __halves2bfloat162(m[0], m[1]); m2[2 * c + 1] = __halves2bfloat162(m[2], m[3]); }
+            const int col = 4 * c;
+            const int64_t at = tile_base + (int64_t)(col / BK) * BM * BK + (col % BK);
+            if (hi) {
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(hi + at);
+                h2[0] = __halves2bfloat162(h[0], h[1]); h2[1] = __halves2bfloat162(h[2], h[3]);
+            }
+            if (mid) {
+                __nv_bfloat162* m2 = reinterpret_cast<__nv_bfloat162*>(mid + at);
+                m2[0] = __halves2bfloat162(m[0], m[1]); m2[1] = __halves2bfloat162(m[2], m[3]);
+            }
         }
     }
 }
 
-// queries: planes (zero-padded to a multiple of 128 queries) and inv|q|
 // qbad[b] = 1: the query's squared norm is not representable in fp32 (under/overflow, NaN) although the query is not
 // all-zero — the screen cannot rank it (the reference accumulates the norm in fp64, RecallSearchService.cs:77-82); the
 // finalize kernel flags such queries and they re-run singly (-> exact path).
@@ -680,6 +699,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// row plane in k-block-major tiles (see orr_build_planes_kernel): a [ceil(rows/128) * dim/64 * 128][64] matrix of bf16
+int make_row_plane_map(CUtensorMap* map, const void* base, int64_t rows, int dim);
+
 int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -700,16 +722,26 @@ int make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int dim, in
     return ORR_OK;
 }
 
+int make_row_plane_map(CUtensorMap* map, const void* base, int64_t rows, int dim) {
+    const int64_t tiles = (rows + BM - 1) / BM;
+    return make_plane_map(map, base, tiles * (dim / BK) * BM, BK, BM);
+}
+
 }  // namespace
 
 // ---- host-side launchers ---------------------------------------------------------------------------
+int64_t orr_batch_plane_elems(int64_t capacity_rows, int dim) {              // capacity rounded up to whole 128-row tiles
+    return (capacity_rows + BM - 1) / BM * BM * (int64_t)dim;
+}
+
 int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first, int64_t n, int dim, float w_cos,
                            cudaStream_t st) {
     if (n <= 0) return ORR_OK;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    orr_build_planes_kernel<<<sms * 8, 256, 0, st>>>(emb, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid, first, n, dim, w_cos);
+    const int64_t n_fill = (first + n + BM - 1) / BM * BM - first;          // up to the end of the last tile (zero rows)
+    orr_build_planes_kernel<<<sms * 8, 256, 0, st>>>(emb, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid, first, n, n_fill, dim, w_cos);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
@@ -812,9 +844,9 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     int rc;
     if ((rc = make_plane_map(&mqh, g.qhi, g.batch_padded, g.dim, q_box)) != ORR_OK) return rc;
     if ((rc = make_plane_map(&mqm, g.qmid, g.batch_padded, g.dim, q_box)) != ORR_OK) return rc;
-    if ((rc = make_plane_map(&meh, g.ehi, g.rows, g.dim, BM)) != ORR_OK) return rc;
+    if ((rc = make_row_plane_map(&meh, g.ehi, g.rows, g.dim)) != ORR_OK) return rc;
     // the bf16 screen (passes == 1) never touches the mid planes: their maps alias the hi planes
-    if ((rc = make_plane_map(&mem, g.passes == 1 ? g.ehi : g.emid, g.rows, g.dim, BM)) != ORR_OK) return rc;
+    if ((rc = make_row_plane_map(&mem, g.passes == 1 ? g.ehi : g.emid, g.rows, g.dim)) != ORR_OK) return rc;
     BatchArgs a{};
     const int64_t all_tiles = (g.rows + UN - 1) / UN;
     a.row_tile_stride = g.tile_stride < 1 ? 1 : g.tile_stride;

@@ -205,6 +205,7 @@ struct OrrBatchGemm {
     int64_t rows; int32_t dim; int32_t batch_padded; int32_t tile_stride; int32_t sms;
     int32_t passes;                          // 3 = split precision (default), 1 = bf16 screen
 };
+int64_t orr_batch_plane_elems(int64_t capacity_rows, int dim);               // bf16 elements of one row plane (tile-padded)
 int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first, int64_t n, int dim, float w_cos,
                            cudaStream_t st);
 int orr_batch_prep_queries(const float* q_dev, void* qhi, void* qmid, float* qscale, int32_t* qbad, int batch, int batch_padded,
