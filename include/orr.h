@@ -131,6 +131,17 @@ int  orr_store_upsert_document_texts(orr_store* s, uint64_t doc_key, int32_t n,
         const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
         const char* contents_utf8, const uint64_t* content_offsets, uint64_t* out_rows);
 
+/* Bulk form of the same (warm load / hydration: the Cosmos store only ever pages `SELECT TOP 300`,
+ * CosmosIngestionStore.cs:178-197, a scan-everything store has to be filled from the full container): n_docs documents in
+ * one call, document d owning chunks [doc_chunk_offsets[d], doc_chunk_offsets[d+1]) of the chunk arrays (each in
+ * ChunkIndex order, keys distinct within a call).  Tokenising runs on all host cores, the rows are copied through pinned
+ * staging buffers while searches keep running (they cannot see rows that are not published yet), and one short exclusive
+ * section publishes them and tombstones the replaced documents' old rows.  Semantics per document as
+ * orr_store_upsert_document_texts. */
+int  orr_store_upsert_documents_texts(orr_store* s, int32_t n_docs, const uint64_t* doc_keys, const uint32_t* doc_chunk_offsets,
+        const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
+        const char* contents_utf8, const uint64_t* content_offsets, uint64_t* out_rows);
+
 /* Distinct tokens held by at least one live chunk (text-level ingest only). */
 int64_t orr_store_vocab_size(const orr_store* s);
 

@@ -65,6 +65,8 @@ _SIGNATURES = {
                                                         C.c_void_p]),
     "orr_store_upsert_document_texts": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_char_p, C.c_void_p, C.c_void_p]),
+    "orr_store_upsert_documents_texts": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_char_p, C.c_void_p, C.c_void_p]),
     "orr_store_vocab_size": (C.c_int64, [C.c_void_p]),
     "orr_search_query": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),

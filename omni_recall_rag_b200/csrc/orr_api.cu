@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "orr_internal.h"
 
@@ -118,6 +119,8 @@ struct orr_store {
     std::unordered_map<uint64_t, std::vector<std::pair<int64_t, int64_t>>> docs;   // doc -> [first,count) runs
     std::vector<int64_t> h_ticks;                                                   // host mirror (lazy)
     std::shared_mutex mu;                                                           // searches shared, mutators exclusive
+    std::mutex mutator_mu;                                                          // one mutator at a time (taken BEFORE mu); the bulk loader
+                                                                                    // copies under it alone and takes mu only to publish
     std::mutex pool_mu;
     std::vector<std::unique_ptr<SearchCtx>> pool;
     // orr_search_device: one scratch context per IN-FLIGHT call (several host threads may enqueue on different streams);
@@ -487,6 +490,7 @@ static int upsert_impl(orr_store* s, uint64_t doc_key, int32_t n, const float* e
             }
         }
     }
+    std::lock_guard<std::mutex> mutator(s->mutator_mu);
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     if (s->rows_used + n > s->cfg.capacity_rows) {
@@ -592,6 +596,7 @@ static void release_doc_words(orr_store* s, uint64_t doc_key) {
 
 int orr_store_delete_document(orr_store* s, uint64_t doc_key) {
     if (!s) { orr_set_error("delete: NULL store"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> mutator(s->mutator_mu);
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     int rc = tombstone_locked(s, doc_key);
@@ -652,6 +657,263 @@ int orr_store_upsert_document_texts(orr_store* s, uint64_t doc_key, int32_t n, c
     return ORR_OK;
 }
 
+// ---- bulk ingest (warm load / hydration of a scan-everything store) ---------------------------
+// Many documents per call.  What the per-document entry point does under the exclusive lock — five synchronous copies per
+// document — is split here:
+//   1. tokenising / lower-casing / hashing of every chunk on all host cores (no lock);
+//   2. the new rows are written BEHIND rows_used through two pinned staging buffers on the mutator stream, under the
+//      mutator mutex only: searches keep running, they cannot see rows beyond rows_used;
+//   3. one short exclusive section publishes: replaced documents' old rows are tombstoned by ONE kernel over their run
+//      list, rows_used / live_rows / version move, the document table and the vocabulary are updated.
+}  // extern "C"
+
+namespace {
+__global__ void orr_tombstone_runs_kernel(int64_t* ticks, const int64_t* runs /* [n][2] first,count */, int n_runs) {
+    for (int r = blockIdx.x; r < n_runs; r += gridDim.x) {
+        const int64_t first = runs[2 * r], count = runs[2 * r + 1];
+        for (int64_t i = threadIdx.x; i < count; i += blockDim.x) ticks[first + i] = ORR_DEAD_TICKS;
+    }
+}
+
+struct Staging {                      // two pinned buffers used alternately: fill one while the other's copy is in flight
+    static constexpr size_t BYTES = (size_t)32 << 20;
+    uint8_t* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int turn = 0;
+    cudaStream_t st = nullptr;
+    int init(cudaStream_t stream) {
+        st = stream;
+        for (int i = 0; i < 2; ++i) {
+            ORR_CUDA_OK(cudaMallocHost(&buf[i], BYTES));
+            ORR_CUDA_OK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        return ORR_OK;
+    }
+    ~Staging() { for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); } }
+    // copies `bytes` produced by fill(dst_host, offset, n) slice by slice to `dev`
+    template <class Fill>
+    int send(void* dev, size_t bytes, size_t granule, Fill fill) {
+        const size_t slice = std::max(granule, BYTES / granule * granule);
+        for (size_t off = 0; off < bytes; off += slice) {
+            const size_t n = std::min(slice, bytes - off);
+            ORR_CUDA_OK(cudaEventSynchronize(ev[turn]));          // the buffer's previous copy has left it
+            fill(buf[turn], off, n);
+            ORR_CUDA_OK(cudaMemcpyAsync((uint8_t*)dev + off, buf[turn], n, cudaMemcpyHostToDevice, st));
+            ORR_CUDA_OK(cudaEventRecord(ev[turn], st));
+            turn ^= 1;
+        }
+        return ORR_OK;
+    }
+};
+
+template <class F>
+void parallel_chunks(int64_t n, F fn) {
+    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const int64_t T = std::max<int64_t>(1, std::min<int64_t>(hw, n / 64 + 1));
+    std::vector<std::thread> th;
+    for (int64_t t = 1; t < T; ++t) th.emplace_back([=] { fn(n * t / T, n * (t + 1) / T, (int)t); });
+    fn(0, n / T, 0);
+    for (auto& x : th) x.join();
+}
+}  // namespace
+
+extern "C" {
+
+int orr_store_upsert_documents_texts(orr_store* s, int32_t n_docs, const uint64_t* doc_keys, const uint32_t* doc_chunk_offsets,
+                                     const float* emb, const uint8_t* has_emb, const int64_t* created_ticks,
+                                     const char* contents_utf8, const uint64_t* content_offsets, uint64_t* out_rows) {
+    if (!s || n_docs < 0 || (n_docs > 0 && (!doc_keys || !doc_chunk_offsets || !created_ticks || !contents_utf8 || !content_offsets))) {
+        orr_set_error("upsert_documents: bad argument");
+        return ORR_E_INVALID;
+    }
+    if (n_docs == 0) return ORR_OK;
+    const int64_t total = doc_chunk_offsets[n_docs];
+    const int dim = s->cfg.dim, slots = s->cfg.term_slots;
+    {
+        std::unordered_map<uint64_t, int> seen;
+        for (int32_t d = 0; d < n_docs; ++d) {
+            if (doc_chunk_offsets[d + 1] < doc_chunk_offsets[d]) { orr_set_error("upsert_documents: chunk offsets must not decrease"); return ORR_E_INVALID; }
+            if (!seen.emplace(doc_keys[d], d).second) { orr_set_error("upsert_documents: document key %llu appears twice in one call", (unsigned long long)doc_keys[d]); return ORR_E_INVALID; }
+        }
+    }
+    for (int64_t i = 0; i < total; ++i) {
+        if (created_ticks[i] == ORR_DEAD_TICKS) { orr_set_error("upsert_documents: ticks value reserved"); return ORR_E_INVALID; }
+        if (content_offsets[i + 1] < content_offsets[i]) { orr_set_error("upsert_documents: bad content offsets at chunk %lld", (long long)i); return ORR_E_INVALID; }
+    }
+    if (total == 0) return ORR_OK;
+    // ---- 1. every chunk's distinct lower-cased tokens (and lower-cased text), on all host cores ----
+    std::vector<std::vector<std::string>> toks((size_t)total);
+    std::vector<std::string> lowered(s->keep_text ? (size_t)total : 0);
+    std::atomic<int64_t> too_long{-1};
+    try {
+        parallel_chunks(total, [&](int64_t lo, int64_t hi, int) {
+            for (int64_t i = lo; i < hi; ++i) {
+                const char* c = contents_utf8 + content_offsets[i];
+                const int64_t cl = (int64_t)(content_offsets[i + 1] - content_offsets[i]);
+                toks[(size_t)i] = orr_distinct_lower_tokens(c, cl);
+                if ((int64_t)toks[(size_t)i].size() > slots && !s->keep_text) too_long.store(i);
+                if (s->keep_text) lowered[(size_t)i] = orr_lower_invariant(c, cl);
+            }
+        });
+    } catch (const std::exception& e) { orr_set_error("upsert_documents: %s", e.what()); return ORR_E_OOM; }
+    if (too_long.load() >= 0) {
+        orr_set_error("upsert_documents: chunk %lld has more distinct tokens than the store's %d term slots (more slots, or option keep_text)",
+                      (long long)too_long.load(), slots);
+        return ORR_E_UNSUPPORTED;
+    }
+    std::vector<uint64_t> toff;
+    uint64_t text_total = 0;
+    if (s->keep_text) {
+        toff.resize((size_t)total + 1, 0ull);
+        for (int64_t i = 0; i < total; ++i) { text_total += lowered[(size_t)i].size(); toff[(size_t)i + 1] = text_total; }
+    }
+
+    // ---- 2. rows written behind rows_used; searches keep running ----
+    std::lock_guard<std::mutex> mutator(s->mutator_mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    const int64_t first = s->rows_used;                        // only mutators move it, and this thread is the mutator
+    if (first + total > s->cfg.capacity_rows) {
+        orr_set_error("upsert_documents: store full (%lld + %lld > %lld rows)", (long long)first, (long long)total, (long long)s->cfg.capacity_rows);
+        return ORR_E_OOM;
+    }
+    if (s->keep_text) {
+        if (s->text_rows != first) { orr_set_error("upsert_documents: chunk text must be given for every row of the store or for none"); return ORR_E_INVALID; }
+        int rc0 = ensure_text_arena(s);
+        if (rc0 != ORR_OK) return rc0;
+        if (s->text_used + text_total > s->text_cap) { orr_set_error("upsert_documents: text arena full (raise option text_bytes_per_row)"); return ORR_E_OOM; }
+    }
+    cudaStream_t st = s->mut_stream;
+    Staging stage;
+    int rc = stage.init(st);
+    if (rc != ORR_OK) return rc;
+    const size_t row_bytes = (size_t)dim * sizeof(float);
+    rc = stage.send(s->d_emb + first * (int64_t)dim, (size_t)total * row_bytes, row_bytes, [&](uint8_t* dst, size_t off, size_t n) {
+        const int64_t r0 = (int64_t)(off / row_bytes), nr = (int64_t)(n / row_bytes);
+        if (emb) memcpy(dst, (const uint8_t*)emb + off, n); else memset(dst, 0, n);
+        if (emb && has_emb)
+            for (int64_t r = 0; r < nr; ++r) if (!has_emb[r0 + r]) memset(dst + (size_t)r * row_bytes, 0, row_bytes);   // :71-72 -> cosine 0
+    });
+    if (rc != ORR_OK) return rc;
+    rc = stage.send(s->d_ticks + first, (size_t)total * 8, 8, [&](uint8_t* dst, size_t off, size_t n) { memcpy(dst, (const uint8_t*)created_ticks + off, n); });
+    if (rc != ORR_OK) return rc;
+    int64_t overflow_total = 0;
+    std::vector<int32_t> doc_over((size_t)n_docs, 0);
+    for (int32_t d = 0; d < n_docs; ++d)
+        for (uint32_t i = doc_chunk_offsets[d]; i < doc_chunk_offsets[d + 1]; ++i)
+            if ((int64_t)toks[i].size() > slots) { ++doc_over[(size_t)d]; ++overflow_total; }
+    auto fill_terms = [&](uint8_t* dst, size_t off, size_t n, bool wide) {
+        const size_t rb = (size_t)slots * (wide ? 8 : 4);
+        const int64_t r0 = (int64_t)(off / rb), nr = (int64_t)(n / rb);
+        memset(dst, 0, n);
+        parallel_chunks(nr, [&](int64_t lo, int64_t hi, int) {
+            for (int64_t r = lo; r < hi; ++r) {
+                const auto& tk = toks[(size_t)(r0 + r)];
+                const size_t keep = std::min(tk.size(), (size_t)slots);
+                for (size_t w = 0; w < keep; ++w) {
+                    const uint64_t h = orr_hash_bytes(tk[w].data(), (int64_t)tk[w].size());
+                    if (wide) ((uint64_t*)dst)[(size_t)r * slots + w] = h; else ((uint32_t*)dst)[(size_t)r * slots + w] = orr_hash_low(h);
+                }
+            }
+        });
+    };
+    rc = stage.send(s->d_terms32 + first * (int64_t)slots, (size_t)total * slots * 4, (size_t)slots * 4,
+                    [&](uint8_t* dst, size_t off, size_t n) { fill_terms(dst, off, n, false); });
+    if (rc != ORR_OK) return rc;
+    rc = stage.send(s->d_terms64 + first * (int64_t)slots, (size_t)total * slots * 8, (size_t)slots * 8,
+                    [&](uint8_t* dst, size_t off, size_t n) { fill_terms(dst, off, n, true); });
+    if (rc != ORR_OK) return rc;
+    if (s->keep_text) {
+        std::vector<uint64_t> off_abs((size_t)total);
+        std::vector<uint32_t> len((size_t)total);
+        for (int64_t i = 0; i < total; ++i) { off_abs[(size_t)i] = s->text_used + toff[(size_t)i]; len[(size_t)i] = (uint32_t)lowered[(size_t)i].size(); }
+        rc = stage.send(s->d_text_off + first, (size_t)total * 8, 8, [&](uint8_t* dst, size_t off, size_t n) { memcpy(dst, (const uint8_t*)off_abs.data() + off, n); });
+        if (rc != ORR_OK) return rc;
+        rc = stage.send(s->d_text_len + first, (size_t)total * 4, 4, [&](uint8_t* dst, size_t off, size_t n) { memcpy(dst, (const uint8_t*)len.data() + off, n); });
+        if (rc != ORR_OK) return rc;
+        int64_t cursor = 0;                                     // chunk whose text contains byte `off` (slices arrive in order)
+        rc = stage.send(s->d_text + s->text_used, (size_t)text_total, 1, [&](uint8_t* dst, size_t off, size_t n) {
+            size_t done = 0;
+            while (done < n) {
+                while (toff[(size_t)cursor + 1] <= off + done) ++cursor;
+                const size_t in = (size_t)(off + done - toff[(size_t)cursor]);
+                const size_t m = std::min(n - done, lowered[(size_t)cursor].size() - in);
+                memcpy(dst + done, lowered[(size_t)cursor].data() + in, m);
+                done += m;
+            }
+        });
+        if (rc != ORR_OK) return rc;
+    }
+    ORR_CUDA_OK(cudaStreamSynchronize(st));
+
+    // ---- 3. publish: one short exclusive section ----
+    std::vector<int64_t> runs;
+    int64_t* d_runs = nullptr;
+    {
+        std::unique_lock<std::shared_mutex> lock(s->mu);
+        int64_t dead_rows = 0;
+        for (int32_t d = 0; d < n_docs; ++d) {
+            auto it = s->docs.find(doc_keys[d]);
+            if (it == s->docs.end()) continue;
+            for (auto& run : it->second) {
+                runs.push_back(run.first); runs.push_back(run.second);
+                dead_rows += run.second;
+                for (int64_t r = run.first; r < run.first + run.second && r < (int64_t)s->h_ticks.size(); ++r) s->h_ticks[(size_t)r] = ORR_DEAD_TICKS;
+            }
+            s->docs.erase(it);
+        }
+        if (!runs.empty()) {
+            rc = [&]() -> int {
+                ORR_CUDA_OK(cudaMalloc(&d_runs, runs.size() * sizeof(int64_t)));
+                ORR_CUDA_OK(cudaMemcpyAsync(d_runs, runs.data(), runs.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+                const int nr = (int)(runs.size() / 2);
+                orr_tombstone_runs_kernel<<<std::min(nr, 1024), 128, 0, st>>>(s->d_ticks, d_runs, nr);
+                ORR_CUDA_OK(cudaGetLastError());
+                ORR_CUDA_OK(cudaStreamSynchronize(st));
+                return ORR_OK;
+            }();
+            cudaFree(d_runs);
+            if (rc != ORR_OK) return rc;
+        }
+        if ((int64_t)s->h_ticks.size() == first) s->h_ticks.insert(s->h_ticks.end(), created_ticks, created_ticks + total);
+        for (int32_t d = 0; d < n_docs; ++d) {
+            const int64_t n = (int64_t)doc_chunk_offsets[d + 1] - doc_chunk_offsets[d];
+            if (n > 0) s->docs[doc_keys[d]].push_back({first + doc_chunk_offsets[d], n});
+        }
+        if (s->keep_text) { s->text_used += text_total; s->text_rows += total; }
+        s->rows_used += total;
+        s->live_rows += total - dead_rows;
+        s->version++;
+    }
+    if (out_rows) for (int64_t i = 0; i < total; ++i) out_rows[i] = s->cfg.row_base + (uint64_t)(first + i);
+
+    // ---- vocabulary: the replaced documents' words leave, the new ones arrive (ids resolved on all cores) ----
+    for (int32_t d = 0; d < n_docs; ++d) release_doc_words(s, doc_keys[d]);
+    std::lock_guard<std::mutex> g(s->vocab_mu);
+    if (!s->vocab) s->vocab = orr_vocab_new(s->cfg.device);
+    std::vector<std::vector<uint32_t>> ids((size_t)total);
+    parallel_chunks(total, [&](int64_t lo, int64_t hi, int) {            // read-only lookups: nobody adds words meanwhile
+        for (int64_t i = lo; i < hi; ++i) {
+            auto& v = ids[(size_t)i];
+            v.resize(toks[(size_t)i].size());
+            for (size_t w = 0; w < v.size(); ++w) v[w] = orr_vocab_find(s->vocab, toks[(size_t)i][w].data(), toks[(size_t)i][w].size());
+        }
+    });
+    for (int32_t d = 0; d < n_docs; ++d) {
+        if (doc_chunk_offsets[d + 1] == doc_chunk_offsets[d]) continue;
+        std::vector<uint32_t>& mine = s->doc_words[doc_keys[d]];
+        for (uint32_t i = doc_chunk_offsets[d]; i < doc_chunk_offsets[d + 1]; ++i)
+            for (size_t w = 0; w < ids[i].size(); ++w) {
+                uint32_t id = ids[i][w];
+                if (id == 0xffffffffu) id = orr_vocab_add(s->vocab, toks[i][w].data(), toks[i][w].size(), 1u);   // a new word
+                else orr_vocab_addref(s->vocab, id, 1u);
+                mine.push_back(id);
+            }
+        if (doc_over[(size_t)d]) { s->doc_overflow[doc_keys[d]] += doc_over[(size_t)d]; }
+    }
+    s->overflow_rows += overflow_total;
+    return ORR_OK;
+}
+
 int orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t first_row, int64_t n) {
     if (!s || !spec || n < 0) { orr_set_error("fill_synthetic: bad argument"); return ORR_E_INVALID; }
     if (spec->dim != s->cfg.dim || spec->terms_per_chunk > s->cfg.term_slots || spec->gen_dim < spec->dim ||
@@ -659,6 +921,7 @@ int orr_store_fill_synthetic(orr_store* s, const orr_synth_spec* spec, uint64_t 
         orr_set_error("fill_synthetic: spec does not match the store");
         return ORR_E_INVALID;
     }
+    std::lock_guard<std::mutex> mutator(s->mutator_mu);
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     if (s->rows_used + n > s->cfg.capacity_rows) { orr_set_error("fill_synthetic: store full"); return ORR_E_OOM; }
@@ -1145,6 +1408,7 @@ int orr_store_save(orr_store* s, const char* path) {
 
 int orr_store_load(orr_store* s, const char* path) {
     if (!s || !path) { orr_set_error("orr_store_load: NULL argument"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> mutator(s->mutator_mu);
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     if (s->rows_used != 0) { orr_set_error("orr_store_load: the store is not empty"); return ORR_E_INVALID; }
@@ -1322,6 +1586,7 @@ int compact_array(void* base, size_t row_bytes, const uint32_t* d_idx, int64_t n
 
 int orr_store_compact(orr_store* s, uint64_t* old_rows_out, int64_t out_cap, int64_t* n_live_out) {
     if (!s || !n_live_out) { orr_set_error("orr_store_compact: NULL argument"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> mutator(s->mutator_mu);
     std::unique_lock<std::shared_mutex> lock(s->mu);
     ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
     { const int wrc = wait_device_searches(s); if (wrc != ORR_OK) return wrc; }   // rows are about to move under any in-flight scan

@@ -101,6 +101,7 @@ struct BatchArgs {
     int64_t   slot_cap;          // term slots per row tile (the pool's capacity)
     const int32_t* q_term_ids;   // [B padded][ORR_BATCH_MAX_TERMS] term slot or -1, packed front to back
     const float*   q_kw_w;       // [B padded] w_kw / |terms_b| (0 if none)
+    int32_t   planes_tiled;      // row planes in k-block-major tiles (else row-major)
 };
 
 // ---- cluster / cta_group::2 helpers ---------------------------------------------------------------
@@ -231,6 +232,14 @@ __device__ __forceinline__ void kw_tree(KwPlanes& kp, const uint4 (&w0)[4], cons
     }
 }
 // `tile_half` = 2 * row tile + (0 | 1): the thread's 128-row half of the tile = 4 of the slot's 8 words
+// brings the 16 bytes kw_load(id, tile_half) will read into L2 (no register, no stall): issued one unit ahead for the 12
+// term words that are not register-prefetched, so the real load pays L2 latency instead of an HBM round trip
+__device__ __forceinline__ void kw_prefetch_l2(const BatchArgs& a, uint32_t id, int64_t tile_half) {
+    if (id != NO_TERM) {
+        const uint4* p = reinterpret_cast<const uint4*>(a.term_bits) + ((tile_half >> 1) * a.slot_cap + id) * 2 + (tile_half & 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+}
 __device__ __forceinline__ uint4 kw_load(const BatchArgs& a, uint32_t id, int64_t tile_half) {
     return id != NO_TERM ? __ldg(reinterpret_cast<const uint4*>(a.term_bits) + ((tile_half >> 1) * a.slot_cap + id) * 2 + (tile_half & 1))
                          : make_uint4(0u, 0u, 0u, 0u);
@@ -467,9 +476,11 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                         if (PASSES == 3)
                             tma_load_2d_pair_mc(base + 1 * PLANE_BYTES + qoff, &map_qmid, kb * BK, qrow + (int)pair * (BM / 2), fb_local, qmask);
                     }
-                    const int ecoord = (int)((etile + kb) * BM);            // row of the [tiles * kblocks * 128][64] view
-                    tma_load_2d_pair(base + E0 * PLANE_BYTES, &map_ehi, 0, ecoord, fb);
-                    if (PASSES == 3) tma_load_2d_pair(base + 3 * PLANE_BYTES, &map_emid, 0, ecoord, fb);
+                    // tiled planes: row (etile + kb) * 128 of the [tiles * kblocks * 128][64] view; row-major: (column, row)
+                    const int ec0 = a.planes_tiled ? 0 : kb * BK;
+                    const int ec1 = a.planes_tiled ? (int)((etile + kb) * BM) : row_tile * UN + (int)half * BM;
+                    tma_load_2d_pair(base + E0 * PLANE_BYTES, &map_ehi, ec0, ec1, fb);
+                    if (PASSES == 3) tma_load_2d_pair(base + 3 * PLANE_BYTES, &map_emid, ec0, ec1, fb);
                     if (++stage == C::NSTAGE) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -566,6 +577,17 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
                     w[8] = kw_load(a, id3.x & 0xFFFFu, word0); w[9] = kw_load(a, id3.x >> 16, word0);
                     w[10] = kw_load(a, id3.y & 0xFFFFu, word0); w[11] = kw_load(a, id3.y >> 16, word0);
                     kw_tree(kp, wn, w);
+                    if (u + 1 < my_units) {                                 // the next unit's 12 further words -> L2, now
+                        bool v2;
+                        const int64_t nword0 = (int64_t)(tile_of(u + 1, &v2) * a.row_tile_stride) * 2 + (c_begin / HC);
+                        const uint2* nidp = reinterpret_cast<const uint2*>(q_ids + (((u + 1) % units_per_tile) * BM + qloc) * ORR_BATCH_MAX_TERMS);
+#pragma unroll
+                        for (int t = 1; t < 4; ++t) {
+                            const uint2 idn = nidp[t];
+                            kw_prefetch_l2(a, idn.x & 0xFFFFu, nword0); kw_prefetch_l2(a, idn.x >> 16, nword0);
+                            kw_prefetch_l2(a, idn.y & 0xFFFFu, nword0); kw_prefetch_l2(a, idn.y >> 16, nword0);
+                        }
+                    }
                 }
                 if (u + 1 < my_units) prefetch_words(u + 1);
             }
@@ -605,7 +627,7 @@ orr_batch_gemm_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_
 // so every box is ONE contiguous 16 KB piece and a CTA's 12 k-blocks of a unit are 192 KB of sequential HBM.  The TMA
 // tensor map sees a [rows_padded * dim / 64][64] matrix.  Rows of the last tile beyond `first + n` are zero-filled.
 __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb, __nv_bfloat16* hi, __nv_bfloat16* mid,
-                                                               int64_t first, int64_t n, int64_t n_fill, int dim, float w_cos) {
+                                                               int64_t first, int64_t n, int64_t n_fill, int dim, float w_cos, int tiled) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -623,7 +645,7 @@ __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         const float scale = (real && ss > 0.f && ss < 3e38f) ? w_cos * rsqrtf(ss) : 0.f;
-        const int64_t tile_base = (row / BM) * (int64_t)kblocks * BM * BK + (row % BM) * BK;
+        const int64_t tile_base = tiled ? (row / BM) * (int64_t)kblocks * BM * BK + (row % BM) * BK : row * (int64_t)dim;
         for (int c = lane; c < dim / 4; c += 32) {                          // second read of the row hits L1/L2
             const float4 v = scale != 0.f ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float e[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
@@ -635,7 +657,7 @@ __global__ void __launch_bounds__(256) orr_build_planes_kernel(const float* emb,
                 m[k] = __float2bfloat16_rn(ek - __bfloat162float(h[k]));
             }
             const int col = 4 * c;
-            const int64_t at = tile_base + (int64_t)(col / BK) * BM * BK + (col % BK);
+            const int64_t at = tiled ? tile_base + (int64_t)(col / BK) * BM * BK + (col % BK) : tile_base + col;
             if (hi) {
                 __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(hi + at);
                 h2[0] = __halves2bfloat162(h[0], h[1]); h2[1] = __halves2bfloat162(h[2], h[3]);
@@ -730,6 +752,12 @@ int make_row_plane_map(CUtensorMap* map, const void* base, int64_t rows, int dim
 }  // namespace
 
 // ---- host-side launchers ---------------------------------------------------------------------------
+// k-block-major tiles (default) or plain row-major planes (ORR_PLANES_TILED=0: the round-1 layout, kept for A/B runs)
+bool orr_batch_planes_tiled() {
+    static const int tiled = [] { const char* e = getenv("ORR_PLANES_TILED"); return (e && *e == '0') ? 0 : 1; }();
+    return tiled != 0;
+}
+
 int64_t orr_batch_plane_elems(int64_t capacity_rows, int dim) {              // capacity rounded up to whole 128-row tiles
     return (capacity_rows + BM - 1) / BM * BM * (int64_t)dim;
 }
@@ -741,7 +769,8 @@ int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_fill = (first + n + BM - 1) / BM * BM - first;          // up to the end of the last tile (zero rows)
-    orr_build_planes_kernel<<<sms * 8, 256, 0, st>>>(emb, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid, first, n, n_fill, dim, w_cos);
+    orr_build_planes_kernel<<<sms * 8, 256, 0, st>>>(emb, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid, first, n, n_fill, dim, w_cos,
+                                                     orr_batch_planes_tiled() ? 1 : 0);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
@@ -844,9 +873,10 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     int rc;
     if ((rc = make_plane_map(&mqh, g.qhi, g.batch_padded, g.dim, q_box)) != ORR_OK) return rc;
     if ((rc = make_plane_map(&mqm, g.qmid, g.batch_padded, g.dim, q_box)) != ORR_OK) return rc;
-    if ((rc = make_row_plane_map(&meh, g.ehi, g.rows, g.dim)) != ORR_OK) return rc;
-    // the bf16 screen (passes == 1) never touches the mid planes: their maps alias the hi planes
-    if ((rc = make_row_plane_map(&mem, g.passes == 1 ? g.ehi : g.emid, g.rows, g.dim)) != ORR_OK) return rc;
+    const bool tiled = orr_batch_planes_tiled();
+    const void* mid_plane = g.passes == 1 ? g.ehi : g.emid;  // the bf16 screen never touches the mid planes: their maps alias the hi planes
+    if ((rc = tiled ? make_row_plane_map(&meh, g.ehi, g.rows, g.dim) : make_plane_map(&meh, g.ehi, g.rows, g.dim, BM)) != ORR_OK) return rc;
+    if ((rc = tiled ? make_row_plane_map(&mem, mid_plane, g.rows, g.dim) : make_plane_map(&mem, mid_plane, g.rows, g.dim, BM)) != ORR_OK) return rc;
     BatchArgs a{};
     const int64_t all_tiles = (g.rows + UN - 1) / UN;
     a.row_tile_stride = g.tile_stride < 1 ? 1 : g.tile_stride;
@@ -867,6 +897,7 @@ int orr_batch_launch_gemm(const OrrBatchGemm& g, cudaStream_t st) {
     a.slot_cap = g.slot_cap;
     a.q_term_ids = g.q_term_ids;
     a.q_kw_w = g.q_kw_w;
+    a.planes_tiled = tiled ? 1 : 0;
     if (a.n_row_tiles < 1) return ORR_OK;
     if (dense)
         return g.passes == 1 ? launch_gemm_t<1, 1>(mqh, mqm, meh, mem, a, plan, st)

@@ -152,8 +152,6 @@ __global__ void __launch_bounds__(512, 2) orr_noemb_scores_kernel(const NoembArg
     constexpr int RPL = 32 / VR;                       // rows one warp-wide load spans (4, 2, 1)
     constexpr int STEPS = (32 * VR) / 256;             // 8-load steps per 32-row block (1, 2, 4)
     const int n_probes = a.pr.n_probes;
-    // REDUX member mask: the lanes that hold the same row as this one within a load
-    const uint32_t seg_mask = RPL == 1 ? FULL : (RPL == 2 ? (lane < 16 ? 0x0000ffffu : 0xffff0000u) : (0xffu << (lane & 24)));
     ExactLite ex;
     ex.sh = a.sh; ex.q_dim = 0; ex.w = a.w; ex.now_ticks = a.now_ticks;
     for (int64_t blk = gw; blk < n_blocks; blk += W) {
@@ -177,30 +175,35 @@ __global__ void __launch_bounds__(512, 2) orr_noemb_scores_kernel(const NoembArg
                 uint32_t m0[8], m1[WIDE ? 8 : 1];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { m0[i] = 0u; if (WIDE) m1[i] = 0u; }
+                // probe-major: one OR-chain of compares per probe over the lane's 32 words, and the per-load bookkeeping
+                // only if SOME lane of the warp saw the probe in this step (a Zipf-tail term: almost never)
                 for (int p = 0; p < n_probes; ++p) {
                     const uint32_t hl = a.pr.h32[p];
-                    const uint32_t t = a.pr.term[p];
-                    const uint32_t b0 = t < 32 ? (1u << t) : 0u, b1 = t < 32 ? 0u : (1u << (t - 32));
+                    bool any = false;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool hit = (x[i].x == hl) | (x[i].y == hl) | (x[i].z == hl) | (x[i].w == hl);
-                        m0[i] |= hit ? b0 : 0u;
-                        if (WIDE) m1[i] |= hit ? b1 : 0u;
+                    for (int i = 0; i < 8; ++i) any |= (x[i].x == hl) | (x[i].y == hl) | (x[i].z == hl) | (x[i].w == hl);
+                    if (__any_sync(FULL, any)) {                             // warp-uniform
+                        const uint32_t t = a.pr.term[p];
+                        const uint32_t b0 = t < 32 ? (1u << t) : 0u, b1 = t < 32 ? 0u : (1u << (t - 32));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const bool hit = (x[i].x == hl) | (x[i].y == hl) | (x[i].z == hl) | (x[i].w == hl);
+                            m0[i] |= hit ? b0 : 0u;
+                            if (WIDE) m1[i] |= hit ? b1 : 0u;
+                        }
                     }
                 }
-                // reduce across the lanes that hold one row, hand the count to the row's lane
+                // OR across the lanes that hold one row (full-warp REDUX per segment: a partial member mask compiles to a
+                // slow collective protocol), then the row's lane keeps the count
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    int c = __popc(__reduce_or_sync(seg_mask, m0[i]));
-                    if (WIDE) c += __popc(__reduce_or_sync(seg_mask, m1[i]));
-                    // load i of step st holds rows (st * 8 + i) * RPL + segment; the segment's count is in all its lanes
                     const int first_row = (st * 8 + i) * RPL;
-                    if (RPL == 1) { if (lane == first_row) my_matches = c; }
-                    else {
-                        // every lane of segment g has row first_row + g's count: hand it to lane (first_row + g)
-                        const int want = lane - first_row;                   // which segment this lane's row is, if in range
-                        const int got = __shfl_sync(FULL, c, (want >= 0 && want < RPL) ? want * VR : 0);
-                        if (want >= 0 && want < RPL) my_matches = got;
+#pragma unroll
+                    for (int g = 0; g < RPL; ++g) {
+                        const bool mine_seg = RPL == 1 || (lane / VR) == g;
+                        int c = __popc(__reduce_or_sync(FULL, mine_seg ? m0[i] : 0u));
+                        if (WIDE) c += __popc(__reduce_or_sync(FULL, mine_seg ? m1[i] : 0u));
+                        if (lane == first_row + g) my_matches = c;
                     }
                 }
             }

@@ -205,6 +205,7 @@ struct OrrBatchGemm {
     int64_t rows; int32_t dim; int32_t batch_padded; int32_t tile_stride; int32_t sms;
     int32_t passes;                          // 3 = split precision (default), 1 = bf16 screen
 };
+bool orr_batch_planes_tiled();
 int64_t orr_batch_plane_elems(int64_t capacity_rows, int dim);               // bf16 elements of one row plane (tile-padded)
 int orr_batch_build_planes(const float* emb, void* hi, void* mid, int64_t first, int64_t n, int dim, float w_cos,
                            cudaStream_t st);
@@ -237,6 +238,8 @@ struct OrrVocab;
 OrrVocab* orr_vocab_new(int device);
 void orr_vocab_free(OrrVocab* v);
 uint32_t orr_vocab_add(OrrVocab* v, const char* word, size_t len, uint32_t count);   // returns the word's id; count = chunks holding it
+uint32_t orr_vocab_find(const OrrVocab* v, const char* word, size_t len);             // 0xffffffff if absent; read-only
+void orr_vocab_addref(OrrVocab* v, uint32_t id, uint32_t count);
 void orr_vocab_release(OrrVocab* v, uint32_t id);
 void orr_vocab_clear(OrrVocab* v);
 uint64_t orr_vocab_live_words(const OrrVocab* v);

@@ -13,9 +13,9 @@
 // CUDA libm exp (<= 1 ulp) instead of the host's: scores agree with the CPU oracle to ~1e-15
 // relative, five orders of magnitude inside the 1e-5 contract.
 //
-// K3 (orr_rescore_kernel): warp per listed row; the last CTA to finish orders the records by
-// the reference tie chain (score desc with NaN last, CreatedAtUtc desc, row asc — :34-35 plus
-// the stable-sort fallback), runs the selection bound check and emits hits.
+// K3 = orr_rescore_kernel (warp per listed row: the exact score) + orr_order_kernel (warp per record: its position
+// under the reference tie chain — score desc with NaN last, CreatedAtUtc desc, row asc, :34-35 plus the stable-sort
+// fallback, SURVEY.md A-6 —, the hits and the selection bound check).
 #include <cfloat>
 #include <cuda_fp16.h>
 
@@ -42,7 +42,6 @@ struct RescoreArgs {
 };
 
 __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = min(a.n_listed ? *a.n_listed : a.n_listed_value, a.n_listed_max);
     const int idx = blockIdx.x * 4 + warp;
@@ -53,74 +52,43 @@ __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
         const double s = exact_row(a.ex, row, lane, nA, &ticks);
         if (lane == 0) { a.exact[idx].score = s; a.exact[idx].ticks = ticks; a.exact[idx].row = (uint64_t)row; }
     }
-    // ---- the last CTA orders the records and emits the hits ----
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(a.ticket, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+}
 
-    OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
+// K3's second half: the records' reference order, the hits and the selection bound check.  One WARP per record, on as
+// many SMs as there are records: the record's position is the number of records that rank before it (keys are unique: the
+// row breaks every tie), the lanes split that count.  Ordering used to be the tail of orr_rescore_kernel, run by the last
+// CTA to finish: 4 warps on one SM working through a latency chain (49 us for the reference's 300 candidates, 3x the
+// scoring itself, ncu profiles/r02_kernels.md); as its own launch it costs ~3 us.
+__global__ void __launch_bounds__(256) orr_order_kernel(const RescoreArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int n = min(a.n_listed ? *a.n_listed : a.n_listed_value, a.n_listed_max);
     const int k = max(1, a.top_k);                                    // Math.Max(1, topK) :36
     const int n_out = min(k, n);
-    const volatile OrrExact* src = a.exact;
-    __shared__ double s_kth;
-    if (tid == 0) s_kth = __longlong_as_double(0x7ff8000000000000LL);
-    if (n <= ORR_RANK_MAX) {
-        for (int i = tid; i < n; i += blockDim.x) { OrrExact v; v.score = src[i].score; v.ticks = src[i].ticks; v.row = src[i].row; e[i] = v; }
-        __syncthreads();
-        rank_emit(e, n, n_out, k, a.ex.sh.row_base, a.hits, &s_kth);
-        __syncthreads();
-    } else {
-        int np2 = 1;
-        while (np2 < n) np2 <<= 1;
-        for (int i = tid; i < np2; i += blockDim.x) {
-            OrrExact v;
-            if (i < n) { v.score = src[i].score; v.ticks = src[i].ticks; v.row = src[i].row; }
-            else { v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull; }  // pads rank last
-            e[i] = v;
-        }
-        __syncthreads();
-        for (int k2 = 2; k2 <= np2; k2 <<= 1) {
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < np2; i += blockDim.x) {
-                    const int p = i ^ j;
-                    if (p > i) {
-                        const OrrExact x = e[i], y = e[p];
-                        const bool up = ((i & k2) == 0);                  // ascending rank in this run
-                        if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        for (int i = tid; i < n_out; i += blockDim.x) {
-            orr_hit h;
-            h.row = a.ex.sh.row_base + e[i].row;
-            h.score = e[i].score;
-            h.created_ticks = e[i].ticks;
-            a.hits[i] = h;
-        }
-        if (tid == 0 && n >= k) s_kth = e[k - 1].score;
-        __syncthreads();
-    }
-    if (tid == 0) {
-        int flags = 0;
-        if (a.check_bound) {
-            // every row outside the list has fp32 score <= tau and |fp32 - exact| <= eps:
-            // safe iff the k-th exact score clears tau by more than eps.
-            const float tau = __int_as_float(*a.tau_bits);
-            if (tau != -INFINITY) {
-                const double sk = s_kth;                                  // NaN when fewer than k rows were listed
-                if (!(sk - a.eps > (double)tau)) flags |= 1;
-            }
-        }
+    const float tau = a.check_bound ? __int_as_float(*a.tau_bits) : -INFINITY;
+    if (i == 0 && lane == 0) {
         a.status[0] = n_out;
+        // fewer rows listed than k: no k-th score exists, the bound cannot be proven (unless nothing was discarded)
+        if (n < k) a.status[1] = (a.check_bound && tau != -INFINITY) ? 1 : 0;
+    }
+    if (i >= n) return;
+    OrrExact x;
+    x.score = a.exact[i].score; x.ticks = a.exact[i].ticks; x.row = a.exact[i].row;
+    int cnt = 0;
+    for (int j = lane; j < n; j += 32) {
+        OrrExact y;
+        y.score = a.exact[j].score; y.ticks = a.exact[j].ticks; y.row = a.exact[j].row;
+        cnt += ranks_before(y, x) ? 1 : 0;
+    }
+    const int pos = __reduce_add_sync(FULL, cnt);
+    if (lane != 0) return;
+    if (pos < n_out) { orr_hit h; h.row = a.ex.sh.row_base + x.row; h.score = x.score; h.created_ticks = x.ticks; a.hits[pos] = h; }
+    if (pos == k - 1) {
+        // every row outside the list has fp32 score <= tau and |fp32 - exact| <= eps: safe iff the k-th exact score clears
+        // tau by more than eps
+        int flags = 0;
+        if (a.check_bound && tau != -INFINITY && !(x.score - a.eps > (double)tau)) flags |= 1;
         a.status[1] = flags;
-        *a.ticket = 0;                                                // re-arm
-        __threadfence();
     }
 }
 
@@ -301,7 +269,6 @@ __global__ void __launch_bounds__(256) orr_xchg_merge_kernel(const OrrXchgArgs a
 int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes& pr,
                        const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
                        int n_listed_max, bool check_bound, cudaStream_t st, int n_listed_host) {
-    ORR_SMEM_OPT_IN((orr_rescore_kernel), ORR_SORT_MAX * (int)sizeof(OrrExact));
     if (n_listed_max < 1) n_listed_max = 1;
     if (n_listed_max > ORR_SORT_MAX) { orr_set_error("rescore: %d rows exceed the sorter", n_listed_max); return ORR_E_INTERNAL; }
     RescoreArgs a;
@@ -318,10 +285,10 @@ int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes
     a.ticket = sc.sel + 3;
     a.hits = sc.hits;
     a.status = sc.status;
-    int np2 = 1;
-    while (np2 < n_listed_max) np2 <<= 1;
     const int grid = (n_listed_max + 3) / 4;
-    orr_rescore_kernel<<<grid, 128, np2 * sizeof(OrrExact), st>>>(a);
+    orr_rescore_kernel<<<grid, 128, 0, st>>>(a);
+    ORR_CUDA_OK(cudaGetLastError());
+    orr_order_kernel<<<(n_listed_max + 7) / 8, 256, 0, st>>>(a);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
@@ -612,13 +579,42 @@ __global__ void __launch_bounds__(BATCH_FIN_THREADS, 3) orr_batch_finalize_kerne
         if (i < ns) { e[i].score = exact_row_finish(a.ex, nA, mine); e[i].ticks = mine.ticks; }
     }
     __syncthreads();
-    // order the survivors by counting, not sorting (ns <= ORR_BATCH_MAX_SURV <= ORR_RANK_MAX)
     __shared__ double s_kth;
     if (tid == 0) s_kth = __longlong_as_double(0x7ff8000000000000LL);
     __syncthreads();
     const int k = max(1, a.top_k);
     const int n_out = min(k, ns);
-    rank_emit(e, ns, n_out, k, a.ex.sh.row_base, a.hits + (int64_t)b * a.k_stride, &s_kth);
+    if (ns <= 128) {
+        // few survivors: positions by counting (no barrier stages)
+        rank_emit(e, ns, n_out, k, a.ex.sh.row_base, a.hits + (int64_t)b * a.k_stride, &s_kth);
+    } else {
+        // the bitonic network: n log^2 n / 4 compare-exchanges against the n^2 comparisons of counting (11.5k vs 262k at
+        // 512 survivors); with 3 CTAs per SM its barrier latency is hidden
+        int ep2 = 1;
+        while (ep2 < ns) ep2 <<= 1;
+        for (int i = ns + tid; i < ep2; i += BATCH_FIN_THREADS) {
+            e[i].score = __longlong_as_double(0x7ff8000000000000LL); e[i].ticks = INT64_MIN; e[i].row = ~0ull;
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= ep2; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < ep2; i += BATCH_FIN_THREADS) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const OrrExact x = e[i], y = e[p];
+                        const bool up = ((i & k2) == 0);
+                        if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < n_out; i += BATCH_FIN_THREADS) {
+            orr_hit h; h.row = a.ex.sh.row_base + e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
+            a.hits[(int64_t)b * a.k_stride + i] = h;
+        }
+        if (tid == 0 && ns >= k) s_kth = e[k - 1].score;
+    }
     __syncthreads();
     if (tid == 0) {
         if (tau != -INFINITY) {

@@ -128,6 +128,19 @@ uint32_t orr_vocab_add(OrrVocab* v, const char* word, size_t len, uint32_t count
     return id;
 }
 
+// read-only lookup (safe from several threads while nobody adds words): the word's id, or 0xffffffff
+uint32_t orr_vocab_find(const OrrVocab* v, const char* word, size_t len) {
+    auto it = v->index.find(std::string(word, len));
+    return it == v->index.end() ? 0xffffffffu : it->second;
+}
+
+// `count` more chunks hold word `id`
+void orr_vocab_addref(OrrVocab* v, uint32_t id, uint32_t count) {
+    if (id >= v->refs.size() || count == 0u) return;
+    if (v->refs[id] == 0u) { v->live_words++; v->version++; }
+    v->refs[id] += count;
+}
+
 void orr_vocab_release(OrrVocab* v, uint32_t id) {
     if (id >= v->refs.size() || v->refs[id] == 0u) return;
     if (--v->refs[id] == 0u) { v->live_words--; v->version++; }

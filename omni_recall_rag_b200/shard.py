@@ -225,6 +225,33 @@ class RecallShard:
         N.check(N.lib().orr_store_upsert_document_texts(self._h, doc_key, n, p(emb), p(has_emb), p(ticks), blob, p(coff), p(out_rows)))
         return out_rows[:n]
 
+    def upsert_documents_texts(self, doc_keys: Sequence[int], chunk_counts: Sequence[int], emb: Optional[np.ndarray],
+                               ticks: np.ndarray, contents: Sequence[str], has_emb: Optional[np.ndarray] = None) -> np.ndarray:
+        """orr_store_upsert_documents_texts: many documents in one call (bulk / warm load).  Document d owns the next
+        chunk_counts[d] entries of the chunk arrays.  Returns the global row ids of all chunks."""
+        ticks = np.ascontiguousarray(ticks, dtype=np.int64)
+        total = int(ticks.shape[0])
+        keys = np.ascontiguousarray(doc_keys, dtype=np.uint64)
+        doff = np.zeros(len(keys) + 1, dtype=np.uint32)
+        doff[1:] = np.cumsum(np.asarray(chunk_counts, dtype=np.int64))
+        if int(doff[-1]) != total or len(contents) != total:
+            raise ValueError(f"chunk_counts sum to {int(doff[-1])}, {total} ticks, {len(contents)} contents")
+        if emb is not None:
+            emb = np.ascontiguousarray(emb, dtype=np.float32)
+            if emb.shape != (total, self.dim):
+                raise ValueError(f"emb must be ({total}, {self.dim}), got {emb.shape}")
+        if has_emb is not None:
+            has_emb = np.ascontiguousarray(has_emb, dtype=np.uint8)
+        enc = [(c or "").encode("utf-8") for c in contents]
+        coff = np.zeros(total + 1, dtype=np.uint64)
+        coff[1:] = np.cumsum([len(b) for b in enc])
+        blob = b"".join(enc) or b"\0"
+        out_rows = np.zeros(max(total, 1), dtype=np.uint64)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        N.check(N.lib().orr_store_upsert_documents_texts(self._h, len(keys), p(keys), p(doff), p(emb), p(has_emb), p(ticks), blob,
+                                                         p(coff), p(out_rows)))
+        return out_rows[:total]
+
     @property
     def vocab_size(self) -> int:
         return int(N.lib().orr_store_vocab_size(self._h))

@@ -93,6 +93,40 @@ class GpuIngestionStore:
             for r, c in zip(rows, ordered):
                 self._chunk_by_row[int(r)] = c
 
+    def upsert_chunks_bulk(self, batches: Sequence[Sequence[CosmosChunkRecord]]) -> None:
+        """Many UpsertChunksAsync calls as ONE native call (orr_store_upsert_documents_texts): warm load / hydration of the
+        store from the full container.  Every batch keeps the single-call semantics (:17-25: filed under its first chunk's
+        DocumentId, ordered by ChunkIndex); a document may appear once per call."""
+        batches = [sorted(b, key=lambda c: c.chunk_index) for b in batches if len(b)]
+        if not batches:
+            return
+        doc_ids = [b[0].document_id for b in batches]
+        total = sum(len(b) for b in batches)
+        emb = np.zeros((total, self.dim), dtype=np.float32)
+        has = np.zeros(total, dtype=np.uint8)
+        ticks = np.zeros(total, dtype=np.int64)
+        contents = []
+        i = 0
+        for b in batches:
+            for c in b:
+                e = c.embedding
+                if e is not None and len(e) == self.dim:
+                    emb[i] = np.asarray(e, dtype=np.float32)
+                    has[i] = 1
+                ticks[i] = c.created_at_utc
+                contents.append(c.content or "")
+                i += 1
+        with self._lock:
+            rows = self.shard.upsert_documents_texts([_doc_key(d) for d in doc_ids], [len(b) for b in batches], emb, ticks, contents, has)
+            at = 0
+            for d, b in zip(doc_ids, batches):
+                self._forget_rows(d)
+                self._chunks_by_document[d] = list(b)
+                self._rows_by_document[d] = rows[at:at + len(b)].copy()
+                for r, c in zip(rows[at:at + len(b)], b):
+                    self._chunk_by_row[int(r)] = c
+                at += len(b)
+
     def get_document(self, document_id: str) -> Optional[CosmosDocumentRecord]:  # :27-31
         return self._documents.get(document_id)
 

@@ -207,3 +207,66 @@ def test_snapshot_carries_the_vocabulary_and_corrupt_snapshots_are_refused(tmp_p
     with orr.RecallShard(8, 128, term_slots=32, row_base=1 << 40) as sh:
         with pytest.raises(N.OrrError):
             sh.load(os.path.join(d, "shard.orrsnap"))
+
+
+def test_bulk_ingest_equals_document_by_document_ingest_and_searches_run_meanwhile():
+    """orr_store_upsert_documents_texts (warm load / hydration) against the per-document path: same rows,
+    same vocabulary, same search results — including replacement of documents that already exist — while another thread
+    keeps searching (it must only ever see published rows: a well-formed, ordered list every time)."""
+    import threading
+
+    rng = np.random.default_rng(77)
+    words = [f"w{i:04d}" for i in range(3000)]
+    dim, n_docs = 64, 400
+    docs = {}
+    for d in range(n_docs):
+        nch = int(rng.integers(1, 9))
+        t = NOW - int(rng.integers(0, 200)) * DAY
+        docs[f"doc{d}"] = [S.CosmosChunkRecord(id=f"doc{d}:{j:04d}", document_id=f"doc{d}", chunk_index=j,
+                                              content=" ".join(rng.choice(words, size=int(rng.integers(5, 40)))),
+                                              embedding=None if rng.random() < 0.1 else rng.standard_normal(dim).astype(np.float32).tolist(),
+                                              created_at_utc=t) for j in range(nch)]
+    second = {k: [S.CosmosChunkRecord(id=c.id, document_id=c.document_id, chunk_index=c.chunk_index, content=c.content + " fresh",
+                                      embedding=c.embedding, created_at_utc=c.created_at_utc + DAY) for c in v[: max(1, len(v) - 1)]]
+              for k, v in list(docs.items())[:150]}                          # 150 documents are replaced (with fewer chunks)
+    a = S.GpuIngestionStore(dim, 8192, term_slots=64)
+    b = S.GpuIngestionStore(dim, 8192, term_slots=64)
+    try:
+        for v in docs.values():
+            a.upsert_chunks(v)
+        for v in second.values():
+            a.upsert_chunks(v)
+        stop, errors = threading.Event(), []
+
+        def searcher():
+            qv = rng.standard_normal(dim).astype(np.float32)
+            try:
+                while not stop.is_set():
+                    h = b.shard.search(qv, orr.QueryTerms.none(), NOW, 10)
+                    assert np.all(np.diff(h.scores) <= 0) and len(set(h.rows.tolist())) == len(h)
+            except Exception as e:                                     # noqa: BLE001
+                errors.append(e)
+
+        b.upsert_chunks_bulk(list(docs.values())[:50])                     # something to search from the start
+        th = threading.Thread(target=searcher)
+        th.start()
+        try:
+            b.upsert_chunks_bulk(list(docs.values())[50:])
+            b.upsert_chunks_bulk(list(second.values()))
+        finally:
+            stop.set()
+            th.join(timeout=60)
+        assert not errors, errors[:1]
+        assert a.shard.count == b.shard.count and a.vocabulary_size == b.vocabulary_size
+        table = {}
+        svc_a = R.GpuRecallSearchService(a, _Emb(table), candidate_cap=0, clock=lambda: NOW)
+        svc_b = R.GpuRecallSearchService(b, _Emb(table), candidate_cap=0, clock=lambda: NOW)
+        for q in ("w0001 w0002 fresh", "w12", "what is the w0999", "nothing-here"):
+            table[q] = rng.standard_normal(dim).astype(np.float32).tolist()
+            ca, cb = svc_a.search(q, 25).citations, svc_b.search(q, 25).citations
+            assert [(c.chunk_id, c.score) for c in ca] == [(c.chunk_id, c.score) for c in cb], q
+        with pytest.raises(N.OrrError):                                    # a document twice in one call is refused whole
+            b.shard.upsert_documents_texts([5, 5], [1, 1], None, np.array([NOW, NOW]), ["x", "y"])
+    finally:
+        a.close()
+        b.close()
