@@ -52,7 +52,7 @@ struct SelState {
     uint32_t n_gathered;
     int32_t  ticket;
     uint32_t n_verified;       // screened keys only: gathered rows whose EXACT key is still at or above the walk's lower edge
-    uint32_t pad;
+    int32_t  n_final;          // candidates the order kernel has to rank (0 until the walk has ended)
 };
 
 // order-preserving key of an exact score: larger key = ranks earlier; dead rows 0, NaN 1 (NaN sorts last, :34;
@@ -334,7 +334,6 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x;
     SelState* st = a.st;
     const SelPoint prev = (a.last_pass == 0) ? sel_initial(a.k) : st->pt[a.last_pass];
@@ -412,36 +411,8 @@ __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a)
         if (tid == 0) { a.status[0] = (int32_t)m; a.status[1] = unproven; }
         return;
     }
-    OrrExact* e = reinterpret_cast<OrrExact*>(smem_raw);
-    int np2 = 1;
-    while (np2 < (int)m) np2 <<= 1;
-    const volatile OrrExact* src = out;
-    for (int i = tid; i < np2; i += blockDim.x) {
-        OrrExact v;
-        if (i < (int)m) { v.score = src[i].score; v.ticks = src[i].ticks; v.row = src[i].row; }
-        else { v.score = __longlong_as_double(0x7ff8000000000000LL); v.ticks = INT64_MIN; v.row = ~0ull; }
-        e[i] = v;
-    }
-    __syncthreads();
-    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < np2; i += blockDim.x) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const OrrExact x = e[i], y = e[p];
-                    const bool up = ((i & k2) == 0);
-                    if (up ? ranks_before(y, x) : ranks_before(x, y)) { e[i] = y; e[p] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    const int n_out = min((int)a.k, (int)m);
-    for (int i = tid; i < n_out; i += blockDim.x) {
-        orr_hit h; h.row = a.row_base + e[i].row; h.score = e[i].score; h.created_ticks = e[i].ticks;
-        a.hits[i] = h;
-    }
-    if (tid == 0) { a.status[0] = n_out; a.status[1] = unproven; }
+    // <= SEL_CAP candidates: orr_order_kernel (the caller's next launch) puts them in reference order; here only the counts
+    if (tid == 0) { st->n_final = (int32_t)m; a.status[0] = (int32_t)min(a.k, m); a.status[1] = unproven; }
 }
 
 // ---- top_k > SEL_CAP: global-memory bitonic sort of the k selected rows, then the hits ---------------------------------
@@ -533,12 +504,16 @@ int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k,
         if (!sc.big || sc.big_cap < k) { orr_set_error("exact path: big-k buffer missing"); return ORR_E_INTERNAL; }
         g.big = sc.big; g.big_cap = (uint32_t)sc.big_cap;
     }
-    ORR_SMEM_OPT_IN((orr_sel_gather_kernel), SEL_CAP * (int)sizeof(OrrExact));
     // the gather resets nothing: n_gathered / ticket are zero from E1's memset unless an earlier round already gathered
     // (it did not: a round that gathers ends the search)
     const int grid = (int)std::min<int64_t>((n + 2047) / 2048, (int64_t)sms * 2);
-    orr_sel_gather_kernel<<<std::max(1, grid), 512, big ? 0 : SEL_CAP * sizeof(OrrExact), st>>>(g);
+    orr_sel_gather_kernel<<<std::max(1, grid), 512, 0, st>>>(g);
     ORR_CUDA_OK(cudaGetLastError());
+    if (!big) {
+        // n_final stays 0 while the walk is incomplete: the order kernel's warps then all exit at once
+        const int rc = orr_launch_order(sc.exact, &state->n_final, SEL_CAP, (int)k, sh.row_base, sc.hits, st);
+        if (rc != ORR_OK) return rc;
+    }
     if (big) {
         // valid only once the walk is done (status[1] == 0); sorting an unfinished list is harmless and is redone
         uint32_t np2 = 1u;

@@ -128,6 +128,9 @@ int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes
                        const OrrWeights& w, int64_t now_ticks, int q_dim, int top_k,
                        int n_listed_max, bool check_bound, cudaStream_t st, int n_listed_host = -1);
 
+// warp-per-record ordering of <= n_max records (orr_rescore.cu); n read from the device
+int orr_launch_order(const OrrExact* recs, const int32_t* n_dev, int n_max, int top_k, uint64_t row_base, orr_hit* hits, cudaStream_t st);
+
 // exact path (orr_exact.cu): every row's fp64 score as an order-preserving key, then an MSB-first radix select of the
 // top-k under (score desc / NaN last, ticks desc, row asc).  orr_launch_exact_select runs digit passes
 // [first_pass, first_pass + n_passes) and the gather; status[1] & ORR_EXACT_INCOMPLETE asks for the next passes.

@@ -54,19 +54,33 @@ __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
     }
 }
 
-// K3's second half: the records' reference order, the hits and the selection bound check.  One WARP per record, on as
-// many SMs as there are records: the record's position is the number of records that rank before it (keys are unique: the
-// row breaks every tie), the lanes split that count.  Ordering used to be the tail of orr_rescore_kernel, run by the last
-// CTA to finish: 4 warps on one SM working through a latency chain (49 us for the reference's 300 candidates, 3x the
-// scoring itself, ncu profiles/r02_kernels.md); as its own launch it costs ~3 us.
-__global__ void __launch_bounds__(256) orr_order_kernel(const RescoreArgs a) {
+// The records' reference order, the hits and (K3) the selection bound check.  One WARP per record, on as many SMs as
+// there are records: the record's position is the number of records that rank before it (keys are unique: the row breaks
+// every tie); the lanes split that count 32 records at a time and the warp STOPS as soon as k records rank before its
+// own — it cannot be a hit — so the cost is ~32 comparisons for most records and n only for the k hits.
+// Ordering used to be the tail of orr_rescore_kernel, run by the last CTA to finish: 4 warps on one SM working through a
+// latency chain (49 us for the reference's 300 candidates, 3x the scoring itself; profiles/r02_kernels.md); as its own
+// launch it costs ~3 us.  The exact path orders its gathered candidates (<= 4096) with the same kernel.
+struct OrderArgs {
+    const OrrExact* exact;
+    const int32_t*  n_ptr;       // device count, or NULL: n_value
+    int32_t   n_value, n_max, top_k;
+    int32_t   check_bound;       // K3: prove the fp32 selection (needs tau_bits, eps)
+    const int32_t* tau_bits;
+    double    eps;
+    uint64_t  row_base;
+    orr_hit*  hits;
+    int32_t*  status;            // {n_out, flags}; NULL: the caller has written it
+};
+
+__global__ void __launch_bounds__(256) orr_order_kernel(const OrderArgs a) {
     const int lane = threadIdx.x & 31;
     const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int n = min(a.n_listed ? *a.n_listed : a.n_listed_value, a.n_listed_max);
+    const int n = min(a.n_ptr ? *a.n_ptr : a.n_value, a.n_max);
     const int k = max(1, a.top_k);                                    // Math.Max(1, topK) :36
     const int n_out = min(k, n);
     const float tau = a.check_bound ? __int_as_float(*a.tau_bits) : -INFINITY;
-    if (i == 0 && lane == 0) {
+    if (i == 0 && lane == 0 && a.status) {
         a.status[0] = n_out;
         // fewer rows listed than k: no k-th score exists, the bound cannot be proven (unless nothing was discarded)
         if (n < k) a.status[1] = (a.check_bound && tau != -INFINITY) ? 1 : 0;
@@ -74,16 +88,21 @@ __global__ void __launch_bounds__(256) orr_order_kernel(const RescoreArgs a) {
     if (i >= n) return;
     OrrExact x;
     x.score = a.exact[i].score; x.ticks = a.exact[i].ticks; x.row = a.exact[i].row;
-    int cnt = 0;
-    for (int j = lane; j < n; j += 32) {
-        OrrExact y;
-        y.score = a.exact[j].score; y.ticks = a.exact[j].ticks; y.row = a.exact[j].row;
-        cnt += ranks_before(y, x) ? 1 : 0;
+    int pos = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        int c = 0;
+        if (j < n) {
+            OrrExact y;
+            y.score = a.exact[j].score; y.ticks = a.exact[j].ticks; y.row = a.exact[j].row;
+            c = ranks_before(y, x) ? 1 : 0;
+        }
+        pos += __reduce_add_sync(FULL, c);
+        if (pos >= k) return;                                         // warp-uniform: not among the first k
     }
-    const int pos = __reduce_add_sync(FULL, cnt);
     if (lane != 0) return;
-    if (pos < n_out) { orr_hit h; h.row = a.ex.sh.row_base + x.row; h.score = x.score; h.created_ticks = x.ticks; a.hits[pos] = h; }
-    if (pos == k - 1) {
+    if (pos < n_out) { orr_hit h; h.row = a.row_base + x.row; h.score = x.score; h.created_ticks = x.ticks; a.hits[pos] = h; }
+    if (pos == k - 1 && a.status) {
         // every row outside the list has fp32 score <= tau and |fp32 - exact| <= eps: safe iff the k-th exact score clears
         // tau by more than eps
         int flags = 0;
@@ -288,7 +307,20 @@ int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes
     const int grid = (n_listed_max + 3) / 4;
     orr_rescore_kernel<<<grid, 128, 0, st>>>(a);
     ORR_CUDA_OK(cudaGetLastError());
-    orr_order_kernel<<<(n_listed_max + 7) / 8, 256, 0, st>>>(a);
+    OrderArgs o;
+    o.exact = a.exact; o.n_ptr = a.n_listed; o.n_value = a.n_listed_value; o.n_max = a.n_listed_max; o.top_k = a.top_k;
+    o.check_bound = a.check_bound; o.tau_bits = a.tau_bits; o.eps = a.eps; o.row_base = sh.row_base; o.hits = a.hits; o.status = a.status;
+    orr_order_kernel<<<(n_listed_max + 7) / 8, 256, 0, st>>>(o);
+    ORR_CUDA_OK(cudaGetLastError());
+    return ORR_OK;
+}
+
+// orders n (device count, <= n_max) records and writes the first top_k as hits; status is left to the caller
+int orr_launch_order(const OrrExact* recs, const int32_t* n_dev, int n_max, int top_k, uint64_t row_base, orr_hit* hits, cudaStream_t st) {
+    OrderArgs o;
+    o.exact = recs; o.n_ptr = n_dev; o.n_value = 0; o.n_max = n_max; o.top_k = top_k; o.check_bound = 0; o.tau_bits = nullptr; o.eps = 0.0;
+    o.row_base = row_base; o.hits = hits; o.status = nullptr;
+    orr_order_kernel<<<(n_max + 7) / 8, 256, 0, st>>>(o);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
