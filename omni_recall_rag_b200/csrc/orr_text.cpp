@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "orr_internal.h"
+#include "orr_lower_table.h"
 
 namespace {
 
@@ -55,22 +56,18 @@ bool is_space(uint32_t c) {
     }
 }
 
-// ToLowerInvariant, simple case mapping over the blocks the scorer is specified for
+// ToLowerInvariant (RecallSearchService.cs:96,110): the Unicode simple lower-case mapping of every code point (surrogate
+// pairs included), U+0130 left unchanged as .NET's invariant casing does.  Table: orr_lower_table.h (generated).
 uint32_t fold(uint32_t c) {
     if (c < 0x80) return (c >= 'A' && c <= 'Z') ? c | 0x20 : c;
-    if (c >= 0xC0 && c <= 0xDE) return c == 0xD7 ? c : c + 0x20;
-    if (c >= 0x100 && c <= 0x17F) {
-        if (c == 0x130) return 'i';
-        if (c == 0x178) return 0xFF;
-        if (c == 0x138 || c == 0x149 || c == 0x17F) return c;
-        const bool pair_starts_even = (c <= 0x137) || (c >= 0x14A && c <= 0x177);
-        if (pair_starts_even) return (c & 1) ? c : c + 1;
-        return (c & 1) ? c + 1 : c;          // 0x139-0x148, 0x179-0x17E: upper case is odd
+    int lo = 0, hi = kOrrLowerRuns - 1;
+    while (lo < hi) {                                    // last run whose `first` <= c
+        const int mid = (lo + hi + 1) >> 1;
+        if (kOrrLower[mid].first <= c) lo = mid; else hi = mid - 1;
     }
-    if (c >= 0x391 && c <= 0x3A9) return c == 0x3A2 ? c : c + 0x20;
-    if (c >= 0x400 && c <= 0x40F) return c + 0x50;
-    if (c >= 0x410 && c <= 0x42F) return c + 0x20;
-    return c;
+    const OrrLowerRun& r = kOrrLower[lo];
+    if (c < r.first || c > r.last || ((c - r.first) % r.stride) != 0) return c;
+    return (uint32_t)((int32_t)c + r.delta);
 }
 
 void put_utf8(std::string& s, uint32_t c) {

@@ -265,18 +265,14 @@ _WS = {0x20, 0x85, 0xA0, 0x1680, 0x2028, 0x2029, 0x202F, 0x205F, 0x3000, *range(
 
 
 def _lower_invariant(s: str) -> str:
+    """ToLowerInvariant (RecallSearchService.cs:96,110): the simple lower-case mapping per code point; U+0130, the one
+    code point whose full lower-casing is two code points, stays as it is (.NET invariant casing)."""
+    if s.isascii():
+        return s.lower()
     out = []
     for ch in s:
-        c = ord(ch)
-        if c < 0x80:
-            out.append(ch.lower())
-        elif c == 0x130:
-            out.append("i")
-        elif (0xC0 <= c <= 0xDE and c != 0xD7) or 0x100 <= c <= 0x17E or 0x391 <= c <= 0x3A9 or 0x400 <= c <= 0x42F:
-            lo = ch.lower()
-            out.append(lo if len(lo) == 1 else ch)
-        else:
-            out.append(ch)
+        lo = ch.lower()
+        out.append(lo if len(lo) == 1 else ch)
     return "".join(out)
 
 

@@ -35,21 +35,12 @@ def is_ws(ch: str) -> bool:
 
 
 def to_lower_invariant(s: str) -> str:
-    """ToLowerInvariant (:96,:110): per-code-point simple case mapping (no context rules,
-    no expansions), restricted to the ranges the C oracle also maps."""
+    """ToLowerInvariant (:96,:110): per-code-point SIMPLE lower-case mapping (no context rules, no
+    expansions); U+0130 stays unchanged, as .NET's invariant casing leaves it."""
     out = []
     for ch in s:
-        c = ord(ch)
-        if c < 0x80:
-            out.append(ch.lower())
-        elif (0xC0 <= c <= 0xDE and c != 0xD7) or (0x100 <= c <= 0x17E) or (0x391 <= c <= 0x3A9) or (0x400 <= c <= 0x42F):
-            if c == 0x130:
-                out.append("i")
-                continue
-            lo = ch.lower()
-            out.append(lo if len(lo) == 1 else ch)
-        else:
-            out.append(ch)
+        lo = ch.lower()
+        out.append(lo if len(lo) == 1 else ch)
     return "".join(out)
 
 

@@ -83,6 +83,34 @@ def test_tokenizers_agree_on_arbitrary_text(text):
     assert list(orr.tokenize_content(text)) == [orr.hash_term(t) for t in _distinct_lower_tokens(text)]
 
 
+def _py_lower_invariant(ch: str) -> str:
+    lo = ch.lower()                      # full mapping; == the simple mapping wherever it is one code point
+    return lo if len(lo) == 1 else ch    # U+0130 -> "i̇" (2 code points) stays U+0130 under .NET's invariant casing
+
+
+def test_to_lower_invariant_covers_every_code_point():
+    """ToLowerInvariant (RecallSearchService.cs:96,110) is the Unicode simple lower-case mapping of EVERY code point, not
+    just Latin/Greek/Cyrillic: the library's run table, the C oracle's pair table and the numpy oracle are each compared
+    with Python's unicodedata over all 0x110000 code points (tokens "<cp>q", 400 per query string)."""
+    from oracle import oracle_np
+    from omni_recall_rag_b200.store import _lower_invariant
+    cps = [c for c in range(0x80, 0x110000) if not (0xD800 <= c <= 0xDFFF) and chr(c).lower() != chr(c)]
+    assert len(cps) > 1300 and 0x130 in cps and 0x10400 in cps and 0x1E900 in cps
+    cps += [0xDF, 0x131, 0x149, 0x3C2, 0x4E2D, 0x1F600, 0x10FFFF]       # unmapped neighbours
+    for at in range(0, len(cps), 400):
+        part = cps[at:at + 400]
+        text = " ".join(chr(c) + "q" for c in part)
+        exp = list(dict.fromkeys(_py_lower_invariant(chr(c)) + "q" for c in part))
+        assert oracle_c.query_terms(text) == exp
+        assert oracle_np.query_terms(text) == exp
+        assert list(orr.tokenize_query(text)) == [orr.hash_term(t) for t in exp]
+        assert list(orr.tokenize_content(text)) == [orr.hash_term(t) for t in exp]
+        assert _distinct_lower_tokens(text) == exp
+        assert _lower_invariant(text) == " ".join(_py_lower_invariant(chr(c)) + "q" for c in part)
+    assert oracle_c.query_terms("İstanbul KELVINK \U00010400") == ["İstanbul", "kelvink", "\U00010428"]
+    assert oracle_c.keyword("ⱥ", "xȺx") == 1.0                          # 2-byte upper -> 3-byte lower in UTF-8
+
+
 def test_hash_properties_on_the_synthetic_vocabulary():
     ids = np.arange(0, 1 << 20, 37, dtype=np.uint32)
     h = np.array([orr.hash_term(synth.term_text(i)) for i in ids], dtype=np.uint64)
