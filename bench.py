@@ -589,6 +589,80 @@ def measure_service(store, spec, n_local: int, steps: int, warmup: int):
     }
 
 
+def measure_cluster(args):
+    """The single-process form (orr_cluster_*, csrc/orr_cluster.cu): one host thread issues, per query and per device,
+    query -> HBM, orr_search_device, the fused peer-memory all-gather + merge; hits come back from device 0.  Host
+    buffers in and out on every call, so `value` IS the end-to-end number (e2e repeats it with the bytes moved); the
+    device-resident figure of the same layout is the torchrun line."""
+    import numpy as np
+    import torch
+
+    import omni_recall_rag_b200 as orr
+    from omni_recall_rag_b200 import synth
+
+    n_dev = args.gpus
+    assert torch.cuda.device_count() >= n_dev, f"--gpus {n_dev} but {torch.cuda.device_count()} visible"
+    n_local = args.rows_per_gpu or (1_000_000 if n_dev == 1 else 5_000_000)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    spec = synth.make_spec(DIM)
+    total_rows = n_local * n_dev
+    queries = [synth.query_host(spec, qi, total_rows, n_terms=N_TERMS) for qi in range(steps + warmup)]
+    with orr.RecallCluster(DIM, n_local, list(range(n_dev)), term_slots=TERM_SLOTS, max_top_k=32) as cl:
+        cl.fill_synthetic(spec, 0, n_local)
+        for q in queries[:warmup]:
+            cl.search(q.q, q.terms, spec.now_ticks, TOP_K)
+        wall = []
+        with ClockSampler(0) as clocks:
+            t0 = time.perf_counter()
+            for q in queries[warmup:]:
+                tq = time.perf_counter()
+                hits = cl.search(q.q, q.terms, spec.now_ticks, TOP_K)
+                wall.append((time.perf_counter() - tq) * 1000.0)
+            dt = time.perf_counter() - t0
+            for q in queries[warmup:warmup + max(1, int(0.6 * steps / max(dt, 1e-3)))]:
+                cl.search(q.q, q.terms, spec.now_ticks, TOP_K)           # keep the sampler under load for ~0.6 s
+        assert len(hits.rows) == TOP_K
+        # batched queries over the cluster (orr_cluster_search_batch): every shard's tcgen05 path, merged per query
+        batch = None
+        if not args.headline_only:
+            bq = np.stack([q.q for q in queries[:256]]) if len(queries) >= 256 else np.stack([queries[i % len(queries)].q for i in range(256)])
+            bt = [queries[i % len(queries)].terms for i in range(256)]
+            try:
+                bh = cl.search_batch(bq, bt, spec.now_ticks, TOP_K)      # builds the bf16 planes on first use
+                t1 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    bh = cl.search_batch(bq, bt, spec.now_ticks, TOP_K)
+                bdt = (time.perf_counter() - t1) / reps
+                h0 = cl.search(queries[0].q, queries[0].terms, spec.now_ticks, TOP_K)
+                assert bh[0].rows.tolist() == h0.rows.tolist(), "cluster batch / single-query paths disagree"
+                batch = {"batch": 256, "ms_per_batch": 1000.0 * bdt, "queries_per_s": 256 / bdt,
+                         "what": "orr_cluster_search_batch: 256 queries x the whole corpus (tcgen05 path on every shard, k-way merge "
+                                 "per query), host buffers in and out; query 0 checked against orr_cluster_search"}
+            except Exception as e:                                        # the single-query figures stand on their own
+                batch = {"error": str(e)[:300]}
+    scale = total_rows / 1.0e6
+    peak, peak_kind = measured_peak()
+    bytes_per_query = total_rows * (4 * DIM + 8 + 4 * TERM_SLOTS)
+    line = {"metric": METRIC, "value": steps / dt * scale, "unit": UNIT, "n_gpus": n_dev, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 scan select + f64 exact re-score", "data": "synthetic",
+            "config": dict(workload_config(args, n_local), rows_total=total_rows, parallelism=f"1 process x {n_dev} GPUs (orr_cluster)"),
+            "corpus_qps": steps / dt, "form": "single process (orr_cluster_search), wall clock, host buffers in and out",
+            "e2e": {"value": steps / dt * scale, "unit": UNIT, "h2d_bytes_per_step": n_dev * (4 * DIM + 12 * N_TERMS),
+                    "d2h_bytes_per_step": 24 * TOP_K + 8, "ms_per_step": 1000.0 * dt / steps,
+                    "call_ms": {"what": "RecallCluster.search wall clock", "median": statistics.median(wall), "p99": p99(wall)}},
+            "gpu_launches": 3 * n_dev * steps,
+            "kernels_per_step": ["orr_scan_kernel<24,1>", "orr_rescore_kernel + orr_order_kernel", "orr_xchg_merge_kernel"],
+            "roofline": {"bound": "hbm", "kernel": "whole query (all devices), wall clock", "achieved": bytes_per_query / (dt / steps) / 1.0e9,
+                         "peak": peak * n_dev, "peak_kind": hbm_peak_kind(peak_kind) + f" x {n_dev}", "unit": "GB/s",
+                         "frac": bytes_per_query / (dt / steps) / 1.0e9 / (peak * n_dev), "traffic": None},
+            "clocks": clocks.summary()}
+    if batch:
+        line["cluster_batch"] = batch
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -605,6 +679,9 @@ def main():
                     help="N>1: how the per-GPU top-k lists meet (fused peer-memory kernel, or NCCL all-gather + merge)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="N>1: every query is a blocking collective step (no exchange/scan overlap between consecutive queries)")
+    ap.add_argument("--cluster", action="store_true",
+                    help="ONE host process driving --gpus N devices through orr_cluster_* (the .NET deployment of the row-sharded "
+                         "layout: no torchrun, no NCCL); launch with plain `python bench.py --cluster --gpus N`")
     ap.add_argument("--batch-passes", type=int, default=0, choices=[0, 1, 3],
                     help="0 = auto (bf16 screen, bf16x3 cascade for unproven queries; the library default), 1, 3")
     args = ap.parse_args()
@@ -615,6 +692,11 @@ def main():
     need_gpu()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cpu_s = 0.0 if args.no_cpu_baseline else 1.0
+    if args.cluster:
+        if world != 1:
+            raise SystemExit("--cluster is ONE process for all GPUs: launch it with plain python, not torchrun")
+        emit(measure_cluster(args))
+        return
     if args.workload == "c1":
         if args.gpus != 1 or world != 1:
             raise SystemExit("--workload c1 is a single-GPU bench")
