@@ -479,6 +479,95 @@ def measure_batch(args, name: str, steps: int, warmup: int, cpu_seconds: float):
     return line
 
 
+def measure_batch_sharded(args, name: str, steps: int, warmup: int):
+    """configs[2] / configs[4] row-sharded over N ranks (torchrun): every rank holds the config's rows (weak scaling: the
+    corpus is N x 5M rows) and answers every query of the batch on its shard (tcgen05 path, answers left in HBM:
+    orr_search_batch_device); the B x k x 24 B lists are all-gathered with NCCL — a bandwidth-type exchange — and merged per
+    query on the device (orr_merge_hits_batch_device).  Host buffers in (queries) and out (merged hits) on every step, so
+    the one figure is end to end; wall clock between barriers, max over ranks.  Returns the line on rank 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import omni_recall_rag_b200 as orr
+    from omni_recall_rag_b200 import sharded, synth
+
+    world, rank, local_rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+    wl = dict(BATCH_WORKLOADS[name])
+    rows, dim, B, k = wl["rows"], wl["dim"], wl["batch"], wl["top_k"]
+    total_rows = rows * world
+    spec = synth.make_spec(dim, dup_row_ppm=wl["dup_ppm"])
+    shard = orr.RecallShard(dim, rows, device=local_rank, term_slots=TERM_SLOTS, row_base=rank * rows)
+    shard.fill_synthetic(spec, rank * rows, rows)
+    shard.set_option("batch_passes", args.batch_passes)
+    sr = sharded.ShardedRecall(shard, exchange="nccl")
+    n_b = steps + warmup
+    Qs, Ts = [], []
+    for i in range(n_b):                          # the same fresh batch on every rank
+        qs = [synth.query_host(spec, i * B + j, total_rows, n_terms=wl["n_terms"], frequent_terms=wl["frequent"]) for j in range(B)]
+        Qs.append(torch.from_numpy(np.stack([q.q for q in qs])).pin_memory())
+        Ts.append(orr.BatchTerms.pack([q.terms for q in qs]))
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        sr.search_batch(Qs[i].numpy(), Ts[i], spec.now_ticks, k)
+    barrier()
+    main_ms = []
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(warmup, n_b):
+            hits = sr.search_batch(Qs[i].numpy(), Ts[i], spec.now_ticks, k)
+            main_ms.append(shard.last_timing()["scan_ms"])
+        barrier()
+        dt = time.perf_counter() - t0
+        for i in range(warmup, warmup + max(1, min(steps, int(0.6 * steps / max(dt, 1e-3))))):
+            sr.search_batch(Qs[i].numpy(), Ts[i], spec.now_ticks, k)     # same count on every rank: each call is a collective
+    assert all(int(n) == k for n in hits.n_out), "short hit lists"
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    line = None
+    if rank == 0:
+        burst, sustained, peak_kind = measured_tensor_peak()
+        useful = 2.0 * rows * dim * B
+        main_avg = sum(main_ms) / len(main_ms)
+        achieved = useful / (main_avg / 1000.0) / 1.0e12
+        scale = total_rows / float(rows)
+        line = {
+            "metric": f"hybrid recall QPS, {wl['name']}", "value": steps * B / dt * scale,
+            "unit": f"queries/s x (rows_total / {rows})", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 tcgen05 screen (fp32 accumulate in TMEM) + f64 exact re-rank of the candidates", "data": "synthetic",
+            "config": dict(batch_config(args, wl), rows_total=total_rows, rows_per_gpu=rows, parallelism=f"row-sharded x {world} (torchrun)"),
+            "corpus_qps": steps * B / dt,
+            "e2e": {"value": steps * B / dt * scale, "unit": f"queries/s x (rows_total / {rows})",
+                    "h2d_bytes_per_step": B * dim * 4 + B * 4 + (B + 1) * 4 + B * wl["n_terms"] * 8,
+                    "d2h_bytes_per_step": B * k * 24 + B * 4, "ms_per_step": 1000.0 * dt / steps},
+            "gpu_launches": 8 * steps,
+            "kernels_per_step": ["orr_prep_queries_kernel", "orr_build_rowaux_kernel", "orr_batch_term_bits_kernel (unseen terms only)",
+                                 "orr_batch_gemm_kernel<1,1> (sampling pass)", "orr_batch_threshold_kernel",
+                                 "orr_batch_gemm_kernel<1,0> (main pass)", "orr_batch_finalize_kernel", "orr_merge_batch_kernel"],
+            "exchange": "nccl all_gather_into_tensor of the B x k x 24 B lists + per-query device merge",
+            "roofline": {"bound": "tensor", "kernel": "orr_batch_gemm_kernel<1,0> (main pass, rank 0)", "achieved": achieved, "peak": sustained,
+                         "peak_kind": f"{peak_kind} cuBLAS bf16 TFLOP/s, sustained; burst {burst}", "unit": "TFLOP/s",
+                         "frac": achieved / sustained, "flops_per_launch": useful, "kernel_ms": main_avg, "traffic": None},
+            "clocks": clocks.summary(),
+        }
+    sr.close()
+    shard.close()
+    dist.destroy_process_group()
+    return line
+
+
 def measure_noemb(shard, spec, n_local: int, steps: int, warmup: int, cpu_seconds: float):
     """The reference's DEFAULT configuration (appsettings.json:30-32, NoOpEmbeddingClient.cs:5-8): no query embedding,
     every cosine is 0 (RecallSearchService.cs:71-72), ranking = keyword + recency.  Same 1M-row corpus, 4 terms, top-10:
@@ -703,10 +792,15 @@ def main():
         emit(measure_c1(max(1, args.steps), max(3, args.warmup), 3.0 * cpu_s))
         return
     if args.workload != "c2":
-        if args.gpus != 1 or world != 1:
-            raise SystemExit("--workload c3/c5 is a single-GPU bench")
-        emit(measure_batch(args, args.workload, max(1, args.steps if args.steps != 200 else 20),
-                           max(3, args.warmup if args.warmup != 20 else 3), 10.0 * cpu_s))
+        b_steps, b_warm = max(1, args.steps if args.steps != 200 else 20), max(3, args.warmup if args.warmup != 20 else 3)
+        if world > 1:
+            line = measure_batch_sharded(args, args.workload, b_steps, b_warm)
+            if line is not None:
+                emit(line)
+            return
+        if args.gpus != 1:
+            raise SystemExit("--workload c3/c5 --gpus N needs torchrun (one rank per GPU)")
+        emit(measure_batch(args, args.workload, b_steps, b_warm, 10.0 * cpu_s))
         return
 
     import numpy as np  # noqa: F401

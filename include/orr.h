@@ -257,6 +257,17 @@ int  orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim
         const uint32_t* probe_offsets,
         int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
 
+/* The same with the answers left in HBM on cfg.device: out_dev is orr_hit[batch][max(1,top_k)], n_out_dev int32[batch]
+ * (row-sharded batches feed them straight into the all-gather + orr_merge_hits_batch_device; queries still come from
+ * host memory).  Complete when the call returns.  Takes what the tcgen05 path takes in one launch (query width = dim,
+ * dim % 64 == 0, top_k <= 128, 8 <= batch <= 1024, <= 16 identity-probe terms per query) and returns
+ * ORR_E_UNSUPPORTED, with nothing usable written, when the batch must go through orr_search_batch instead (shape
+ * outside the path, or a query whose selection the bound check could not prove). */
+int  orr_search_batch_device(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
+        const int32_t* n_terms, const uint64_t* probe_hash, const int32_t* probe_term,
+        const uint32_t* probe_offsets,
+        int64_t now_ticks, int32_t top_k, orr_hit* out_dev, int32_t* n_out_dev);
+
 /* Diagnostic for the batched path: the raw fused GEMM scores (w_cos*cos + w_rec*rec, no
  * keyword term; fp32) of every `tile_stride`-th 128-row tile, out[b*out_ld + i]. */
 int  orr_debug_batch_scores(orr_store* s, int32_t batch, const float* q, int32_t q_dim,

@@ -91,6 +91,8 @@ _SIGNATURES = {
     "orr_search_device_timing": (C.c_int, [C.c_void_p, C.POINTER(OrrTiming)]),
     "orr_search_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "orr_search_batch_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "orr_debug_batch_scores": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                          C.c_void_p, C.c_int64]),
     "orr_debug_scan_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

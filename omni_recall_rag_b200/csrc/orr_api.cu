@@ -1855,9 +1855,11 @@ static double batch_eps(const OrrWeights& w, int passes) {
 }
 
 // the GEMM path proper; `redo` receives the queries whose selection could not be proven safe
+// out_dev / n_out_dev (both or neither): the hits stay in HBM — `out` is then not written
 static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const int32_t* n_terms,
                            const uint64_t* probe_hash, const uint32_t* probe_offsets, int64_t now_ticks, int32_t top_k,
-                           orr_hit* out, int32_t* n_out, int passes, std::vector<int32_t>* redo) {
+                           orr_hit* out, int32_t* n_out, int passes, std::vector<int32_t>* redo,
+                           orr_hit* out_dev = nullptr, int32_t* n_out_dev = nullptr) {
     std::call_once(s->batch_once, [&] { s->batch.reset(new BatchState()); });    // searches hold the lock SHARED: create once
     BatchState* bs = s->batch.get();
     std::lock_guard<std::mutex> g(bs->mu);
@@ -2015,7 +2017,13 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
     int32_t* st_host = bs->h_status;
     ORR_CUDA_OK(cudaEventRecord(bs->ev[4], st));
     ORR_CUDA_OK(cudaMemcpyAsync(st_host, bs->status, sizeof(int32_t) * 2 * (size_t)batch, cudaMemcpyDeviceToHost, st));
-    ORR_CUDA_OK(cudaMemcpyAsync(out, bs->hits, sizeof(orr_hit) * (size_t)batch * k, cudaMemcpyDeviceToHost, st));
+    if (out_dev) {
+        ORR_CUDA_OK(cudaMemcpyAsync(out_dev, bs->hits, sizeof(orr_hit) * (size_t)batch * k, cudaMemcpyDeviceToDevice, st));
+        ORR_CUDA_OK(cudaMemcpy2DAsync(n_out_dev, sizeof(int32_t), bs->status, 2 * sizeof(int32_t), sizeof(int32_t), (size_t)batch,
+                                      cudaMemcpyDeviceToDevice, st));       // status is {n_out, flags} per query
+    } else {
+        ORR_CUDA_OK(cudaMemcpyAsync(out, bs->hits, sizeof(orr_hit) * (size_t)batch * k, cudaMemcpyDeviceToHost, st));
+    }
     ORR_CUDA_OK(cudaEventRecord(bs->ev[5], st));
     ORR_CUDA_OK(cudaStreamSynchronize(st));
     float ms_sample = 0.f, ms_main = 0.f, ms_all = 0.f;
@@ -2031,7 +2039,7 @@ static int batch_gemm_path(orr_store* s, int32_t batch, const float* q, const in
                 batch, k, passes, M, stride, g_batch_terms_built, ms_prep, ms_sample, ms_main, ms_fin, ms_d2h);
     }
     for (int32_t b = 0; b < batch; ++b) {
-        n_out[b] = st_host[(size_t)2 * b];
+        if (n_out) n_out[b] = st_host[(size_t)2 * b];
         if (st_host[(size_t)2 * b + 1] != 0) redo->push_back(b);
     }
     g_timing.scan_ms = ms_main;                  // the main tcgen05 pass
@@ -2164,6 +2172,48 @@ int orr_search_batch(orr_store* s, int32_t batch, const float* q, int32_t q_dim,
         g_timing.n_survivors = (int32_t)redo.size() | (batch_timing.n_survivors << 16);   // low half: queries re-run singly
     }
     g_timing.wall_ms = (float)(now_ms() - t0);
+    return ORR_OK;
+}
+
+// orr_search_batch with the answers left in HBM: the row-sharded form feeds them straight into the all-gather.  Takes what the
+// tcgen05 path takes in ONE launch and returns ORR_E_UNSUPPORTED — nothing usable written — when the batch has to go
+// through orr_search_batch instead (shape outside the path, or a query whose selection could not be proven).
+int orr_search_batch_device(orr_store* s, int32_t batch, const float* q, int32_t q_dim, const int32_t* n_terms,
+                            const uint64_t* probe_hash, const int32_t* probe_term, const uint32_t* probe_offsets,
+                            int64_t now_ticks, int32_t top_k, orr_hit* out_dev, int32_t* n_out_dev) {
+    const double t0 = now_ms();
+    if (!s || batch <= 0 || !out_dev || !n_out_dev || !q) { orr_set_error("orr_search_batch_device: bad argument"); return ORR_E_INVALID; }
+    const int k = std::max(1, top_k);
+    bool ok = (q_dim == s->cfg.dim) && (s->cfg.dim % 64 == 0) && k <= 128 && batch >= 8 && batch <= ORR_BATCH_MAX_QUERIES;
+    int64_t terms_sum = 0;
+    if (ok && n_terms) {
+        for (int32_t b = 0; b < batch && ok; ++b) {
+            const int32_t nt = n_terms[b];
+            if (nt < 0 || nt > ORR_BATCH_TERMS) ok = false;
+            if (nt > 0) {
+                if (!probe_offsets || !probe_hash) ok = false;
+                else if ((int32_t)(probe_offsets[b + 1] - probe_offsets[b]) != nt) ok = false;
+                else if (probe_term) for (int32_t t = 0; t < nt; ++t) if (probe_term[probe_offsets[b] + t] != t) ok = false;
+            }
+            terms_sum += std::max(0, nt);
+        }
+    }
+    if (!ok || terms_sum > BATCH_MAX_TERM_IDS) { orr_set_error("orr_search_batch_device: batch outside the single-launch tcgen05 path"); return ORR_E_UNSUPPORTED; }
+    std::shared_lock<std::shared_mutex> lock(s->mu);
+    ORR_CUDA_OK(cudaSetDevice(s->cfg.device));
+    if (s->live_rows <= 0) { orr_set_error("orr_search_batch_device: empty store"); return ORR_E_UNSUPPORTED; }
+    memset(&g_timing, 0, sizeof g_timing);
+    const int passes = s->batch_passes == 0 ? (s->batch_hold.load() > 0 ? 3 : 1) : s->batch_passes;
+    std::vector<int32_t> redo;
+    int rc = batch_gemm_path(s, batch, q, n_terms, probe_hash, probe_offsets, now_ticks, top_k, nullptr, nullptr, passes, &redo,
+                             out_dev, n_out_dev);
+    if (rc != ORR_OK) return rc;
+    g_timing.wall_ms = (float)(now_ms() - t0);
+    if (!redo.empty()) {
+        orr_set_error("orr_search_batch_device: %d of %d queries not proven by the screen; run the batch through orr_search_batch",
+                      (int)redo.size(), batch);
+        return ORR_E_UNSUPPORTED;
+    }
     return ORR_OK;
 }
 

@@ -387,6 +387,27 @@ class RecallShard:
                                          int(now_ticks), int(top_k), p(raw), p(n_out)))
         return BatchHits(raw[:B], n_out[:B])
 
+    def search_batch_device(self, q: np.ndarray, terms, now_ticks: int, top_k: int, out_dev_ptr: int, n_out_dev_ptr: int) -> bool:
+        """orr_search_batch_device: the answers stay in HBM (out_dev_ptr: orr_hit[B][k], n_out_dev_ptr: int32[B] on this
+        shard's device).  False = the batch has to go through search_batch instead (outside the single-launch tcgen05
+        path, or a query the screen could not prove); the buffers then hold nothing usable."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B, qd = int(q.shape[0]), int(q.shape[1]) if q.ndim == 2 else 0
+        bt = None
+        if terms is not None:
+            bt = terms if isinstance(terms, BatchTerms) else BatchTerms.pack(terms)
+            if bt.n_terms.shape[0] != B:
+                raise ValueError(f"terms describe {bt.n_terms.shape[0]} queries, q has {B}")
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        rc = N.lib().orr_search_batch_device(self._h, B, p(q) if q.size else None, qd,
+                                             p(bt.n_terms) if bt else None, p(bt.probe_hash) if bt else None,
+                                             p(bt.probe_term) if bt else None, p(bt.probe_offsets) if bt else None,
+                                             int(now_ticks), int(top_k), C.c_void_p(out_dev_ptr), C.c_void_p(n_out_dev_ptr))
+        if rc == N.ORR_E_UNSUPPORTED:
+            return False
+        N.check(rc)
+        return True
+
     def debug_scan_scores(self, q: np.ndarray, terms: QueryTerms, now_ticks: int) -> np.ndarray:
         """The fp32 score the fused scan computes for every physical row (orr_debug_scan_scores)."""
         q = np.ascontiguousarray(q, dtype=np.float32)

@@ -21,7 +21,7 @@ from typing import Callable, Optional, Tuple
 import numpy as np
 
 from . import _native as N
-from .shard import BatchHits, Hits, QueryTerms, RecallShard, merge_hits, _HIT_DTYPE
+from .shard import BatchHits, BatchTerms, Hits, QueryTerms, RecallShard, merge_hits, _HIT_DTYPE
 
 HIT_BYTES = 24  # sizeof(orr_hit)
 
@@ -177,25 +177,40 @@ class ShardedRecall:
         (orr_merge_hits_batch_device, one CTA per query) with the reference tie chain."""
         import torch
 
-        local = self.shard.search_batch(q, terms, now_ticks, top_k)
         if self.world == 1:
-            return local
-        B, k = len(local), max(1, int(top_k))
+            return self.shard.search_batch(q, terms, now_ticks, top_k)
         if self.dist.get_backend(self.group) != "nccl":
             raise RuntimeError("sharded search_batch needs the nccl backend (device merge)")
         dev = torch.device("cuda", self.shard.device)
-        mine = torch.from_numpy(local.raw.view(np.uint8).reshape(-1)).to(dev, non_blocking=True)
-        mine_n = torch.from_numpy(np.ascontiguousarray(local.n_out, dtype=np.int32)).to(dev, non_blocking=True)
-        allh = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=dev)
-        alln = torch.empty(self.world * B, dtype=torch.int32, device=dev)
-        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
-        self.dist.all_gather_into_tensor(alln, mine_n, group=self.group)
-        out = torch.empty(B * k * HIT_BYTES, dtype=torch.uint8, device=dev)
-        out_n = torch.empty(B, dtype=torch.int32, device=dev)
-        N.check(N.lib().orr_merge_hits_batch_device(self.shard.device, allh.data_ptr(), alln.data_ptr(), self.world, B, k,
-                                                    out.data_ptr(), out_n.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
-        raw = np.frombuffer(out.cpu().numpy().tobytes(), dtype=_HIT_DTYPE).reshape(B, k).copy()
-        return BatchHits(raw, out_n.cpu().numpy())
+        B, k = int(np.asarray(q).shape[0]), max(1, int(top_k))
+        bt = terms if (terms is None or isinstance(terms, BatchTerms)) else BatchTerms.pack(terms)
+        key = ("batch", B, k)
+        if key not in self._dev_bufs:                      # device buffers and the pinned landing zone, once per shape
+            nb = B * k * HIT_BYTES
+            self._dev_bufs[key] = dict(
+                mine=torch.empty(nb, dtype=torch.uint8, device=dev), mine_n=torch.empty(B, dtype=torch.int32, device=dev),
+                allh=torch.empty(self.world * nb, dtype=torch.uint8, device=dev),
+                alln=torch.empty(self.world * B, dtype=torch.int32, device=dev),
+                out=torch.empty(nb, dtype=torch.uint8, device=dev), out_n=torch.empty(B, dtype=torch.int32, device=dev),
+                h_out=torch.empty(nb, dtype=torch.uint8).pin_memory(), h_n=torch.empty(B, dtype=torch.int32).pin_memory())
+        bufs = self._dev_bufs[key]
+        mine, mine_n = bufs["mine"], bufs["mine_n"]
+        # the local answers stay in HBM and go straight into the all-gather (orr_search_batch_device); a batch that path
+        # does not take (or could not prove) comes back through host memory instead
+        if not self.shard.search_batch_device(q, bt, now_ticks, top_k, mine.data_ptr(), mine_n.data_ptr()):
+            local = self.shard.search_batch(q, bt, now_ticks, top_k)
+            mine.copy_(torch.from_numpy(local.raw.view(np.uint8).reshape(-1)), non_blocking=True)
+            mine_n.copy_(torch.from_numpy(np.ascontiguousarray(local.n_out, dtype=np.int32)), non_blocking=True)
+        self.dist.all_gather_into_tensor(bufs["allh"], mine, group=self.group)
+        self.dist.all_gather_into_tensor(bufs["alln"], mine_n, group=self.group)
+        N.check(N.lib().orr_merge_hits_batch_device(self.shard.device, bufs["allh"].data_ptr(), bufs["alln"].data_ptr(), self.world, B, k,
+                                                    bufs["out"].data_ptr(), bufs["out_n"].data_ptr(),
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+        bufs["h_out"].copy_(bufs["out"], non_blocking=True)
+        bufs["h_n"].copy_(bufs["out_n"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        raw = bufs["h_out"].numpy().view(_HIT_DTYPE).reshape(B, k).copy()     # one host copy: the pinned buffer is reused
+        return BatchHits(raw, bufs["h_n"].numpy().copy())
 
     # -- device-resident path (query and hits stay in HBM; nothing synchronises the host) -----
     def search_device(self, q_dev, terms: QueryTerms, now_ticks: int, top_k: int):

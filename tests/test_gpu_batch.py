@@ -270,3 +270,30 @@ def test_auto_mode_cascades_to_split_precision_when_the_screen_cannot_prove_a_qu
         single = sh.search_batch(Q, None, NOW, k)
         assert all(single[b].rows.tolist() == got[b].rows.tolist() and single[b].scores.tolist() == got[b].scores.tolist()
                    for b in range(B))
+
+
+def test_device_resident_answers_equal_the_host_form_and_unsupported_shapes_are_refused():
+    """orr_search_batch_device leaves the hits in HBM (row-sharded batches feed them to the all-gather): same bytes as
+    orr_search_batch; shapes outside the single-launch tcgen05 path return False instead of half an answer."""
+    import torch
+
+    dim, n, B, k = 128, 9_000, 40, 12
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=16, dup_row_ppm=20000)
+    qs = [synth.query_host(spec, 300 + i, n, n_terms=i % 5) for i in range(B)]
+    Q = np.stack([q.q for q in qs])
+    terms = [q.terms for q in qs]
+    dev = torch.device("cuda", 0)
+    with orr.RecallShard(dim, n, term_slots=32) as sh:
+        sh.fill_synthetic(spec, 0, n)
+        host = sh.search_batch(Q, terms, NOW, k)
+        out = torch.zeros(B * k * 24, dtype=torch.uint8, device=dev)
+        out_n = torch.zeros(B, dtype=torch.int32, device=dev)
+        assert sh.search_batch_device(Q, terms, NOW, k, out.data_ptr(), out_n.data_ptr())
+        assert sh.last_timing()["path"] & 0xff == N.PATH_BATCH
+        raw = np.frombuffer(out.cpu().numpy().tobytes(), dtype=host.raw.dtype).reshape(B, k)
+        assert out_n.cpu().tolist() == host.n_out.tolist()
+        for b in range(B):
+            nb = int(host.n_out[b])
+            assert raw[b][:nb].tobytes() == host.raw[b][:nb].tobytes(), b
+        assert not sh.search_batch_device(Q[:4], terms[:4], NOW, k, out.data_ptr(), out_n.data_ptr())      # batch < 8
+        assert not sh.search_batch_device(Q, terms, NOW, 200, out.data_ptr(), out_n.data_ptr())            # k > 128

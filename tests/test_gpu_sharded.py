@@ -234,3 +234,22 @@ def test_pipelined_device_search_equals_the_blocking_form_on_one_rank():
             b = sh.search(q.q, q.terms, NOW, k)
             assert fa == 0 and a.rows.tolist() == b.rows.tolist() and a.scores.tolist() == b.scores.tolist()
         sr.close()
+
+
+def test_single_process_cluster_batch_matches_the_oracle():
+    """orr_cluster_search_batch: the tcgen05 batched path on every shard (one host thread per GPU) and a per-query k-way
+    merge under the reference tie chain -> the oracle's global ranking for every query of the batch, duplicates included."""
+    dim, per, world, k, B = 256, 3_000, 3, 10, 24
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=16, dup_row_ppm=20000)
+    rows = synth.rows_host(spec, 0, per * world)
+    to_global = lambda r: ((int(r) // per) << 40) | (int(r) % per)
+    with orr.RecallCluster(dim, per + 64, [0] * world, max_top_k=32) as cl:
+        cl.fill_synthetic(spec, 0, per)
+        qs = [synth.query_host(spec, 100 + i, per * world, n_terms=1 + i % 4) for i in range(B)]
+        got = cl.search_batch(np.stack([q.q for q in qs]), [q.terms for q in qs], NOW, k)
+        assert len(got) == B
+        for b, q in enumerate(qs):
+            er, es, _ = oracle_search_synth(rows, q, NOW, k)
+            assert_same_ranking(got[b].rows, got[b].scores, [to_global(r) for r in er], es, what=f"cluster batch b={b}")
+        one = cl.search(qs[5].q, qs[5].terms, NOW, k)                       # and the same hits as the single-query form
+        assert got[5].rows.tolist() == one.rows.tolist() and got[5].scores.tolist() == one.scores.tolist()
