@@ -711,6 +711,15 @@ def measure_cluster(args):
             for q in queries[warmup:warmup + max(1, int(0.6 * steps / max(dt, 1e-3)))]:
                 cl.search(q.q, q.terms, spec.now_ticks, TOP_K)           # keep the sampler under load for ~0.6 s
         assert len(hits.rows) == TOP_K
+        # the throughput form: the same queries as ONE pipelined run (orr_cluster_search_many: three queries in flight, the
+        # exchange of query i on a side stream of every device while it scans query i+1); host buffers in and out
+        Qrun = np.stack([q.q for q in queries[warmup:]])
+        Trun = [q.terms for q in queries[warmup:]]
+        cl.search_many(Qrun[:8], Trun[:8], spec.now_ticks, TOP_K)
+        t1 = time.perf_counter()
+        many = cl.search_many(Qrun, Trun, spec.now_ticks, TOP_K)
+        dt_many = time.perf_counter() - t1
+        assert many[len(many) - 1].rows.tolist() == hits.rows.tolist(), "pipelined run / single call disagree"
         # batched queries over the cluster (orr_cluster_search_batch): every shard's tcgen05 path, merged per query
         batch = None
         if not args.headline_only:
@@ -738,6 +747,8 @@ def measure_cluster(args):
             "dtype": "f32 scan select + f64 exact re-score", "data": "synthetic",
             "config": dict(workload_config(args, n_local), rows_total=total_rows, parallelism=f"1 process x {n_dev} GPUs (orr_cluster)"),
             "corpus_qps": steps / dt, "form": "single process (orr_cluster_search), wall clock, host buffers in and out",
+            "pipelined_run": {"value": steps / dt_many * scale, "corpus_qps": steps / dt_many, "ms_per_query": 1000.0 * dt_many / steps,
+                              "what": f"orr_cluster_search_many: the same {steps} queries as one pipelined run (3 in flight), host buffers in and out"},
             "e2e": {"value": steps / dt * scale, "unit": UNIT, "h2d_bytes_per_step": n_dev * (4 * DIM + 12 * N_TERMS),
                     "d2h_bytes_per_step": 24 * TOP_K + 8, "ms_per_step": 1000.0 * dt / steps,
                     "call_ms": {"what": "RecallCluster.search wall clock", "median": statistics.median(wall), "p99": p99(wall)}},

@@ -354,6 +354,14 @@ int  orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim,
         int32_t n_terms, const uint64_t* probe_hash, const int32_t* probe_term, int32_t n_probes,
         int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
 
+/* A run of n_queries SINGLE queries, pipelined — the throughput form of orr_cluster_search: the exchange + merge of query i
+ * runs on a side stream of every device while that device already scans query i+1 (three queries in flight, each with its
+ * own buffers).  q is n_queries x q_dim; terms as a CSR over the queries (as orr_search_batch); out is
+ * n_queries x max(1,top_k).  Returns exactly the hits of n_queries orr_cluster_search calls. */
+int  orr_cluster_search_many(orr_cluster* c, int32_t n_queries, const float* q, int32_t q_dim,
+        const int32_t* n_terms, const uint64_t* probe_hash, const int32_t* probe_term, const uint32_t* probe_offsets,
+        int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out);
+
 /* Batched queries over the cluster: orr_search_batch on every shard (one host thread per GPU), then a k-way merge of each
  * query's per-shard lists under the reference tie chain.  Arguments as orr_search_batch. */
 int  orr_cluster_search_batch(orr_cluster* c, int32_t batch, const float* q, int32_t q_dim,

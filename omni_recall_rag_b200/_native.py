@@ -126,6 +126,8 @@ _SIGNATURES = {
                                      C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "orr_cluster_search_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "orr_cluster_search_many": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "orr_last_error": (C.c_char_p, []),
     "orr_last_timing": (C.c_int, [C.POINTER(OrrTiming)]),
     "orr_synth_spec_default": (None, [C.POINTER(OrrSynthSpec), C.c_int32]),

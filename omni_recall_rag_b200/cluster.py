@@ -95,6 +95,25 @@ class RecallCluster:
             int(ph.size), int(now_ticks), int(top_k), C.cast(out, C.c_void_p), C.byref(n)))
         return _hits_from(out, n.value)
 
+    def search_many(self, q: np.ndarray, terms, now_ticks: int, top_k: int) -> BatchHits:
+        """orr_cluster_search_many: a run of SINGLE queries (q is [n, dim]; `terms` a sequence of n QueryTerms or a packed
+        BatchTerms), pipelined — the exchange of query i overlaps every device's scan of query i+1.  Same hits as n
+        search() calls."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        n, qd = int(q.shape[0]), int(q.shape[1]) if q.ndim == 2 else 0
+        k = max(1, int(top_k))
+        raw = np.zeros((max(n, 1), k), dtype=_HIT_DTYPE)
+        n_out = np.zeros(max(n, 1), dtype=np.int32)
+        bt = None
+        if terms is not None:
+            bt = terms if isinstance(terms, BatchTerms) else BatchTerms.pack(terms)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        N.check(N.lib().orr_cluster_search_many(self._h, n, p(q) if q.size else None, qd,
+                                                p(bt.n_terms) if bt else None, p(bt.probe_hash) if bt else None,
+                                                p(bt.probe_term) if bt else None, p(bt.probe_offsets) if bt else None,
+                                                int(now_ticks), int(top_k), p(raw), p(n_out)))
+        return BatchHits(raw[:n], n_out[:n])
+
     def search_batch(self, q: np.ndarray, terms, now_ticks: int, top_k: int) -> BatchHits:
         """orr_cluster_search_batch: orr_search_batch on every shard (one host thread per GPU) + per-query k-way merge."""
         q = np.ascontiguousarray(q, dtype=np.float32)

@@ -15,6 +15,7 @@
 namespace {
 constexpr int CLUSTER_MAX = ORR_XCHG_MAX_WORLD;
 constexpr int CLUSTER_ROW_SHIFT = 40;          // global row id = shard << 40 | local row
+constexpr int CLUSTER_RING = 3;                // queries in flight in orr_cluster_search_many (< the exchange's 4 slots)
 }
 
 struct orr_cluster {
@@ -33,6 +34,19 @@ struct orr_cluster {
     float* h_q = nullptr;                       // pinned
     orr_hit* h_out = nullptr;                   // pinned
     int32_t* h_status = nullptr;                // pinned
+    // orr_cluster_search_many: a ring of CLUSTER_RING queries in flight (allocated on first use)
+    bool ring_ready = false;
+    cudaStream_t xstream[CLUSTER_MAX] = {};     // the exchange + merge of query i runs here while stream[d] scans query i+1
+    float* r_q[CLUSTER_MAX][CLUSTER_RING] = {};
+    orr_hit* r_hits[CLUSTER_MAX][CLUSTER_RING] = {};
+    int32_t* r_status[CLUSTER_MAX][CLUSTER_RING] = {};
+    orr_hit* r_out[CLUSTER_MAX][CLUSTER_RING] = {};
+    int32_t* r_out_status[CLUSTER_MAX][CLUSTER_RING] = {};
+    cudaEvent_t ev_scan[CLUSTER_MAX][CLUSTER_RING] = {};
+    cudaEvent_t ev_done[CLUSTER_MAX][CLUSTER_RING] = {};
+    float* rh_q = nullptr;                      // pinned [RING][dim]
+    orr_hit* rh_out = nullptr;                  // pinned [RING][max_k]
+    int32_t* rh_status = nullptr;               // pinned [RING][2]
     std::unordered_map<uint64_t, int> doc_shard;
     std::mutex mu;                              // one search / mutation at a time per cluster
 };
@@ -49,10 +63,17 @@ void orr_cluster_destroy(orr_cluster* c) {
         cudaSetDevice(c->devices[d]);
         if (c->xchg[d]) orr_xchg_destroy(c->xchg[d]);
         cudaFree(c->d_q[d]); cudaFree(c->d_hits[d]); cudaFree(c->d_status[d]); cudaFree(c->d_out[d]); cudaFree(c->d_out_status[d]);
+        if (c->xstream[d]) { cudaStreamSynchronize(c->xstream[d]); cudaStreamDestroy(c->xstream[d]); }
+        for (int r = 0; r < CLUSTER_RING; ++r) {
+            cudaFree(c->r_q[d][r]); cudaFree(c->r_hits[d][r]); cudaFree(c->r_status[d][r]); cudaFree(c->r_out[d][r]); cudaFree(c->r_out_status[d][r]);
+            if (c->ev_scan[d][r]) cudaEventDestroy(c->ev_scan[d][r]);
+            if (c->ev_done[d][r]) cudaEventDestroy(c->ev_done[d][r]);
+        }
         if (c->stream[d]) cudaStreamDestroy(c->stream[d]);
         if (c->store[d]) orr_store_destroy(c->store[d]);
     }
     cudaFreeHost(c->h_q); cudaFreeHost(c->h_out); cudaFreeHost(c->h_status);
+    cudaFreeHost(c->rh_q); cudaFreeHost(c->rh_out); cudaFreeHost(c->rh_status);
     delete c;
 }
 
@@ -157,6 +178,7 @@ static void cluster_recover(orr_cluster* c) {
     for (int d = 0; d < c->n; ++d) {
         cudaSetDevice(c->devices[d]);
         cudaStreamSynchronize(c->stream[d]);
+        if (c->xstream[d]) cudaStreamSynchronize(c->xstream[d]);
         top = std::max(top, orr_xchg_sequence(c->xchg[d]));
     }
     cudaGetLastError();
@@ -180,12 +202,12 @@ static int for_each_shard_parallel(orr_cluster* c, F fn) {
 
 extern "C" {
 
-int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
-                       const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
-    if (!c || !out || !n_out || q_dim < 0 || (q_dim > 0 && !q)) { orr_set_error("orr_cluster_search: bad argument"); return ORR_E_INVALID; }
+// one query, the cluster's mutex held by the caller
+static int cluster_search_locked(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
+                                 const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, int32_t top_k, orr_hit* out,
+                                 int32_t* n_out) {
     *n_out = 0;
     const int k = std::max(1, top_k);
-    std::lock_guard<std::mutex> g(c->mu);
     bool fused = q_dim == c->dim && k <= c->max_k;
     if (fused) {
         memcpy(c->h_q, q, sizeof(float) * (size_t)q_dim);
@@ -234,6 +256,132 @@ int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_
     });
     if (rc != ORR_OK) return rc;
     return orr_merge_hits(lists.data(), lens.data(), c->n, k, top_k, out, n_out);
+}
+
+static int cluster_ring_init(orr_cluster* c) {
+    if (c->ring_ready) return ORR_OK;
+    for (int d = 0; d < c->n; ++d) {
+        ORR_CUDA_OK(cudaSetDevice(c->devices[d]));
+        ORR_CUDA_OK(cudaStreamCreateWithFlags(&c->xstream[d], cudaStreamNonBlocking));
+        for (int r = 0; r < CLUSTER_RING; ++r) {
+            ORR_CUDA_OK(cudaMalloc(&c->r_q[d][r], sizeof(float) * (size_t)c->dim));
+            ORR_CUDA_OK(cudaMalloc(&c->r_hits[d][r], sizeof(orr_hit) * (size_t)c->max_k));
+            ORR_CUDA_OK(cudaMalloc(&c->r_status[d][r], sizeof(int32_t) * 2));
+            ORR_CUDA_OK(cudaMalloc(&c->r_out[d][r], sizeof(orr_hit) * (size_t)c->max_k));
+            ORR_CUDA_OK(cudaMalloc(&c->r_out_status[d][r], sizeof(int32_t) * 2));
+            ORR_CUDA_OK(cudaEventCreateWithFlags(&c->ev_scan[d][r], cudaEventDisableTiming));
+            ORR_CUDA_OK(cudaEventCreateWithFlags(&c->ev_done[d][r], cudaEventDisableTiming));
+        }
+    }
+    ORR_CUDA_OK(cudaMallocHost(&c->rh_q, sizeof(float) * (size_t)c->dim * CLUSTER_RING));
+    ORR_CUDA_OK(cudaMallocHost(&c->rh_out, sizeof(orr_hit) * (size_t)c->max_k * CLUSTER_RING));
+    ORR_CUDA_OK(cudaMallocHost(&c->rh_status, sizeof(int32_t) * 2 * CLUSTER_RING));
+    c->ring_ready = true;
+    return ORR_OK;
+}
+
+int orr_cluster_search(orr_cluster* c, const float* q, int32_t q_dim, int32_t n_terms, const uint64_t* probe_hash,
+                       const int32_t* probe_term, int32_t n_probes, int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
+    if (!c || !out || !n_out || q_dim < 0 || (q_dim > 0 && !q)) { orr_set_error("orr_cluster_search: bad argument"); return ORR_E_INVALID; }
+    std::lock_guard<std::mutex> g(c->mu);
+    return cluster_search_locked(c, q, q_dim, n_terms, probe_hash, probe_term, n_probes, now_ticks, top_k, out, n_out);
+}
+
+// A run of single queries, pipelined (the throughput form; the one-process counterpart of search_device_pipelined): the
+// exchange + merge of query i runs on a side stream of every device while that device already scans query i + 1, and the
+// merged hits of query i come down from device 0 behind it — CLUSTER_RING queries in flight, each with its own buffers.
+// Every query is still the complete search: the hits are those of n_queries calls of orr_cluster_search.
+int orr_cluster_search_many(orr_cluster* c, int32_t n_queries, const float* q, int32_t q_dim, const int32_t* n_terms,
+                            const uint64_t* probe_hash, const int32_t* probe_term, const uint32_t* probe_offsets,
+                            int64_t now_ticks, int32_t top_k, orr_hit* out, int32_t* n_out) {
+    if (!c || n_queries < 0 || !out || !n_out || q_dim < 0 || (n_queries > 0 && q_dim > 0 && !q)) {
+        orr_set_error("orr_cluster_search_many: bad argument");
+        return ORR_E_INVALID;
+    }
+    const int k = std::max(1, top_k);
+    std::lock_guard<std::mutex> g(c->mu);
+    auto terms_of = [&](int32_t i, int32_t* nt, const uint64_t** ph, const int32_t** pt, int32_t* np) {
+        *nt = n_terms ? n_terms[i] : 0;
+        const uint32_t p0 = probe_offsets ? probe_offsets[i] : 0u, p1 = probe_offsets ? probe_offsets[i + 1] : 0u;
+        *ph = probe_hash ? probe_hash + p0 : nullptr;
+        *pt = probe_term ? probe_term + p0 : nullptr;
+        *np = (int32_t)(p1 - p0);
+    };
+    auto single = [&](int32_t i) {
+        int32_t nt, np; const uint64_t* ph; const int32_t* pt;
+        terms_of(i, &nt, &ph, &pt, &np);
+        return cluster_search_locked(c, q ? q + (int64_t)i * q_dim : nullptr, q_dim, nt, ph, pt, np, now_ticks, top_k,
+                                     out + (int64_t)i * k, n_out + i);
+    };
+    if (q_dim != c->dim || k > c->max_k || c->n < 1) {            // not the fused path: one query at a time
+        for (int32_t i = 0; i < n_queries; ++i) { const int rc = single(i); if (rc != ORR_OK) return rc; }
+        return ORR_OK;
+    }
+    int rc = cluster_ring_init(c);
+    if (rc != ORR_OK) return rc;
+    std::vector<int32_t> redo;
+    bool timed_out = false;
+    auto finish = [&](int32_t i) -> int {                          // query i's merged hits have reached pinned memory
+        const int s = i % CLUSTER_RING;
+        ORR_CUDA_OK(cudaEventSynchronize(c->ev_done[0][s]));
+        const int32_t* st = c->rh_status + 2 * s;
+        n_out[i] = 0;
+        if (st[1] & ORR_STATUS_XCHG_TIMEOUT) { timed_out = true; return ORR_OK; }
+        if (st[1] != 0) { redo.push_back(i); return ORR_OK; }      // a shard could not prove its fp32 selection
+        const int got = std::min(st[0], k);
+        memcpy(out + (int64_t)i * k, c->rh_out + (size_t)s * c->max_k, sizeof(orr_hit) * (size_t)got);
+        n_out[i] = got;
+        return ORR_OK;
+    };
+    for (int32_t i = 0; i < n_queries && rc == ORR_OK; ++i) {
+        const int s = i % CLUSTER_RING;
+        if (i >= CLUSTER_RING) { rc = finish(i - CLUSTER_RING); if (rc != ORR_OK) break; }
+        int32_t nt, np; const uint64_t* ph; const int32_t* pt;
+        terms_of(i, &nt, &ph, &pt, &np);
+        float* hq = c->rh_q + (size_t)s * c->dim;
+        memcpy(hq, q + (int64_t)i * q_dim, sizeof(float) * (size_t)q_dim);
+        for (int d = 0; d < c->n && rc == ORR_OK; ++d) {
+            rc = [&]() -> int {
+                ORR_CUDA_OK(cudaSetDevice(c->devices[d]));
+                // slot s of this device is free once the exchange of query i - RING has read its local list
+                if (i >= CLUSTER_RING) ORR_CUDA_OK(cudaStreamWaitEvent(c->stream[d], c->ev_done[d][s], 0));
+                ORR_CUDA_OK(cudaMemcpyAsync(c->r_q[d][s], hq, sizeof(float) * (size_t)q_dim, cudaMemcpyHostToDevice, c->stream[d]));
+                int r = orr_search_device(c->store[d], c->r_q[d][s], q_dim, nt, ph, pt, np, now_ticks, top_k, c->r_hits[d][s],
+                                          c->r_status[d][s], c->stream[d]);
+                if (r != ORR_OK) return r;
+                ORR_CUDA_OK(cudaEventRecord(c->ev_scan[d][s], c->stream[d]));
+                ORR_CUDA_OK(cudaStreamWaitEvent(c->xstream[d], c->ev_scan[d][s], 0));
+                r = orr_xchg_allgather_merge(c->xchg[d], c->r_hits[d][s], c->r_status[d][s], top_k, c->r_out[d][s], c->r_out_status[d][s],
+                                             c->xstream[d]);
+                if (r != ORR_OK) return r;
+                if (d == 0) {
+                    ORR_CUDA_OK(cudaMemcpyAsync(c->rh_status + 2 * s, c->r_out_status[0][s], sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->xstream[0]));
+                    ORR_CUDA_OK(cudaMemcpyAsync(c->rh_out + (size_t)s * c->max_k, c->r_out[0][s], sizeof(orr_hit) * (size_t)k,
+                                                cudaMemcpyDeviceToHost, c->xstream[0]));
+                }
+                ORR_CUDA_OK(cudaEventRecord(c->ev_done[d][s], c->xstream[d]));
+                return ORR_OK;
+            }();
+        }
+    }
+    if (rc != ORR_OK) {
+        const std::string msg = orr_last_error();
+        cluster_recover(c);                                        // devices that did launch wait for the one that did not
+        orr_set_error("%s", msg.c_str());
+        return rc;
+    }
+    for (int32_t i = std::max(0, n_queries - CLUSTER_RING); i < n_queries; ++i) { rc = finish(i); if (rc != ORR_OK) return rc; }
+    for (int d = 0; d < c->n; ++d) {                               // the other devices' side streams end with the same queries
+        ORR_CUDA_OK(cudaSetDevice(c->devices[d]));
+        ORR_CUDA_OK(cudaStreamSynchronize(c->xstream[d]));
+    }
+    if (timed_out) {
+        cluster_recover(c);
+        orr_set_error("orr_cluster_search_many: a shard never published its list");
+        return ORR_E_CUDA;
+    }
+    for (int32_t i : redo) { rc = single(i); if (rc != ORR_OK) return rc; }
+    return ORR_OK;
 }
 
 // Batched queries over the shards: every shard runs orr_search_batch (tcgen05 contraction + exact re-rank, with its own

@@ -253,3 +253,31 @@ def test_single_process_cluster_batch_matches_the_oracle():
             assert_same_ranking(got[b].rows, got[b].scores, [to_global(r) for r in er], es, what=f"cluster batch b={b}")
         one = cl.search(qs[5].q, qs[5].terms, NOW, k)                       # and the same hits as the single-query form
         assert got[5].rows.tolist() == one.rows.tolist() and got[5].scores.tolist() == one.scores.tolist()
+
+
+def test_cluster_search_many_pipelines_a_run_of_queries_to_the_same_hits():
+    """orr_cluster_search_many: a run of single queries with three in flight (exchange of query i on a side stream while the
+    devices scan query i+1) returns, query by query, exactly what orr_cluster_search returns — also for runs shorter than
+    the ring, for queries without an embedding (per-shard exact path) and after a mutation."""
+    dim, per, world, k = 256, 3_000, 3, 10
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=16, dup_row_ppm=20000)
+    rows = synth.rows_host(spec, 0, per * world)
+    to_global = lambda r: ((int(r) // per) << 40) | (int(r) % per)
+    with orr.RecallCluster(dim, per + 64, [0] * world, max_top_k=32) as cl:
+        cl.fill_synthetic(spec, 0, per)
+        qs = [synth.query_host(spec, 500 + i, per * world, n_terms=i % 4) for i in range(11)]
+        for n in (11, 2, 1, 0):
+            many = cl.search_many(np.stack([q.q for q in qs[:n]]) if n else np.zeros((0, dim), np.float32), [q.terms for q in qs[:n]], NOW, k)
+            assert len(many) == n
+            for i in range(n):
+                one = cl.search(qs[i].q, qs[i].terms, NOW, k)
+                assert many[i].rows.tolist() == one.rows.tolist() and many[i].scores.tolist() == one.scores.tolist(), (n, i)
+        many = cl.search_many(np.stack([q.q for q in qs]), [q.terms for q in qs], NOW, k)
+        for i in (1, 7, 10):                                                # and the oracle's global ranking
+            er, es, _ = oracle_search_synth(rows, qs[i], NOW, k)
+            assert_same_ranking(many[i].rows, many[i].scores, [to_global(r) for r in er], es, what=f"many q={i}")
+        # larger k than the fused path takes -> the one-at-a-time fallback inside the same call
+        big = cl.search_many(np.stack([q.q for q in qs[:3]]), [q.terms for q in qs[:3]], NOW, 40)
+        for i in range(3):
+            one = cl.search(qs[i].q, qs[i].terms, NOW, 40)
+            assert big[i].rows.tolist() == one.rows.tolist()
