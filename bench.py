@@ -534,7 +534,26 @@ def measure_batch_sharded(args, name: str, steps: int, warmup: int):
     assert all(int(n) == k for n in hits.n_out), "short hit lists"
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt_blocking = float(t.item())
+    # the throughput form: batch i's all-gather + merge (and its wait for the slowest rank) overlap batch i+1's search
+    barrier()
+    t0 = time.perf_counter()
+    pending, last = None, None
+    for i in range(warmup, n_b):
+        nxt = sr.search_batch_async(Qs[i].numpy(), Ts[i], spec.now_ticks, k)
+        if pending is not None:
+            last = pending()
+        pending = nxt
+    last = pending()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt_pipelined = float(t.item())
+    assert last.raw.tobytes() == hits.raw.tobytes(), "pipelined / blocking batch forms disagree"
+    # both forms do the same work and return the same hits; the line's value is the faster one (the side-stream NCCL kernels
+    # can delay the next persistent GEMM's launch as well as hide the wait for the slowest rank), the other is reported beside it
+    pipelined = dt_pipelined < dt_blocking
+    dt = min(dt_pipelined, dt_blocking)
     line = None
     if rank == 0:
         burst, sustained, peak_kind = measured_tensor_peak()
@@ -548,7 +567,9 @@ def measure_batch_sharded(args, name: str, steps: int, warmup: int):
             "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 tcgen05 screen (fp32 accumulate in TMEM) + f64 exact re-rank of the candidates", "data": "synthetic",
             "config": dict(batch_config(args, wl), rows_total=total_rows, rows_per_gpu=rows, parallelism=f"row-sharded x {world} (torchrun)"),
-            "corpus_qps": steps * B / dt,
+            "corpus_qps": steps * B / dt, "pipelined_exchange": pipelined,
+            "value_blocking_exchange": steps * B / dt_blocking * scale, "ms_per_step_blocking": 1000.0 * dt_blocking / steps,
+            "value_pipelined_exchange": steps * B / dt_pipelined * scale, "ms_per_step_pipelined": 1000.0 * dt_pipelined / steps,
             "e2e": {"value": steps * B / dt * scale, "unit": f"queries/s x (rows_total / {rows})",
                     "h2d_bytes_per_step": B * dim * 4 + B * 4 + (B + 1) * 4 + B * wl["n_terms"] * 8,
                     "d2h_bytes_per_step": B * k * 24 + B * 4, "ms_per_step": 1000.0 * dt / steps},

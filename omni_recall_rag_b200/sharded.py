@@ -212,6 +212,59 @@ class ShardedRecall:
         raw = bufs["h_out"].numpy().view(_HIT_DTYPE).reshape(B, k).copy()     # one host copy: the pinned buffer is reused
         return BatchHits(raw, bufs["h_n"].numpy().copy())
 
+    def search_batch_async(self, q: np.ndarray, terms, now_ticks: int, top_k: int) -> Callable[[], BatchHits]:
+        """Throughput form of search_batch for a stream of batches: the local tcgen05 search runs now (the call returns when
+        this rank's answers are in HBM), the all-gather + per-query merge + copy to pinned memory are enqueued on a side
+        stream, and the returned function waits for them and hands out the BatchHits.  Calling it for batch i+1 before
+        collecting batch i overlaps i's exchange — and its wait for the slowest rank — with i+1's search.  At most two
+        batches may be outstanding (two buffer sets); every rank must issue the same sequence of batches."""
+        import torch
+
+        if self.world == 1:
+            local = self.shard.search_batch(q, terms, now_ticks, top_k)
+            return lambda: local
+        if self.dist.get_backend(self.group) != "nccl":
+            raise RuntimeError("sharded search_batch needs the nccl backend (device merge)")
+        dev = torch.device("cuda", self.shard.device)
+        B, k = int(np.asarray(q).shape[0]), max(1, int(top_k))
+        bt = terms if (terms is None or isinstance(terms, BatchTerms)) else BatchTerms.pack(terms)
+        key = ("batch_async", B, k)
+        if key not in self._dev_bufs:
+            nb = B * k * HIT_BYTES
+            self._dev_bufs[key] = dict(side=torch.cuda.Stream(device=dev), idx=0, slots=[dict(
+                mine=torch.empty(nb, dtype=torch.uint8, device=dev), mine_n=torch.empty(B, dtype=torch.int32, device=dev),
+                allh=torch.empty(self.world * nb, dtype=torch.uint8, device=dev),
+                alln=torch.empty(self.world * B, dtype=torch.int32, device=dev),
+                out=torch.empty(nb, dtype=torch.uint8, device=dev), out_n=torch.empty(B, dtype=torch.int32, device=dev),
+                h_out=torch.empty(nb, dtype=torch.uint8).pin_memory(), h_n=torch.empty(B, dtype=torch.int32).pin_memory(),
+                done=torch.cuda.Event(), pending=False) for _ in range(2)])
+        pipe = self._dev_bufs[key]
+        b = pipe["slots"][pipe["idx"] % 2]
+        pipe["idx"] += 1
+        if b["pending"]:
+            raise RuntimeError("search_batch_async: collect the batch issued two calls ago before issuing another")
+        if not self.shard.search_batch_device(q, bt, now_ticks, top_k, b["mine"].data_ptr(), b["mine_n"].data_ptr()):
+            local = self.shard.search_batch(q, bt, now_ticks, top_k)
+            b["mine"].copy_(torch.from_numpy(local.raw.view(np.uint8).reshape(-1)))
+            b["mine_n"].copy_(torch.from_numpy(np.ascontiguousarray(local.n_out, dtype=np.int32)))
+            torch.cuda.current_stream(dev).synchronize()
+        side = pipe["side"]                                   # the local answers are complete (the call above synchronised)
+        with torch.cuda.stream(side):
+            self.dist.all_gather_into_tensor(b["allh"], b["mine"], group=self.group)
+            self.dist.all_gather_into_tensor(b["alln"], b["mine_n"], group=self.group)
+            N.check(N.lib().orr_merge_hits_batch_device(self.shard.device, b["allh"].data_ptr(), b["alln"].data_ptr(), self.world, B, k,
+                                                        b["out"].data_ptr(), b["out_n"].data_ptr(), side.cuda_stream))
+            b["h_out"].copy_(b["out"], non_blocking=True)
+            b["h_n"].copy_(b["out_n"], non_blocking=True)
+            b["done"].record(side)
+        b["pending"] = True
+
+        def collect() -> BatchHits:
+            b["done"].synchronize()
+            b["pending"] = False
+            return BatchHits(b["h_out"].numpy().view(_HIT_DTYPE).reshape(B, k).copy(), b["h_n"].numpy().copy())
+        return collect
+
     # -- device-resident path (query and hits stay in HBM; nothing synchronises the host) -----
     def search_device(self, q_dev, terms: QueryTerms, now_ticks: int, top_k: int):
         """q_dev: torch float32 CUDA tensor [dim].  Returns (hits_dev uint8[k*24], status_dev
