@@ -1,5 +1,6 @@
 #!/bin/bash
-# N=8: the single-process cluster (single calls, pipelined run, batch) and the row-sharded batched configs under torchrun
+# gpurun --gpus 8 -- bash tools/gpu_multi.sh 8
+# N GPUs: the single-process cluster (single calls, pipelined run, batch) and the row-sharded batched configs under torchrun
 set -u
 O=gpurun_out; mkdir -p $O
 N=${1:-8}
