@@ -368,11 +368,18 @@ __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a)
             // exact recount on the full hashes: one thread per candidate, 16-byte loads over the row's slots
             uint32_t m0 = 0u, m1 = 0u;
             const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(a.terms64 + row * (int64_t)a.slots);
-            for (int v = 0; v < a.slots / 2; ++v) {
-                const ulonglong2 h2 = __ldg(t2 + v);
+            // 8 loads in flight per step: one by one, the 32 loads of a 64-slot row were a chain of 32 L2 round trips
+            // (the kernel spent 20 us on a few hundred candidates)
+            for (int v0 = 0; v0 < a.slots / 2; v0 += 8) {
+                ulonglong2 h2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h2[i] = __ldg(t2 + v0 + i);        // slots is a multiple of 32: no tail
                 for (int p = 0; p < a.pr.n_probes; ++p) {
                     const uint64_t h = a.pr.h64[p];
-                    if (h2.x == h || h2.y == h) { const uint32_t t = a.pr.term[p]; if (t < 32) m0 |= 1u << t; else m1 |= 1u << (t - 32); }
+                    bool hit = false;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hit |= (h2[i].x == h) | (h2[i].y == h);
+                    if (hit) { const uint32_t t = a.pr.term[p]; if (t < 32) m0 |= 1u << t; else m1 |= 1u << (t - 32); }
                 }
             }
             ExactLite ex = {};

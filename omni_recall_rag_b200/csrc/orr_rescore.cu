@@ -73,7 +73,12 @@ struct OrderArgs {
     int32_t*  status;            // {n_out, flags}; NULL: the caller has written it
 };
 
+constexpr int ORDER_STAGE = 1024;               // records staged in shared memory per round (24 KB)
 __global__ void __launch_bounds__(256) orr_order_kernel(const OrderArgs a) {
+    // every warp compares its record with ALL records: the list is staged in shared memory ORDER_STAGE records at a
+    // time (one coalesced round trip per CTA) instead of each warp walking it through L2 32 records per round trip
+    // (10 dependent round trips for the reference's 300 candidates: the kernel took 9-10 us, now one round trip)
+    __shared__ OrrExact stage[ORDER_STAGE];
     const int lane = threadIdx.x & 31;
     const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int n = min(a.n_ptr ? *a.n_ptr : a.n_value, a.n_max);
@@ -85,22 +90,28 @@ __global__ void __launch_bounds__(256) orr_order_kernel(const OrderArgs a) {
         // fewer rows listed than k: no k-th score exists, the bound cannot be proven (unless nothing was discarded)
         if (n < k) a.status[1] = (a.check_bound && tau != -INFINITY) ? 1 : 0;
     }
-    if (i >= n) return;
+    if ((int)((blockIdx.x * blockDim.x) >> 5) >= n) return;           // the whole CTA is beyond the list (CTA-uniform)
+    const bool mine = i < n;
     OrrExact x;
-    x.score = a.exact[i].score; x.ticks = a.exact[i].ticks; x.row = a.exact[i].row;
+    if (mine) { x.score = a.exact[i].score; x.ticks = a.exact[i].ticks; x.row = a.exact[i].row; }
+    else { x.score = 0.0; x.ticks = 0; x.row = 0; }
     int pos = 0;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane;
-        int c = 0;
-        if (j < n) {
-            OrrExact y;
-            y.score = a.exact[j].score; y.ticks = a.exact[j].ticks; y.row = a.exact[j].row;
-            c = ranks_before(y, x) ? 1 : 0;
+    bool live = mine;                                                 // false once k records rank before this one
+    for (int base = 0; base < n; base += ORDER_STAGE) {
+        const int m = min(ORDER_STAGE, n - base);
+        if (!__syncthreads_or(live ? 1 : 0)) break;                   // previous round's readers are done; nobody left: stop staging
+        for (int j = threadIdx.x; j < m; j += blockDim.x) stage[j] = a.exact[base + j];
+        __syncthreads();
+        if (live) {
+            for (int j0 = 0; j0 < m; j0 += 32) {
+                const int j = j0 + lane;
+                const int c = (j < m && ranks_before(stage[j], x)) ? 1 : 0;
+                pos += __reduce_add_sync(FULL, c);
+                if (pos >= k) { live = false; break; }                // warp-uniform: not among the first k
+            }
         }
-        pos += __reduce_add_sync(FULL, c);
-        if (pos >= k) return;                                         // warp-uniform: not among the first k
     }
-    if (lane != 0) return;
+    if (!live || lane != 0) return;
     if (pos < n_out) { orr_hit h; h.row = a.row_base + x.row; h.score = x.score; h.created_ticks = x.ticks; a.hits[pos] = h; }
     if (pos == k - 1 && a.status) {
         // every row outside the list has fp32 score <= tau and |fp32 - exact| <= eps: safe iff the k-th exact score clears
