@@ -58,8 +58,8 @@ FALLBACK_BF16_TFLOPS = 1500.0
 # dram__bytes_read.sum + dram__bytes_write.sum of orr_scan_kernel<24,1,0> per launch and row at 1M x 3072, 4 terms: a
 # CONSTANT taken from the ncu --set full capture summarised in the file below (not measured in this run); it scales
 # linearly with rows.
-NCU_SCAN_TRAFFIC_BYTES_PER_ROW = 12556.9
-NCU_SCAN_TRAFFIC_SOURCE = "profiles/r01_final_kernels.md"
+NCU_SCAN_TRAFFIC_BYTES_PER_ROW = 12557.2
+NCU_SCAN_TRAFFIC_SOURCE = "profiles/r02_ncu_scan_kernel.md"
 BATCH_WORKLOADS = {
     "c3": dict(rows=5_000_000, dim=768, batch=1024, top_k=100, n_terms=4, frequent=0, dup_ppm=0,
                name="5M chunks x 768 fp32 (truncated embeddings), batch 1024 queries, 4 terms, top-100"),
@@ -631,11 +631,14 @@ def measure_noemb(shard, spec, n_local: int, steps: int, warmup: int, cpu_second
                      "bytes_per_row": "4 B x 64 low hash words + 8 B ticks = 264 B: the kernel screens on the scan's 32-bit term table and confirms "
                                       "the (rare) 32-bit hits against the 64-bit table; embeddings are never read",
                      "achieved_if_counted_as_520B_per_row": n_local * 520 / (k_ms / 1000.0) / 1.0e9, "kernel_ms": k_ms,
-                     "select_ms": sum(sel_ms) / steps, "traffic": None,
+                     "select_ms": sum(sel_ms) / steps, "traffic": 264.0e6 * n_local / 1.0e6,
+                     "traffic_source": "CONSTANT from the ncu --set full capture in profiles/r02_ncu_noemb_kernel.md (264.0 MB read per 1M rows)",
                      "note": "kernel_ms spans the 48 KB state clear + the scoring kernel (CUDA events); select_ms = digit passes + gather + "
-                             "D2H + host sync of the exact path"},
-        "gpu_launches": 4 * steps,
-        "kernels_per_step": ["orr_noemb_scores_kernel<2,0>", "orr_sel_pass_kernel x2", "orr_sel_gather_kernel"],
+                             "order + host sync of the exact path.  ncu: this kernel moves exactly its algorithmic bytes but is ALU-bound "
+                             "(78 % ALU pipe, 62 % issue slots, 50 % DRAM): the HBM fraction is reported, the limiter is the compare / "
+                             "REDUX / fp64 recency work per row"},
+        "gpu_launches": 5 * steps,
+        "kernels_per_step": ["orr_noemb_scores_kernel<2,0>", "orr_sel_pass_kernel x2", "orr_sel_gather_kernel", "orr_order_kernel"],
     }
     if cpu_seconds > 0:
         from oracle import oracle_c
@@ -1006,7 +1009,7 @@ def main():
                          "kernel_ms": scan_avg_ms, "finalize_kernel_ms": sum(fin_ms) / len(fin_ms),
                          "traffic": NCU_SCAN_TRAFFIC_BYTES_PER_ROW * n_local,
                          "traffic_source": f"CONSTANT, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per launch from the "
-                                           f"ncu --set full capture summarised in {NCU_SCAN_TRAFFIC_SOURCE} (12556.9 B/row), scaled by rows"},
+                                           f"ncu --set full capture summarised in {NCU_SCAN_TRAFFIC_SOURCE} ({NCU_SCAN_TRAFFIC_BYTES_PER_ROW} B/row), scaled by rows"},
             "clocks": clock_summary,
             "bound_check_escalations": escalated, "device_flags": flags_seen,
         }
