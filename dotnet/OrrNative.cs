@@ -81,6 +81,19 @@ internal static partial class OrrNative
     [LibraryImport(Lib)] internal static unsafe partial int orr_cluster_search(
         nint cluster, float* q, int qDim, int nTerms, ulong* probeHash, int* probeTerm, int nProbes,
         long nowTicks, int topK, OrrHit* hits, out int nOut);
+    // throughput forms over the cluster: a pipelined run of single queries (three in flight) and whole batches
+    [LibraryImport(Lib)] internal static unsafe partial int orr_cluster_search_many(
+        nint cluster, int nQueries, float* q, int qDim, int* nTerms, ulong* probeHash, int* probeTerm, uint* probeOffsets,
+        long nowTicks, int topK, OrrHit* hits, int* nOut);
+    [LibraryImport(Lib)] internal static unsafe partial int orr_cluster_search_batch(
+        nint cluster, int batch, float* q, int qDim, int* nTerms, ulong* probeHash, int* probeTerm, uint* probeOffsets,
+        long nowTicks, int topK, OrrHit* hits, int* nOut);
+    [LibraryImport(Lib)] internal static partial int orr_cluster_size(nint cluster);
+    [LibraryImport(Lib)] internal static partial nint orr_cluster_shard(nint cluster, int i);   // borrowed orr_store: options, snapshot, compaction
+    // bulk ingest (warm load / hydration): many documents per call, searches keep running meanwhile
+    [LibraryImport(Lib)] internal static unsafe partial int orr_store_upsert_documents_texts(
+        nint store, int nDocs, ulong* docKeys, uint* docChunkOffsets, float* emb, byte* hasEmb, long* createdTicks,
+        byte* contentsUtf8, ulong* contentOffsets, ulong* outRows);
     [LibraryImport(Lib)] internal static unsafe partial int orr_merge_hits(
         OrrHit* lists, int* listLen, int nLists, int listStride, int topK, OrrHit* hits, out int nOut);
     [LibraryImport(Lib)] internal static partial nint orr_last_error();
