@@ -138,3 +138,38 @@ def test_random_store_history_and_queries_match_the_oracle(seed):
                 assert got_ids == [ids[int(r)] for r in er], what
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_batches_match_the_oracle(seed):
+    """The batched tcgen05 path on random shapes: width, rows (not a multiple of the 256-row tile), batch size (one to three
+    query blocks, padded), top_k up to the path's 128, 0..16 terms MIXED inside one batch, frequent terms, planted duplicate
+    rows, every screen setting (auto / bf16 / bf16x3), zero and vanishing-norm query vectors — every query against the oracle."""
+    import omni_recall_rag_b200 as orr
+    from tests.util import oracle_search_synth
+
+    rng = np.random.default_rng(9100 + seed)
+    dim = int(rng.choice([64, 128, 192, 768]))
+    n = int(rng.integers(300, 12_000))
+    B = int(rng.choice([8, 9, 31, 64, 257, 300, 520]))
+    k = int(rng.choice([1, 10, 50, 128]))
+    spec = synth.make_spec(dim, gen_dim=dim, terms_per_chunk=int(rng.choice([8, 16, 32])), dup_row_ppm=int(rng.choice([0, 20000, 200000])))
+    rows = synth.rows_host(spec, 0, n)
+    qs = []
+    for b in range(B):
+        nt = int(rng.integers(0, 17))
+        q = synth.query_host(spec, 7000 * seed + b, n, n_terms=nt, frequent_terms=int(rng.integers(0, nt + 1)))
+        r = rng.random()
+        if r < 0.05:
+            q = synth.HostQuery(np.zeros(dim, np.float32), q.term_ids, q.text, q.terms)                 # zero query: cosine 0
+        elif r < 0.10:
+            q = synth.HostQuery((q.q * np.float32(1e-22)).astype(np.float32), q.term_ids, q.text, q.terms)   # norm leaves fp32
+        qs.append(q)
+    with orr.RecallShard(dim, n + 16, term_slots=32) as sh:
+        sh.fill_synthetic(spec, 0, n)
+        sh.set_option("batch_passes", int(rng.choice([0, 1, 3])))
+        got = sh.search_batch(np.stack([q.q for q in qs]), [q.terms for q in qs], NOW, k)
+        assert len(got) == B
+        for b in rng.choice(B, size=min(B, 24), replace=False):
+            er, es, et = oracle_search_synth(rows, qs[int(b)], NOW, k)
+            assert_same_ranking(got[int(b)].rows, got[int(b)].scores, er, es, what=f"seed={seed} b={b} dim={dim} n={n} B={B} k={k}")
