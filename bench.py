@@ -342,6 +342,28 @@ def measure_c1(steps: int, warmup: int, cpu_seconds: float):
             e2e_s = time.perf_counter() - t0
             res[cap] = dict(qps_device=steps / (sum(dev_ms) / 1000.0), qps_e2e=steps / e2e_s, device_ms=sum(dev_ms) / steps,
                             call_ms_median=statistics.median(wall), call_ms_p99=p99(wall), path=tm["path"])
+    # a web API serves requests concurrently: T host threads through the same store (orr_search takes its own search context
+    # and stream per call, ctypes releases the GIL), each request still a blocking call with host buffers in and out
+    import threading
+    conc = {}
+    for T in (4, 16):
+        per = max(50, min(400, steps))
+        done = []
+
+        def worker(t):
+            for i in range(per):
+                j = (t * per + i) % n_q
+                shard.search(q_pinned[j].numpy(), queries[j].terms, spec.now_ticks, TOP_K, candidate_cap=300)
+            done.append(t)
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        dt = time.perf_counter() - t0
+        assert len(done) == T
+        conc[T] = {"threads": T, "value": T * per / dt, "unit": "queries/s", "requests": T * per}
     peak, peak_kind = measured_peak()
     bytes_all = rows_n * (4 * DIM + 8 + 4 * TERM_SLOTS)
     line = {
@@ -356,6 +378,8 @@ def measure_c1(steps: int, warmup: int, cpu_seconds: float):
                 "d2h_bytes_per_step": 24 * TOP_K + 8, "call_ms": {"median": res[300]["call_ms_median"], "p99": res[300]["call_ms_p99"]}},
         "all_rows": {"candidate_cap": 0, "value": res[0]["qps_device"], "e2e": res[0]["qps_e2e"], "device_ms": res[0]["device_ms"],
                      "call_ms": {"median": res[0]["call_ms_median"], "p99": res[0]["call_ms_p99"]}},
+        "concurrent_callers": {"what": "blocking orr_search calls (candidate_cap=300) from T host threads on one store, host buffers in and out",
+                               "t4": conc[4], "t16": conc[16]},
         "gpu_launches": 2 * steps * 2,
         "roofline": {"bound": "hbm", "kernel": "orr_scan_kernel (all rows, cap=0)", "achieved": bytes_all / (res[0]["device_ms"] / 1000.0) / 1.0e9,
                      "peak": peak, "peak_kind": hbm_peak_kind(peak_kind), "unit": "GB/s",
