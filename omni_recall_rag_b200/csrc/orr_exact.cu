@@ -309,6 +309,8 @@ __device__ __forceinline__ void sel_accumulate(const SelPoint& cur, int pass, co
 __global__ void __launch_bounds__(256) orr_sel_pass_kernel(SelState* st, int pass, uint32_t k, const uint64_t* skey,
                                                            const int64_t* ticks, int64_t rows) {
     __shared__ uint32_t s_hist[SEL_BINS];
+    ORR_GRID_DEP_WAIT();                                              // the histogram / walk state of the kernel before this one
+    ORR_GRID_DEP_LAUNCH();
     const SelPoint prev = (pass == 1) ? sel_initial(k) : st->pt[pass - 1];
     const SelPoint cur = sel_advance(prev, st->hist[(pass - 1) % 3], pass - 1);
     if (blockIdx.x == 0 && threadIdx.x == 0) st->pt[pass] = cur;
@@ -334,6 +336,8 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(512) orr_sel_gather_kernel(const GatherArgs a) {
+    ORR_GRID_DEP_WAIT();
+    ORR_GRID_DEP_LAUNCH();
     const int tid = threadIdx.x;
     SelState* st = a.st;
     const SelPoint prev = (a.last_pass == 0) ? sel_initial(a.k) : st->pt[a.last_pass];
@@ -496,7 +500,9 @@ int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k,
     int last = std::max(0, first_pass - 1);
     for (int p = std::max(1, first_pass); p < first_pass + n_passes && p < SEL_NPASS; ++p) {
         const int grid = (int)std::min<int64_t>((n + 1023) / 1024, (int64_t)sms * 4);
-        orr_sel_pass_kernel<<<std::max(1, grid), 256, 0, st>>>(state, p, k, sc.skey, sh.ticks, n);
+        // the first pass of a round follows the scoring kernel (or the host's read of the previous round): a plain launch
+        if (p == std::max(1, first_pass)) orr_sel_pass_kernel<<<std::max(1, grid), 256, 0, st>>>(state, p, k, sc.skey, sh.ticks, n);
+        else ORR_CUDA_OK(orr_launch_dependent(orr_sel_pass_kernel, std::max(1, grid), 256, st, state, p, k, sc.skey, sh.ticks, n));
         ORR_CUDA_OK(cudaGetLastError());
         last = p;
     }
@@ -514,11 +520,12 @@ int orr_launch_exact_select(const OrrShard& sh, const OrrScratch& sc, int top_k,
     // the gather resets nothing: n_gathered / ticket are zero from E1's memset unless an earlier round already gathered
     // (it did not: a round that gathers ends the search)
     const int grid = (int)std::min<int64_t>((n + 2047) / 2048, (int64_t)sms * 2);
-    orr_sel_gather_kernel<<<std::max(1, grid), 512, 0, st>>>(g);
+    if (last >= std::max(1, first_pass)) ORR_CUDA_OK(orr_launch_dependent(orr_sel_gather_kernel, std::max(1, grid), 512, st, g));
+    else orr_sel_gather_kernel<<<std::max(1, grid), 512, 0, st>>>(g);
     ORR_CUDA_OK(cudaGetLastError());
     if (!big) {
         // n_final stays 0 while the walk is incomplete: the order kernel's warps then all exit at once
-        const int rc = orr_launch_order(sc.exact, &state->n_final, SEL_CAP, (int)k, sh.row_base, sc.hits, st);
+        const int rc = orr_launch_order(sc.exact, &state->n_final, SEL_CAP, (int)k, sh.row_base, sc.hits, st, true);
         if (rc != ORR_OK) return rc;
     }
     if (big) {

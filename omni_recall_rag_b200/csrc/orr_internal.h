@@ -1,3 +1,4 @@
+#include <utility>
 // orr_internal.h — shared declarations of liborr.so (not part of the public ABI).
 #pragma once
 #include <cuda_runtime.h>
@@ -129,7 +130,29 @@ int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes
                        int n_listed_max, bool check_bound, cudaStream_t st, int n_listed_host = -1);
 
 // warp-per-record ordering of <= n_max records (orr_rescore.cu); n read from the device
-int orr_launch_order(const OrrExact* recs, const int32_t* n_dev, int n_max, int top_k, uint64_t row_base, orr_hit* hits, cudaStream_t st);
+int orr_launch_order(const OrrExact* recs, const int32_t* n_dev, int n_max, int top_k, uint64_t row_base, orr_hit* hits, cudaStream_t st,
+                     bool dependent = false);
+
+// Launches `kernel` as a PROGRAMMATIC DEPENDENT of the kernel before it on `st`: its CTAs may become resident while the
+// predecessor still runs and must execute griddepcontrol.wait before touching anything the predecessor writes; the
+// predecessor calls griddepcontrol.launch_dependents to allow it.  Hides the 2-3 us launch gap between the short kernels
+// of a latency-bound chain (K3's re-score -> order, the exact path's digit passes -> gather -> order).
+template <class... KArgs, class... Args>
+inline cudaError_t orr_launch_dependent(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define ORR_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define ORR_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 
 // exact path (orr_exact.cu): every row's fp64 score as an order-preserving key, then an MSB-first radix select of the
 // top-k under (score desc / NaN last, ticks desc, row asc).  orr_launch_exact_select runs digit passes

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) orr_rescore_kernel(const RescoreArgs a) {
     // programmatic dependent launch: the ordering kernel behind this one may be scheduled now; its CTAs wait in
     // griddepcontrol.wait until this grid has completed and its stores are visible (saves the launch gap between the two
     // kernels of K3: 2-3 us of a 24 us small-store query)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    ORR_GRID_DEP_LAUNCH();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = min(a.n_listed ? *a.n_listed : a.n_listed_value, a.n_listed_max);
     const int idx = blockIdx.x * 4 + warp;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) orr_order_kernel(const OrderArgs a) {
     // time (one coalesced round trip per CTA) instead of each warp walking it through L2 32 records per round trip
     // (10 dependent round trips for the reference's 300 candidates: the kernel took 9-10 us, now one round trip)
     __shared__ OrrExact stage[ORDER_STAGE];
-    asm volatile("griddepcontrol.wait;" ::: "memory");                // no-op unless launched as a programmatic dependent (K3)
+    ORR_GRID_DEP_WAIT();                                              // no-op unless launched as a programmatic dependent
     const int lane = threadIdx.x & 31;
     const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int n = min(a.n_ptr ? *a.n_ptr : a.n_value, a.n_max);
@@ -326,28 +326,18 @@ int orr_launch_rescore(const OrrShard& sh, const OrrScratch& sc, const OrrProbes
     OrderArgs o;
     o.exact = a.exact; o.n_ptr = a.n_listed; o.n_value = a.n_listed_value; o.n_max = a.n_listed_max; o.top_k = a.top_k;
     o.check_bound = a.check_bound; o.tau_bits = a.tau_bits; o.eps = a.eps; o.row_base = sh.row_base; o.hits = a.hits; o.status = a.status;
-    {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)((n_listed_max + 7) / 8), 1, 1);
-        cfg.blockDim = dim3(256, 1, 1);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        ORR_CUDA_OK(cudaLaunchKernelEx(&cfg, orr_order_kernel, o));
-    }
+    ORR_CUDA_OK(orr_launch_dependent(orr_order_kernel, (n_listed_max + 7) / 8, 256, st, o));
     return ORR_OK;
 }
 
 // orders n (device count, <= n_max) records and writes the first top_k as hits; status is left to the caller
-int orr_launch_order(const OrrExact* recs, const int32_t* n_dev, int n_max, int top_k, uint64_t row_base, orr_hit* hits, cudaStream_t st) {
+int orr_launch_order(const OrrExact* recs, const int32_t* n_dev, int n_max, int top_k, uint64_t row_base, orr_hit* hits, cudaStream_t st,
+                     bool dependent) {
     OrderArgs o;
     o.exact = recs; o.n_ptr = n_dev; o.n_value = 0; o.n_max = n_max; o.top_k = top_k; o.check_bound = 0; o.tau_bits = nullptr; o.eps = 0.0;
     o.row_base = row_base; o.hits = hits; o.status = nullptr;
-    orr_order_kernel<<<(n_max + 7) / 8, 256, 0, st>>>(o);
+    if (dependent) ORR_CUDA_OK(orr_launch_dependent(orr_order_kernel, (n_max + 7) / 8, 256, st, o));
+    else orr_order_kernel<<<(n_max + 7) / 8, 256, 0, st>>>(o);
     ORR_CUDA_OK(cudaGetLastError());
     return ORR_OK;
 }
