@@ -37,6 +37,15 @@ def test_library_exports_every_declared_symbol():
     assert set(names) <= exported
 
 
+def test_every_declared_entry_point_has_a_ctypes_signature():
+    """include/orr.h is the boundary; the Python host (and the tests through it) may only call what it declares, with
+    argument types spelled out — no entry point reaches ctypes with default int marshalling."""
+    names = _header_functions()
+    missing = [n for n in names if n not in N._SIGNATURES]
+    extra = [n for n in N._SIGNATURES if n not in names]
+    assert not missing and not extra, (missing, extra)
+
+
 def test_library_is_sm100a_only_with_tma_bulk_copies():
     """The scan kernel must be real Blackwell code: UBLKCP (cp.async.bulk) in sm_100a SASS."""
     r = subprocess.run(["cuobjdump", "-lelf", N.library_path()], capture_output=True, text=True)
